@@ -1,0 +1,227 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (the reference lives at /root/reference and does not
+travel to the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference package is imported as-is through a loader that
+  * stubs matplotlib / mpl_toolkits (not installed; only used for plotting),
+  * provides a pykeops-free stand-in for diffICP.tools.point_sets (its line 8 hard-imports
+    pykeops, which is absent), restating intrinsic_scale / decimate with torch,
+  * leaves pykeops absent so every "keops" request falls back to the reference's own
+    torch twin (tools/kernel.py:93-96, core/GMM.py:130-133).
+Inputs are fp32-representable; every case is evaluated by the reference in fp32
+("ref32") and in fp64 ("gold").  All seeds are fixed.
+"""
+
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+REF_ROOT = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_reference():
+    class _Anything(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return _Anything(self.__name__ + "." + name)
+
+        def __call__(self, *a, **k):
+            return _Anything("call")
+
+    for name in ["matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors",
+                 "matplotlib.ticker", "mpl_toolkits", "mpl_toolkits.mplot3d"]:
+        sys.modules.setdefault(name, _Anything(name))
+    sys.path.insert(0, REF_ROOT)
+    warnings.filterwarnings("ignore")
+    import diffICP.tools  # noqa: F401
+    ps = types.ModuleType("diffICP.tools.point_sets")
+
+    def intrinsic_scale(x):
+        d2 = ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+        return float(d2.topk(2, dim=1, largest=False).values[:, 1].mean().sqrt())
+
+    def decimate(x, R):
+        raise NotImplementedError
+
+    ps.intrinsic_scale, ps.decimate = intrinsic_scale, decimate
+    sys.modules["diffICP.tools.point_sets"] = ps
+    import diffICP.tools.kernel as rk
+    import diffICP.core.LDDMM as rl
+    import diffICP.core.GMM as rg
+    return rk, rl, rg
+
+
+def spec_of(dt):
+    return {"device": "cpu", "dtype": dt}
+
+
+def np32(t):
+    return t.detach().to(torch.float32).numpy() if t.dtype == torch.float32 else t.detach().numpy()
+
+
+def gen_kernels(rk):
+    """All ten reductions, at the author's own self-check size (tools/kernel.py:352) and a 3-D case."""
+    out = {}
+    for tag, (M, N, D, sig, seed) in {"a": (100, 1000, 2, 2.0, 11), "b": (64, 200, 3, 0.7, 12),
+                                      "c": (33, 77, 3, 0.25, 13)}.items():
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(M, D, generator=g)
+        y = torch.randn(N, D, generator=g)
+        b = torch.randn(N, D, generator=g)
+        c = torch.randn(M, D, generator=g)
+        d = torch.randn(N, generator=g)
+        out[f"{tag}_meta"] = np.array([M, N, D, sig], dtype=np.float64)
+        for nm, t in [("x", x), ("y", y), ("b", b), ("c", c), ("d", d)]:
+            out[f"{tag}_in_{nm}"] = t.numpy()
+        for prec, dt in [("ref32", torch.float32), ("gold", torch.float64)]:
+            GK = rk.GaussKernel(sig, D, computversion="torch", spec=spec_of(dt))
+            X, Y, B, Cc, Dd = (t.to(dt) for t in (x, y, b, c, d))
+            res = {
+                "KBase": GK.KBase(X, Y), "KRedScal": GK.KRedScal(X, Y, Dd), "KRed": GK.KRed(X, Y, B),
+                "GradKRed": GK.GradKRed(X, Y), "DDKRed": GK.DDKRed(X, Y, B),
+                "GenDKRed": GK.GenDKRed(X, Y, B, Cc), "HessKRed": GK.HessKRed(X, Y, B, Cc),
+                "LapKRed": GK.LapKRed(X, Y), "GradLapKRed": GK.GradLapKRed(X, Y),
+                "GradKRed_rev": GK.GradKRed_rev(X, Y, Cc),
+            }
+            for k, v in res.items():
+                out[f"{tag}_{prec}_{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "kernels.npz"), **out)
+    print("kernels.npz", len(out))
+
+
+def gen_lddmm(rl):
+    """Shoot + trajloss + quadratic data loss + gradients for every model variant / scheme / x mode."""
+    out = {}
+    cases = []
+    for D in (2, 3):
+        for version in ("classic", "hybrid", "logdet"):
+            for scheme in ("Euler", "Ralston"):
+                for with_x in (False, True):
+                    cases.append((D, version, scheme, with_x))
+    names = []
+    for ci, (D, version, scheme, with_x) in enumerate(cases):
+        g = torch.Generator().manual_seed(100 + ci)
+        Nq, Nx, nt = 37, 91, 5
+        sig, lam = 0.35, 7.0
+        q0 = torch.rand(Nq, D, generator=g)
+        p0 = 0.3 * torch.randn(Nq, D, generator=g)
+        x0 = torch.rand(Nx, D, generator=g) if with_x else None
+        ny = Nx if with_x else Nq
+        y = torch.rand(ny, D, generator=g)
+        sig2 = 0.05 + 0.1 * torch.rand(ny, generator=g)          # per-point GMM sigma^2 (core/PSR.py:511)
+        tag = f"{D}d_{version}_{scheme}_{'x' if with_x else 'nox'}"
+        names.append(tag)
+        out[f"{tag}_meta"] = np.array([D, Nq, Nx if with_x else 0, nt, sig, lam], dtype=np.float64)
+        out[f"{tag}_in_q0"], out[f"{tag}_in_p0"] = q0.numpy(), p0.numpy()
+        out[f"{tag}_in_y"], out[f"{tag}_in_sig2"] = y.numpy(), sig2.numpy()
+        if with_x:
+            out[f"{tag}_in_x0"] = x0.numpy()
+        for prec, dt in [("ref32", torch.float32), ("gold", torch.float64)]:
+            LM = rl.LDDMMModel(sigma=sig, D=D, lambd=lam, spec=spec_of(dt), version=version,
+                               computversion="torch", scheme=scheme, nt=nt)
+            q = q0.to(dt).requires_grad_(True)
+            p = p0.to(dt).requires_grad_(True)
+            xx = x0.to(dt).requires_grad_(True) if with_x else None
+            sh = LM.Shoot(q, p, xx)
+            tl = LM.trajloss(sh)
+            moved = sh[-1][3] if with_x else sh[-1][0]
+            dl = ((moved - y.to(dt)) ** 2 / (2 * sig2.to(dt)[:, None])).sum()
+            L = tl + dl
+            grads = torch.autograd.grad(L, [q, p] + ([xx] if with_x else []))
+            out[f"{tag}_{prec}_q1"] = sh[-1][0].detach().numpy()
+            out[f"{tag}_{prec}_p1"] = sh[-1][1].detach().numpy()
+            out[f"{tag}_{prec}_cost1"] = sh[-1][2].detach().numpy()
+            if with_x:
+                out[f"{tag}_{prec}_x1"] = sh[-1][3].detach().numpy()
+                out[f"{tag}_{prec}_gx0"] = grads[2].numpy()
+            out[f"{tag}_{prec}_qmid"] = sh[nt // 2][0].detach().numpy()
+            out[f"{tag}_{prec}_trajloss"] = np.array(float(tl))
+            out[f"{tag}_{prec}_loss"] = np.array(float(L))
+            out[f"{tag}_{prec}_H0"] = np.array(float(LM.Hamiltonian(q, p)))
+            out[f"{tag}_{prec}_gq0"] = grads[0].numpy()
+            out[f"{tag}_{prec}_gp0"] = grads[1].numpy()
+            # single right-hand-side evaluation (core/LDDMM.py:176-227)
+            ode = LM.ODE(q.detach(), p.detach(), torch.zeros(1, dtype=dt), None if not with_x else xx.detach())
+            out[f"{tag}_{prec}_ode_vq"] = ode[0].numpy()
+            out[f"{tag}_{prec}_ode_dp"] = ode[1].numpy()
+            out[f"{tag}_{prec}_ode_dcost"] = np.array(float(ode[2].sum()))
+            if with_x:
+                out[f"{tag}_{prec}_ode_vx"] = ode[3].numpy()
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "lddmm.npz"), **out)
+    print("lddmm.npz", len(out))
+
+
+def gen_gmm(rg):
+    """EM_step_torch (the executable twin): skip_M, full M step, outliers, frozen mu/w, EM_optimization."""
+    out = {}
+    names = []
+    cfgs = [
+        # tag, D, N, C, outliers, to_optimize, skip_M, steps
+        ("2d_full", 2, 500, 20, False, dict(mu=True, sigma=True, w=True, eta0=True), False, 1),
+        ("2d_skipM", 2, 500, 20, False, dict(mu=True, sigma=True, w=True, eta0=True), True, 1),
+        ("3d_full", 3, 400, 13, False, dict(mu=True, sigma=True, w=True, eta0=True), False, 1),
+        ("3d_frozen", 3, 300, 150, False, dict(mu=False, sigma=True, w=False, eta0=False), False, 1),
+        ("2d_outl", 2, 500, 20, True, dict(mu=True, sigma=True, w=True, eta0=True), False, 1),
+        ("2d_outl_skipM", 2, 500, 20, True, dict(mu=True, sigma=True, w=True, eta0=True), True, 1),
+        ("2d_now", 2, 500, 20, False, dict(mu=True, sigma=True, w=False, eta0=True), False, 1),
+        ("2d_opt5", 2, 500, 20, False, dict(mu=True, sigma=True, w=True, eta0=True), False, 5),
+        ("3d_offset", 3, 600, 10, False, dict(mu=True, sigma=True, w=True, eta0=True), False, 1),
+    ]
+    for ci, (tag, D, N, C, outl, topt, skip, steps) in enumerate(cfgs):
+        g = torch.Generator().manual_seed(300 + ci)
+        cent = torch.rand(C, D, generator=g)
+        if tag == "3d_offset":
+            cent = cent + 5.0
+        X = cent[torch.randint(0, C, (N,), generator=g)] + 0.05 * torch.randn(N, D, generator=g)
+        mu0 = cent + 0.03 * torch.randn(C, D, generator=g)
+        w0 = 0.3 * torch.randn(C, generator=g)
+        sig0 = 0.08
+        names.append(tag)
+        out[f"{tag}_meta"] = np.array([D, N, C, int(outl), int(skip), steps, sig0], dtype=np.float64)
+        out[f"{tag}_opt"] = np.array([int(topt[k]) for k in ("mu", "sigma", "w", "eta0")])
+        out[f"{tag}_in_X"], out[f"{tag}_in_mu"], out[f"{tag}_in_w"] = X.numpy(), mu0.numpy(), w0.numpy()
+        for prec, dt in [("ref32", torch.float32), ("gold", torch.float64)]:
+            G = rg.GaussianMixtureUnif(mu0.to(dt), sigma=sig0, use_outliers=outl, spec=spec_of(dt),
+                                       computversion="torch")
+            G.w = w0.to(dt)
+            G.to_optimize = dict(topt)
+            if outl:
+                G.outliers["eta0"] = -1.0
+            Xd = X.to(dt)
+            if prec == "gold":
+                out[f"{tag}_gold_lgam"] = G.log_responsibilities(Xd).numpy()
+            fes = []
+            for _ in range(steps):
+                Y, Cfe, FE = G.EM_step(Xd, skip_M=skip)
+                fes.append(float(FE))
+            out[f"{tag}_{prec}_Y"] = Y.numpy()
+            out[f"{tag}_{prec}_Cfe"] = np.array(float(Cfe))
+            out[f"{tag}_{prec}_FE"] = np.array(fes)
+            out[f"{tag}_{prec}_mu"] = G.mu.numpy()
+            out[f"{tag}_{prec}_w"] = G.w.numpy()
+            out[f"{tag}_{prec}_sigma"] = np.array(float(G.sigma))
+            if outl:
+                out[f"{tag}_{prec}_eta0"] = np.array(float(G.outliers["eta0"]))
+                out[f"{tag}_{prec}_vol0"] = np.array(float(G.outliers["vol0"]))
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "gmm.npz"), **out)
+    print("gmm.npz", len(out))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    rk, rl, rg = load_reference()
+    gen_kernels(rk)
+    gen_lddmm(rl)
+    gen_gmm(rg)
