@@ -1,0 +1,226 @@
+"""LDDMM model for point sets on the B200: drop-in for the reference's ``diffICP/core/LDDMM.py`` (live class,
+core/LDDMM.py:28-398).
+
+Vector fields  v(x) = sum_j [ p_j K(x-q_j) - eta (grad K)(x-q_j) ],  eta = 0 (classic / hybrid) or 1/lambda (logdet).
+Hamiltonian    H(q,p) = 1/2 sum_ij [ (p_i.p_j) K - eta (p_i-p_j).gradK - eta^2 LapK ](q_i-q_j).
+
+Same constructor, attributes and methods as the reference.  What changes is where the arithmetic happens:
+
+* ``ODE`` evaluates the whole right-hand side with the fused kernels (one exponential per visited pair instead of
+  2 / 4 / 7 separate reductions, core/LDDMM.py:194-226);
+* ``Shoot`` runs the Euler / Ralston loop as back-to-back device launches (optionally one CUDA-graph replay) and
+  carries a hand-written discrete adjoint, so ``loss.backward()`` in the L-BFGS closure (tools/optim.py:34-47) costs
+  one adjoint sweep instead of an autograd walk over hundreds of KeOps nodes;
+* ``trajloss`` reuses the Hamiltonian pieces that the first right-hand-side evaluation already produced.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import ops, shooting
+from ..tools.kernel import GaussKernel, SVDpow
+from ..tools.spec import defspec, getspec
+from ..tools.optim import LBFGS_optimization
+from ..tools.integrators import EulerIntegrator, RalstonIntegrator
+
+
+class ShootResult(list):
+    """The reference's "shoot" variable (list of nt+1 tuples (q, p, cost[, x])), plus the Hamiltonian at t = 0
+    as a differentiable 0-d tensor (``H0``) so that trajloss needs no extra kernel sum."""
+
+    H0 = None
+
+
+class LDDMMModel:
+
+    def __init__(self, sigma=1.0, D=2, lambd=2.0,
+                 spec=defspec, gradcomponent=True, withlogdet=True, version=None,
+                 computversion="keops", scheme="Ralston", nonsupprev=False, nt=10):
+        self.Kernel = GaussKernel(sigma, D, computversion=computversion, spec=spec)
+        self.D = D
+        self.lam = lambd
+        self.nt = nt
+        # "version" shortcut (reference: core/LDDMM.py:43-49)
+        if version == "classic":
+            gradcomponent, withlogdet = False, False
+        elif version == "logdet":
+            gradcomponent, withlogdet = True, True
+        elif version == "hybrid":
+            gradcomponent, withlogdet = False, True
+        self.withlogdet = withlogdet
+        self.gradcomponent = gradcomponent
+        self.eta = 1.0 / lambd if gradcomponent else 0
+        self.nonsupprev = nonsupprev
+        self.scheme, self.Integrator = None, None
+        self.set_integration_scheme(scheme)
+        self.try_trajcost_optim = False
+        # B200 build: replay each shoot / adjoint sweep as one CUDA graph (set False for eager launches)
+        self.use_cuda_graph = False
+
+    def set_integration_scheme(self, scheme: str):
+        if scheme == "Euler":
+            self.Integrator = EulerIntegrator
+        elif scheme == "Ralston":
+            self.Integrator = RalstonIntegrator
+        else:
+            raise ValueError(f"Unkown numerical scheme : {scheme}")
+        self.scheme = scheme
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.Kernel = GaussKernel(self.Kernel.sigma, self.Kernel.D, self.Kernel.computversion, spec=defspec)
+
+    # ------------------------------------------------------------------------------------------------------
+    # Hamiltonian building blocks (generic entry points; the fused path below does not go through them)
+
+    def v(self, x, q, p):
+        """v(x) = sum_j [p_j K(x-q_j) - eta gradK(x-q_j)]  -> (Nx,D)   (reference: core/LDDMM.py:100-116)."""
+        spec = getspec(x, q, p)
+        if x.numel() == 0:
+            return torch.empty(x.shape, **spec)
+        if self.gradcomponent:
+            return self.Kernel.KRed(x, q, p) - self.eta * self.Kernel.GradKRed(x, q)
+        return self.Kernel.KRed(x, q, p)
+
+    def mdivsum(self, x, q, p, rev=False):
+        """-sum_k div v(x_k)   (reference: core/LDDMM.py:120-138)."""
+        spec = getspec(x, q, p)
+        if x.numel() == 0:
+            return torch.tensor([0.0], **spec)
+        if rev:
+            out = self.Kernel.GradKRed_rev(q, x, p).sum()
+        else:
+            out = (p * self.Kernel.GradKRed(q, x)).sum()
+        if self.gradcomponent:
+            out = out + self.eta * (self.Kernel.LapKRed(x, q).sum() if rev else self.Kernel.LapKRed(q, x).sum())
+        return out
+
+    def Hamiltonian(self, q, p):
+        """H(q,p)   (reference: core/LDDMM.py:142-159)."""
+        getspec(q, p)
+        H = 0.5 * (p * self.Kernel.KRed(q, q, p)).sum()
+        if self.gradcomponent:
+            H = H - self.eta * (p * self.Kernel.GradKRed(q, q)).sum() \
+                - 0.5 * self.eta ** 2 * self.Kernel.LapKRed(q, q).sum()
+        return H
+
+    def dtrajcost(self, q, p):
+        """lambda*H + mdivsum(q,q,p) shortcut (reference: core/LDDMM.py:163-172)."""
+        getspec(q, p)
+        return 0.5 * self.lam * (p * self.Kernel.KRed(q, q, p)).sum() + 0.5 * self.eta * self.Kernel.LapKRed(q, q).sum()
+
+    # ------------------------------------------------------------------------------------------------------
+
+    def _spec_for(self, M, Nx, device):
+        return shooting.ShootSpec(self.D, M, Nx, self.nt, self.scheme, self.withlogdet,
+                                  self.Kernel.sigma, self.eta, device)
+
+    def ODE(self, q, p, cost, x=None):
+        """d/dt (q, p, cost[, x])   (reference: core/LDDMM.py:176-227). Fused evaluation, forward only:
+        gradients of the shooting path are produced by ``Shoot``'s adjoint."""
+        spec = getspec(q, p, cost, x)
+        if self.withlogdet and self.gradcomponent and self.try_trajcost_optim and x is None:
+            vq = self.v(q, q, p)
+            Gq = self.Kernel.GenDKRed(q, q, p, p) - self.eta * self.Kernel.HessKRed(q, q, p, p) \
+                - self.eta ** 2 * self.Kernel.GradLapKRed(q, q)
+            return vq, -Gq, self.dtrajcost(q, p)
+        sp = self._spec_for(q.shape[0], 0 if x is None else x.shape[0], q.device)
+        F = torch.zeros(sp.S + 3, **spec)
+        state = torch.cat([q.detach().reshape(-1), p.detach().reshape(-1)] +
+                          ([x.detach().reshape(-1)] if x is not None else []) + [cost.detach().reshape(-1)[:1]])
+        ws = shooting.workspace(max(sp.M, sp.Nx), max(sp.M, sp.Nx), q.device)
+        shooting._rhs(sp, state, F, ws)
+        vq, dp, vx, dcost = shooting._views(sp, F)
+        if x is None:
+            return vq, dp, dcost
+        return vq, dp, dcost, vx
+
+    # ------------------------------------------------------------------------------------------------------
+    # v <-> p conversions (setup-time, not on the hot path)
+
+    def v2p(self, q, v, rcond=1e-3, alpha=1e-4, version='pinv'):
+        """Momenta p with self.v(q,q,p) ~ v (reference: core/LDDMM.py:235-253)."""
+        getspec(q, v)
+        rhs = v + self.eta * self.Kernel.GradKRed(q, q) if self.eta != 0 else v
+        if version == 'pinv':
+            return self.Kernel.KpinvSolve(q, rhs, rcond)
+        if version == 'ridge_keops':
+            return self.Kernel.KridgeSolve_keops(q, rhs, alpha)
+        if version == 'ridge_pytorch':
+            return self.Kernel.KridgeSolve_torch(q, rhs, alpha)
+        raise ValueError("unknown version")
+
+    def random_p(self, q, rcond=1e-3, alpha=1e-4, version='svd'):
+        """p ~ exp(-lambda H(q,p))  (reference: core/LDDMM.py:257-280); dense, small M only."""
+        spec = getspec(q)
+        if self.eta != 0:
+            raise ValueError("random_p not implemented yet when gradcomponent=True. (But it shouldn't be too hard!) ")
+        K = self.Kernel.K_torch(q, q)
+        zeta = torch.randn(q.shape, **spec) / math.sqrt(self.lam)
+        if version == 'svd':
+            return (SVDpow(K, -0.5, rcond) @ zeta).contiguous()
+        if version == 'ridge':
+            return torch.linalg.solve(torch.linalg.cholesky(K + alpha * torch.eye(K.shape[0], **spec)), zeta).contiguous()
+        raise ValueError("Unknown version")
+
+    # ------------------------------------------------------------------------------------------------------
+    # Shooting and optimisation
+
+    def Shoot(self, q0, p0, x0=None):
+        """Geodesic shooting from (q0,p0); returns the list of (q,p,cost[,x]) at the nt+1 time points
+        (reference: core/LDDMM.py:286-299), differentiable w.r.t. q0, p0, x0."""
+        getspec(q0, p0, x0)
+        if self.withlogdet and self.gradcomponent and self.try_trajcost_optim and x0 is None:
+            cost0 = torch.tensor([0.0], **getspec(q0))
+            return self.Integrator(self.ODE, (q0, p0, cost0), self.nt)
+        sp = self._spec_for(q0.shape[0], 0 if x0 is None else x0.shape[0], q0.device)
+        states, H0 = shooting.shoot(sp, q0, p0, x0, use_graph=self.use_cuda_graph)
+        res = ShootResult(states)
+        res.H0 = H0
+        return res
+
+    def BasicQuadLossFunctor(self, y, cmul=1):
+        """x -> cmul/2 |x-y|^2 (reference: core/LDDMM.py:303-314)."""
+        y = y.detach()
+
+        def dataloss(x):
+            return ((x - y) ** 2).sum() * cmul / 2
+        return dataloss
+
+    def trajloss(self, shoot):
+        """lambda*H(q0,p0) + cost(1)   (reference: core/LDDMM.py:318-334)."""
+        arrival = shoot[-1]
+        cost = arrival[2]
+        is_x = len(arrival) == 4
+        if not is_x and self.withlogdet and self.gradcomponent and self.try_trajcost_optim:
+            return cost
+        H0 = getattr(shoot, "H0", None)
+        if H0 is None:
+            q0, p0 = shoot[0][:2]
+            H0 = self.Hamiltonian(q0, p0)
+        return self.lam * H0 + cost
+
+    def Optimize(self, dataloss, q0, p0, x0=None, nmax=10, tol=1e-3, errthresh=1e8):
+        """min_{p0} trajloss(p0) + dataloss(arrival points)  by L-BFGS (reference: core/LDDMM.py:338-398).
+        Returns (p0, shoot, trajloss, dataloss, nsteps, change)."""
+        getspec(q0, p0, x0)
+        is_x = x0 is not None
+        q0 = q0.detach()
+        if is_x:
+            x0 = x0.detach()
+
+        def lossfunc(p0):
+            shoot = self.Shoot(q0, p0, x0)
+            moved = shoot[-1][-1] if is_x else shoot[-1][0]
+            return self.trajloss(shoot) + dataloss(moved)
+
+        p0, _, nsteps, change = LBFGS_optimization([p0], lossfunc, nmax=nmax, tol=tol, errthresh=errthresh)
+        p0 = p0[0]
+        with torch.no_grad():
+            shoot = self.Shoot(q0, p0, x0)
+            trajl = self.trajloss(shoot).item()
+            datal = dataloss(shoot[-1][-1] if is_x else shoot[-1][0]).item()
+        return p0, shoot, trajl, datal, nsteps, change

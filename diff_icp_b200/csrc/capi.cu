@@ -1,0 +1,141 @@
+// extern "C" entry points of libdicp_b200.so (see include/dicp_b200.h).
+#include "../../include/dicp_b200.h"
+#include "dispatch.cuh"
+
+using namespace dicp;
+
+namespace {
+
+__global__ void axpy_kernel(long long n, float* __restrict__ out, const float* __restrict__ a, float alpha,
+                            const float* __restrict__ f1, float beta, const float* __restrict__ f2) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float v = fmaf(alpha, f1[i], a[i]);
+        if (f2 != nullptr) v = fmaf(beta, f2[i], v);
+        out[i] = v;
+    }
+}
+
+// dcost contribution of the (q,q) pass:  scal[0] = withdiv ? B + eta*C : 0   (scal = {_, A, B, C})
+__global__ void rhs_scal_fix_kernel(float* scal, float eta, int withdiv) {
+    if (threadIdx.x == 0) scal[0] = withdiv ? fmaf(eta, scal[3], scal[2]) : 0.f;
+}
+
+struct DeviceExec {
+    void* ws;
+    size_t wsb;
+    cudaStream_t st;
+    template <class Op>
+    int run(const typename Op::Params& prm, int M, int N, float* scal_out, int accumulate) {
+        return run_pair<Op>(prm, M, N, scal_out, accumulate, ws, wsb, st);
+    }
+    void scal_fix(float* scal, float eta, int withdiv) { rhs_scal_fix_kernel<<<1, 32, 0, st>>>(scal, eta, withdiv); }
+};
+
+inline int last_error(int rc) {
+    if (rc != DICP_OK) return rc;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DICP_OK : (int)e;
+}
+
+// ---- pipe probes ---------------------------------------------------------------------------------
+template <int WHICH>
+__global__ void __launch_bounds__(256) probe_kernel(int iters, float* out) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 1.0f + 1e-3f * (threadIdx.x + k);
+    const float m = 0.9999f, c = 1e-4f;
+    if (WHICH == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], m, c);
+        }
+    } else if (WHICH == 1) {
+        unsigned long long w[4], mm, cc;
+        float2 m2 = make_float2(m, m), c2 = make_float2(c, c);
+        mm = *reinterpret_cast<unsigned long long*>(&m2);
+        cc = *reinterpret_cast<unsigned long long*>(&c2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 t = make_float2(v[2 * k], v[2 * k + 1]);
+            w[k] = *reinterpret_cast<unsigned long long*>(&t);
+        }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(w[k]) : "l"(w[k]), "l"(mm), "l"(cc));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 t = *reinterpret_cast<float2*>(&w[k]);
+            v[2 * k] = t.x; v[2 * k + 1] = t.y;
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = ex2_neg(v[k]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dicp_version(void) { return 100; }
+
+int dicp_sm_count(void) { return device_info().sms; }
+
+size_t dicp_pair_workspace_bytes(int64_t rows, int64_t cols) { return pair_workspace_bound(rows, cols); }
+
+int dicp_ksum(int D, unsigned mask, float sigma, const float* x, int64_t M, const float* y, int64_t N,
+              const float* b, const float* c, const float* d,
+              float* o_base, float* o_redscal, float* o_red, float* o_grad, float* o_dd, float* o_gend,
+              float* o_hess, float* o_lap, float* o_gradlap, float* o_minsq, float* o_dot,
+              void* workspace, size_t workspace_bytes, void* stream) {
+    float* outs[11] = {o_base, o_redscal, o_red, o_grad, o_dd, o_gend, o_hess, o_lap, o_gradlap, o_minsq, o_dot};
+    DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream};
+    return last_error(ksum_entry(ex, D, mask, sigma, x, M, y, N, b, c, d, outs));
+}
+
+int dicp_rhs_forward(int D, int withlogdet, float sigma, float eta, const float* q, const float* p, int64_t M,
+                     const float* x, int64_t Nx, float* vq, float* dp, float* vx, float* scal,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream};
+    return last_error(rhs_forward_entry(ex, D, withlogdet, sigma, eta, q, p, M, x, Nx, vq, dp, vx, scal));
+}
+
+int dicp_rhs_adjoint(int D, int withlogdet, float sigma, float eta, const float* q, const float* p, int64_t M,
+                     const float* x, int64_t Nx, const float* a, const float* u, const float* wx, const float* gc,
+                     float* gq, float* gp, float* gx, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream};
+    return last_error(rhs_adjoint_entry(ex, D, withlogdet, sigma, eta, q, p, M, x, Nx, a, u, wx, gc, gq, gp, gx));
+}
+
+int dicp_axpy(int64_t n, float* out, const float* a, float alpha, const float* f1, float beta, const float* f2,
+              void* stream) {
+    if (n < 0 || (n > 0 && (!out || !a || !f1))) return DICP_EBADARG;
+    if (n == 0) return DICP_OK;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)device_info().sms * 16;
+    if (blocks > cap) blocks = cap;
+    axpy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, out, a, alpha, f1, beta, f2);
+    return last_error(DICP_OK);
+}
+
+int dicp_pipe_probe(int which, int blocks, int iters, float* out, void* stream) {
+    if (!out || blocks < 1 || iters < 1) return DICP_EBADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (which == 0) probe_kernel<0><<<blocks, 256, 0, st>>>(iters, out);
+    else if (which == 1) probe_kernel<1><<<blocks, 256, 0, st>>>(iters, out);
+    else if (which == 2) probe_kernel<2><<<blocks, 256, 0, st>>>(iters, out);
+    else return DICP_EBADARG;
+    return last_error(DICP_OK);
+}
+
+}  // extern "C"

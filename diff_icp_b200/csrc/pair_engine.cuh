@@ -1,0 +1,318 @@
+// Tiled N x M pair-reduction engine (sm_100a).
+//
+// One template serves every "for each row i: reduce over all columns j of f(row_i, col_j)" kernel on
+// the diffICP hot path: the ten Gaussian kernel sums and their VJPs, the fused Hamiltonian right-hand
+// side and its adjoint, and the GMM row pass.  An `Op` supplies
+//
+//   struct Params;                     raw device pointers + scalars (passed by value to the kernel)
+//   THREADS, R, TILE, COLF4            CTA size, rows per thread, columns per tile, float4 per packed column
+//   NACC, NSCAL                        accumulators per row, row-scalars that are summed over all rows
+//   pack_col(prm, j, N, float* c)      build the packed record of column j (pads j >= N so that it contributes 0)
+//   load_row(prm, i, Row&)             read row i from the raw arrays (pre-scaling coordinates)
+//   init(acc), pair(prm, row, c, acc)  the per-pair arithmetic  (c = COLF4*4 floats of the packed column)
+//   combine(a, b)                      how two partial accumulators merge across column splits (default: +)
+//   finish(prm, i, row, acc, scal)     write the outputs of row i, fill its NSCAL row-scalars
+//
+// Data movement: columns are packed ONCE per launch into a 16-byte aligned, pre-scaled record array
+// (pack_kernel), then streamed tile by tile into shared memory by the TMA engine with 1-D bulk copies
+// (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP), NSTAGE-deep.  Every thread keeps R rows and their
+// accumulators in registers and reads the staged column records with broadcast LDS.128.  The kernels are
+// FFMA / MUFU.EX2 bound (D = 2,3 is not a dense contraction): no tensor cores on purpose.
+//
+// Parallelism: grid = (row blocks, column splits).  When there are too few rows to fill 148 SMs the
+// column range is split; partial accumulators go to a workspace and `finish_kernel` merges them in a fixed
+// order (deterministic, no float atomics).  Row-scalars (dcost, Hamiltonian pieces, ...) are block-reduced
+// with a fixed tree and summed over blocks by `scalar_reduce_kernel`, also deterministic.
+#pragma once
+#include "common.cuh"
+
+namespace dicp {
+
+static constexpr int kStages = 3;
+
+struct PairPlan {
+    int M, N;
+    int ntiles;      // column tiles of Op::TILE
+    int nrb;         // row blocks
+    int nsplit;      // column splits (grid.y)
+    size_t col_bytes, part_bytes, scal_bytes;
+    size_t total_bytes() const { return col_bytes + part_bytes + scal_bytes; }
+};
+
+#if defined(__CUDACC__)
+
+template <class Op>
+__global__ void pack_kernel(typename Op::Params prm, float4* __restrict__ colpack, int N, int Npad) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Npad) return;
+    float c[Op::COLF4 * 4];
+    Op::pack_col(prm, j, N, c);
+#pragma unroll
+    for (int k = 0; k < Op::COLF4; ++k)
+        colpack[(size_t)j * Op::COLF4 + k] = make_float4(c[4 * k], c[4 * k + 1], c[4 * k + 2], c[4 * k + 3]);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(Op::THREADS, Op::MINB)
+pair_kernel(typename Op::Params prm, const float4* __restrict__ colpack, float* __restrict__ part,
+            float* __restrict__ blockscal, int M, int ntiles) {
+    constexpr int R = Op::R, TILE = Op::TILE, CF4 = Op::COLF4, NACC = Op::NACC, NSCAL = Op::NSCAL;
+    constexpr uint32_t STAGE_BYTES = TILE * CF4 * 16;
+    __shared__ __align__(128) float4 stage[kStages][TILE * CF4];
+    __shared__ __align__(8) uint64_t full[kStages];
+    __shared__ float red[32];
+
+    const int tid = threadIdx.x;
+    const int nsplit = gridDim.y;
+    const int t0 = (int)(((long long)blockIdx.y * ntiles) / nsplit);
+    const int t1 = (int)(((long long)(blockIdx.y + 1) * ntiles) / nsplit);
+    const int nt = t1 - t0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s)
+            if (s < nt) {
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                bulk_g2s(stage[s], colpack + (size_t)(t0 + s) * TILE * CF4, STAGE_BYTES, &full[s]);
+            }
+    }
+
+    typename Op::Row row[R];
+    float acc[R][NACC];
+    const int rbase = blockIdx.x * (Op::THREADS * R) + tid;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int i = rbase + r * Op::THREADS;
+        Op::load_row(prm, i < M ? i : M - 1, row[r]);
+        Op::init(acc[r]);
+    }
+
+    for (int t = 0; t < nt; ++t) {
+        const int s = t % kStages;
+        mbar_wait(&full[s], (uint32_t)((t / kStages) & 1));
+        const float4* sp = stage[s];
+#pragma unroll 2
+        for (int j = 0; j < TILE; ++j) {
+            float c[CF4 * 4];
+#pragma unroll
+            for (int k = 0; k < CF4; ++k) {
+                float4 v = sp[j * CF4 + k];
+                c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) Op::pair(prm, row[r], c, acc[r]);
+        }
+        __syncthreads();   // every thread is done with stage s -> it may be refilled
+        if (tid == 0 && t + kStages < nt) {
+            mbar_expect_tx(&full[s], STAGE_BYTES);
+            bulk_g2s(stage[s], colpack + (size_t)(t0 + t + kStages) * TILE * CF4, STAGE_BYTES, &full[s]);
+        }
+    }
+
+    if (nsplit == 1) {
+        float scal[NSCAL > 0 ? NSCAL : 1];
+#pragma unroll
+        for (int k = 0; k < NSCAL; ++k) scal[k] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int i = rbase + r * Op::THREADS;
+            if (i < M) {
+                float rs[NSCAL > 0 ? NSCAL : 1];
+                Op::finish(prm, i, row[r], acc[r], rs);
+#pragma unroll
+                for (int k = 0; k < NSCAL; ++k) scal[k] += rs[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NSCAL; ++k) {
+            float v = block_sum(scal[k], red);
+            if (tid == 0) blockscal[(size_t)blockIdx.x * NSCAL + k] = v;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int i = rbase + r * Op::THREADS;
+            if (i < M) {
+                float* dst = part + ((size_t)blockIdx.y * M + i) * NACC;
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) dst[k] = acc[r][k];
+            }
+        }
+    }
+}
+
+// Merge the column-split partials of each row in split order, then run the Op's finish.
+template <class Op>
+__global__ void finish_kernel(typename Op::Params prm, const float* __restrict__ part,
+                              float* __restrict__ blockscal, int M, int nsplit) {
+    constexpr int NACC = Op::NACC, NSCAL = Op::NSCAL;
+    __shared__ float red[32];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float rs[NSCAL > 0 ? NSCAL : 1];
+#pragma unroll
+    for (int k = 0; k < NSCAL; ++k) rs[k] = 0.f;
+    if (i < M) {
+        float acc[NACC];
+        const float* src = part + (size_t)i * NACC;
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = src[k];
+        for (int s = 1; s < nsplit; ++s) {
+            src = part + ((size_t)s * M + i) * NACC;
+            float b[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) b[k] = src[k];
+            Op::combine(acc, b);
+        }
+        typename Op::Row row;
+        Op::load_row(prm, i, row);
+        Op::finish(prm, i, row, acc, rs);
+    }
+#pragma unroll
+    for (int k = 0; k < NSCAL; ++k) {
+        float v = block_sum(rs[k], red);
+        if (threadIdx.x == 0) blockscal[(size_t)blockIdx.x * NSCAL + k] = v;
+    }
+}
+
+// out[k] (+)= scale * sum_b blockscal[b][k]   -- single CTA, fixed order.
+__global__ void scalar_reduce_kernel(const float* __restrict__ blockscal, int nblocks, int nscal,
+                                     float* __restrict__ out, int accumulate) {
+    __shared__ float red[32];
+    for (int k = 0; k < nscal; ++k) {
+        float v = 0.f;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += blockscal[(size_t)b * nscal + k];
+        v = block_sum(v, red);
+        if (threadIdx.x == 0) out[k] = accumulate ? out[k] + v : v;
+        __syncthreads();
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+struct DeviceInfo {
+    int sms = 0;
+};
+inline const DeviceInfo& device_info() {
+    static DeviceInfo info = [] {
+        DeviceInfo d;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (d.sms <= 0) d.sms = 148;
+        return d;
+    }();
+    return info;
+}
+
+template <class Op>
+inline int op_occupancy() {
+    static int occ = [] {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, pair_kernel<Op>, Op::THREADS, 0);
+        return o > 0 ? o : 1;
+    }();
+    return occ;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Upper bound of the workspace any Op needs for an (M rows, N columns) launch on this device.
+// The Ops are held to these limits by static_asserts in make_plan.
+static constexpr int kMaxColF4 = 4, kMaxAcc = 16, kMaxScal = 8, kMaxRowsPerCta = 256, kMaxOcc = 16;
+inline size_t pair_workspace_bound(long long M, long long N) {
+    const long long sms = device_info().sms;
+    if (M < 1) M = 1;
+    if (N < 1) N = 1;
+    size_t col = align_up((size_t)(N + 256) * kMaxColF4 * 16, 256);
+    long long rows_a = 2 * sms * kMaxOcc * kMaxRowsPerCta + M;      // nsplit <= 2*slots/nrb
+    long long rows_b = M * ((N + 127) / 128);                        // nsplit <= number of column tiles
+    long long rows = rows_a < rows_b ? rows_a : rows_b;
+    size_t part = align_up((size_t)rows * kMaxAcc * 4, 256);
+    size_t scal = align_up((size_t)((M + 127) / 128 + 1) * kMaxScal * 4, 256);
+    return col + part + scal + 1024;
+}
+
+template <class Op>
+inline PairPlan make_plan(int M, int N) {
+    static_assert(Op::COLF4 <= kMaxColF4 && Op::NACC <= kMaxAcc && Op::NSCAL <= kMaxScal, "workspace bound");
+    static_assert(Op::THREADS * Op::R <= kMaxRowsPerCta && Op::TILE >= 128, "workspace bound");
+    PairPlan p{};
+    p.M = M; p.N = N;
+    p.ntiles = (N + Op::TILE - 1) / Op::TILE;
+    if (p.ntiles < 1) p.ntiles = 1;
+    const int rows_per_cta = Op::THREADS * Op::R;
+    p.nrb = (M + rows_per_cta - 1) / rows_per_cta;
+    int occ = op_occupancy<Op>();
+    if (occ > kMaxOcc) occ = kMaxOcc;
+    const long long slots = (long long)device_info().sms * occ;
+    long long s = (2 * slots) / p.nrb;
+    if (s < 1) s = 1;
+    if (s > p.ntiles) s = p.ntiles;
+    if ((long long)p.nrb >= slots) s = 1;
+    p.nsplit = (int)s;
+    p.col_bytes = align_up((size_t)p.ntiles * Op::TILE * Op::COLF4 * 16, 256);
+    p.part_bytes = p.nsplit > 1 ? align_up((size_t)p.nsplit * M * Op::NACC * 4, 256) : 0;
+    int nfin = p.nsplit > 1 ? (M + 127) / 128 : p.nrb;
+    p.scal_bytes = align_up((size_t)(nfin > p.nrb ? nfin : p.nrb) * (Op::NSCAL > 0 ? Op::NSCAL : 1) * 4, 256);
+    return p;
+}
+
+// Pack columns, run the pair kernel (+ finish / scalar reduction when needed).
+// scal_out: device pointer receiving the NSCAL summed row-scalars (may be null if NSCAL == 0).
+template <class Op>
+inline int run_pair(const typename Op::Params& prm, int M, int N, float* scal_out, int scal_accumulate,
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (M <= 0) return DICP_OK;
+    PairPlan p = make_plan<Op>(M, N);
+    if (ws == nullptr || p.total_bytes() > ws_bytes) return DICP_EWORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(ws) & 127) != 0) return DICP_EBADARG;
+    char* base = (char*)ws;
+    float4* colpack = (float4*)base;
+    float* part = (float*)(base + p.col_bytes);
+    float* blockscal = (float*)(base + p.col_bytes + p.part_bytes);
+    const int Npad = p.ntiles * Op::TILE;
+    pack_kernel<Op><<<(Npad + 255) / 256, 256, 0, st>>>(prm, colpack, N, Npad);
+    dim3 grid(p.nrb, p.nsplit);
+    pair_kernel<Op><<<grid, Op::THREADS, 0, st>>>(prm, colpack, part, blockscal, M, p.ntiles);
+    int nblk = p.nrb;
+    if (p.nsplit > 1) {
+        nblk = (M + 127) / 128;
+        finish_kernel<Op><<<nblk, 128, 0, st>>>(prm, part, blockscal, M, p.nsplit);
+    }
+    if (Op::NSCAL > 0 && scal_out != nullptr)
+        scalar_reduce_kernel<<<1, 256, 0, st>>>(blockscal, nblk, Op::NSCAL, scal_out, scal_accumulate);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DICP_OK : (int)e;
+}
+
+#endif  // __CUDACC__
+
+// ---- host emulation (tests only): the same Op arithmetic, executed row by row on the CPU ----------
+template <class Op>
+inline void run_pair_host(const typename Op::Params& prm, int M, int N, float* scal_out) {
+    const int Npad = ((N + Op::TILE - 1) / Op::TILE) * Op::TILE;
+    double scal[Op::NSCAL > 0 ? Op::NSCAL : 1] = {0};
+    for (int i = 0; i < M; ++i) {
+        typename Op::Row row;
+        Op::load_row(prm, i, row);
+        float acc[Op::NACC];
+        Op::init(acc);
+        for (int j = 0; j < Npad; ++j) {
+            float c[Op::COLF4 * 4];
+            Op::pack_col(prm, j, N, c);
+            Op::pair(prm, row, c, acc);
+        }
+        float rs[Op::NSCAL > 0 ? Op::NSCAL : 1] = {0};
+        Op::finish(prm, i, row, acc, rs);
+        for (int k = 0; k < Op::NSCAL; ++k) scal[k] += rs[k];
+    }
+    if (scal_out)
+        for (int k = 0; k < Op::NSCAL; ++k) scal_out[k] = (float)scal[k];
+}
+
+}  // namespace dicp

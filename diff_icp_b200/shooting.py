@@ -1,0 +1,231 @@
+"""Geodesic shooting on the device: fused right-hand side + Euler / Ralston steps + hand-written discrete adjoint.
+
+Replaces the Python integrator loop of the reference (tools/integrators.py:20-51) driving LDDMMModel.ODE
+(core/LDDMM.py:176-227), and the reverse-mode autograd pass through that loop (tools/optim.py:34-47), by
+back-to-back launches of the fused kernels (dicp_rhs_forward / dicp_rhs_adjoint / dicp_axpy) on the current
+stream.  The adjoint is the exact transpose of the discrete Euler / Ralston step sequence, so gradients match
+"autograd through the loop" to rounding.  With `use_graph` the whole launch sequence of one shoot (and of one
+adjoint sweep) is captured once per problem shape into a CUDA graph and replayed (north_star item 3).
+
+State layout (one flat fp32 vector of S = 2*M*D + Nx*D + 1 floats):   [ q (M,D) | p (M,D) | x (Nx,D) | cost ]
+Right-hand-side buffers carry 3 extra floats: [ vq | dp | vx | dcost | A | B | C ]  (A,B,C: Hamiltonian pieces).
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import require_cuda, workspace
+
+
+class ShootSpec:
+    """Static description of one shooting problem (shapes + model), hashable: the key of the graph cache."""
+
+    __slots__ = ("D", "M", "Nx", "nt", "scheme", "withlogdet", "sigma", "eta", "device")
+
+    def __init__(self, D, M, Nx, nt, scheme, withlogdet, sigma, eta, device):
+        self.D, self.M, self.Nx, self.nt = int(D), int(M), int(Nx), int(nt)
+        self.scheme, self.withlogdet = scheme, bool(withlogdet)
+        self.sigma, self.eta, self.device = float(sigma), float(eta), device
+
+    def key(self):
+        return (self.D, self.M, self.Nx, self.nt, self.scheme, self.withlogdet, self.sigma, self.eta, str(self.device))
+
+    @property
+    def S(self):
+        return 2 * self.M * self.D + self.Nx * self.D + 1
+
+
+def _views(spec, flat):
+    """(q, p, x, cost) views of a flat state / cotangent vector."""
+    MD = spec.M * spec.D
+    q = flat[0:MD].view(spec.M, spec.D)
+    p = flat[MD:2 * MD].view(spec.M, spec.D)
+    x = flat[2 * MD:2 * MD + spec.Nx * spec.D].view(spec.Nx, spec.D) if spec.Nx else None
+    cost = flat[spec.S - 1:spec.S]
+    return q, p, x, cost
+
+
+def _rhs(spec, state, F, ws):
+    q, p, x, _ = _views(spec, state)
+    vq, dp, vx, _ = _views(spec, F)
+    ops.rhs_forward(spec.D, spec.withlogdet, spec.sigma, spec.eta, q, p, x, vq, dp, vx, F[spec.S - 1:], ws)
+
+
+def _vjp(spec, state, lam, G, ws):
+    """G = J_F(state)^T lam  (G's cost entry stays 0: the right-hand side does not depend on cost)."""
+    q, p, x, _ = _views(spec, state)
+    a, u, wx, gc = _views(spec, lam)
+    gq, gp, gx, _ = _views(spec, G)
+    ops.rhs_adjoint(spec.D, spec.withlogdet, spec.sigma, spec.eta, q, p, x, a, u, wx, gc, gq, gp, gx, ws)
+
+
+def forward_sweep(spec, traj, mid, F1, F2, F0, ws):
+    """traj[0] holds the initial state; fills traj[1..nt] (and mid[0..nt-1] for Ralston), F0 = rhs(traj[0])."""
+    h = 1.0 / spec.nt
+    S = spec.S
+    for t in range(spec.nt):
+        Fa = F0 if t == 0 else F1
+        _rhs(spec, traj[t], Fa, ws)
+        if spec.scheme == "Euler":
+            ops.axpy(traj[t + 1], traj[t], h, Fa, n=S)
+        else:
+            ops.axpy(mid[t], traj[t], 2.0 * h / 3.0, Fa, n=S)
+            _rhs(spec, mid[t], F2, ws)
+            ops.axpy(traj[t + 1], traj[t], 0.25 * h, Fa, 0.75 * h, F2, n=S)
+
+
+def adjoint_sweep(spec, traj, mid, gtraj, lam, mu, G1, G2, ws):
+    """lam <- d(loss)/d(traj[0]) given gtraj[t] = d(loss)/d(traj[t]) (direct dependence on every stored state)."""
+    h = 1.0 / spec.nt
+    S = spec.S
+    lam.copy_(gtraj[spec.nt])
+    for t in range(spec.nt - 1, -1, -1):
+        if spec.scheme == "Euler":
+            _vjp(spec, traj[t], lam, G1, ws)
+            ops.axpy(lam, lam, h, G1, 1.0, gtraj[t], n=S)
+        else:
+            _vjp(spec, mid[t], lam, G2, ws)
+            ops.axpy(mu, lam, 2.0 * h, G2, n=S)
+            _vjp(spec, traj[t], mu, G1, ws)
+            ops.axpy(lam, lam, 0.75 * h, G2, 0.25 * h, G1, n=S)
+            ops.axpy(lam, lam, 1.0, gtraj[t], n=S)
+
+
+class ShootPlan:
+    """Buffers (and, optionally, captured CUDA graphs) for one ShootSpec. Cached per spec."""
+
+    _cache = {}
+
+    def __init__(self, spec: ShootSpec, use_graph: bool):
+        self.spec = spec
+        dev = spec.device
+        S, nt = spec.S, spec.nt
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.traj = torch.zeros(nt + 1, S, **f32)
+        self.mid = torch.zeros(nt, S, **f32) if spec.scheme == "Ralston" else None
+        self.F0 = torch.zeros(S + 3, **f32)
+        self.F1 = torch.zeros(S + 3, **f32)
+        self.F2 = torch.zeros(S + 3, **f32)
+        self.gtraj = torch.zeros(nt + 1, S, **f32)
+        self.lam = torch.zeros(S, **f32)
+        self.mu = torch.zeros(S, **f32)
+        self.G1 = torch.zeros(S, **f32)
+        self.G2 = torch.zeros(S, **f32)
+        rows = max(spec.M, spec.Nx)
+        self.ws = torch.empty(int(ops.load().dicp_pair_workspace_bytes(rows, rows)), dtype=torch.uint8, device=dev)
+        self.version = 0
+        self.use_graph = use_graph
+        self.fwd_graph = None
+        self.bwd_graph = None
+
+    @classmethod
+    def get(cls, spec: ShootSpec, use_graph: bool):
+        key = spec.key() + (bool(use_graph),)
+        plan = cls._cache.get(key)
+        if plan is None:
+            if len(cls._cache) > 64:
+                cls._cache.clear()
+            plan = cls(spec, use_graph)
+            cls._cache[key] = plan
+        return plan
+
+    # -- forward ---------------------------------------------------------------------------------------
+    def _fwd_body(self):
+        forward_sweep(self.spec, self.traj, self.mid, self.F1, self.F2, self.F0, self.ws)
+
+    def run_forward(self, q0, p0, x0):
+        spec = self.spec
+        q, p, x, cost = _views(spec, self.traj[0])
+        q.copy_(q0)
+        p.copy_(p0)
+        if x is not None:
+            x.copy_(x0)
+        cost.zero_()
+        if self.use_graph:
+            if self.fwd_graph is None:
+                self._fwd_body()                      # warm-up outside capture (lazy init, occupancy queries)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._fwd_body()
+                self.fwd_graph = g
+            self.fwd_graph.replay()
+        else:
+            self._fwd_body()
+        self.version += 1
+
+    # -- backward --------------------------------------------------------------------------------------
+    def _bwd_body(self):
+        adjoint_sweep(self.spec, self.traj, self.mid, self.gtraj, self.lam, self.mu, self.G1, self.G2, self.ws)
+
+    def run_backward(self, gtraj):
+        self.gtraj.copy_(gtraj)
+        if self.use_graph:
+            if self.bwd_graph is None:
+                self._bwd_body()
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._bwd_body()
+                self.bwd_graph = g
+            self.bwd_graph.replay()
+        else:
+            self._bwd_body()
+
+
+class _ShootFn(torch.autograd.Function):
+    """(q0, p0, x0) -> (trajectory (nt+1, S), H(q0,p0) as a 0-d tensor)."""
+
+    @staticmethod
+    def forward(ctx, spec, use_graph, q0, p0, x0):
+        plan = ShootPlan.get(spec, use_graph)
+        plan.run_forward(q0, p0, x0)
+        traj = plan.traj.clone()
+        hs = plan.F0[spec.S - 1:spec.S + 3]                  # dcost(0), A, B, C  (core/LDDMM.py:150-155)
+        H0 = 0.5 * hs[1] - spec.eta * hs[2] - (0.5 * spec.eta ** 2) * hs[3]
+        ctx.spec, ctx.plan, ctx.version = spec, plan, plan.version
+        need = any(t is not None and t.requires_grad for t in (q0, p0, x0))
+        if need:
+            ctx.saved_mid = plan.mid.clone() if plan.mid is not None else None
+            ctx.F0 = plan.F0[:spec.S].clone()
+            ctx.save_for_backward(traj)
+        ctx.has_x = x0 is not None
+        return traj, H0
+
+    @staticmethod
+    def backward(ctx, g_traj, g_H):
+        spec, plan = ctx.spec, ctx.plan
+        (traj,) = ctx.saved_tensors
+        if plan.version != ctx.version:                       # plan buffers were reused by another shoot
+            plan.traj.copy_(traj)
+            if plan.mid is not None:
+                plan.mid.copy_(ctx.saved_mid)
+            plan.version += 1
+            ctx.version = plan.version
+        if g_traj is None:
+            g_traj = torch.zeros_like(traj)
+        plan.run_backward(g_traj.contiguous())
+        lam = plan.lam.clone()
+        gq, gp, gx, _ = _views(spec, lam)
+        if g_H is not None:
+            # Hamilton's equations: dH/dp = vq(0), dH/dq = Gq(0) = -dp(0)  (core/LDDMM.py:156-158), both
+            # already produced by the first right-hand-side evaluation of the forward sweep.
+            vq0, dp0, _, _ = _views(spec, ctx.F0)
+            gp.add_(g_H * vq0)
+            gq.sub_(g_H * dp0)
+        return None, None, gq, gp, (gx if ctx.has_x else None)
+
+
+def shoot(spec: ShootSpec, q0, p0, x0=None, use_graph=False):
+    """Returns (list of nt+1 state tuples like the reference's Shoot, H(q0,p0)) with autograd attached."""
+    require_cuda(q0, p0, x0)
+    q0c, p0c = q0.contiguous(), p0.contiguous()
+    x0c = None if x0 is None else x0.contiguous()
+    traj, H0 = _ShootFn.apply(spec, use_graph, q0c, p0c, x0c)
+    states = []
+    for t in range(spec.nt + 1):
+        q, p, x, cost = _views(spec, traj[t])
+        states.append((q, p, cost) if x0 is None else (q, p, cost, x))
+    return states, H0

@@ -1,0 +1,100 @@
+/* dicp_b200.h -- C ABI of the B200-native diffICP hot path (libdicp_b200.so).
+ *
+ * Drop-in boundary: these entry points are what the reference's two dispatch seams would bind
+ *   - GenKernel.set_computversion   /root/reference/diffICP/tools/kernel.py:91-110   (ten kernel reductions)
+ *   - GaussianMixtureUnif.set_computversion  /root/reference/diffICP/core/GMM.py:126-144  (EM_step)
+ * plus the fused forms of their callers LDDMMModel.ODE / Shoot (core/LDDMM.py:176-227, 286-299) and the
+ * integrator updates (tools/integrators.py:20-51).  See INTEGRATION.md for the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (row-major (n,D), D in {2,3}) unless stated;
+ *   - the caller allocates every output and the workspace; the library never allocates, frees or keeps pointers;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host synchronisation, no host
+ *     reads of device results: every call is CUDA-graph capturable;
+ *   - return value: 0 = ok, <0 = DICP_E* argument error, >0 = cudaError_t of the launch;
+ *   - workspace: at least dicp_pair_workspace_bytes(rows, cols) bytes, 128-byte aligned, private to the
+ *     call sequence on that stream;
+ *   - results are deterministic (no floating-point atomics).
+ */
+#ifndef DICP_B200_H
+#define DICP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DICP_OK 0
+#define DICP_EBADARG (-1)
+#define DICP_EUNSUPPORTED (-2)
+#define DICP_EWORKSPACE (-3)
+
+/* output selectors of dicp_ksum (bit mask; any supported subset is computed in ONE sweep) */
+#define DICP_K_BASE 1u      /* KBase      kernel.py:131/178   sum_j K                    -> (M)   */
+#define DICP_K_REDSCAL 2u   /* KRedScal   kernel.py:135/182   sum_j K d_j                -> (M)   */
+#define DICP_K_RED 4u       /* KRed       kernel.py:138/186   sum_j K b_j                -> (M,D) */
+#define DICP_K_GRAD 8u      /* GradKRed   kernel.py:142/190   sum_j gradK                -> (M,D) */
+#define DICP_K_DD 16u       /* DDKRed     kernel.py:151/198   sum_j d_dK b_j^d           -> (M,D) */
+#define DICP_K_GEND 32u     /* GenDKRed   kernel.py:155/202   sum_j gradK (c_i.b_j)      -> (M,D) */
+#define DICP_K_HESS 64u     /* HessKRed   kernel.py:160/284   sum_j HessK (c_i-b_j)      -> (M,D) */
+#define DICP_K_LAP 128u     /* LapKRed    kernel.py:164/206   sum_j LapK                 -> (M)   */
+#define DICP_K_GRADLAP 256u /* GradLapKRed kernel.py:168/289  sum_j grad LapK            -> (M,D) */
+#define DICP_K_MINSQ 512u   /* check_coverage kernel.py:324   min_j |x_i-y_j|^2          -> (M)   */
+#define DICP_K_DOT 1024u    /* GradKRed_rev kernel.py:147/194 (rows=y, cols=x, b=d)      -> (M)   */
+
+int dicp_version(void);
+
+/* number of SMs of the current device (148 on B200) */
+int dicp_sm_count(void);
+
+/* Upper bound of the workspace needed by any pair kernel with `rows` rows and `cols` columns. */
+size_t dicp_pair_workspace_bytes(int64_t rows, int64_t cols);
+
+/* Gaussian kernel reductions, K(z) = exp(-|z|^2 / (2 sigma^2)), z = x_i - y_j.
+ * b: (N,D) column vectors, c: (M,D) row vectors, d: (N) column scalars (null when unused).
+ * o_*: outputs, null unless selected in `mask`. */
+int dicp_ksum(int D, unsigned mask, float sigma,
+              const float* x, int64_t M, const float* y, int64_t N,
+              const float* b, const float* c, const float* d,
+              float* o_base, float* o_redscal, float* o_red, float* o_grad, float* o_dd, float* o_gend,
+              float* o_hess, float* o_lap, float* o_gradlap, float* o_minsq, float* o_dot,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused right-hand side of the Hamiltonian ODE (LDDMMModel.ODE, core/LDDMM.py:176-227).
+ *   withlogdet: 0 = no divergence cost, 1 = dcost = -sum div v at the data points (x if given, else q)
+ *   eta: 0 (classic / hybrid) or 1/lambda (logdet model)
+ *   x / Nx: optional external data points (null / 0 => data points are the support points)
+ * outputs: vq (M,D) = dq/dt, dp (M,D) = dp/dt, vx (Nx,D) = dx/dt,
+ *          scal[4] = { dcost, A = sum p.KRed(q,q,p), B = sum p.GradKRed(q,q), C = sum LapKRed(q,q) }
+ *          (B is only produced when withlogdet && !x or eta != 0; C only when eta != 0; else 0)
+ *          H(q,p) = A/2 - eta*B - eta^2*C/2  (core/LDDMM.py:142-159). */
+int dicp_rhs_forward(int D, int withlogdet, float sigma, float eta,
+                     const float* q, const float* p, int64_t M, const float* x, int64_t Nx,
+                     float* vq, float* dp, float* vx, float* scal,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Adjoint (vector-Jacobian product) of dicp_rhs_forward: given cotangents a (of vq), u (of dp), wx (of vx)
+ * and the device scalar gc (of dcost; null => 0), writes gq, gp (M,D) and gx (Nx,D). */
+int dicp_rhs_adjoint(int D, int withlogdet, float sigma, float eta,
+                     const float* q, const float* p, int64_t M, const float* x, int64_t Nx,
+                     const float* a, const float* u, const float* wx, const float* gc,
+                     float* gq, float* gp, float* gx,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* out = a + alpha*f1 + beta*f2  (f2 may be null) over n floats: the Euler / Ralston state updates
+ * (tools/integrators.py:27-29, 42-48) and the adjoint accumulations. */
+int dicp_axpy(int64_t n, float* out, const float* a, float alpha, const float* f1, float beta, const float* f2,
+              void* stream);
+
+/* Pipe-throughput probes used by bench.py to measure the FP32 / SFU roofline denominators live:
+ * which = 0: FFMA, 1: FFMA2 (packed f32x2), 2: MUFU.EX2.  Runs `iters` dependent-chain steps x 8 chains per
+ * thread on `blocks` x 256 threads; out[blocks*256] receives a checksum.  ops per thread = iters * 8
+ * (FFMA2 counts 2 FMAs per instruction). */
+int dicp_pipe_probe(int which, int blocks, int iters, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DICP_B200_H */
