@@ -13,7 +13,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdicp_b200.so")
+LIB_PATH = os.environ.get("DICP_B200_LIB", os.path.join(_HERE, "libdicp_b200.so"))   # override: tuning sweeps only
 
 _lib = None
 _lock = threading.Lock()
@@ -29,6 +29,7 @@ _sz = ctypes.c_size_t
 SIGNATURES = {
     "dicp_version": (_int, []),
     "dicp_sm_count": (_int, []),
+    "dicp_launch_count": (ctypes.c_ulonglong, []),
     "dicp_pair_workspace_bytes": (_sz, [_i64, _i64]),
     "dicp_ksum": (_int, [_int, _u, _f, _vp, _i64, _vp, _i64, _vp, _vp, _vp] + [_vp] * 11 + [_vp, _sz, _vp]),
     "dicp_rhs_forward": (_int, [_int, _int, _f, _f, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -30,7 +30,10 @@ struct DeviceExec {
     int run(const typename Op::Params& prm, int M, int N, float* scal_out, int accumulate) {
         return run_pair<Op>(prm, M, N, scal_out, accumulate, ws, wsb, st);
     }
-    void scal_fix(float* scal, float eta, int withdiv) { rhs_scal_fix_kernel<<<1, 32, 0, st>>>(scal, eta, withdiv); }
+    void scal_fix(float* scal, float eta, int withdiv) {
+        rhs_scal_fix_kernel<<<1, 32, 0, st>>>(scal, eta, withdiv);
+        launch_counter() += 1;
+    }
 };
 
 inline int last_error(int rc) {
@@ -91,6 +94,8 @@ int dicp_version(void) { return 100; }
 
 int dicp_sm_count(void) { return device_info().sms; }
 
+unsigned long long dicp_launch_count(void) { return launch_counter(); }
+
 size_t dicp_pair_workspace_bytes(int64_t rows, int64_t cols) { return pair_workspace_bound(rows, cols); }
 
 int dicp_ksum(int D, unsigned mask, float sigma, const float* x, int64_t M, const float* y, int64_t N,
@@ -125,6 +130,7 @@ int dicp_axpy(int64_t n, float* out, const float* a, float alpha, const float* f
     const long long cap = (long long)device_info().sms * 16;
     if (blocks > cap) blocks = cap;
     axpy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, out, a, alpha, f1, beta, f2);
+    launch_counter() += 1;
     return last_error(DICP_OK);
 }
 

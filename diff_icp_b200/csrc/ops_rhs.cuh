@@ -23,6 +23,20 @@
 #pragma once
 #include "pair_engine.cuh"
 
+// tuning knobs (overridable at compile time for sweeps: -DDICP_RHS_R=4 ...)
+#ifndef DICP_RHS_R
+#define DICP_RHS_R 2
+#endif
+#ifndef DICP_RHS_THREADS
+#define DICP_RHS_THREADS 128
+#endif
+#ifndef DICP_RHS_TILE
+#define DICP_RHS_TILE 128
+#endif
+#ifndef DICP_RHS_MINB
+#define DICP_RHS_MINB 1
+#endif
+
 namespace dicp {
 
 struct RhsParams {
@@ -39,10 +53,10 @@ struct RhsParams {
 // ------------------------------------------------------------------------------------------------
 // forward, (q,q)
 // ------------------------------------------------------------------------------------------------
-template <int D, bool DIV, bool ETA, int R_ = 2>
+template <int D, bool DIV, bool ETA, int R_ = DICP_RHS_R>
 struct RhsQQ {
     using Params = RhsParams;
-    static constexpr int THREADS = 128, MINB = 1, R = R_, TILE = 128;
+    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
     static constexpr int COLF4 = (2 * D + 3) / 4;
     static constexpr int A_V = 0, A_T = D, A_Z = 2 * D;
     static constexpr bool NEEDZ = DIV || ETA;
@@ -140,10 +154,10 @@ struct RhsQQ {
 // ------------------------------------------------------------------------------------------------
 // forward, (x,q): rows = data points, cols = (q,p)
 // ------------------------------------------------------------------------------------------------
-template <int D, bool DIV, bool ETA, int R_ = 2>
+template <int D, bool DIV, bool ETA, int R_ = DICP_RHS_R>
 struct RhsXQ {
     using Params = RhsParams;
-    static constexpr int THREADS = 128, MINB = 1, R = R_, TILE = 128;
+    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
     static constexpr int COLF4 = (2 * D + 3) / 4;
     static constexpr int A_V = 0, A_DS = D;
     static constexpr int A_Z = A_DS + (DIV ? 1 : 0);
@@ -208,10 +222,10 @@ struct RhsXQ {
 //                                                                       [- gc s sum_j K (dp - beta (dp.z') z') if DIV]
 //   with du = u_i - u_j, dp = p_i - p_j, w = p_i.p_j.
 // ------------------------------------------------------------------------------------------------
-template <int D, bool DIV, int R_ = 2>
+template <int D, bool DIV, int R_ = DICP_RHS_R>
 struct AdjQQ {
     using Params = RhsParams;
-    static constexpr int THREADS = 128, MINB = 1, R = R_, TILE = 128;
+    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
     static constexpr int COLF4 = (4 * D + 3) / 4;
     static constexpr int A_GP = 0, A_GQ = D;
     static constexpr int NACC = 2 * D;
@@ -310,10 +324,10 @@ struct AdjQQ {
 // adjoint of the (x,q) pass w.r.t. x: rows = (x_k, wx_k), cols = (q, p)      (eta = 0)
 //   gx_k = - sum_j K [alpha (wx_k.p_j) + gc s beta (p_j.z')] z' + gc s sum_j K p_j
 // ------------------------------------------------------------------------------------------------
-template <int D, bool DIV, int R_ = 2>
+template <int D, bool DIV, int R_ = DICP_RHS_R>
 struct AdjXQx {
     using Params = RhsParams;
-    static constexpr int THREADS = 128, MINB = 1, R = R_, TILE = 128;
+    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
     static constexpr int COLF4 = (2 * D + 3) / 4;
     static constexpr int NACC = D, NSCAL = 0;
     struct Row { float x[D], w[D], gc; };
@@ -372,10 +386,10 @@ struct AdjXQx {
 //   gq_j = - sum_k K [alpha (wx_k.p_j) - gc s beta (p_j.zeta')] zeta' - gc s p_j sum_k K
 //   gp_j =   sum_k K wx_k - gc alpha sum_k K zeta'
 // ------------------------------------------------------------------------------------------------
-template <int D, bool DIV, int R_ = 2>
+template <int D, bool DIV, int R_ = DICP_RHS_R>
 struct AdjXQq {
     using Params = RhsParams;
-    static constexpr int THREADS = 128, MINB = 1, R = R_, TILE = 128;
+    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
     static constexpr int COLF4 = (2 * D + 3) / 4;
     static constexpr int A_GP = 0, A_GQ = D, A_S0 = 2 * D;
     static constexpr int NACC = 2 * D + (DIV ? 1 : 0), NSCAL = 0;

@@ -49,6 +49,10 @@ int dicp_version(void);
 /* number of SMs of the current device (148 on B200) */
 int dicp_sm_count(void);
 
+/* number of kernel launches this library has issued so far in this process (launches recorded into a CUDA graph
+ * are counted once, at capture) */
+unsigned long long dicp_launch_count(void);
+
 /* Upper bound of the workspace needed by any pair kernel with `rows` rows and `cols` columns. */
 size_t dicp_pair_workspace_bytes(int64_t rows, int64_t cols);
 
