@@ -1,0 +1,294 @@
+"""Isotropic-uniform Gaussian mixture with a fused EM step on the B200: drop-in for the reference's
+``diffICP/core/GMM.py`` (live class, core/GMM.py:40-721).
+
+Model: centroids mu (C,D), ONE shared scalar sigma, component scores w (pi = softmax(w)), optional uniform outlier
+component encoded by a log-odds ratio eta0 and a reference volume vol0 (core/GMM.py:42-109).
+
+EM step (core/GMM.py:236-325 torch twin, :402-529 KeOps formulation), per call:
+  * mu, w frozen or skip_M=True : ONE sweep over points x components (dicp_em_rowpass) produces the row
+    log-sum-exp, the targets Y, and the four sums from which sigma', Cfe and FE follow;
+  * otherwise                    : row LSE sweep -> column sweep (log-domain sufficient statistics of every
+    component, dicp_em_colstats) -> tiny M step on (C, D+3) numbers -> full row sweep (old gamma, new theta).
+One host synchronisation per EM step (the reference has >= 3 ``.item()`` calls).
+
+``computversion`` keeps the reference's two SEMANTIC variants (they differ when the M step runs):
+  "keops" / "b200" : sigma' from squared distances to the NEW centroids, Gaussian normalisation from the NEW sigma
+                     (core/GMM.py:453-455, :483) -- the reference's default and GPU behaviour;
+  "torch"          : sigma' from distances to the OLD centroids, normalisation from the OLD sigma (:263-264, :296, :314).
+Both run on the same CUDA kernels; nothing here computes on the CPU.
+
+Multi-GPU (groupwise mode, points sharded by frame): set ``self.comm`` to a ``diff_icp_b200.dist.StatsComm``; the
+column statistics and the four sums are then all-reduced (MAX on the exponents, SUM on the rescaled sums) -- the only
+collective of the whole algorithm.
+"""
+
+from __future__ import annotations
+
+import copy
+import math
+
+import numpy as np
+import torch
+from torch.nn import Module
+from torch.nn.functional import log_softmax, softmax, softplus
+
+from .. import em_ops
+from ..tools.point_sets import intrinsic_scale
+from ..tools.spec import defspec
+
+_LOG2E = 1.4426950408889634
+_LN2 = 0.6931471805599453
+_ACCEPTED = ("b200", "keops", "torch")
+
+
+class GaussianMixtureUnif(Module):
+
+    def __init__(self, mu, sigma=None, use_outliers=False, spec=defspec, computversion="keops"):
+        super().__init__()
+        self.params = {}
+        self.spec = spec
+        self.mu = mu.clone().detach().to(**spec)
+        self.C, self.D = self.mu.shape
+        self.sigma = sigma
+        if self.sigma is None:
+            # ad hoc: 0.1 x "typical radius" of the volume owned by one centroid (reference: core/GMM.py:83-88)
+            r = self.mu.var(0).sum().sqrt().item()
+            self.sigma = max(0.1 * (r / self.C ** (1 / self.D)), 1e-6)
+        self.w = torch.zeros(self.C, **spec)
+        self.to_optimize = {"sigma": True, "mu": True, "w": True, "eta0": True}
+        self.outliers = {"vol0": None, "eta0": 0.0} if use_outliers else None
+        self.ensure_continuum = False
+        self.comm = None                      # multi-GPU statistics reducer (diff_icp_b200.dist.StatsComm) or None
+        self.set_computversion(computversion)
+
+    # ------------------------------------------------------------------------------------------------------
+    def __deepcopy__(self, memo):
+        G2 = GaussianMixtureUnif(self.mu, spec=self.spec, computversion=self.computversion)
+        G2.sigma = self.sigma
+        G2.w = self.w.clone().detach()
+        G2.to_optimize = copy.deepcopy(self.to_optimize)
+        G2.outliers = copy.deepcopy(self.outliers)
+        G2.ensure_continuum = self.ensure_continuum
+        G2.comm = self.comm
+        return G2
+
+    def set_computversion(self, version):
+        if version not in _ACCEPTED:
+            raise ValueError(f"unkown computversion : {version}. Choices are 'b200', 'keops' or 'torch'")
+        self.computversion = version
+        self.EM_step = self.EM_step_b200
+        return self
+
+    def fix(self):
+        self.to_optimize = {"sigma": False, "mu": False, "w": False, "eta0": False}
+        return self
+
+    def set_vol0(self, X: torch.Tensor):
+        if self.outliers is not None:
+            self.outliers["vol0"] = (X.max(dim=0)[0] - X.min(dim=0)[0]).prod().item()
+        return self
+
+    def __str__(self):
+        s = super().__str__()
+        s += ": Gaussian Mixture with Uniform covariances. Parameters:\n"
+        s += "    C [# components] : " + str(self.C) + "\n"
+        s += "    sigma [unif. std] : " + str(self.sigma) + "\n"
+        s += "    mu_c [centroids] :" + str(self.mu) + "\n"
+        s += "    w_c [component scores]:" + str(self.w) + "\n"
+        if self.outliers is not None:
+            s += "    vol0 [ref. volume for outliers]:" + str(self.outliers["vol0"]) + "\n"
+            s += "    eta0 [outlier vs GMM log-ratio]:" + str(self.outliers["eta0"]) + "\n"
+        return s
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.spec = defspec
+        self.EM_step = self.EM_step_b200
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("EM_step", None)            # bound method: rebuilt on load
+        state["comm"] = None
+        return state
+
+    # ------------------------------------------------------------------------------------------------------
+    def log_ratio_to_proba(self, eta):
+        """(log p, log q) of a Bernoulli with log-odds eta = log(p/q) (reference: core/GMM.py:205-217)."""
+        if not isinstance(eta, torch.Tensor):
+            eta = torch.tensor(eta, **self.spec)
+        Z = softplus(eta)
+        return eta - Z, -Z
+
+    def log_responsibilities(self, X):
+        """(N,C) log gamma_nc without outliers (reference: core/GMM.py:221-232)."""
+        lgam, _ = em_ops.log_resp(self.sigma, X.detach().contiguous(), self.mu.contiguous(), self.w.contiguous())
+        return lgam
+
+    def hard_assignments(self, X):
+        """argmax_c gamma_nc, (N,) int64, first index on ties (what the reference computes as
+        log_responsibilities(X).argmax(dim=1), core/GMM.py:677-680) without materialising the (N,C) matrix."""
+        _, amax = em_ops.log_resp(self.sigma, X.detach().contiguous(), self.mu.contiguous(), self.w.contiguous(),
+                                  want_lgam=False, want_argmax=True)
+        return amax
+
+    # ------------------------------------------------------------------------------------------------------
+    def _lgn(self, sigma):
+        return self.D * (math.log(sigma) + 0.5 * math.log(2 * math.pi))
+
+    def EM_step_b200(self, X, skip_M=False):
+        """One (E step, M step) alternation; returns (Y, Cfe, FE) like the reference (core/GMM.py:236-325, :501-529).
+        Y (N,D): quadratic targets sum_c gamma_nc mu_c;  Cfe: free-energy offset;  FE = Cfe + sum_n (1-gamma0_n)|x_n-y_n|^2/(2 sigma^2)."""
+        X = X.detach().contiguous()
+        N_local = X.shape[0]
+        D, C = self.D, self.C
+        opt = self.to_optimize
+        keops_sem = self.computversion != "torch"
+        do_M = not skip_M
+        do_mu, do_w, do_sig = do_M and opt["mu"], do_M and opt["w"], do_M and opt["sigma"]
+        use_out = self.outliers is not None
+        comm = self.comm
+
+        sigma_old = float(self.sigma)
+        lgn_old = self._lgn(sigma_old)
+        mu_old = self.mu.contiguous()
+        wl2 = ((self.w - torch.logsumexp(self.w, 0) - lgn_old) * _LOG2E).contiguous()
+
+        # ---- M step for mu / w (and the column form of sigma) from log-domain column statistics ------------
+        nds2 = None
+        mu_new, w_new = mu_old, self.w
+        if do_mu or do_w:
+            T2 = em_ops.rowpass(sigma_old, X, mu_old, wl2)
+            stats = em_ops.colstats(sigma_old, X, T2, mu_old, wl2) if N_local > 0 else _empty_stats(C, D, X.device)
+            if comm is not None:
+                stats = comm.merge_colstats(stats)
+            m, S0, B, A = stats[:, 0], stats[:, 1], stats[:, 2:2 + D], stats[:, 2 + D]
+            if do_mu:
+                mu_new = (mu_old + B / S0[:, None]).contiguous()
+            if do_w:
+                w_new = (m + torch.log2(S0)) * _LN2
+            if do_sig:
+                if keops_sem and do_mu:
+                    nds2 = (torch.exp2(m) * (A - (B * B).sum(-1) / S0)).sum()
+                else:
+                    nds2 = (torch.exp2(m) * A).sum()
+        lpi_new = (w_new - torch.logsumexp(w_new, 0)).contiguous()
+
+        # ---- full row pass: old responsibilities, new centroids / weights ------------------------------------
+        T2, Y, scal, rowP, rowQ, sq = em_ops.rowpass(sigma_old, X, mu_old, wl2, mu_new, lpi_new, per_point=use_out)
+        parts = [scal, torch.tensor([float(N_local)], device=scal.device)]
+        if nds2 is not None:
+            parts.append(nds2.reshape(1))
+        if use_out:
+            if self.outliers["vol0"] is None:
+                self.set_vol0(X)
+            logJ0 = -math.log(self.outliers["vol0"])
+            eta_n = self.outliers["eta0"] + logJ0 - T2 * _LN2
+            lg0, lgT = self.log_ratio_to_proba(eta_n)
+            if do_M and opt["eta0"]:
+                # log-domain sums over n (reference: core/GMM.py:290 / :450)
+                l0, lT = torch.logsumexp(lg0, 0), torch.logsumexp(lgT, 0)
+                if comm is not None:
+                    l0, lT = comm.logsumexp_pair(l0, lT)
+                parts.append(torch.stack((l0, lT)))
+        vec = torch.cat(parts)
+        if comm is not None:
+            head = comm.sum(vec[:5].clone())                    # P, Q, SQ, DS, N are plain sums over frames
+            vec = torch.cat((head, vec[5:]))
+        vals = vec.tolist()                                     # the ONE host synchronisation of this EM step
+        P, Q, SQ, DS, N = vals[:5]
+        k = 5
+        if do_sig:
+            nd = vals[k] if nds2 is not None else DS
+            k += 1 if nds2 is not None else 0
+            self.sigma = math.sqrt(max(nd, 0.0) / (D * N))
+            if self.ensure_continuum:
+                self.sigma = max(self.sigma, intrinsic_scale(mu_new))
+        if use_out and do_M and opt["eta0"]:
+            self.outliers["eta0"] = vals[k] - vals[k + 1]
+        if do_mu:
+            self.mu = mu_new
+        if do_w:
+            self.w = w_new
+
+        sig = float(self.sigma)
+        lgn = self._lgn(sig) if keops_sem else lgn_old
+        inv2s2 = 1.0 / (2 * sig * sig)
+        if not use_out:
+            Cfe_val = P * inv2s2 + Q + N * lgn
+            FE_val = Cfe_val + SQ * inv2s2
+            Cfe = torch.tensor(Cfe_val, **self.spec)
+            FE = torch.tensor(FE_val, **self.spec)
+            return Y, Cfe, FE
+        g0, gT = lg0.exp(), lgT.exp()
+        lpi0, lpiT = self.log_ratio_to_proba(self.outliers["eta0"])
+        cfe_n = rowP * inv2s2 + rowQ + lgn
+        tot = torch.stack(((gT * (cfe_n + lgT - lpiT) + g0 * (-logJ0 + lg0 - lpi0)).sum(), (gT * sq).sum()))
+        if comm is not None:
+            tot = comm.sum(tot)
+        c_out, q_out = tot.tolist()
+        return Y, c_out, c_out + q_out * inv2s2
+
+    # ------------------------------------------------------------------------------------------------------
+    def EM_optimization(self, X, max_iterations=100, tol=1e-5):
+        """Repeat EM steps until the relative change of FE is below tol (reference: core/GMM.py:330-357).
+        Returns (Y, Cfe, FE, number of steps)."""
+        if X.shape[0] == 0 and self.comm is None:
+            return torch.empty(X.shape, **self.spec), torch.tensor(0.0), torch.tensor(0.0), 0
+        Y = Cfe = FE = last_FE = None
+        for i in range(max_iterations):
+            Y, Cfe, FE = self.EM_step(X)
+            if last_FE is not None and tol is not None and abs(FE - last_FE) < tol * abs(last_FE):
+                return Y, Cfe, FE, i + 1
+            last_FE = FE
+        print(f"GMM optimization - reached maximum number of iterations : {max_iterations}")
+        return Y, Cfe, FE, i + 1
+
+    @staticmethod
+    def get_GMM_model(X, C, fixed_sigma=None, optimize_w=False, use_outliers=False, max_iterations=100, tol=1e-5,
+                      spec=defspec, computversion="keops"):
+        """GMM with C components fitted to X from C random data points (reference: core/GMM.py:361-383)."""
+        mu = X[torch.randint(0, X.shape[0], (C,)), :]
+        GMM = GaussianMixtureUnif(mu, use_outliers=use_outliers, spec=spec, computversion=computversion)
+        GMM.to_optimize = {"mu": True, "sigma": True, "w": optimize_w, "eta0": True}
+        if fixed_sigma is not None:
+            GMM.to_optimize["sigma"] = False
+            GMM.sigma = fixed_sigma
+        GMM.EM_optimization(X, max_iterations=max_iterations, tol=tol)
+        return GMM
+
+    # ------------------------------------------------------------------------------------------------------
+    def pi(self):
+        return softmax(self.w, dim=0)
+
+    def get_sample(self, N):
+        """N random points from the mixture, without the outlier term (reference: core/GMM.py:543-550)."""
+        samp = self.sigma * torch.randn(N, self.D, **self.spec)
+        c = torch.distributions.categorical.Categorical(logits=self.w).sample((N,))
+        return samp + self.mu[c, :]
+
+    def update_covariances(self):
+        self.params["gamma"] = (torch.eye(self.D, **self.spec) * self.sigma ** (-2))[None, :, :].repeat([self.C, 1, 1]).view(self.C, self.D ** 2)
+
+    def weights(self):
+        return softmax(self.w, 0) / self.sigma ** self.D
+
+    def weights_log(self):
+        return log_softmax(self.w, 0) - self.D * math.log(self.sigma)
+
+    def log_likelihoods(self, sample):
+        """Log-density sampled on a point cloud, with the reference's normalisation (core/GMM.py:714-721:
+        weights_log already carries -D ln sigma and loggaussnorm is subtracted on top of it)."""
+        sample = sample.to(**self.spec).contiguous()
+        wl2 = ((self.weights_log() - self._lgn(self.sigma)) * _LOG2E).contiguous()
+        T2 = em_ops.rowpass(self.sigma, sample, self.mu.contiguous(), wl2)
+        return T2 * _LN2
+
+    def likelihoods(self, sample):
+        """Density sampled on a point cloud (reference: core/GMM.py:706-712)."""
+        return self.log_likelihoods(sample).exp()
+
+
+def _empty_stats(C, D, device):
+    s = torch.zeros(C, D + 3, dtype=torch.float32, device=device)
+    s[:, 0] = -3.0e38
+    return s

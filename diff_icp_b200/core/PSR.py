@@ -1,0 +1,301 @@
+"""Outer alternation of diffICP (GMM fit <-> LDDMM registration) on the B200: drop-in for the reference's
+``diffICP/core/PSR.py`` classes ``MultiPSR`` and ``DiffPSR`` (core/PSR.py:42-569).
+
+Same storage (object arrays x0 / x1 / y indexed [frame k, structure s]; lists a0[k], q0[k], shoot[k]; GMMi[s]) and the
+same public methods.  The arithmetic runs in the CUDA kernels through ``GaussianMixtureUnif`` and ``LDDMMModel``.
+
+Groupwise multi-GPU mode: construct one DiffPSR per rank on that rank's frames and pass ``comm`` (a
+``diff_icp_b200.dist.StatsComm``).  Registration of a frame uses only that frame's data (core/PSR.py:528), so Reg_opt is
+purely local; the GMM fit couples frames through O(C) sufficient statistics that the GMM all-reduces (the only
+collective); the free energy and the re-initialisation statistics are summed over ranks here.
+"""
+
+from __future__ import annotations
+
+import copy
+import warnings
+
+import numpy as np
+import torch
+
+from .GMM import GaussianMixtureUnif
+from .LDDMM import LDDMMModel
+from .registrations import LDDMMRegistration
+from ..tools.in_out import read_point_sets
+from ..tools.point_sets import decimate
+from ..tools.spec import defspec
+
+
+def get_bounds(*xlist, relmargin=0.2):
+    """Per-dimension (min, max) over several point sets, enlarged by a relative margin
+    (reference: visualization/visu.py:35-50, 2-D there; any D here)."""
+    mins = torch.stack([x.min(0).values for x in xlist if len(x) > 0]).min(0).values.cpu().numpy()
+    maxs = torch.stack([x.max(0).values for x in xlist if len(x) > 0]).max(0).values.cpu().numpy()
+    return (1 + relmargin) * mins - relmargin * maxs, (1 + relmargin) * maxs - relmargin * mins
+
+
+class MultiPSR:
+    """Base class: multiple point-set registration to per-structure GMMs (reference: core/PSR.py:42-345)."""
+
+    def __init__(self, x, GMMi, dataspec=defspec, compspec=defspec, comm=None):
+        self.dataspec, self.compspec = dataspec, compspec
+        self.comm = comm
+        self.printstuff = True
+        x, self.K, self.S, self.D = read_point_sets(x)
+
+        self.x0 = np.empty((self.K, self.S), dtype=object)     # unregistered point sets
+        self.x1 = np.empty((self.K, self.S), dtype=object)     # registered (warped) point sets
+        self.y = np.empty((self.K, self.S), dtype=object)      # quadratic targets from the GMM E step
+        for k in range(self.K):
+            for s in range(self.S):
+                self.x0[k, s] = x[k][s].contiguous().detach().to(**self.dataspec)
+                self.x1[k, s] = self.x0[k, s].clone()
+                self.y[k, s] = self.x0[k, s].clone()
+        self.N = np.array([[self.x0[k, s].shape[0] for s in range(self.S)] for k in range(self.K)]).reshape(self.K, self.S)
+
+        if isinstance(GMMi, GaussianMixtureUnif):
+            self.GMMi = [copy.deepcopy(GMMi) for _ in range(self.S)]
+        else:
+            if not isinstance(GMMi, list) or len(GMMi) != self.S:
+                raise ValueError("GMMi should be a single GMM model, or a list with S GMM models")
+            self.GMMi = [copy.deepcopy(gmm) for gmm in GMMi]
+        if any(gmm.spec != compspec for gmm in self.GMMi):
+            raise ValueError("Spec (dtype+device) error : GMM 'spec' and multiPSR 'compspec' attributes should be the same")
+        for gmm in self.GMMi:
+            gmm.comm = comm
+
+        # full EM free energy  F = sum_{k,s} quadloss[k,s] + sum_k regloss[k] + sum_s Cfe[s]   (core/PSR.py:114-121)
+        self.Cfe = [None] * self.S
+        self.regloss = [0] * self.K
+        self.quadloss = torch.zeros(self.K, self.S, **self.compspec)
+        self.FE = None
+        self.update_GMM_targets()
+        self.shoot = [None] * self.K
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.dataspec = defspec
+        self.compspec = defspec
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["comm"] = None
+        return state
+
+    # ------------------------------------------------------------------------------------------------------
+    def _cat_structure(self, arr, s):
+        return torch.cat(tuple(arr[:, s]), dim=0).to(**self.compspec) if self.K > 0 else torch.empty(0, self.D, **self.compspec)
+
+    def reinitialize_GMM(self, s=None, do_mu=True, do_sigma=True):
+        """Centroids near the centre of mass of all unwarped points, sigma = std/4 (reference: core/PSR.py:143-167).
+        With `comm`, mean and std are those of the points of ALL ranks, and the random draw is made identical on every
+        rank by drawing on rank 0's generator state broadcast through `comm`."""
+        for s in (range(self.S) if s is None else [s]):
+            allx0s = self._cat_structure(self.x0, s)
+            if self.comm is None:
+                mean, std = allx0s.mean(dim=0), allx0s.std().item()
+            else:
+                # global mean / std (over all coordinates, unbiased like torch's .std()) from per-rank sums in fp64
+                a = allx0s.double()
+                red = self.comm.sum(torch.cat((torch.tensor([float(a.numel())], dtype=torch.float64, device=a.device),
+                                               a.sum(0), (a ** 2).sum().reshape(1))))
+                n, sm, sq = float(red[0]), red[1:1 + self.D], float(red[1 + self.D])
+                mean = (sm / (n / self.D)).to(**self.compspec)
+                tot = float(sm.sum())
+                std = max((sq - tot * tot / n) / (n - 1), 0.0) ** 0.5
+            gmm = self.GMMi[s]
+            if do_mu and gmm.to_optimize["mu"]:
+                noise = torch.randn(gmm.C, self.D, **self.dataspec)
+                if self.comm is not None:
+                    noise = self.comm.broadcast(noise)
+                gmm.mu = (mean + 0.05 * std * noise).to(**self.compspec)
+            if do_sigma and gmm.to_optimize["sigma"]:
+                gmm.sigma = 0.25 * std
+        self.update_GMM_targets()
+
+    # accessors (reference: core/PSR.py:174-190)
+    def get_data_points(self, k=0, s=0):
+        return self.x0[k, s]
+
+    def get_warped_data_points(self, k=0, s=0):
+        return self.x1[k, s]
+
+    def get_template(self, s=0):
+        return self.GMMi[s].mu
+
+    # ------------------------------------------------------------------------------------------------------
+    def _scatter_targets(self, allys, s):
+        last = 0
+        for k in range(self.K):
+            first, last = last, last + self.N[k, s]
+            self.y[k, s] = allys[first:last].to(**self.dataspec)
+            self.update_quadloss(k, s)
+
+    def update_GMM_targets(self):
+        """Recompute y, Cfe, quadloss, FE without any GMM parameter update (reference: core/PSR.py:197-213)."""
+        for s in range(self.S):
+            allys, self.Cfe[s], _ = self.GMMi[s].EM_step(self._cat_structure(self.x1, s), skip_M=True)
+            self._scatter_targets(allys, s)
+        self.update_FE()
+
+    def update_quadloss(self, k, s):
+        self.quadloss[k, s] = ((self.x1[k, s].to(**self.compspec) - self.y[k, s].to(**self.compspec)) ** 2).sum() \
+            / (2 * self.GMMi[s].sigma ** 2)
+
+    def update_FE(self, message=None):
+        """F = sum Cfe + sum regloss + sum quadloss (reference: core/PSR.py:226-236); regloss and quadloss are per-frame
+        quantities and are summed over ranks in multi-GPU mode, Cfe is already global."""
+        local = float(sum(self.regloss)) + self.quadloss.sum().item()
+        if self.comm is not None:
+            local = float(self.comm.sum(torch.tensor([local], dtype=torch.float64, device=self.compspec["device"]))[0])
+        FE = float(sum(float(c) for c in self.Cfe)) + local
+        if self.printstuff and message is not None:
+            print(message.ljust(70) + f"Total free energy = {FE:.8}")
+        if self.FE is not None and FE > self.FE:
+            print("WARNING: measured increase in free energy ! Should not happen.")
+        self.FE = FE
+
+    # ------------------------------------------------------------------------------------------------------
+    def GMM_opt(self, max_iterations=100, tol=1e-5):
+        """GMM part of the alternation, one structure at a time on the points of all frames
+        (reference: core/PSR.py:242-271)."""
+        for s in range(self.S):
+            allys, self.Cfe[s], _, i = self.GMMi[s].EM_optimization(self._cat_structure(self.x1, s),
+                                                                    max_iterations=max_iterations, tol=tol)
+            self._scatter_targets(allys, s)
+            message = f"GMM optim (structure {s}) : {i} EM steps"
+            if self.GMMi[s].outliers:
+                p0 = 1 / (1 + np.exp(-self.GMMi[s].outliers["eta0"]))
+                message += f", p_outlier={p0:.4}"
+            else:
+                message += "."
+            self.update_FE(message=message)
+
+    def Reg_opt(self, tol=1e-5):
+        raise NotImplementedError("function Reg_opt must be written in derived classes.")
+
+    def Registration(self, k=0):
+        """Registration object of frame k (reference: core/PSR.py:294-304)."""
+        if isinstance(self, DiffPSR):
+            return LDDMMRegistration(self.LMi, self.q0[k], self.a0[k])
+        raise NotImplementedError("only diffeomorphic registrations are part of the B200 hot path")
+
+
+class DiffPSR(MultiPSR):
+    """MultiPSR with diffeomorphic (LDDMM) registrations (reference: core/PSR.py:354-569)."""
+
+    def __init__(self, x, GMMi, LMi: LDDMMModel, dataspec=defspec, compspec=defspec, comm=None):
+        super().__init__(x, GMMi, dataspec=dataspec, compspec=compspec, comm=comm)
+        if LMi.Kernel.spec != compspec:
+            raise ValueError("Spec (dtype+device) error : LDDMMmodel kernel 'spec' and diffPSR 'compspec' attributes should be the same")
+        self.LMi = LMi
+        self.allx0 = [torch.cat(tuple(self.x0[k, :]), dim=0).to(**self.compspec).contiguous() for k in range(self.K)]
+        self.support_scheme, self.rho = None, None
+        self.q0 = self.allx0                       # dense scheme by default: support points = data points
+        self.a0 = [None] * self.K
+        self.initialize_a0()
+
+    def initialize_a0(self, **v2p_args):
+        """Momenta giving (approximately) zero initial speeds (reference: core/PSR.py:406-413)."""
+        for k in range(self.K):
+            v0 = torch.zeros(self.q0[k].shape, **self.compspec)
+            self.a0[k] = self.LMi.v2p(self.q0[k], v0, **v2p_args)
+
+    def update_a0(self, q0_prev, a0_prev=None, **v2p_args):
+        """Project v(q0_prev, a0_prev) on the span of the new support points (reference: core/PSR.py:415-425)."""
+        if a0_prev is None:
+            a0_prev = self.a0
+        for k in range(self.K):
+            v0 = self.LMi.v(self.q0[k], q0_prev[k], a0_prev[k])
+            self.a0[k] = self.LMi.v2p(self.q0[k], v0, **v2p_args)
+
+    def set_support_scheme(self, scheme="decim", rho=1.0, xticks=None, yticks=None, q0=None, zticks=None):
+        """Choose the LDDMM support points: "decim" (greedy covering of the data), "grid" (regular grid of step
+        rho*sigma over the data bounds; the reference's grid is 2-D only, core/PSR.py:472-482 -- here any D) or
+        "custom" (reference: core/PSR.py:430-493)."""
+        self.rho = rho
+        Rcover = rho * self.LMi.Kernel.sigma
+        self.support_scheme = scheme
+        q0_prev = self.q0
+
+        if scheme == "decim":
+            self.q0 = [None] * self.K
+            for k in range(self.K):
+                ids = [decimate(self.x0[k, s], Rcover)[0] for s in range(self.S)]
+                nd = sum(len(i) for i in ids)
+                if self.printstuff:
+                    print(f"Decimation, frame {k} : {nd} support points ({nd / sum(self.N[k, :]):.0%} of original sets)")
+                self.q0[k] = torch.cat(tuple(self.x0[k, s][ids[s]] for s in range(self.S)), dim=0).to(**self.compspec).contiguous()
+
+        elif scheme == "grid":
+            given = [xticks, yticks, zticks][:self.D]
+            if any(t is None for t in given):
+                lo, hi = get_bounds(*self.allx0, relmargin=0.1)
+                if self.comm is not None:
+                    lo = -self.comm.max(torch.tensor(-lo, dtype=torch.float64, device=self.compspec["device"])).cpu().numpy()
+                    hi = self.comm.max(torch.tensor(hi, dtype=torch.float64, device=self.compspec["device"])).cpu().numpy()
+            ticks = [np.arange(lo[d] - Rcover / 2, hi[d] + Rcover / 2, Rcover) if given[d] is None else np.asarray(given[d])
+                     for d in range(self.D)]
+            if self.D == 2:     # same point ordering as the reference (meshgrid 'xy' + Fortran reshape)
+                pts = np.stack(np.meshgrid(ticks[0], ticks[1]), axis=2).reshape((-1, 2), order="F")
+            else:
+                pts = np.stack(np.meshgrid(*ticks, indexing="ij"), axis=-1).reshape(-1, self.D)
+            grid = torch.tensor(pts, **self.compspec).contiguous()
+            self.q0 = [grid] * self.K
+
+        elif scheme == "custom":
+            assert q0 is not None, "For a custom support scheme, please specify argument q0"
+            self.q0 = [q0.clone().detach().to(**self.compspec).contiguous()] * self.K
+
+        else:
+            raise ValueError(f"Unknown value of support point scheme : {scheme}. Only values available are 'decim', 'grid' and 'custom'.")
+
+        self.update_a0(q0_prev, rcond=1e-1)
+
+    def QuadLossFunctor(self, k):
+        """x -> sum_n |x_n - y_n|^2 / (2 sigma_s(n)^2) over all points of frame k (reference: core/PSR.py:498-516)."""
+        y = torch.cat(tuple(self.y[k, :]), dim=0).to(**self.compspec).contiguous()
+        inv = torch.cat(tuple(torch.full((int(self.N[k, s]),), 1.0 / (2 * self.GMMi[s].sigma ** 2)) for s in range(self.S))
+                        ).to(**self.compspec).contiguous()
+
+        def dataloss_func(x):
+            return (((x - y) ** 2) * inv[:, None]).sum()
+        return dataloss_func
+
+    def Reg_opt(self, nmax=10, tol=1e-3):
+        """LDDMM registration of every (local) frame to its current targets (reference: core/PSR.py:521-569)."""
+        for k in range(self.K):
+            if self.support_scheme is None:
+                self.a0[k], self.shoot[k], self.regloss[k], datal, isteps, change = \
+                    self.LMi.Optimize(self.QuadLossFunctor(k), self.q0[k], self.a0[k], tol=tol, nmax=nmax)
+                allx1k = self.shoot[k][-1][0]
+            else:
+                self.a0[k], self.shoot[k], self.regloss[k], datal, isteps, change = \
+                    self.LMi.Optimize(self.QuadLossFunctor(k), self.q0[k], self.a0[k], self.allx0[k], tol=tol, nmax=nmax)
+                allx1k = self.shoot[k][-1][-1]
+
+            last = 0
+            for s in range(self.S):
+                first, last = last, last + self.N[k, s]
+                self.x1[k, s] = allx1k[first:last].to(**self.dataspec)
+            for s in range(self.S):
+                self.update_quadloss(k, s)
+
+            # coverage of the warped data points by the support points at every time step (core/PSR.py:559-566);
+            # one host read for the whole trajectory
+            if self.support_scheme is not None:
+                Rcoverwarning = 2.0
+                counts = torch.stack([self.LMi.Kernel.check_coverage(st[-1], st[0], Rcoverwarning).sum()
+                                      for st in self.shoot[k]]).tolist()
+                for t, c in enumerate(counts):
+                    if c > 0:
+                        print(f"WARNING : shooting, time step {t} : {c} uncovered points ({c / self.allx0[k].shape[0]:.2%})")
+                        warnings.warn("Uncovered points during LDDMM shooting. Choose a smaller rho when defining the support scheme.", RuntimeWarning)
+
+            message = f"Frame {k} : {isteps} optim steps, loss={self.regloss[k] + datal:.4}, change={change:.4}."
+            if self.comm is None:
+                self.update_FE(message=message)
+            elif self.printstuff:
+                print(message)
+        if self.comm is not None:           # ranks hold different numbers of frames: ONE collective per Reg_opt
+            self.update_FE(message="Registration of all frames done.")

@@ -42,6 +42,47 @@ inline int last_error(int rc) {
     return e == cudaSuccess ? DICP_OK : (int)e;
 }
 
+// log-responsibilities lgamma_nc = log_softmax_c(w_c - |x_n - mu_c|^2 / (2 sigma^2)) and their arg max
+// (GaussianMixtureUnif.log_responsibilities, core/GMM.py:221-232; plot_bis :677-680).  One thread per point; the
+// distance is evaluated un-fused in the reference's operation order so that arg max decisions agree on tie-free rows.
+template <int D>
+__global__ void log_resp_kernel(const float* __restrict__ X, int N, const float* __restrict__ mu,
+                                const float* __restrict__ w, int C, float den, float* __restrict__ lgam,
+                                long long* __restrict__ amax) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float x[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[k] = X[(size_t)n * D + k];
+    float best = -INFINITY, m = -INFINITY, S = 0.f;
+    int bi = 0;
+    for (int c = 0; c < C; ++c) {
+        float d2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float dk = __fsub_rn(x[k], mu[(size_t)c * D + k]);
+            d2 = __fadd_rn(d2, __fmul_rn(dk, dk));
+        }
+        const float t = __fsub_rn(w[c], __fdiv_rn(d2, den));
+        if (t > best) { best = t; bi = c; }
+        if (t > m) { S = S * __expf(m - t) + 1.f; m = t; }
+        else S += __expf(t - m);
+    }
+    if (amax) amax[n] = bi;
+    if (lgam) {
+        const float T = m + __logf(S);
+        for (int c = 0; c < C; ++c) {
+            float d2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float dk = __fsub_rn(x[k], mu[(size_t)c * D + k]);
+                d2 = __fadd_rn(d2, __fmul_rn(dk, dk));
+            }
+            lgam[(size_t)n * C + c] = __fsub_rn(w[c], __fdiv_rn(d2, den)) - T;
+        }
+    }
+}
+
 // ---- pipe probes ---------------------------------------------------------------------------------
 template <int WHICH>
 __global__ void __launch_bounds__(256) probe_kernel(int iters, float* out) {
@@ -120,6 +161,34 @@ int dicp_rhs_adjoint(int D, int withlogdet, float sigma, float eta, const float*
                      float* gq, float* gp, float* gx, void* workspace, size_t workspace_bytes, void* stream) {
     DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream};
     return last_error(rhs_adjoint_entry(ex, D, withlogdet, sigma, eta, q, p, M, x, Nx, a, u, wx, gc, gq, gp, gx));
+}
+
+int dicp_em_rowpass(int D, int lite, float sigma_old, const float* X, int64_t N, const float* mu_old,
+                    const float* wl2, int64_t C, const float* mu_new, const float* lpi_new, float* T2, float* Y,
+                    float* rowP, float* rowQ, float* sq, float* scal4, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+    DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream};
+    return last_error(em_rowpass_entry(ex, D, lite, sigma_old, X, N, mu_old, wl2, C, mu_new, lpi_new, T2, Y, rowP, rowQ,
+                                       sq, scal4));
+}
+
+int dicp_em_colstats(int D, float sigma_old, const float* X, int64_t N, const float* T2, const float* mu_old,
+                     const float* wl2, int64_t C, float* stats, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream};
+    return last_error(em_colstats_entry(ex, D, sigma_old, X, N, T2, mu_old, wl2, C, stats));
+}
+
+int dicp_log_resp(int D, float sigma, const float* X, int64_t N, const float* mu, const float* w, int64_t C,
+                  float* lgam, long long* argmax, void* stream) {
+    if ((D != 2 && D != 3) || !(sigma > 0.f) || N < 0 || C < 1 || N > INT32_MAX || C > INT32_MAX) return DICP_EBADARG;
+    if (N == 0) return DICP_OK;
+    if (!X || !mu || !w || (!lgam && !argmax)) return DICP_EBADARG;
+    const float den = 2.f * sigma * sigma;
+    const int blocks = (int)((N + 127) / 128);
+    if (D == 2) log_resp_kernel<2><<<blocks, 128, 0, (cudaStream_t)stream>>>(X, (int)N, mu, w, (int)C, den, lgam, argmax);
+    else log_resp_kernel<3><<<blocks, 128, 0, (cudaStream_t)stream>>>(X, (int)N, mu, w, (int)C, den, lgam, argmax);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
 }
 
 int dicp_axpy(int64_t n, float* out, const float* a, float alpha, const float* f1, float beta, const float* f2,

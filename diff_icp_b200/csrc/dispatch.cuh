@@ -6,6 +6,7 @@
 #include <math.h>
 #include "ops_ksum.cuh"
 #include "ops_rhs.cuh"
+#include "ops_em.cuh"
 
 namespace dicp {
 
@@ -137,6 +138,38 @@ int rhs_adjoint_entry(Exec& ex, int D, int withlogdet, float sigma, float eta, c
     prm.gq = gq; prm.gp = gp; prm.gx = gx;
     return D == 2 ? rhs_adjoint_d<2>(ex, withlogdet, prm, (int)M, (int)Nx)
                   : rhs_adjoint_d<3>(ex, withlogdet, prm, (int)M, (int)Nx);
+}
+
+// ---- GMM EM ---------------------------------------------------------------------------------------------
+template <class Exec>
+int em_rowpass_entry(Exec& ex, int D, int lite, float sigma_old, const float* X, int64_t N, const float* mu_old,
+                     const float* wl2, int64_t C, const float* mu_new, const float* lpi_new, float* T2, float* Y,
+                     float* rowP, float* rowQ, float* sq, float* scal4) {
+    if ((D != 2 && D != 3) || !(sigma_old > 0.f) || N < 0 || C < 1 || N > INT32_MAX || C > INT32_MAX) return DICP_EBADARG;
+    if (N == 0) return DICP_OK;
+    if (!X || !mu_old || !wl2 || !T2) return DICP_EBADARG;
+    if (!lite && (!mu_new || !lpi_new || !Y || !scal4)) return DICP_EBADARG;
+    EmParams prm{};
+    prm.X = X; prm.mu_old = mu_old; prm.wl2 = wl2; prm.mu_new = mu_new; prm.lpi_new = lpi_new; prm.origin = mu_old;
+    prm.kappa = gauss_const(sigma_old).kappa;
+    prm.o_T2 = T2; prm.o_Y = Y; prm.o_rowP = rowP; prm.o_rowQ = rowQ; prm.o_sq = sq;
+    if (lite) return D == 2 ? ex.template run<EmRow<2, true>>(prm, (int)N, (int)C, nullptr, 0)
+                            : ex.template run<EmRow<3, true>>(prm, (int)N, (int)C, nullptr, 0);
+    return D == 2 ? ex.template run<EmRow<2, false>>(prm, (int)N, (int)C, scal4, 0)
+                  : ex.template run<EmRow<3, false>>(prm, (int)N, (int)C, scal4, 0);
+}
+
+template <class Exec>
+int em_colstats_entry(Exec& ex, int D, float sigma_old, const float* X, int64_t N, const float* T2,
+                      const float* mu_old, const float* wl2, int64_t C, float* stats) {
+    if ((D != 2 && D != 3) || !(sigma_old > 0.f) || N < 1 || C < 1 || N > INT32_MAX || C > INT32_MAX) return DICP_EBADARG;
+    if (!X || !T2 || !mu_old || !wl2 || !stats) return DICP_EBADARG;
+    EmParams prm{};
+    prm.X = X; prm.T2 = T2; prm.mu_old = mu_old; prm.wl2 = wl2; prm.origin = mu_old;
+    prm.kappa = gauss_const(sigma_old).kappa;
+    prm.o_stats = stats;
+    return D == 2 ? ex.template run<EmCol<2>>(prm, (int)C, (int)N, nullptr, 0)
+                  : ex.template run<EmCol<3>>(prm, (int)C, (int)N, nullptr, 0);
 }
 
 // CPU executor: tests only (tests/hostemu).  Never part of libdicp_b200.so.

@@ -1,0 +1,236 @@
+// GMM EM step (isotropic, one shared sigma) as pair-engine Ops.
+//
+// Replaces the six KeOps reductions of GaussianMixtureUnif.EM_step_keops
+// (/root/reference/diffICP/core/GMM.py:402-496: row LSE :410-415, sumsoftmaxweight :443, column logsumexp :446,
+// weighted logsumexp :455, targets :473, free-energy offset :485-486) / the dense (N,C) block of EM_step_torch
+// (:263-317) by at most three sweeps over points x components, each with one exponential per pair:
+//
+//   EmRow<D, LITE=true>   row pass, T_n = LSE_c t_nc only                       (needed before the column pass)
+//   EmCol<D>              column pass: log-domain sufficient statistics of every component
+//                         (m_c, S0_c, B_c, A_c) = online-softmax sums over n of gamma_nc, gamma_nc (x_n - mu_c),
+//                         gamma_nc |x_n - mu_c|^2, centred on the OLD mu (well conditioned)
+//   EmRow<D, LITE=false>  row pass with payload: responsibilities from the OLD parameters, targets Y_n and the
+//                         free-energy sums from the NEW ones (old gamma x new theta, GMM.py:303,312-314 / :473,485)
+//
+// When mu and w are frozen (two-set matching, GMM.py / api/ICP_two_set.py:179-187) or skip_M=True, ONE full row pass
+// is the whole EM step.  Everything is evaluated in the log2 domain: with kappa = sqrt(log2(e)/2)/sigma and
+// x' = kappa (x - origin), t2_nc = wl2_c - |x'_n - mu'_c|^2 is log2(pi_c N(x_n | mu_c, sigma)) and one MUFU.EX2 per
+// pair gives the unnormalised responsibility.  Row / column maxima are tracked online; accumulators are only
+// rescaled when the running maximum grows by more than 2^8 (exact in exact arithmetic, no overflow in fp32).
+#pragma once
+#include "pair_engine.cuh"
+
+namespace dicp {
+
+struct EmParams {
+    const float* X;        // (N,D) data points
+    const float* mu_old;   // (C,D) centroids that define the responsibilities
+    const float* wl2;      // (C)   log2-domain scores (w_c - LSE(w) - D(ln sigma + ln(2 pi)/2)) * log2(e), old params
+    const float* mu_new;   // (C,D) centroids used for the targets / free energy
+    const float* lpi_new;  // (C)   natural-log mixture weights used for the free energy
+    const float* T2;       // (N)   row LSE in log2 units (input of the column pass)
+    const float* origin;   // D floats subtracted before scaling (= mu_old)
+    float kappa;           // sqrt(log2(e)/2) / sigma_old
+    float* o_T2;           // (N)   row LSE, log2 units
+    float* o_Y;            // (N,D) quadratic targets
+    float* o_rowP;         // (N)   sum_c gamma |mu'_c|^2 - |Y_n|^2            (optional, null = not written)
+    float* o_rowQ;         // (N)   sum_c gamma (ln gamma - ln pi'_c)          (optional)
+    float* o_sq;           // (N)   |x_n - Y_n|^2                              (optional)
+    float* o_stats;        // (C, D+3) column statistics: m (log2), S0, B (D, unscaled), A (unscaled)
+};
+
+static constexpr float kRescaleSlack = 8.0f;
+static constexpr float kLn2 = 0.6931471805599453f;
+
+// ------------------------------------------------------------------------------------------------------------
+// row pass: rows = points, cols = components
+// ------------------------------------------------------------------------------------------------------------
+template <int D, bool LITE>
+struct EmRow {
+    using Params = EmParams;
+    static constexpr int THREADS = 128, MINB = 1, R = 2, TILE = 128;
+    static constexpr int COLN = LITE ? (D + 1) : (2 * D + 3);
+    static constexpr int COLF4 = (COLN + 3) / 4;
+    // accumulators: m, S, then (full) Y(D), M2, L, T, DS
+    static constexpr int A_M = 0, A_S = 1, A_Y = 2, A_M2 = 2 + D, A_L = 3 + D, A_T = 4 + D, A_DS = 5 + D;
+    static constexpr int NACC = LITE ? 2 : (6 + D);
+    static constexpr int NSCAL = LITE ? 0 : 4;   // P, Q, SQ, DS
+    struct Row { float x[D]; float raw[D]; };   // raw = x - origin (unscaled)
+
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) {
+#pragma unroll
+        for (int k = 0; k < COLF4 * 4; ++k) c[k] = 0.f;
+        if (j < N) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) c[k] = (P.mu_old[(size_t)j * D + k] - P.origin[k]) * P.kappa;
+            c[D] = P.wl2[j];
+            if (!LITE) {
+                float m2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const float v = P.mu_new[(size_t)j * D + k] - P.origin[k];   // centred: well-conditioned rowP
+                    c[D + 1 + k] = v;
+                    m2 = fmaf(v, v, m2);
+                }
+                c[2 * D + 1] = m2;
+                c[2 * D + 2] = P.lpi_new[j];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) c[k] = DICP_FAR;
+            c[D] = -1.0e30f;    // padded component: t2 = -inf-ish, never the maximum, e = 0
+        }
+    }
+    static DICP_HD void load_row(const Params& P, int i, Row& r) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            r.raw[k] = P.X[(size_t)i * D + k] - P.origin[k];
+            r.x[k] = r.raw[k] * P.kappa;
+        }
+    }
+    static DICP_HD void init(float* a) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
+        a[A_M] = -3.0e38f;
+    }
+    static DICP_HD void rescale(float* a, float m_new) {
+        const float sc = ex2f_fast(a[A_M] - m_new);     // 0 when a[A_M] is the initial -3e38
+#pragma unroll
+        for (int k = 1; k < NACC; ++k) a[k] *= sc;
+        a[A_M] = m_new;
+    }
+    static DICP_HD void combine(float* a, const float* b) {
+        float bb[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) bb[k] = b[k];
+        const float m = fmaxf(a[A_M], bb[A_M]);
+        rescale(a, m);
+        rescale(bb, m);
+#pragma unroll
+        for (int k = 1; k < NACC; ++k) a[k] += bb[k];
+    }
+    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* a) {
+        float r2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float z = r.x[k] - c[k];
+            r2 = fmaf(z, z, r2);
+        }
+        const float t2 = c[D] - r2;
+        if (t2 > a[A_M] + kRescaleSlack) rescale(a, t2);
+        const float e = ex2f_fast(t2 - a[A_M]);
+        a[A_S] += e;
+        if (!LITE) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) a[A_Y + k] = fmaf(e, c[D + 1 + k], a[A_Y + k]);
+            a[A_M2] = fmaf(e, c[2 * D + 1], a[A_M2]);
+            a[A_L] = fmaf(e, c[2 * D + 2], a[A_L]);
+            a[A_T] = fmaf(e, t2, a[A_T]);
+            a[A_DS] = fmaf(e, r2, a[A_DS]);
+        }
+    }
+    static DICP_HD void finish(const Params& P, int i, const Row& r, const float* a, float* scal) {
+        const float S = a[A_S];
+        const float T2 = a[A_M] + lg2f_fast(S);
+        P.o_T2[i] = T2;
+        if (!LITE) {
+            const float inv = 1.0f / S;
+            float y2 = 0.f, sq = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float y = a[A_Y + k] * inv;                    // target relative to the origin
+                P.o_Y[(size_t)i * D + k] = y + P.origin[k];
+                y2 = fmaf(y, y, y2);
+                const float dxy = r.raw[k] - y;
+                sq = fmaf(dxy, dxy, sq);
+            }
+            const float rowP = a[A_M2] * inv - y2;
+            const float rowQ = (a[A_T] * inv - T2) * kLn2 - a[A_L] * inv;   // sum_c gamma (ln gamma_nc - ln pi'_c)
+            const float ds = a[A_DS] * inv / (P.kappa * P.kappa);           // sum_c gamma |x_n - mu_c|^2 (old mu)
+            if (P.o_rowP) P.o_rowP[i] = rowP;
+            if (P.o_rowQ) P.o_rowQ[i] = rowQ;
+            if (P.o_sq) P.o_sq[i] = sq;
+            scal[0] = rowP; scal[1] = rowQ; scal[2] = sq; scal[3] = ds;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// column pass: rows = components, cols = points (x'_n, T2_n)
+// ------------------------------------------------------------------------------------------------------------
+template <int D>
+struct EmCol {
+    using Params = EmParams;
+    static constexpr int THREADS = 128, MINB = 1, R = 1, TILE = 128;
+    static constexpr int COLF4 = (D + 1 + 3) / 4;
+    static constexpr int A_M = 0, A_S = 1, A_B = 2, A_A = 2 + D;
+    static constexpr int NACC = 3 + D, NSCAL = 0;
+    struct Row { float mu[D]; float wl2; };
+
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) {
+#pragma unroll
+        for (int k = 0; k < COLF4 * 4; ++k) c[k] = 0.f;
+        if (j < N) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) c[k] = (P.X[(size_t)j * D + k] - P.origin[k]) * P.kappa;
+            c[D] = P.T2[j];
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) c[k] = DICP_FAR;
+            c[D] = 1.0e30f;      // padded point: log2 gamma = -huge, e = 0, never a new maximum
+        }
+    }
+    static DICP_HD void load_row(const Params& P, int i, Row& r) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) r.mu[k] = (P.mu_old[(size_t)i * D + k] - P.origin[k]) * P.kappa;
+        r.wl2 = P.wl2[i];
+    }
+    static DICP_HD void init(float* a) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
+        a[A_M] = -3.0e38f;
+    }
+    static DICP_HD void rescale(float* a, float m_new) {
+        const float sc = ex2f_fast(a[A_M] - m_new);
+#pragma unroll
+        for (int k = 1; k < NACC; ++k) a[k] *= sc;
+        a[A_M] = m_new;
+    }
+    static DICP_HD void combine(float* a, const float* b) {
+        float bb[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) bb[k] = b[k];
+        const float m = fmaxf(a[A_M], bb[A_M]);
+        rescale(a, m);
+        rescale(bb, m);
+#pragma unroll
+        for (int k = 1; k < NACC; ++k) a[k] += bb[k];
+    }
+    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* a) {
+        float z[D];
+        float r2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            z[k] = c[k] - r.mu[k];                       // x'_n - mu'_c
+            r2 = fmaf(z[k], z[k], r2);
+        }
+        const float l2 = (r.wl2 - c[D]) - r2;            // log2 gamma_nc  (<= 0 up to rounding)
+        if (l2 > a[A_M] + kRescaleSlack) rescale(a, l2);
+        const float e = ex2f_fast(l2 - a[A_M]);
+        a[A_S] += e;
+#pragma unroll
+        for (int k = 0; k < D; ++k) a[A_B + k] = fmaf(e, z[k], a[A_B + k]);
+        a[A_A] = fmaf(e, r2, a[A_A]);
+    }
+    static DICP_HD void finish(const Params& P, int i, const Row&, const float* a, float*) {
+        float* o = P.o_stats + (size_t)i * (D + 3);
+        const float ik = 1.0f / P.kappa;
+        o[0] = a[A_M];
+        o[1] = a[A_S];
+#pragma unroll
+        for (int k = 0; k < D; ++k) o[2 + k] = a[A_B + k] * ik;
+        o[2 + D] = a[A_A] * ik * ik;
+    }
+};
+
+}  // namespace dicp

@@ -1,0 +1,61 @@
+"""Functional wrappers over the EM entry points of the C ABI (dicp_em_rowpass / dicp_em_colstats / dicp_log_resp).
+
+Inputs and outputs are contiguous fp32 CUDA tensors; everything is enqueued on the current stream without host
+synchronisation.  No CPU path.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from ._lib import check, load, ptr, require_cuda, stream_ptr, workspace
+
+
+def rowpass(sigma_old, X, mu_old, wl2, mu_new=None, lpi_new=None, per_point=False):
+    """Row pass of the EM step.  lite (mu_new is None): returns T2 (N,), log2-domain row LSE.
+    full: returns (T2, Y, scal4, rowP, rowQ, sq) with the per-point arrays only when per_point=True."""
+    dev = require_cuda(X, mu_old, wl2, mu_new, lpi_new)
+    N, D = X.shape
+    C = mu_old.shape[0]
+    f32 = dict(dtype=torch.float32, device=dev)
+    T2 = torch.empty(N, **f32)
+    lite = mu_new is None
+    Y = scal = rowP = rowQ = sq = None
+    if not lite:
+        Y = torch.empty(N, D, **f32)
+        scal = torch.zeros(4, **f32)
+        if per_point:
+            rowP, rowQ, sq = (torch.empty(N, **f32) for _ in range(3))
+    if N > 0:
+        ws = workspace(max(N, C), max(N, C), dev)
+        rc = load().dicp_em_rowpass(D, int(lite), float(sigma_old), ptr(X), N, ptr(mu_old), ptr(wl2), C,
+                                    ptr(mu_new), ptr(lpi_new), ptr(T2), ptr(Y), ptr(rowP), ptr(rowQ), ptr(sq),
+                                    ptr(scal), ptr(ws), ws.numel(), stream_ptr())
+        check(rc, "dicp_em_rowpass")
+    if lite:
+        return T2
+    return T2, Y, scal, rowP, rowQ, sq
+
+
+def colstats(sigma_old, X, T2, mu_old, wl2):
+    """Column statistics (C, D+3) = [m (log2), S0, B (D), A] of every component over the points X."""
+    dev = require_cuda(X, T2, mu_old, wl2)
+    N, D = X.shape
+    C = mu_old.shape[0]
+    stats = torch.empty(C, D + 3, dtype=torch.float32, device=dev)
+    ws = workspace(max(N, C), max(N, C), dev)
+    rc = load().dicp_em_colstats(D, float(sigma_old), ptr(X), N, ptr(T2), ptr(mu_old), ptr(wl2), C, ptr(stats),
+                                 ptr(ws), ws.numel(), stream_ptr())
+    check(rc, "dicp_em_colstats")
+    return stats
+
+
+def log_resp(sigma, X, mu, w, want_lgam=True, want_argmax=False):
+    dev = require_cuda(X, mu, w)
+    N, D = X.shape
+    C = mu.shape[0]
+    lgam = torch.empty(N, C, dtype=torch.float32, device=dev) if want_lgam else None
+    amax = torch.empty(N, dtype=torch.int64, device=dev) if want_argmax else None
+    rc = load().dicp_log_resp(D, float(sigma), ptr(X), N, ptr(mu), ptr(w), C, ptr(lgam), ptr(amax), stream_ptr())
+    check(rc, "dicp_log_resp")
+    return lgam, amax

@@ -87,6 +87,38 @@ int dicp_rhs_adjoint(int D, int withlogdet, float sigma, float eta,
                      float* gq, float* gp, float* gx,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- GMM EM step (GaussianMixtureUnif.EM_step, core/GMM.py:236-325 torch twin, :402-529 KeOps formulation) ----
+ * Row pass over points x components.  Responsibilities come from the OLD parameters
+ *      t_nc = w_c - LSE(w) - |x_n - mu_old_c|^2 / (2 sigma_old^2) - D (ln sigma_old + ln(2 pi)/2)
+ * given as wl2[c] = (w_c - LSE(w) - D(ln sigma_old + ln(2 pi)/2)) * log2(e); targets and free-energy sums use the NEW
+ * ones (mu_new, lpi_new = natural-log mixture weights).
+ *   lite != 0 : only T2[n] = log2 sum_c exp(t_nc) is produced (needed before the column pass)
+ *   lite == 0 : also Y (N,D) = sum_c gamma_nc mu_new_c, optional per-point rowP, rowQ, sq (null = skip), and
+ *               scal4 = { P = sum_n (sum_c gamma |mu_new_c|^2 - |Y_n|^2),  Q = sum_nc gamma (ln gamma - lpi_new_c),
+ *                         SQ = sum_n |x_n - Y_n|^2,  DS = sum_nc gamma |x_n - mu_old_c|^2 }
+ *               so that  Cfe = P/(2 sigma'^2) + Q + N D (ln sigma'' + ln(2 pi)/2),  FE = Cfe + SQ/(2 sigma'^2)
+ *               (core/GMM.py:312-317 / :485-488, :527) for whatever sigma', sigma'' the caller's variant prescribes. */
+int dicp_em_rowpass(int D, int lite, float sigma_old, const float* X, int64_t N, const float* mu_old,
+                    const float* wl2, int64_t C, const float* mu_new, const float* lpi_new,
+                    float* T2, float* Y, float* rowP, float* rowQ, float* sq, float* scal4,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Column pass: log-domain sufficient statistics of every component (M step, core/GMM.py:286-297 / :442-456):
+ * stats[c] = { m_c, S0_c, B_c (D), A_c } with, for l_nc = log2 gamma_nc = wl2_c - kappa^2|x_n-mu_c|^2 - T2_n,
+ *   m_c ~ max_n l_nc (a reference exponent),  S0_c = sum_n 2^(l_nc-m_c),  B_c = sum_n 2^(l_nc-m_c) (x_n - mu_old_c),
+ *   A_c = sum_n 2^(l_nc-m_c) |x_n - mu_old_c|^2.
+ * Then  w'_c = (m_c + log2 S0_c) ln 2,  mu'_c = mu_old_c + B_c/S0_c,
+ *       N D sigma'^2 = sum_c 2^m_c (A_c - |B_c|^2/S0_c)  [distances to the NEW mu, KeOps formulation :453-455]
+ *                    = sum_c 2^m_c A_c                    [distances to the OLD mu, torch twin :263,296].
+ * Statistics of disjoint point subsets (frames on different GPUs) merge by max on m_c and rescaled sums. */
+int dicp_em_colstats(int D, float sigma_old, const float* X, int64_t N, const float* T2, const float* mu_old,
+                     const float* wl2, int64_t C, float* stats, void* workspace, size_t workspace_bytes, void* stream);
+
+/* lgam (N,C) = log_softmax_c(w_c - |x_n-mu_c|^2/(2 sigma^2)) (core/GMM.py:221-232) and/or argmax (N) int64
+ * (first index wins ties, core/GMM.py:677-680); either output may be null. */
+int dicp_log_resp(int D, float sigma, const float* X, int64_t N, const float* mu, const float* w, int64_t C,
+                  float* lgam, long long* argmax, void* stream);
+
 /* out = a + alpha*f1 + beta*f2  (f2 may be null) over n floats: the Euler / Ralston state updates
  * (tools/integrators.py:27-29, 42-48) and the adjoint accumulations. */
 int dicp_axpy(int64_t n, float* out, const float* a, float alpha, const float* f1, float beta, const float* f2,

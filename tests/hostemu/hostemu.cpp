@@ -34,3 +34,18 @@ int emu_rhs_adjoint(int D, int withlogdet, float sigma, float eta, const float* 
 }
 
 }
+
+extern "C" {
+int emu_em_rowpass(int D, int lite, float sigma_old, const float* X, int64_t N, const float* mu_old, const float* wl2,
+                   int64_t C, const float* mu_new, const float* lpi_new, float* T2, float* Y, float* rowP, float* rowQ,
+                   float* sq, float* scal4) {
+    HostExec ex;
+    return em_rowpass_entry(ex, D, lite, sigma_old, X, N, mu_old, wl2, C, mu_new, lpi_new, T2, Y, rowP, rowQ, sq, scal4);
+}
+int emu_em_colstats(int D, float sigma_old, const float* X, int64_t N, const float* T2, const float* mu_old,
+                    const float* wl2, int64_t C, float* stats) {
+    HostExec ex;
+    return em_colstats_entry(ex, D, sigma_old, X, N, T2, mu_old, wl2, C, stats);
+}
+}
+
