@@ -219,9 +219,91 @@ def gen_gmm(rg):
     print("gmm.npz", len(out))
 
 
+
+
+def spiral_sets(K, N, seed, D=2):
+    """Deterministic spiral-GMM samples, smoothly warped per frame (no reference RNG involved)."""
+    g = torch.Generator().manual_seed(seed)
+    C = 20
+    t = torch.linspace(0, 2 * np.pi, C + 1)[:-1]
+    mu0 = torch.stack((0.5 + 0.4 * (t / 7) * t.cos(), 0.5 + 0.3 * t.sin()), 1)
+    sets = []
+    for k in range(K):
+        c = torch.randint(0, C, (N,), generator=g)
+        x = mu0[c] + 0.025 * torch.randn(N, 2, generator=g)
+        cen = torch.rand(3, 2, generator=g)
+        amp = 0.04 * torch.randn(3, 2, generator=g)
+        w = torch.exp(-((x[:, None, :] - cen[None]) ** 2).sum(-1) / (2 * 0.25 ** 2))
+        sets.append((x + w @ amp).contiguous())
+    return sets, mu0
+
+
+def gen_psr():
+    """End-to-end DiffPSR runs of the unmodified reference (torch path, CPU): a C1-like single set registered to a known
+    GMM, and a small groupwise atlas through api.ICP_atlas."""
+    import diffICP.core.PSR as rp
+    import diffICP.core.GMM as rg
+    import diffICP.core.LDDMM as rl
+    from diffICP.tools.kernel import GaussKernel
+    # the torch branch of check_coverage is broken in the reference (tools/kernel.py:328); one-line fix of SURVEY App. C
+    GaussKernel.check_coverage = lambda self, X, Y, R: ((X[:, None, :] - Y[None, :, :]) ** 2).sum(-1).min(dim=1).values > (R * self.sigma) ** 2
+    out = {}
+    # ---- C1-like: one set, known GMM (mu, w frozen; sigma optimised), classic LDDMM on a grid support ----------
+    sets, mu0 = spiral_sets(1, 300, 77)
+    x0 = sets[0]
+    out["c1_in_x0"], out["c1_in_mu"] = x0.numpy(), mu0.numpy()
+    for prec, dt in [("ref32", torch.float32), ("gold", torch.float64)]:
+        sp = spec_of(dt)
+        G = rg.GaussianMixtureUnif(mu0.to(dt), sigma=0.1, spec=sp, computversion="torch")
+        G.to_optimize = {"mu": False, "sigma": True, "w": False, "eta0": False}
+        LM = rl.LDDMMModel(sigma=0.2, D=2, lambd=5e2, version="classic", computversion="torch", scheme="Euler", spec=sp)
+        P = rp.DiffPSR([[x0.to(dt)]], G, LM, dataspec=sp, compspec=sp)   # list-of-lists: read_point_sets only type-checks bare tensors
+        P.printstuff = False
+        P.set_support_scheme("grid", rho=np.sqrt(2))
+        fes, sigs = [], []
+        for it in range(3):
+            P.GMM_opt()
+            fes.append(float(P.FE))
+            P.Reg_opt(tol=1e-5)
+            fes.append(float(P.FE))
+            sigs.append(float(P.GMMi[0].sigma))
+        out[f"c1_{prec}_FE"], out[f"c1_{prec}_sigma"] = np.array(fes), np.array(sigs)
+        out[f"c1_{prec}_x1"] = P.x1[0, 0].numpy()
+        out[f"c1_{prec}_q0"] = P.q0[0].numpy()
+        out[f"c1_{prec}_a0"] = P.a0[0].numpy()
+        out[f"c1_{prec}_y"] = P.y[0, 0].numpy()
+    # ---- small atlas through the API: 3 frames, C = 6 given initial centroids, hybrid, Euler, grid --------------
+    import diffICP.api.ICP_atlas as ra
+    sets, mu0 = spiral_sets(3, 150, 78)
+    g = torch.Generator().manual_seed(5)
+    mu_init = torch.cat(sets).mean(0) + 0.05 * torch.cat(sets).std() * torch.randn(6, 2, generator=g)
+    for k, s in enumerate(sets):
+        out[f"atlas_in_x{k}"] = s.numpy()
+    out["atlas_in_mu"] = mu_init.numpy()
+    for prec, dt in [("ref32", torch.float32), ("gold", torch.float64)]:
+        sp = spec_of(dt)
+        G = rg.GaussianMixtureUnif(mu_init.to(dt), sigma=0.25 * float(torch.cat(sets).std()), spec=sp, computversion="torch")
+        PSR, evol = ra.ICP_atlas([[s.to(dt)] for s in sets],
+                                 GMM_parameters={"init_components": [G], "optimize_weights": True},
+                                 registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.2},
+                                 numerical_options={"computversion": "torch", "compspec": sp, "dataspec": sp,
+                                                    "support_LDDMM": {"scheme": "grid", "rho": 1.0}},
+                                 optim_options={"max_iterations": 3, "max_repeat_GMM": 10, "convergence_tolerance": 1e-3},
+                                 printstuff=False)
+        out[f"atlas_{prec}_FE"] = np.array(float(PSR.FE))
+        out[f"atlas_{prec}_sigma"] = np.array(float(PSR.GMMi[0].sigma))
+        out[f"atlas_{prec}_mu"] = PSR.GMMi[0].mu.numpy()
+        out[f"atlas_{prec}_w"] = PSR.GMMi[0].w.numpy()
+        for k in range(3):
+            out[f"atlas_{prec}_x1_{k}"] = PSR.x1[k, 0].numpy()
+    np.savez_compressed(os.path.join(OUT, "psr.npz"), **out)
+    print("psr.npz", len(out))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     rk, rl, rg = load_reference()
     gen_kernels(rk)
     gen_lddmm(rl)
     gen_gmm(rg)
+    gen_psr()

@@ -1,0 +1,174 @@
+"""GPU parity tests of the GMM EM step, the outer PSR alternation and the API entry points against the reference's
+own outputs (golden fixtures; fp64 "gold" and the reference's fp32 run "ref32") and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+SPEC = None
+
+
+def spec():
+    return {"device": dev(), "dtype": torch.float32}
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(dev())
+
+
+def build(g, tag, version):
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    D, N, C, outl, skip, steps, sig0 = g[f"{tag}_meta"]
+    G = GaussianMixtureUnif(cu(g[f"{tag}_in_mu"]), sigma=float(sig0), use_outliers=bool(outl), spec=spec(), computversion=version)
+    G.w = cu(g[f"{tag}_in_w"])
+    G.to_optimize = dict(zip(("mu", "sigma", "w", "eta0"), (bool(v) for v in g[f"{tag}_opt"])))
+    if outl:
+        G.outliers["eta0"] = -1.0
+    return G, cu(g[f"{tag}_in_X"]), bool(skip), int(steps)
+
+
+def test_em_step_matches_reference_torch_twin(golden):
+    g = golden("gmm")
+    for tag in g["cases"]:
+        tag = str(tag)
+        G, X, skip, steps = build(g, tag, "torch")
+        lg = G.log_responsibilities(X)
+        assert relerr(lg.cpu().numpy(), g[f"{tag}_gold_lgam"]) < 2e-5, tag
+        fes = []
+        for _ in range(steps):
+            Y, Cfe, FE = G.EM_step(X, skip_M=skip)
+            fes.append(float(FE))
+
+        def ok(a, key, base=2e-5):
+            gold, ref = g[f"{tag}_gold_{key}"], g[f"{tag}_ref32_{key}"]
+            e, e_ref = relerr(a, gold), relerr(ref, gold)
+            assert e < max(base, 2 * e_ref), (tag, key, e, e_ref)
+        ok(Y.cpu().numpy(), "Y")
+        ok(G.mu.cpu().numpy(), "mu")
+        ok(G.w.cpu().numpy(), "w", 5e-5)
+        ok(np.array(G.sigma), "sigma")
+        ok(np.array(float(Cfe)), "Cfe", 5e-5)
+        ok(np.array(fes), "FE", 5e-5)
+        if G.outliers is not None:
+            assert abs(G.outliers["eta0"] - float(g[f"{tag}_gold_eta0"])) < 1e-4
+
+
+def test_argmax_assignments_bit_exact_on_tie_free_rows(golden):
+    g = golden("gmm")
+    for tag in ["2d_full", "3d_frozen", "3d_offset"]:
+        G, X, _, _ = build(g, tag, "torch")
+        lg = torch.from_numpy(g[f"{tag}_gold_lgam"])
+        top2 = lg.topk(2, dim=1).values
+        safe = (top2[:, 0] - top2[:, 1]) > 1e-4            # rows whose decision does not hinge on fp32 rounding
+        got = G.hard_assignments(X).cpu()
+        assert got.dtype == torch.int64
+        assert torch.equal(got[safe], lg.argmax(1)[safe])
+        assert int((~safe).sum()) <= max(2, int(0.01 * len(safe))), (tag, int((~safe).sum()))
+        assert torch.equal(G.log_responsibilities(X).argmax(1).cpu()[safe], lg.argmax(1)[safe])
+
+
+def test_em_large_vs_oracle_both_variants():
+    """640k x 50 is the atlas size of BASELINE configs[2]; checked here at 40k x 50 (oracle finishes in seconds) plus a
+    size-independent property at full size: sum_c gamma_nc = 1 => Y inside the bounding box of mu, FE decreasing."""
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    from oracle.gmm import GMMOracle
+    g = torch.Generator().manual_seed(11)
+    C, D, N = 50, 2, 40000
+    cent = torch.rand(C, D, generator=g)
+    X = cent[torch.randint(0, C, (N,), generator=g)] + 0.03 * torch.randn(N, D, generator=g)
+    mu0 = cent + 0.02 * torch.randn(C, D, generator=g)
+    for variant in ("keops", "torch"):
+        G = GaussianMixtureUnif(mu0.to(dev()), sigma=0.05, spec=spec(), computversion=variant)
+        O = GMMOracle(mu0.double(), 0.05)
+        for _ in range(3):
+            Y, Cfe, FE = G.EM_step(X.to(dev()))
+            Yo, Cfeo, FEo = O.em_step(X.double(), variant=variant)
+        assert relerr(Y.cpu().numpy(), Yo.numpy()) < 2e-5
+        assert relerr(G.mu.cpu().numpy(), O.mu.numpy()) < 2e-5
+        assert abs(G.sigma - O.sigma) < 2e-5 * O.sigma
+        assert abs(float(FE) - float(FEo)) < 2e-5 * abs(float(FEo))
+    # full size property run
+    N = 640000
+    X = (cent[torch.randint(0, C, (N,), generator=g)] + 0.03 * torch.randn(N, D, generator=g)).to(dev())
+    G = GaussianMixtureUnif(mu0.to(dev()), sigma=0.05, spec=spec())
+    last = None
+    for _ in range(4):
+        Y, Cfe, FE = G.EM_step(X)
+        assert last is None or float(FE) <= last + 1e-6 * abs(last)
+        last = float(FE)
+    lo, hi = G.mu.min(0).values, G.mu.max(0).values
+    assert bool(((Y >= lo - 1e-4) & (Y <= hi + 1e-4)).all())
+
+
+def test_c1_single_set_registration_matches_reference(golden):
+    """BASELINE configs[0]-like: one 2-D set registered to a known GMM (sigma optimised), classic LDDMM, grid support."""
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from diff_icp_b200.core.PSR import DiffPSR
+    g = golden("psr")
+    x0, mu0 = cu(g["c1_in_x0"]), cu(g["c1_in_mu"])
+    G = GaussianMixtureUnif(mu0, sigma=0.1, spec=spec())
+    G.to_optimize = {"mu": False, "sigma": True, "w": False, "eta0": False}
+    LM = LDDMMModel(sigma=0.2, D=2, lambd=5e2, version="classic", scheme="Euler", spec=spec())
+    P = DiffPSR(x0, G, LM, dataspec=spec(), compspec=spec())
+    P.printstuff = False
+    P.set_support_scheme("grid", rho=np.sqrt(2))
+    assert relerr(P.q0[0].cpu().numpy(), g["c1_gold_q0"]) < 1e-6
+    fes, sigs = [], []
+    for it in range(3):
+        P.GMM_opt()
+        fes.append(P.FE)
+        P.Reg_opt(tol=1e-5)
+        fes.append(P.FE)
+        sigs.append(P.GMMi[0].sigma)
+    # the reference's own fp32 run sits at ~1e-5 of its fp64 run on this problem; allow 10x that
+    assert np.allclose(fes, g["c1_gold_FE"], rtol=2e-4), (fes, g["c1_gold_FE"])
+    assert np.allclose(sigs, g["c1_gold_sigma"], rtol=2e-4)
+    assert np.abs(P.x1[0, 0].cpu().numpy() - g["c1_gold_x1"]).max() < 1e-3 * 0.2
+    assert np.abs(P.y[0, 0].cpu().numpy() - g["c1_gold_y"]).max() < 1e-3 * 0.2
+
+
+def test_atlas_api_matches_reference(golden):
+    """Small groupwise atlas through ICP_atlas (3 frames, C = 6, hybrid, Euler, grid): L-BFGS paths of the reference's
+    own fp32 and fp64 runs already differ by 0.17 % in FE here, so the bar is 'as close to gold as ref32 is'."""
+    from diff_icp_b200.api.ICP_atlas import ICP_atlas
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    g = golden("psr")
+    sets = [cu(g[f"atlas_in_x{k}"]) for k in range(3)]
+    allx = torch.cat(sets)
+    G = GaussianMixtureUnif(cu(g["atlas_in_mu"]), sigma=0.25 * float(allx.std()), spec=spec(), computversion="torch")
+    PSR, evol = ICP_atlas(sets, GMM_parameters={"init_components": [G], "optimize_weights": True},
+                          registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.2},
+                          numerical_options={"computversion": "torch", "compspec": spec(), "dataspec": spec(),
+                                             "support_LDDMM": {"scheme": "grid", "rho": 1.0}},
+                          optim_options={"max_iterations": 3, "max_repeat_GMM": 10, "convergence_tolerance": 1e-3},
+                          printstuff=False)
+    gold, ref = float(g["atlas_gold_FE"]), float(g["atlas_ref32_FE"])
+    assert abs(PSR.FE - gold) < 3 * abs(ref - gold) + 1e-3 * abs(gold), (PSR.FE, gold, ref)
+    assert abs(PSR.GMMi[0].sigma - float(g["atlas_gold_sigma"])) < 3 * abs(float(g["atlas_ref32_sigma"]) - float(g["atlas_gold_sigma"])) + 1e-4
+    assert len(evol["a0"]) == 3 and len(evol["GMMi"]) == 3
+
+
+def test_two_set_api_runs_logdet_default_small():
+    """api.ICP_two_set builds the full logdet model (reference quirk, api/ICP_two_set.py:203-207)."""
+    from diff_icp_b200.api.ICP_two_set import ICP_two_set
+    g = torch.Generator().manual_seed(3)
+    xA = torch.rand(300, 3, generator=g)
+    xB = xA + 0.02 * torch.randn(300, 3, generator=g) + 0.03
+    try:
+        PSR, evol = ICP_two_set(xA.to(dev()), xB.to(dev()), {"sigma": 0.1, "optimize_sigma": True, "outlier_weight": None},
+                                {"type": "diffeomorphic", "lambda_LDDMM": 500.0, "sigma_LDDMM": 0.2},
+                                numerical_options={"support_LDDMM": {"scheme": "dense"}},
+                                optim_options={"max_iterations": 2}, plotstuff=False, printstuff=False)
+    except Exception as e:        # until the logdet adjoint lands this raises DicpError("unsupported configuration")
+        pytest.xfail(f"logdet adjoint pending: {e}")
+    assert PSR.LMi.gradcomponent and PSR.LMi.eta == 1 / 500.0
+    assert np.isfinite(PSR.FE)
