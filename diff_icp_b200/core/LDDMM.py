@@ -131,7 +131,7 @@ class LDDMMModel:
         F = torch.zeros(sp.S + 3, **spec)
         state = torch.cat([q.detach().reshape(-1), p.detach().reshape(-1)] +
                           ([x.detach().reshape(-1)] if x is not None else []) + [cost.detach().reshape(-1)[:1]])
-        ws = shooting.workspace(max(sp.M, sp.Nx), max(sp.M, sp.Nx), q.device)
+        ws = ops.alloc_workspace(max(sp.M, sp.Nx), max(sp.M, sp.Nx), q.device)
         shooting._rhs(sp, state, F, ws)
         vq, dp, vx, dcost = shooting._views(sp, F)
         if x is None:

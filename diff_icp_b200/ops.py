@@ -79,6 +79,11 @@ def axpy(out, a, alpha, f1, beta=0.0, f2=None, n=None):
     check(rc, "dicp_axpy")
 
 
+def alloc_workspace(rows, cols, device):
+    """A private workspace tensor for a long-lived plan (e.g. a CUDA-graph-captured shoot)."""
+    return torch.empty(int(load().dicp_pair_workspace_bytes(int(rows), int(cols))), dtype=torch.uint8, device=device)
+
+
 def pipe_probe(which: int, blocks: int, iters: int, out):
     rc = load().dicp_pipe_probe(which, blocks, iters, ptr(out), stream_ptr())
     check(rc, "dicp_pipe_probe")

@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from ._lib import require_cuda, workspace
+from . import _lib
 
 
 class ShootSpec:
@@ -114,7 +114,7 @@ class ShootPlan:
         self.G1 = torch.zeros(S, **f32)
         self.G2 = torch.zeros(S, **f32)
         rows = max(spec.M, spec.Nx)
-        self.ws = torch.empty(int(ops.load().dicp_pair_workspace_bytes(rows, rows)), dtype=torch.uint8, device=dev)
+        self.ws = ops.alloc_workspace(rows, rows, dev)
         self.version = 0
         self.use_graph = use_graph
         self.fwd_graph = None
@@ -220,7 +220,7 @@ class _ShootFn(torch.autograd.Function):
 
 def shoot(spec: ShootSpec, q0, p0, x0=None, use_graph=False):
     """Returns (list of nt+1 state tuples like the reference's Shoot, H(q0,p0)) with autograd attached."""
-    require_cuda(q0, p0, x0)
+    _lib.require_cuda(q0, p0, x0)
     q0c, p0c = q0.contiguous(), p0.contiguous()
     x0c = None if x0 is None else x0.contiguous()
     traj, H0 = _ShootFn.apply(spec, use_graph, q0c, p0c, x0c)

@@ -66,3 +66,80 @@ def install(monkeypatch):
     from diff_icp_b200 import em_ops
     monkeypatch.setattr(em_ops, "rowpass", rowpass)
     monkeypatch.setattr(em_ops, "colstats", colstats)
+
+
+# ---- kernel sums / LDDMM right-hand side on the CPU emulation -------------------------------------------------------
+_SLOTS = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024]
+_VECTOR = {4, 8, 16, 32, 64, 256}
+
+
+def ksum(mask, sigma, x, y, b=None, c=None, d=None, ws=None):
+    M, D = x.shape
+    N = y.shape[0]
+    xa, ya, ba, ca, da = _np(x), _np(y), _np(b), _np(c), _np(d)
+    outs, args = {}, []
+    for sel in _SLOTS:
+        if mask & sel:
+            outs[sel] = np.zeros((M, D) if sel in _VECTOR else (M,), np.float32)
+            args.append(_p(outs[sel]))
+        else:
+            args.append(None)
+    if M > 0:
+        rc = lib().emu_ksum(D, ctypes.c_uint(mask), ctypes.c_float(sigma), _p(xa), ctypes.c_int64(M), _p(ya),
+                            ctypes.c_int64(N), _p(ba), _p(ca), _p(da), *args)
+        assert rc == 0, rc
+    return {k: torch.from_numpy(v) for k, v in outs.items()}
+
+
+def _inplace(fn, outs):
+    """Run fn on numpy copies of the output tensors, then copy the results back into the (possibly strided) views."""
+    arrs = [None if o is None else np.zeros(tuple(o.shape), np.float32) for o in outs]
+    fn(arrs)
+    for o, a in zip(outs, arrs):
+        if o is not None:
+            o.copy_(torch.from_numpy(a))
+
+
+def rhs_forward(D, withlogdet, sigma, eta, q, p, x, vq, dp, vx, scal, ws):
+    M, Nx = q.shape[0], (0 if x is None else x.shape[0])
+    qa, pa, xa = _np(q), _np(p), _np(x)
+
+    def run(a):
+        rc = lib().emu_rhs_forward(D, int(bool(withlogdet)), ctypes.c_float(sigma), ctypes.c_float(eta), _p(qa), _p(pa),
+                                   ctypes.c_int64(M), _p(xa), ctypes.c_int64(Nx), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]))
+        assert rc == 0, rc
+    _inplace(run, [vq, dp, vx, scal[:4]])
+
+
+def rhs_adjoint(D, withlogdet, sigma, eta, q, p, x, a, u, wx, gc, gq, gp, gx, ws):
+    M, Nx = q.shape[0], (0 if x is None else x.shape[0])
+    qa, pa, xa, aa, ua, wa, ga = _np(q), _np(p), _np(x), _np(a), _np(u), _np(wx), _np(gc)
+
+    def run(o):
+        rc = lib().emu_rhs_adjoint(D, int(bool(withlogdet)), ctypes.c_float(sigma), ctypes.c_float(eta), _p(qa), _p(pa),
+                                   ctypes.c_int64(M), _p(xa), ctypes.c_int64(Nx), _p(aa), _p(ua), _p(wa), _p(ga),
+                                   _p(o[0]), _p(o[1]), _p(o[2]))
+        if rc != 0:
+            raise RuntimeError(f"emu_rhs_adjoint rc={rc}")
+    _inplace(run, [gq, gp, gx])
+
+
+def axpy(out, a, alpha, f1, beta=0.0, f2=None, n=None):
+    n = out.numel() if n is None else n
+    r = a[:n] + np.float32(alpha) * f1[:n]
+    if f2 is not None:
+        r = r + np.float32(beta) * f2[:n]
+    out[:n] = r
+
+
+def install_all(monkeypatch):
+    """Route every C-ABI wrapper of the product through the CPU emulation (tests of host logic only)."""
+    from diff_icp_b200 import _lib, em_ops, ops
+    install(monkeypatch)
+    monkeypatch.setattr(ops, "ksum", ksum)
+    monkeypatch.setattr(ops, "rhs_forward", rhs_forward)
+    monkeypatch.setattr(ops, "rhs_adjoint", rhs_adjoint)
+    monkeypatch.setattr(ops, "axpy", axpy)
+    monkeypatch.setattr(ops, "alloc_workspace", lambda r, c, dev: torch.empty(16, dtype=torch.uint8))
+    monkeypatch.setattr(_lib, "require_cuda", lambda *t: torch.device("cpu"))
+    monkeypatch.setattr(em_ops, "log_resp", None, raising=False)

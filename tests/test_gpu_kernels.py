@@ -189,8 +189,13 @@ def test_hamiltonian_is_conserved_and_flow_inverts():
     drift_o = float(OR.hamiltonian(so[-1][0], so[-1][1]) - OR.hamiltonian(q0.cpu().double(), p0.cpu().double()))
     assert abs((H1 - H0) - drift_o) < 2e-5 * abs(H0)          # and drifts exactly like the fp64 oracle does
     reg = LDDMMRegistration(LM, q0, p0)
-    back = reg.backward(reg.apply(X))
-    assert float((back - X).abs().max()) < 2e-5
+    fwd = reg.apply(X)
+    back = reg.backward(fwd)
+    assert float((back - X).abs().max()) < 2e-4               # inverse flow by re-shooting (q1,-p1): exact up to O(dt^2)
+    xo = so = OR.shoot(q0.cpu().double(), p0.cpu().double(), X.cpu().double())
+    assert float((fwd.cpu().double() - xo[-1][3]).abs().max()) < 1e-5
+    bo = OR.shoot(xo[-1][0], -xo[-1][1], xo[-1][3])[-1][3]
+    assert float((back.cpu().double() - bo).abs().max()) < 1e-5   # same round trip as the fp64 oracle
 
 
 def test_library_fails_loudly_on_cpu_tensors(GK):
