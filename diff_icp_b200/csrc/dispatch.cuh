@@ -105,10 +105,17 @@ int rhs_forward_entry(Exec& ex, int D, int withlogdet, float sigma, float eta, c
 template <int D, class Exec>
 int rhs_adjoint_d(Exec& ex, int withlogdet, RhsParams prm, int M, int Nx) {
     const bool hasx = prm.x != nullptr && Nx > 0;
-    if (prm.eta != 0.f) return DICP_EUNSUPPORTED;   // logdet adjoint: next milestone
-    const bool div_qq = withlogdet && !hasx;
     int rc;
     prm.accumulate = 0;
+    if (prm.eta != 0.f) {                           // logdet model (withlogdet is implied)
+        rc = ex.template run<AdjQQEta<D>>(prm, M, M, nullptr, 0);
+        if (rc != DICP_OK || !hasx) return rc;
+        rc = ex.template run<AdjXQxEta<D>>(prm, Nx, M, nullptr, 0);
+        if (rc != DICP_OK) return rc;
+        prm.accumulate = 1;
+        return ex.template run<AdjXQqEta<D>>(prm, M, Nx, nullptr, 0);
+    }
+    const bool div_qq = withlogdet && !hasx;
     if (div_qq) rc = ex.template run<AdjQQ<D, true>>(prm, M, M, nullptr, 0);
     else rc = ex.template run<AdjQQ<D, false>>(prm, M, M, nullptr, 0);
     if (rc != DICP_OK) return rc;

@@ -466,4 +466,217 @@ struct AdjXQq {
     }
 };
 
+
+// ================================================================================================================
+// Adjoint of the logdet model (eta = 1/lambda != 0).  Derivation in DESIGN.md §5.3; checked against torch autograd of
+// the oracle (tests/test_host_emulation.py).  Notation per pair (row m, column n), scaled z' = kappa (row - col):
+//   w = p_m.p_n, e = p_m - p_n, du = u_m - u_n, dA = a_m - a_n, t0 = beta r'^2 - D, t1 = beta r'^2 - (D+2), g = gc
+//   Phi  = (a_m.p_n + a_n.p_m) + eta alpha (dA.z') + alpha w (du.z') + eta s beta (z'.e)(du.z') - eta s (du.e)
+//          - eta^2 s alpha t1 (du.z') - g alpha (e.z') + 2 g eta s t0
+//   gq_m = sum_n K { eta s dA + [s w + eta s alpha (z'.e) - eta^2 s^2 t1] du + [eta s alpha (du.z') - g s] e
+//                    + [-2 eta^2 s^2 beta (du.z') + 4 g eta s alpha - alpha Phi] z' }
+//   gp_m = sum_n K { a_n + alpha (du.z') p_n + eta s beta (du.z') z' - eta s du - g alpha z' }
+// ================================================================================================================
+template <int D, int R_ = DICP_RHS_R>
+struct AdjQQEta {
+    using Params = RhsParams;
+    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
+    static constexpr int COLF4 = (4 * D + 3) / 4;
+    static constexpr int A_GP = 0, A_GQ = D;
+    static constexpr int NACC = 2 * D, NSCAL = 0;
+    struct Row { float q[D], p[D], a[D], u[D], gc; };
+
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { AdjQQ<D, true, R_>::pack_col(P, j, N, c); }
+    static DICP_HD void load_row(const Params& P, int i, Row& r) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const size_t o = (size_t)i * D + k;
+            r.q[k] = (P.q[o] - P.origin[k]) * P.kappa;
+            r.p[k] = P.p[o];
+            r.a[k] = P.a[o];
+            r.u[k] = P.u[o];
+        }
+        r.gc = (P.gc != nullptr && P.x == nullptr) ? P.gc[0] : 0.f;   // dcost comes from the (q,q) pass only when x is absent
+    }
+    static DICP_HD void init(float* a) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
+    }
+    static DICP_HD void combine(float* a, const float* b) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] += b[k];
+    }
+    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* acc) {
+        const float eta = P.eta, s = P.s, al = P.alpha, be = P.beta, g = r.gc;
+        float z[D], e[D], du[D], dA[D];
+        float r2 = 0.f, w = 0.f, ze = 0.f, duz = 0.f, dAz = 0.f, due = 0.f, appa = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            z[k] = r.q[k] - c[k];
+            e[k] = r.p[k] - c[D + k];
+            dA[k] = r.a[k] - c[2 * D + k];
+            du[k] = r.u[k] - c[3 * D + k];
+            r2 = fmaf(z[k], z[k], r2);
+            w = fmaf(r.p[k], c[D + k], w);
+            ze = fmaf(z[k], e[k], ze);
+            duz = fmaf(du[k], z[k], duz);
+            dAz = fmaf(dA[k], z[k], dAz);
+            due = fmaf(du[k], e[k], due);
+            appa = fmaf(r.a[k], c[D + k], fmaf(r.p[k], c[2 * D + k], appa));
+        }
+        const float K = ex2_neg(r2);
+        const float t0 = fmaf(be, r2, -(float)D), t1 = fmaf(be, r2, -(float)(D + 2));
+        const float es = eta * s;
+        const float c_du = s * w + es * al * ze - es * es * t1;
+        const float c_e = es * al * duz - g * s;
+        const float Phi = appa + eta * al * dAz + al * w * duz + es * be * ze * duz - es * due - eta * es * al * t1 * duz
+                          - g * al * ze + 2.f * g * es * t0;
+        const float Cz = -2.f * es * es * be * duz + 4.f * g * es * al - al * Phi;
+        const float pz = es * be * duz - g * al;           // coefficient of z' in gp
+        const float pp = al * duz;                         // coefficient of p_n in gp
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float gq = es * dA[k] + c_du * du[k] + c_e * e[k] + Cz * z[k];
+            const float gp = c[2 * D + k] + pp * c[D + k] + pz * z[k] - es * du[k];
+            acc[A_GQ + k] = fmaf(K, gq, acc[A_GQ + k]);
+            acc[A_GP + k] = fmaf(K, gp, acc[A_GP + k]);
+        }
+    }
+    static DICP_HD void finish(const Params& P, int i, const Row& r, const float* acc, float*) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const size_t o = (size_t)i * D + k;
+            if (P.accumulate) {
+                P.gp[o] += acc[A_GP + k];
+                P.gq[o] += acc[A_GQ + k];
+            } else {
+                P.gp[o] = acc[A_GP + k];
+                P.gq[o] = acc[A_GQ + k];
+            }
+        }
+    }
+};
+
+// logdet, (x,q) pass w.r.t. x: rows = (x_k, wx_k), cols = (q,p)
+//   psi  = wx.p + eta alpha (wx.z') + g [alpha (p.z') + eta s t0]
+//   gx_k = sum_j K { eta s wx_k + g s p_j + (2 g eta s alpha - alpha psi) z' }
+template <int D, int R_ = DICP_RHS_R>
+struct AdjXQxEta {
+    using Params = RhsParams;
+    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
+    static constexpr int COLF4 = (2 * D + 3) / 4;
+    static constexpr int NACC = D, NSCAL = 0;
+    struct Row { float x[D], w[D], gc; };
+
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { RhsQQ<D, true, true, R_>::pack_col(P, j, N, c); }
+    static DICP_HD void load_row(const Params& P, int i, Row& r) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            r.x[k] = (P.x[(size_t)i * D + k] - P.origin[k]) * P.kappa;
+            r.w[k] = P.wx[(size_t)i * D + k];
+        }
+        r.gc = P.gc != nullptr ? P.gc[0] : 0.f;
+    }
+    static DICP_HD void init(float* a) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
+    }
+    static DICP_HD void combine(float* a, const float* b) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] += b[k];
+    }
+    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* acc) {
+        const float es = P.eta * P.s, al = P.alpha, g = r.gc;
+        float z[D];
+        float r2 = 0.f, wp = 0.f, wz = 0.f, pz = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            z[k] = r.x[k] - c[k];
+            r2 = fmaf(z[k], z[k], r2);
+            wp = fmaf(r.w[k], c[D + k], wp);
+            wz = fmaf(r.w[k], z[k], wz);
+            pz = fmaf(c[D + k], z[k], pz);
+        }
+        const float K = ex2_neg(r2);
+        const float psi = wp + P.eta * al * wz + g * (al * pz + es * fmaf(P.beta, r2, -(float)D));
+        const float cz = 2.f * g * es * al - al * psi;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            acc[k] = fmaf(K, es * r.w[k] + g * P.s * c[D + k] + cz * z[k], acc[k]);
+    }
+    static DICP_HD void finish(const Params& P, int i, const Row&, const float* acc, float*) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const size_t o = (size_t)i * D + k;
+            if (P.accumulate) P.gx[o] += acc[k]; else P.gx[o] = acc[k];
+        }
+    }
+};
+
+// logdet, (x,q) pass w.r.t. (q,p): rows = (q_j, p_j), cols = (x_k, wx_k); zeta' = kappa (q_j - x_k)
+//   psi  = wx.p - eta alpha (wx.zeta') + g [-alpha (p.zeta') + eta s t0]
+//   gq_j = sum_k K { -eta s wx_k - g s p_j + (2 g eta s alpha - alpha psi) zeta' }
+//   gp_j = sum_k K { wx_k - g alpha zeta' }
+template <int D, int R_ = DICP_RHS_R>
+struct AdjXQqEta {
+    using Params = RhsParams;
+    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
+    static constexpr int COLF4 = (2 * D + 3) / 4;
+    static constexpr int A_GP = 0, A_GQ = D;
+    static constexpr int NACC = 2 * D, NSCAL = 0;
+    struct Row { float q[D], p[D], gc; };
+
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { AdjXQq<D, true, R_>::pack_col(P, j, N, c); }
+    static DICP_HD void load_row(const Params& P, int i, Row& r) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            r.q[k] = (P.q[(size_t)i * D + k] - P.origin[k]) * P.kappa;
+            r.p[k] = P.p[(size_t)i * D + k];
+        }
+        r.gc = P.gc != nullptr ? P.gc[0] : 0.f;
+    }
+    static DICP_HD void init(float* a) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
+    }
+    static DICP_HD void combine(float* a, const float* b) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] += b[k];
+    }
+    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* acc) {
+        const float es = P.eta * P.s, al = P.alpha, g = r.gc;
+        float z[D];
+        float r2 = 0.f, wp = 0.f, wz = 0.f, pz = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            z[k] = r.q[k] - c[k];
+            r2 = fmaf(z[k], z[k], r2);
+            wp = fmaf(c[D + k], r.p[k], wp);
+            wz = fmaf(c[D + k], z[k], wz);
+            pz = fmaf(r.p[k], z[k], pz);
+        }
+        const float K = ex2_neg(r2);
+        const float psi = wp - P.eta * al * wz + g * (-al * pz + es * fmaf(P.beta, r2, -(float)D));
+        const float cz = 2.f * g * es * al - al * psi;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            acc[A_GQ + k] = fmaf(K, -es * c[D + k] - g * P.s * r.p[k] + cz * z[k], acc[A_GQ + k]);
+            acc[A_GP + k] = fmaf(K, c[D + k] - g * al * z[k], acc[A_GP + k]);
+        }
+    }
+    static DICP_HD void finish(const Params& P, int i, const Row&, const float* acc, float*) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const size_t o = (size_t)i * D + k;
+            if (P.accumulate) {
+                P.gp[o] += acc[A_GP + k];
+                P.gq[o] += acc[A_GQ + k];
+            } else {
+                P.gp[o] = acc[A_GP + k];
+                P.gq[o] = acc[A_GQ + k];
+            }
+        }
+    }
+};
+
 }  // namespace dicp

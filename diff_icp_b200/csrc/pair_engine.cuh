@@ -7,7 +7,7 @@
 //   struct Params;                     raw device pointers + scalars (passed by value to the kernel)
 //   THREADS, R, TILE, COLF4            CTA size, rows per thread, columns per tile, float4 per packed column
 //   NACC, NSCAL                        accumulators per row, row-scalars that are summed over all rows
-//   pack_col(prm, j, N, float* c)      build the packed record of column j (pads j >= N so that it contributes 0)
+//   pack_col(prm, j, N, float* c)      build the packed record of column j (records j >= N are padding, never visited)
 //   load_row(prm, i, Row&)             read row i from the raw arrays (pre-scaling coordinates)
 //   init(acc), pair(prm, row, c, acc)  the per-pair arithmetic  (c = COLF4*4 floats of the packed column)
 //   combine(a, b)                      how two partial accumulators merge across column splits (default: +)
@@ -55,7 +55,7 @@ __global__ void pack_kernel(typename Op::Params prm, float4* __restrict__ colpac
 template <class Op>
 __global__ void __launch_bounds__(Op::THREADS, Op::MINB)
 pair_kernel(typename Op::Params prm, const float4* __restrict__ colpack, float* __restrict__ part,
-            float* __restrict__ blockscal, int M, int ntiles) {
+            float* __restrict__ blockscal, int M, int N, int ntiles) {
     constexpr int R = Op::R, TILE = Op::TILE, CF4 = Op::COLF4, NACC = Op::NACC, NSCAL = Op::NSCAL;
     constexpr uint32_t STAGE_BYTES = TILE * CF4 * 16;
     __shared__ __align__(128) float4 stage[kStages][TILE * CF4];
@@ -97,8 +97,10 @@ pair_kernel(typename Op::Params prm, const float4* __restrict__ colpack, float* 
         const int s = t % kStages;
         mbar_wait(&full[s], (uint32_t)((t / kStages) & 1));
         const float4* sp = stage[s];
+        const int left = N - (t0 + t) * TILE;            // the last tile may be partial: padded records are never visited
+        const int ncol = left < TILE ? left : TILE;
 #pragma unroll 2
-        for (int j = 0; j < TILE; ++j) {
+        for (int j = 0; j < ncol; ++j) {
             float c[CF4 * 4];
 #pragma unroll
             for (int k = 0; k < CF4; ++k) {
@@ -283,7 +285,7 @@ inline int run_pair(const typename Op::Params& prm, int M, int N, float* scal_ou
     const int Npad = p.ntiles * Op::TILE;
     pack_kernel<Op><<<(Npad + 255) / 256, 256, 0, st>>>(prm, colpack, N, Npad);
     dim3 grid(p.nrb, p.nsplit);
-    pair_kernel<Op><<<grid, Op::THREADS, 0, st>>>(prm, colpack, part, blockscal, M, p.ntiles);
+    pair_kernel<Op><<<grid, Op::THREADS, 0, st>>>(prm, colpack, part, blockscal, M, N, p.ntiles);
     launch_counter() += 2;
     int nblk = p.nrb;
     if (p.nsplit > 1) {
@@ -304,14 +306,13 @@ inline int run_pair(const typename Op::Params& prm, int M, int N, float* scal_ou
 // ---- host emulation (tests only): the same Op arithmetic, executed row by row on the CPU ----------
 template <class Op>
 inline void run_pair_host(const typename Op::Params& prm, int M, int N, float* scal_out) {
-    const int Npad = ((N + Op::TILE - 1) / Op::TILE) * Op::TILE;
     double scal[Op::NSCAL > 0 ? Op::NSCAL : 1] = {0};
     for (int i = 0; i < M; ++i) {
         typename Op::Row row;
         Op::load_row(prm, i, row);
         float acc[Op::NACC];
         Op::init(acc);
-        for (int j = 0; j < Npad; ++j) {
+        for (int j = 0; j < N; ++j) {
             float c[Op::COLF4 * 4];
             Op::pack_col(prm, j, N, c);
             Op::pair(prm, row, c, acc);

@@ -165,12 +165,9 @@ def test_two_set_api_runs_logdet_default_small():
     g = torch.Generator().manual_seed(3)
     xA = torch.rand(300, 3, generator=g)
     xB = xA + 0.02 * torch.randn(300, 3, generator=g) + 0.03
-    try:
-        PSR, evol = ICP_two_set(xA.to(dev()), xB.to(dev()), {"sigma": 0.1, "optimize_sigma": True, "outlier_weight": None},
-                                {"type": "diffeomorphic", "lambda_LDDMM": 500.0, "sigma_LDDMM": 0.2},
-                                numerical_options={"support_LDDMM": {"scheme": "dense"}},
-                                optim_options={"max_iterations": 2}, plotstuff=False, printstuff=False)
-    except Exception as e:        # until the logdet adjoint lands this raises DicpError("unsupported configuration")
-        pytest.xfail(f"logdet adjoint pending: {e}")
+    PSR, evol = ICP_two_set(xA.to(dev()), xB.to(dev()), {"sigma": 0.1, "optimize_sigma": True, "outlier_weight": None},
+                            {"type": "diffeomorphic", "lambda_LDDMM": 500.0, "sigma_LDDMM": 0.2},
+                            numerical_options={"support_LDDMM": {"scheme": "dense"}},
+                            optim_options={"max_iterations": 2}, plotstuff=False, printstuff=False)
     assert PSR.LMi.gradcomponent and PSR.LMi.eta == 1 / 500.0
     assert np.isfinite(PSR.FE)

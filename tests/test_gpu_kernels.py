@@ -138,8 +138,6 @@ def test_lddmm_shoot_and_gradients_match_reference_gold(golden):
             assert relerr(sh[-1][3].detach().cpu().numpy(), g[f"{tag}_gold_x1"]) < 5e-5, tag
         tl = LM.trajloss(sh)
         assert abs(float(tl) - float(g[f"{tag}_gold_trajloss"])) < 2e-5 * max(1.0, abs(float(g[f"{tag}_gold_trajloss"]))), tag
-        if version == "logdet":
-            continue                                   # adjoint of the logdet model: see test_gpu_logdet.py
         moved = sh[-1][3] if x is not None else sh[-1][0]
         L = tl + ((moved - y) ** 2 / (2 * sig2[:, None])).sum()
         assert abs(float(L) - float(g[f"{tag}_gold_loss"])) < 2e-5 * abs(float(g[f"{tag}_gold_loss"])), tag

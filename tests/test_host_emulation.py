@@ -119,7 +119,7 @@ def test_emulated_rhs_forward_matches_oracle(emu, D, version, with_x):
 
 
 @pytest.mark.parametrize("D", [2, 3])
-@pytest.mark.parametrize("version", ["classic", "hybrid"])
+@pytest.mark.parametrize("version", ["classic", "hybrid", "logdet"])
 @pytest.mark.parametrize("with_x", [False, True])
 def test_emulated_rhs_adjoint_matches_autograd(emu, D, version, with_x):
     sig, lam = 0.3, 5.0
