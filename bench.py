@@ -2,15 +2,20 @@
 """bench.py -- headline benchmark of the diffICP hot path on B200.
 
 Workload (BASELINE.json configs[1], "api two-point-set diffeomorphic ICP matching, 3D synthetic clouds 20k x 20k"):
-one STEP = one L-BFGS closure evaluation of the LDDMM registration of a 20 000-point 3-D cloud with dense support
-(support points = data points, the only 3-D-capable scheme of the reference): geodesic shoot (Euler, nt = 10) +
-trajectory loss + quadratic data loss against the GMM targets, then the adjoint sweep (= `L.backward()` of the
-reference, tools/optim.py:34-47).  The reference spends > 99 % of an ICP iteration in these evaluations (~23 per
-frame per outer iteration).
+one STEP = one slice of an ICP_two_set iteration on a 20 000-point 3-D cloud registered to a 20 000-centroid GMM with
+dense support (support points = data points, the only 3-D-capable scheme of the reference):
+  (1) one EM step of the GMM (E step 20k x 20k, mu/w frozen, sigma re-estimated; api/ICP_two_set.py:179-187) giving the
+      quadratic targets; with N > 1 GPUs every rank holds its own frame and the sigma statistics are all-reduced (NCCL) --
+      the only collective of the algorithm;
+  (2) one L-BFGS closure evaluation of the registration: geodesic shoot (Euler, nt = 10) + trajectory loss + quadratic
+      data loss, then the adjoint sweep (= `L.backward()` of the reference, tools/optim.py:34-47).  The reference spends
+      > 99 % of an ICP iteration in these evaluations (~23 per frame per outer iteration).
+The LDDMM model is the API default of the two-set path: the full logdet model; --variant selects
+hybrid / classic.
 
-Metric: Gaussian kernel pairs / second, where one "pair" is one (i,j) visit in one right-hand-side evaluation or in
-one adjoint evaluation: pairs/step = 2 * nt * M^2 (implementation independent: the reference visits each such pair
-2-7 times per evaluation with separate reductions, this build once).
+Metric: Gaussian kernel pairs / second, where one "pair" is one (i,j) visit in the E step, in one right-hand-side
+evaluation or in one adjoint evaluation: pairs/step = M*C + 2 * nt * M^2 (implementation independent: the reference
+visits each such pair 2-7 times per evaluation with separate reductions, this build once).
 
     python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
     python bench.py --impl reference ...                      CPU arm: the oracle port of the reference's algorithm
@@ -54,7 +59,7 @@ def make_workload(seed, M=M_POINTS, D=DIM):
 
 
 def pairs_per_step(M, nt=NT):
-    return 2.0 * nt * M * M
+    return float(M) * M + 2.0 * nt * M * M
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -126,8 +131,20 @@ def cpu_sample_seconds(variant, m_rows, xA, p0, threads):
         Gq3 = K.GradLapKRed(qs, q)
         L = L + eta * (vq2 ** 2).sum() + eta * (Gq2 ** 2).sum() + eta ** 2 * (Gq3 ** 2).sum() + eta * K.LapKRed(qs, q).sum()
     L.backward()
-    dt = time.perf_counter() - t0
-    return dt, 2.0 * len(idx) * xA.shape[0]
+    dt_rhs = time.perf_counter() - t0
+    # E step of the same rows against all M centroids (dense (m,M) block, core/GMM.py:263-317)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        d2 = ((xA[idx][:, None, :] - xA[None, :, :]) ** 2).sum(-1)
+        t = -d2 / (2 * SIGMA_GMM ** 2)
+        T = t.logsumexp(1)
+        gam = (t - T[:, None]).exp()
+        Y = gam @ xA
+        _ = (gam * d2).sum() + (gam * (t - T[:, None])).sum() + (Y ** 2).sum()
+    dt_em = time.perf_counter() - t0
+    # same workload mix as the GPU arm: a step has ONE E step per nt (RHS + adjoint) evaluations, so the sampled E step
+    # enters with weight 1/nt in both the time and the pair count
+    return dt_rhs + dt_em / NT, len(idx) * xA.shape[0] * (2.0 + 1.0 / NT)
 
 
 def run_reference(args, rank, world):
@@ -145,7 +162,8 @@ def run_reference(args, rank, world):
         tot_t += dt
         tot_pairs += npairs
     value = tot_pairs / tot_t
-    sample = f"{m_rows} of {M_POINTS} rows x {M_POINTS} columns, one RHS evaluation + autograd backward per step"
+    sample = (f"{m_rows} of {M_POINTS} rows x {M_POINTS} columns per step: one RHS evaluation + autograd backward, plus "
+              f"1/{NT} of one dense E step (the mix of a full step)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -160,7 +178,7 @@ def run_reference(args, rank, world):
 def workload_config(variant):
     return {"workload": "two_set_3d_20k_dense: LBFGS closure evaluation (shoot + loss + adjoint), "
                         f"M=N={M_POINTS}, D={DIM}, Euler nt={NT}, sigma_LDDMM={SIGMA_LDDMM}, lambda={LAMBDA_LDDMM}",
-            "model_variant": variant, "pairs_per_step": pairs_per_step(M_POINTS),
+            "model_variant": variant, "pairs_per_step": pairs_per_step(M_POINTS), "gmm": f"C={M_POINTS} centroids frozen, sigma optimised",
             "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)"}
 
 
@@ -179,10 +197,20 @@ def run_b200(args, rank, world, local_rank):
     inv2s2 = 1.0 / (2 * SIGMA_GMM ** 2)
     q_d, y_d, p_d = xA.to(dev), y.to(dev), p0.to(dev)
 
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    GMM = GaussianMixtureUnif(y.to(dev), sigma=SIGMA_GMM, spec=spec)
+    GMM.to_optimize = {"mu": False, "sigma": True, "w": False, "eta0": False}
+    if world > 1:
+        from diff_icp_b200.dist import StatsComm
+        GMM.comm = StatsComm()
+
     def closure(q, p_init, yy):
+        """(1) EM step on the current (warped) points -> targets; (2) shoot + loss + adjoint."""
+        GMM.sigma = SIGMA_GMM
+        Y, Cfe, FE = GMM.EM_step(q)
         p = p_init.detach().clone().requires_grad_(True)
         sh = LM.Shoot(q, p)
-        L = LM.trajloss(sh) + ((sh[-1][0] - yy) ** 2).sum() * inv2s2
+        L = LM.trajloss(sh) + ((sh[-1][0] - Y) ** 2).sum() * inv2s2
         L.backward()
         return L.detach(), p.grad
 
@@ -276,7 +304,7 @@ def run_b200(args, rank, world, local_rank):
             tt += dt
             pp_ += npairs
         cpu = {"value": pp_ / tt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"256 of {M} rows x {M} columns per evaluation (RHS + autograd backward), repeated for 10 s"}
+               "sample": f"256 of {M} rows x {M} columns per evaluation (RHS + autograd backward + 1/{NT} E step), repeated for 10 s"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -350,9 +378,9 @@ def kernel_roofline(args, LM, q, p, dev, ops):
 
 # algorithmic FP32 instruction counts per pair, D = 3 (hand count of the formulas in csrc/ops_rhs.cuh)
 ALG_WORK = {
-    "classic": {"fwd_fp32": 16, "adj_fp32": 46},
+    "classic": {"fwd_fp32": 16, "adj_fp32": 42},
     "hybrid": {"fwd_fp32": 19, "adj_fp32": 58},
-    "logdet": {"fwd_fp32": 31, "adj_fp32": 120},
+    "logdet": {"fwd_fp32": 31, "adj_fp32": 88},
 }
 
 
@@ -362,7 +390,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", default="hybrid", choices=["classic", "hybrid", "logdet"])
+    ap.add_argument("--variant", default="logdet", choices=["classic", "hybrid", "logdet"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -26,11 +26,15 @@ from ..tools.point_sets import decimate
 from ..tools.spec import defspec
 
 
-def get_bounds(*xlist, relmargin=0.2):
+def get_bounds(*xlist, relmargin=0.2, comm=None):
     """Per-dimension (min, max) over several point sets, enlarged by a relative margin
-    (reference: visualization/visu.py:35-50, 2-D there; any D here)."""
-    mins = torch.stack([x.min(0).values for x in xlist if len(x) > 0]).min(0).values.cpu().numpy()
-    maxs = torch.stack([x.max(0).values for x in xlist if len(x) > 0]).max(0).values.cpu().numpy()
+    (reference: visualization/visu.py:35-50, 2-D there; any D here).  With `comm`: over the point sets of all ranks."""
+    mins = torch.stack([x.min(0).values for x in xlist if len(x) > 0]).min(0).values
+    maxs = torch.stack([x.max(0).values for x in xlist if len(x) > 0]).max(0).values
+    if comm is not None:
+        both = comm.max(torch.cat((-mins, maxs)))
+        mins, maxs = -both[:mins.numel()], both[mins.numel():]
+    mins, maxs = mins.cpu().numpy(), maxs.cpu().numpy()
     return (1 + relmargin) * mins - relmargin * maxs, (1 + relmargin) * maxs - relmargin * mins
 
 
@@ -230,10 +234,7 @@ class DiffPSR(MultiPSR):
         elif scheme == "grid":
             given = [xticks, yticks, zticks][:self.D]
             if any(t is None for t in given):
-                lo, hi = get_bounds(*self.allx0, relmargin=0.1)
-                if self.comm is not None:
-                    lo = -self.comm.max(torch.tensor(-lo, dtype=torch.float64, device=self.compspec["device"])).cpu().numpy()
-                    hi = self.comm.max(torch.tensor(hi, dtype=torch.float64, device=self.compspec["device"])).cpu().numpy()
+                lo, hi = get_bounds(*self.allx0, relmargin=0.1, comm=self.comm)
             ticks = [np.arange(lo[d] - Rcover / 2, hi[d] + Rcover / 2, Rcover) if given[d] is None else np.asarray(given[d])
                      for d in range(self.D)]
             if self.D == 2:     # same point ordering as the reference (meshgrid 'xy' + Fortran reshape)

@@ -1,0 +1,153 @@
+"""CPU, world_size = 2 over gloo: the only collective of the algorithm (GMM statistics all-reduce) and the frame-sharded
+groupwise mode give the same model as a single process holding all frames.  Kernels' arithmetic runs on the CPU
+emulation (tests/hostemu); the NCCL path is exercised by bench.py --gpus N on the GPU box."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CPU = {"device": "cpu", "dtype": torch.float32}
+
+
+class _Patch:
+    def setattr(self, obj, name, val, raising=True):
+        setattr(obj, name, val)
+
+
+def _setup(rank, world, port):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import emu_backend
+    emu_backend.install_all(_Patch())
+    torch.set_num_threads(1)
+
+
+def _frames(K=4, N=120, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    cent = torch.rand(5, 2, generator=g)
+    return [(cent[torch.randint(0, 5, (N + 7 * k,), generator=g)] + 0.04 * torch.randn(N + 7 * k, 2, generator=g)).contiguous()
+            for k in range(K)], cent
+
+
+def _worker_em(rank, world, port, out):
+    _setup(rank, world, port)
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    from diff_icp_b200.dist import StatsComm, shard_frames
+    frames, cent = _frames()
+    mine = shard_frames(len(frames), rank, world)
+    X = torch.cat([frames[k] for k in mine])
+    G = GaussianMixtureUnif(cent + 0.05, sigma=0.1, use_outliers=True, spec=CPU)
+    G.outliers["vol0"] = 1.0
+    G.comm = StatsComm()
+    fes = []
+    for _ in range(3):
+        Y, Cfe, FE = G.EM_step(X)
+        fes.append(float(FE))
+    torch.save({"mu": G.mu, "w": G.w, "sigma": G.sigma, "FE": fes, "eta0": G.outliers["eta0"], "Y": Y, "mine": mine},
+               os.path.join(out, f"em{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def _worker_psr(rank, world, port, out):
+    _setup(rank, world, port)
+    from diff_icp_b200.api.ICP_atlas import ICP_atlas
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    from diff_icp_b200.dist import StatsComm, shard_frames
+    frames, cent = _frames(K=3, N=60)
+    comm = StatsComm()
+    mine = shard_frames(len(frames), rank, world)
+    G = GaussianMixtureUnif(cent + 0.05, sigma=0.1, spec=CPU)
+    PSR, evol = ICP_atlas([frames[k] for k in mine], GMM_parameters={"init_components": [G]},
+                          registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.3},
+                          numerical_options={"compspec": CPU, "dataspec": CPU, "comm": comm,
+                                             "support_LDDMM": {"scheme": "grid", "rho": 1.0}},
+                          optim_options={"max_iterations": 2, "max_repeat_GMM": 3}, printstuff=False)
+    torch.save({"mu": PSR.GMMi[0].mu, "sigma": PSR.GMMi[0].sigma, "FE": PSR.FE, "q0": PSR.q0[0]},
+               os.path.join(out, f"psr{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def _spawn(fn, port):
+    out = tempfile.mkdtemp()
+    mp.spawn(fn, args=(2, port, out), nprocs=2, join=True)
+    return out
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _build_emulation():
+    sys.path.insert(0, HERE)
+    import emu_backend
+    emu_backend.lib()
+
+
+def test_em_statistics_allreduce_equals_single_process(monkeypatch):
+    out = _spawn(_worker_em, 29611)
+    r0, r1 = (torch.load(os.path.join(out, f"em{r}.pt"), weights_only=False) for r in (0, 1))
+    # identical replicated model on both ranks
+    assert torch.equal(r0["mu"], r1["mu"]) and torch.equal(r0["w"], r1["w"]) and r0["sigma"] == r1["sigma"]
+    assert r0["FE"] == r1["FE"] and r0["eta0"] == r1["eta0"]
+    # and the same as one process holding all frames
+    import emu_backend
+    emu_backend.install_all(monkeypatch)
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    frames, cent = _frames()
+    G = GaussianMixtureUnif(cent + 0.05, sigma=0.1, use_outliers=True, spec=CPU)
+    G.outliers["vol0"] = 1.0
+    fes = []
+    for _ in range(3):
+        Y, Cfe, FE = G.EM_step(torch.cat(frames))
+        fes.append(float(FE))
+    assert torch.allclose(G.mu, r0["mu"], rtol=0, atol=2e-6)
+    assert torch.allclose(G.w, r0["w"], rtol=0, atol=2e-5)
+    assert abs(G.sigma - r0["sigma"]) < 1e-6 * G.sigma
+    assert np.allclose(fes, r0["FE"], rtol=2e-5)          # fp32 sums in a different order
+    assert abs(G.outliers["eta0"] - r0["eta0"]) < 1e-5
+    # targets of rank 0's frames are the corresponding rows of the global targets
+    sizes = [f.shape[0] for f in frames]
+    offs = np.concatenate(([0], np.cumsum(sizes)))
+    Yg = torch.cat([Y[offs[k]:offs[k + 1]] for k in r0["mine"]])
+    assert torch.allclose(Yg, r0["Y"], atol=2e-6)
+
+
+def test_sharded_atlas_equals_single_process(monkeypatch):
+    out = _spawn(_worker_psr, 29613)
+    r0, r1 = (torch.load(os.path.join(out, f"psr{r}.pt"), weights_only=False) for r in (0, 1))
+    assert torch.equal(r0["mu"], r1["mu"]) and r0["sigma"] == r1["sigma"] and r0["FE"] == r1["FE"]
+    assert torch.equal(r0["q0"], r1["q0"])                    # same grid support on every rank (global bounds)
+    import emu_backend
+    emu_backend.install_all(monkeypatch)
+    from diff_icp_b200.api.ICP_atlas import ICP_atlas
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    frames, cent = _frames(K=3, N=60)
+    G = GaussianMixtureUnif(cent + 0.05, sigma=0.1, spec=CPU)
+    PSR, _ = ICP_atlas(frames, GMM_parameters={"init_components": [G]},
+                       registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.3},
+                       numerical_options={"compspec": CPU, "dataspec": CPU, "support_LDDMM": {"scheme": "grid", "rho": 1.0}},
+                       optim_options={"max_iterations": 2, "max_repeat_GMM": 3}, printstuff=False)
+    assert torch.allclose(PSR.q0[0], r0["q0"], atol=1e-6)
+    assert torch.allclose(PSR.GMMi[0].mu, r0["mu"], atol=5e-4)       # frames are registered independently, in a
+    assert abs(PSR.GMMi[0].sigma - r0["sigma"]) < 5e-3 * r0["sigma"]   # different order: L-BFGS paths agree to ~1e-4
+    assert abs(PSR.FE - r0["FE"]) < 5e-3 * abs(r0["FE"])
+
+
+def test_shard_frames_balances_work():
+    from diff_icp_b200.dist import shard_frames
+    K, W = 10, 4
+    owned = [shard_frames(K, r, W) for r in range(W)]
+    assert sorted(sum(owned, [])) == list(range(K))
+    w = [100, 1, 1, 1, 50, 50, 1, 1, 1, 1]
+    owned = [shard_frames(K, r, W, weights=w) for r in range(W)]
+    assert sorted(sum(owned, [])) == list(range(K))
+    loads = [sum(w[k] for k in o) for o in owned]
+    assert max(loads) == 100
