@@ -78,7 +78,15 @@ def _worker_psr(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def _spawn(fn, port):
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def _spawn(fn, port=None):
+    port = _free_port() if port is None else port
     out = tempfile.mkdtemp()
     mp.spawn(fn, args=(2, port, out), nprocs=2, join=True)
     return out
@@ -92,7 +100,7 @@ def _build_emulation():
 
 
 def test_em_statistics_allreduce_equals_single_process(monkeypatch):
-    out = _spawn(_worker_em, 29611)
+    out = _spawn(_worker_em)
     r0, r1 = (torch.load(os.path.join(out, f"em{r}.pt"), weights_only=False) for r in (0, 1))
     # identical replicated model on both ranks
     assert torch.equal(r0["mu"], r1["mu"]) and torch.equal(r0["w"], r1["w"]) and r0["sigma"] == r1["sigma"]
@@ -121,7 +129,7 @@ def test_em_statistics_allreduce_equals_single_process(monkeypatch):
 
 
 def test_sharded_atlas_equals_single_process(monkeypatch):
-    out = _spawn(_worker_psr, 29613)
+    out = _spawn(_worker_psr)
     r0, r1 = (torch.load(os.path.join(out, f"psr{r}.pt"), weights_only=False) for r in (0, 1))
     assert torch.equal(r0["mu"], r1["mu"]) and r0["sigma"] == r1["sigma"] and r0["FE"] == r1["FE"]
     assert torch.equal(r0["q0"], r1["q0"])                    # same grid support on every rank (global bounds)
