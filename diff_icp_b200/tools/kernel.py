@@ -139,16 +139,31 @@ class GaussKernel(GenKernel):
         return self.min_sqdist(X, Y) > (Rthreshold * self.sigma) ** 2
 
     # ---- linear solves with K(x,x): setup-time, NOT on the hot path ---------------------
+    DENSE_SOLVE_MAX = 4000          # above this the reference's dense O(M^3) CPU lstsq is replaced by matrix-free CG
+
     def KpinvSolve(self, x, v, rcond=None):
-        """Least-squares b with sum_j K(x_i-x_j) b_j ~ v_i (reference: tools/kernel.py:227-232, numpy lstsq).
-        Exact shortcut: v == 0  =>  b = 0 (the minimum-norm solution), which is the case that runs before every
-        optimisation (DiffPSR.initialize_a0 with eta = 0); otherwise the dense M x M system is solved like the
-        reference does, which is only feasible for small M."""
+        """Least-squares b with sum_j K(x_i-x_j) b_j ~ v_i (reference: tools/kernel.py:227-232, numpy lstsq on the
+        dense M x M matrix, rcond = relative singular-value cut-off).
+        * v == 0  =>  b = 0 exactly (minimum-norm solution): the case that runs before every optimisation
+          (DiffPSR.initialize_a0 / update_a0 with eta = 0 and zero initial speeds).
+        * M <= DENSE_SOLVE_MAX: dense numpy lstsq, like the reference.
+        * larger M (where the reference is infeasible): matrix-free conjugate gradient on
+          (K + alpha I) b = v with alpha = rcond * lambda_max(K) (power iteration), i.e. Tikhonov damping at the scale
+          where the pseudo-inverse truncates; the KRed kernel is the mat-vec."""
         if not bool(v.any()):
             return torch.zeros_like(v)
-        K_xx = self.K_torch(x, x)
-        sol = np.linalg.lstsq(K_xx.detach().cpu().numpy(), v.detach().cpu().numpy(), rcond=rcond)[0]
-        return torch.from_numpy(sol).to(**getspec(x, v))
+        if x.shape[0] <= self.DENSE_SOLVE_MAX:
+            K_xx = self.K_torch(x, x)
+            sol = np.linalg.lstsq(K_xx.detach().cpu().numpy(), v.detach().cpu().numpy(), rcond=rcond)[0]
+            return torch.from_numpy(sol).to(**getspec(x, v))
+        u = torch.ones_like(v)
+        lam = 1.0
+        for _ in range(8):
+            Ku = ops.ksum(ops.K_RED, self.sigma, x, x, b=u)[ops.K_RED]
+            lam = float(Ku.norm() / u.norm())
+            u = Ku / Ku.norm()
+        rc = 1e-6 if rcond is None else rcond
+        return self.KridgeSolve_keops(x, v, alpha=rc * lam)
 
     def KridgeSolve_torch(self, x, v, alpha=1e-4):
         K_xx = self.K_torch(x, x)
