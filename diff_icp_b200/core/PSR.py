@@ -263,37 +263,79 @@ class DiffPSR(MultiPSR):
             return (((x - y) ** 2) * inv[:, None]).sum()
         return dataloss_func
 
+    # number of frames registered concurrently (one Python thread + one CUDA stream each). Frames are independent
+    # (core/PSR.py:528), and every frame's computation is deterministic, so results do not depend on this setting;
+    # it only fills the GPU when single frames are too small to do so (SURVEY.md §7 "small-problem regime").
+    frame_workers = 16
+
+    def _register_frame(self, k, nmax, tol):
+        """Optimise a0[k] and collect everything Reg_opt's bookkeeping needs (no shared state is written here)."""
+        x0 = None if self.support_scheme is None else self.allx0[k]
+        a0, shoot, regloss, datal, isteps, change = \
+            self.LMi.Optimize(self.QuadLossFunctor(k), self.q0[k], self.a0[k], x0, tol=tol, nmax=nmax)
+        allx1k = shoot[-1][0] if x0 is None else shoot[-1][-1]
+        counts = None
+        if self.support_scheme is not None:
+            # coverage of the warped data points by the support points at every time step (core/PSR.py:559-566);
+            # one host read for the whole trajectory
+            counts = torch.stack([self.LMi.Kernel.check_coverage(st[-1], st[0], 2.0).sum() for st in shoot]).tolist()
+        return dict(a0=a0, shoot=shoot, regloss=regloss, datal=datal, isteps=isteps, change=change, x1=allx1k, counts=counts)
+
+    def _register_all(self, nmax, tol):
+        K = self.K
+        dev = torch.device(self.compspec["device"])
+        W = min(int(self.frame_workers), K)
+        if W <= 1 or dev.type != "cuda":
+            return [self._register_frame(k, nmax, tol) for k in range(K)]
+        import threading
+        from .. import shooting
+        if self.LMi.use_cuda_graph:          # capture every plan up front, sequentially, on this thread
+            for k in range(K):
+                sp = self.LMi._spec_for(self.q0[k].shape[0], 0 if self.support_scheme is None else self.allx0[k].shape[0], dev)
+                shooting.ShootPlan.get(sp, True, slot=1 + k % W).ensure_captured()
+        main = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(dev) for _ in range(W)]
+        results, errors = [None] * K, []
+
+        def work(wid):
+            try:
+                shooting.set_plan_slot(1 + wid)
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(streams[wid]):
+                    streams[wid].wait_stream(main)
+                    for k in range(wid, K, W):
+                        results[k] = self._register_frame(k, nmax, tol)
+            except BaseException as e:          # surfaced on the main thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(w,)) for w in range(W)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for st in streams:
+            main.wait_stream(st)
+        if errors:
+            raise errors[0]
+        return results
+
     def Reg_opt(self, nmax=10, tol=1e-3):
         """LDDMM registration of every (local) frame to its current targets (reference: core/PSR.py:521-569)."""
-        for k in range(self.K):
-            if self.support_scheme is None:
-                self.a0[k], self.shoot[k], self.regloss[k], datal, isteps, change = \
-                    self.LMi.Optimize(self.QuadLossFunctor(k), self.q0[k], self.a0[k], tol=tol, nmax=nmax)
-                allx1k = self.shoot[k][-1][0]
-            else:
-                self.a0[k], self.shoot[k], self.regloss[k], datal, isteps, change = \
-                    self.LMi.Optimize(self.QuadLossFunctor(k), self.q0[k], self.a0[k], self.allx0[k], tol=tol, nmax=nmax)
-                allx1k = self.shoot[k][-1][-1]
-
+        results = self._register_all(nmax, tol)
+        for k, r in enumerate(results):
+            self.a0[k], self.shoot[k], self.regloss[k] = r["a0"], r["shoot"], r["regloss"]
             last = 0
             for s in range(self.S):
                 first, last = last, last + self.N[k, s]
-                self.x1[k, s] = allx1k[first:last].to(**self.dataspec)
+                self.x1[k, s] = r["x1"][first:last].to(**self.dataspec)
             for s in range(self.S):
                 self.update_quadloss(k, s)
-
-            # coverage of the warped data points by the support points at every time step (core/PSR.py:559-566);
-            # one host read for the whole trajectory
-            if self.support_scheme is not None:
-                Rcoverwarning = 2.0
-                counts = torch.stack([self.LMi.Kernel.check_coverage(st[-1], st[0], Rcoverwarning).sum()
-                                      for st in self.shoot[k]]).tolist()
-                for t, c in enumerate(counts):
+            if r["counts"] is not None:
+                for t, c in enumerate(r["counts"]):
                     if c > 0:
                         print(f"WARNING : shooting, time step {t} : {c} uncovered points ({c / self.allx0[k].shape[0]:.2%})")
                         warnings.warn("Uncovered points during LDDMM shooting. Choose a smaller rho when defining the support scheme.", RuntimeWarning)
-
-            message = f"Frame {k} : {isteps} optim steps, loss={self.regloss[k] + datal:.4}, change={change:.4}."
+            message = f"Frame {k} : {r['isteps']} optim steps, loss={r['regloss'] + r['datal']:.4}, change={r['change']:.4}."
             if self.comm is None:
                 self.update_FE(message=message)
             elif self.printstuff:

@@ -15,8 +15,22 @@ from __future__ import annotations
 
 import torch
 
+import threading
+
 from . import ops
 from . import _lib
+
+# Concurrent registration of several frames (DiffPSR.Reg_opt with frame_workers > 1) runs one Python thread + one CUDA
+# stream per worker; each worker uses its own plan instances (buffers, captured graphs), selected by this slot.
+_tls = threading.local()
+
+
+def set_plan_slot(slot):
+    _tls.slot = slot
+
+
+def _plan_slot():
+    return getattr(_tls, "slot", 0)
 
 
 class ShootSpec:
@@ -120,16 +134,49 @@ class ShootPlan:
         self.fwd_graph = None
         self.bwd_graph = None
 
+    _lock = threading.Lock()
+
     @classmethod
-    def get(cls, spec: ShootSpec, use_graph: bool):
-        key = spec.key() + (bool(use_graph),)
+    def get(cls, spec: ShootSpec, use_graph: bool, slot=None):
+        key = spec.key() + (bool(use_graph), _plan_slot() if slot is None else slot)
         plan = cls._cache.get(key)
         if plan is None:
-            if len(cls._cache) > 64:
-                cls._cache.clear()
-            plan = cls(spec, use_graph)
-            cls._cache[key] = plan
+            with cls._lock:
+                plan = cls._cache.get(key)
+                if plan is None:
+                    if len(cls._cache) > 1024:
+                        cls._cache.clear()
+                    plan = cls(spec, use_graph)
+                    cls._cache[key] = plan
         return plan
+
+    def ensure_captured(self):
+        """Capture the forward and adjoint graphs now (on the calling thread / current stream), so that later replays
+        from worker threads never capture concurrently."""
+        if not self.use_graph:
+            return
+        if self.fwd_graph is None:
+            self.traj[0].zero_()
+            self._capture_forward()
+        if self.bwd_graph is None:
+            self.gtraj.zero_()
+            self._capture_backward()
+
+    def _capture_forward(self):
+        self._fwd_body()                      # warm-up outside capture (lazy init, occupancy queries)
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self._fwd_body()
+        self.fwd_graph = g
+
+    def _capture_backward(self):
+        self._bwd_body()
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self._bwd_body()
+        self.bwd_graph = g
 
     # -- forward ---------------------------------------------------------------------------------------
     def _fwd_body(self):
@@ -145,12 +192,8 @@ class ShootPlan:
         cost.zero_()
         if self.use_graph:
             if self.fwd_graph is None:
-                self._fwd_body()                      # warm-up outside capture (lazy init, occupancy queries)
-                torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._fwd_body()
-                self.fwd_graph = g
+                with ShootPlan._lock:
+                    self._capture_forward()
             self.fwd_graph.replay()
         else:
             self._fwd_body()
@@ -164,12 +207,8 @@ class ShootPlan:
         self.gtraj.copy_(gtraj)
         if self.use_graph:
             if self.bwd_graph is None:
-                self._bwd_body()
-                torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._bwd_body()
-                self.bwd_graph = g
+                with ShootPlan._lock:
+                    self._capture_backward()
             self.bwd_graph.replay()
         else:
             self._bwd_body()

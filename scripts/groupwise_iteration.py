@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--C", type=int, default=50)
+    ap.add_argument("--workers", type=int, default=16)
     args = ap.parse_args()
     rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     dev = torch.device("cuda", lr)
@@ -64,6 +65,7 @@ def main():
     LM.use_cuda_graph = bool(args.graph)
     P = DiffPSR([frames[k].to(dev) for k in mine], G, LM, dataspec=spec, compspec=spec, comm=comm)
     P.printstuff = False
+    P.frame_workers = args.workers
     P.set_support_scheme("grid", rho=math.sqrt(2))
     P.reinitialize_GMM()
     times = []
@@ -88,7 +90,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "groupwise_psr_iteration_ms", "n_gpus": world, "frames": args.frames,
                           "points_per_frame": args.points, "C": args.C, "support_points": int(P.q0[0].shape[0]),
-                          "cuda_graph": bool(args.graph), "FE": P.FE, "sigma": P.GMMi[0].sigma,
+                          "cuda_graph": bool(args.graph), "frame_workers": args.workers, "FE": P.FE, "sigma": P.GMMi[0].sigma,
                           "gmm_opt_ms": [1e3 * a for a, _ in times], "reg_opt_ms": [1e3 * b for _, b in times],
                           "iteration_ms_steady": 1e3 * sum(times[-1])}))
     if comm is not None:
