@@ -213,4 +213,5 @@ int dicp_pipe_probe(int which, int blocks, int iters, float* out, void* stream) 
     return last_error(DICP_OK);
 }
 
+
 }  // extern "C"

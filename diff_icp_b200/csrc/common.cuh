@@ -53,6 +53,59 @@ DICP_HD float lg2f_fast(float t) {
 #endif
 }
 
+// ---- lane-generic arithmetic: V = float (one column) or F2 (two columns packed in one 64-bit register, evaluated with
+// the Blackwell packed-fp32 instructions FFMA2 / FADD2 / FMUL2; a row-side scalar broadcasts through the .F32 operand
+// form, which ptxas selects for f2(a,a)).  The Ops' per-pair formulas are written once against this interface.
+DICP_HD float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+DICP_HD float vmul(float a, float b) { return a * b; }
+DICP_HD float vadd(float a, float b) { return a + b; }
+DICP_HD float vsub(float a, float b) { return a - b; }
+DICP_HD float vex2n(float a) { return ex2_neg(a); }
+template <class V> DICP_HD V vbc(float a);
+template <> DICP_HD float vbc<float>(float a) { return a; }
+
+// F2: two fp32 lanes in one 64-bit register.  Device: packed PTX instructions; host (tests): plain per-lane arithmetic.
+struct F2 { unsigned long long v; };
+DICP_HD F2 f2(float a, float b) {
+    F2 r;
+#if defined(__CUDA_ARCH__)
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r.v) : "f"(a), "f"(b));
+#else
+    float t[2] = {a, b};
+    __builtin_memcpy(&r.v, t, 8);
+#endif
+    return r;
+}
+DICP_HD void f2_unpack(F2 x, float& a, float& b) {
+#if defined(__CUDA_ARCH__)
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v));
+#else
+    float t[2];
+    __builtin_memcpy(t, &x.v, 8);
+    a = t[0]; b = t[1];
+#endif
+}
+#if defined(__CUDA_ARCH__)
+#define DICP_F2_OP3(name, ptx)                                                                                      \
+    DICP_HD F2 name(F2 a, F2 b, F2 c) { F2 r; asm(ptx " %0,%1,%2,%3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+#define DICP_F2_OP2(name, ptx, hostop)                                                                              \
+    DICP_HD F2 name(F2 a, F2 b) { F2 r; asm(ptx " %0,%1,%2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+#else
+#define DICP_F2_OP3(name, ptx)                                                                                      \
+    DICP_HD F2 name(F2 a, F2 b, F2 c) { float a0, a1, b0, b1, c0, c1; f2_unpack(a, a0, a1); f2_unpack(b, b0, b1);    \
+        f2_unpack(c, c0, c1); return f2(fmaf(a0, b0, c0), fmaf(a1, b1, c1)); }
+#define DICP_F2_OP2(name, ptx, hostop)                                                                              \
+    DICP_HD F2 name(F2 a, F2 b) { float a0, a1, b0, b1; f2_unpack(a, a0, a1); f2_unpack(b, b0, b1);                  \
+        return f2(a0 hostop b0, a1 hostop b1); }
+#endif
+DICP_F2_OP3(vfma, "fma.rn.f32x2")
+DICP_F2_OP2(vmul, "mul.rn.f32x2", *)
+DICP_F2_OP2(vadd, "add.rn.f32x2", +)
+DICP_F2_OP2(vsub, "sub.rn.f32x2", -)
+DICP_HD F2 vex2n(F2 a) { float x, y; f2_unpack(a, x, y); return f2(ex2_neg(x), ex2_neg(y)); }
+template <> DICP_HD F2 vbc<F2>(float a) { return f2(a, a); }
+DICP_HD float f2_sum(F2 a) { float x, y; f2_unpack(a, x, y); return x + y; }
+
 #if defined(__CUDACC__)
 // ---- mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) ------------------------------
 DICP_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -48,6 +48,7 @@ static constexpr float kLn2 = 0.6931471805599453f;
 template <int D, bool LITE>
 struct EmRow {
     using Params = EmParams;
+    static constexpr bool PACKED = false;
     static constexpr int THREADS = 128, MINB = 1, R = 2, TILE = 128;
     static constexpr int COLN = LITE ? (D + 1) : (2 * D + 3);
     static constexpr int COLF4 = (COLN + 3) / 4;
@@ -161,6 +162,7 @@ struct EmRow {
 template <int D>
 struct EmCol {
     using Params = EmParams;
+    static constexpr bool PACKED = false;
     static constexpr int THREADS = 128, MINB = 1, R = 1, TILE = 128;
     static constexpr int COLF4 = (D + 1 + 3) / 4;
     static constexpr int A_M = 0, A_S = 1, A_B = 2, A_A = 2 + D;

@@ -32,6 +32,7 @@ struct KsumParams {
 template <int D, unsigned MASK, int R_ = 2>
 struct KsumOp {
     using Params = KsumParams;
+    static constexpr bool PACKED = false;
     static constexpr int THREADS = 128, MINB = 1, R = R_, TILE = 128;
     static constexpr bool NEED_B = (MASK & (K_RED | K_DD | K_GEND | K_HESS | K_DOT)) != 0;
     static constexpr bool NEED_D = (MASK & K_REDSCAL) != 0;

@@ -17,9 +17,14 @@
 // Forward, rows = data points x, cols = (q,p):
 //   vx_k   = sum_j K p_j + eta*alpha * sum_j K z'
 //   dcost  = alpha sum_kj K (p_j.z') + eta s sum_kj K (beta r'^2 - D)
+// Adjoint: formulas above each Op, derivation in DESIGN.md §5.3; all checked against torch autograd of the oracle
+// (tests/test_host_emulation.py).
 //
-// Adjoint (eta = 0 models; cotangents a of vq, u of dp, wx of vx, gc of dcost, gh of A [= lambda/2 * dL/dH ... see capi]):
-//   derived in DESIGN.md §5; checked against torch autograd of the oracle in tests/test_host_emulation.py.
+// Every `pair` is written ONCE against the lane-generic interface of common.cuh: instantiated with V = F2 it processes
+// TWO columns per call with packed-fp32 instructions (FFMA2 / FADD2 / FMUL2; row-side scalars ride the broadcast
+// operand form), which is what the device kernel (pair_kernel_p) uses; with V = float it is the one-column form used for
+// an odd trailing column and by the CPU emulation of the tests.  PACKED Ops declare NF, the (even) number of floats of a
+// column record.
 #pragma once
 #include "pair_engine.cuh"
 
@@ -50,36 +55,74 @@ struct RhsParams {
     int accumulate;                // adjoint outputs: 0 overwrite, 1 add to existing
 };
 
+#define DICP_RHS_COMMON(NF_)                                                                                   \
+    using Params = RhsParams;                                                                                 \
+    static constexpr bool PACKED = true;                                                                      \
+    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;      \
+    static constexpr int NF = (NF_);                                                                          \
+    static constexpr int COLF4 = (NF + 3) / 4;                                                                \
+    static DICP_HD void init(float* a) {                                                                      \
+        for (int k = 0; k < NACC; ++k) a[k] = 0.f;                                                            \
+    }                                                                                                         \
+    static DICP_HD void combine(float* a, const float* b) {                                                   \
+        for (int k = 0; k < NACC; ++k) a[k] += b[k];                                                          \
+    }
+
+// column record (q', p): used by RhsQQ, RhsXQ, AdjXQx*
+template <int D>
+DICP_HD void pack_qp(const RhsParams& P, int j, int N, float* c, int nfloat) {
+    for (int k = 0; k < nfloat; ++k) c[k] = 0.f;
+    if (j < N) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            c[k] = (P.q[(size_t)j * D + k] - P.origin[k]) * P.kappa;
+            c[D + k] = P.p[(size_t)j * D + k];
+        }
+    }
+}
+// column record (q', p, a, u): used by AdjQQ*
+template <int D>
+DICP_HD void pack_qpau(const RhsParams& P, int j, int N, float* c, int nfloat) {
+    for (int k = 0; k < nfloat; ++k) c[k] = 0.f;
+    if (j < N) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const size_t o = (size_t)j * D + k;
+            c[k] = (P.q[o] - P.origin[k]) * P.kappa;
+            c[D + k] = P.p[o];
+            c[2 * D + k] = P.a[o];
+            c[3 * D + k] = P.u[o];
+        }
+    }
+}
+// column record (x', wx): used by AdjXQq*
+template <int D>
+DICP_HD void pack_xw(const RhsParams& P, int j, int N, float* c, int nfloat) {
+    for (int k = 0; k < nfloat; ++k) c[k] = 0.f;
+    if (j < N) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            c[k] = (P.x[(size_t)j * D + k] - P.origin[k]) * P.kappa;
+            c[D + k] = P.wx[(size_t)j * D + k];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward, (q,q)
 // ------------------------------------------------------------------------------------------------
 template <int D, bool DIV, bool ETA, int R_ = DICP_RHS_R>
 struct RhsQQ {
-    using Params = RhsParams;
-    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
-    static constexpr int COLF4 = (2 * D + 3) / 4;
     static constexpr int A_V = 0, A_T = D, A_Z = 2 * D;
     static constexpr bool NEEDZ = DIV || ETA;
     static constexpr int A_S0 = A_Z + (NEEDZ ? D : 0);
     static constexpr int A_R2 = A_S0 + (ETA ? 1 : 0);
     static constexpr int NACC = A_R2 + (ETA ? 1 : 0);
     static constexpr int NSCAL = 3;   // A, B, C
+    DICP_RHS_COMMON(2 * D)
     struct Row { float q[D], p[D]; };
 
-    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) {
-#pragma unroll
-        for (int k = 0; k < COLF4 * 4; ++k) c[k] = 0.f;
-        if (j < N) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                c[k] = (P.q[(size_t)j * D + k] - P.origin[k]) * P.kappa;
-                c[D + k] = P.p[(size_t)j * D + k];
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < D; ++k) c[k] = DICP_FAR;
-        }
-    }
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { pack_qp<D>(P, j, N, c, COLF4 * 4); }
     static DICP_HD void load_row(const Params& P, int i, Row& r) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -87,43 +130,40 @@ struct RhsQQ {
             r.p[k] = P.p[(size_t)i * D + k];
         }
     }
-    static DICP_HD void init(float* a) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
-    }
-    static DICP_HD void combine(float* a, const float* b) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] += b[k];
-    }
-    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* a) {
-        float z[D];
-        float r2 = 0.f, w = 0.f;
+    template <class V>
+    static DICP_HD void pair(const Params& P, const Row& r, const V* c, V* a) {
+        V z[D];
+        V r2, w;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            z[k] = r.q[k] - c[k];
-            r2 = fmaf(z[k], z[k], r2);
-            w = fmaf(r.p[k], c[D + k], w);
+            z[k] = vsub(vbc<V>(r.q[k]), c[k]);
+            r2 = k == 0 ? vmul(z[k], z[k]) : vfma(z[k], z[k], r2);
+            w = k == 0 ? vmul(vbc<V>(r.p[k]), c[D + k]) : vfma(vbc<V>(r.p[k]), c[D + k], w);
         }
-        const float K = ex2_neg(r2);
-        float coef;
+        const V K = vex2n(r2);
+        V coef;
         if (ETA) {
-            float ze = 0.f;
+            V ze;
 #pragma unroll
-            for (int k = 0; k < D; ++k) ze = fmaf(z[k], r.p[k] - c[D + k], ze);
+            for (int k = 0; k < D; ++k) {
+                const V ek = vsub(vbc<V>(r.p[k]), c[D + k]);
+                ze = k == 0 ? vmul(z[k], ek) : vfma(z[k], ek, ze);
+            }
             // alpha w + eta s beta (z'.e) - eta^2 s alpha (beta r'^2 - (D+2))
             const float c1 = P.eta * P.s * P.beta, c2 = P.eta * P.eta * P.s * P.alpha;
-            coef = fmaf(P.alpha, w, fmaf(c1, ze, -c2 * fmaf(P.beta, r2, -(float)(D + 2))));
-            a[A_S0] += K;
-            a[A_R2] = fmaf(K, r2, a[A_R2]);
+            const V t1 = vfma(vbc<V>(-c2 * P.beta), r2, vbc<V>(c2 * (float)(D + 2)));
+            coef = vfma(vbc<V>(P.alpha), w, vfma(vbc<V>(c1), ze, t1));
+            a[A_S0] = vadd(a[A_S0], K);
+            a[A_R2] = vfma(K, r2, a[A_R2]);
         } else {
             coef = w;   // alpha applied in finish
         }
-        const float Kc = K * coef;
+        const V Kc = vmul(K, coef);
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            a[A_V + k] = fmaf(K, c[D + k], a[A_V + k]);
-            a[A_T + k] = fmaf(Kc, z[k], a[A_T + k]);
-            if (NEEDZ) a[A_Z + k] = fmaf(K, z[k], a[A_Z + k]);
+            a[A_V + k] = vfma(K, c[D + k], a[A_V + k]);
+            a[A_T + k] = vfma(Kc, z[k], a[A_T + k]);
+            if (NEEDZ) a[A_Z + k] = vfma(K, z[k], a[A_Z + k]);
         }
     }
     static DICP_HD void finish(const Params& P, int i, const Row& r, const float* a, float* scal) {
@@ -156,49 +196,40 @@ struct RhsQQ {
 // ------------------------------------------------------------------------------------------------
 template <int D, bool DIV, bool ETA, int R_ = DICP_RHS_R>
 struct RhsXQ {
-    using Params = RhsParams;
-    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
-    static constexpr int COLF4 = (2 * D + 3) / 4;
     static constexpr int A_V = 0, A_DS = D;
     static constexpr int A_Z = A_DS + (DIV ? 1 : 0);
     static constexpr int A_S0 = A_Z + (ETA ? D : 0);
     static constexpr int A_R2 = A_S0 + (ETA ? 1 : 0);
     static constexpr int NACC = A_R2 + (ETA ? 1 : 0);
     static constexpr int NSCAL = 1;   // dcost contribution
+    DICP_RHS_COMMON(2 * D)
     struct Row { float x[D]; };
 
-    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { RhsQQ<D, DIV, ETA, R_>::pack_col(P, j, N, c); }
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { pack_qp<D>(P, j, N, c, COLF4 * 4); }
     static DICP_HD void load_row(const Params& P, int i, Row& r) {
 #pragma unroll
         for (int k = 0; k < D; ++k) r.x[k] = (P.x[(size_t)i * D + k] - P.origin[k]) * P.kappa;
     }
-    static DICP_HD void init(float* a) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
-    }
-    static DICP_HD void combine(float* a, const float* b) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] += b[k];
-    }
-    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* a) {
-        float z[D];
-        float r2 = 0.f, pz = 0.f;
+    template <class V>
+    static DICP_HD void pair(const Params& P, const Row& r, const V* c, V* a) {
+        V z[D];
+        V r2, pz;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            z[k] = r.x[k] - c[k];
-            r2 = fmaf(z[k], z[k], r2);
-            if (DIV) pz = fmaf(c[D + k], z[k], pz);
+            z[k] = vsub(vbc<V>(r.x[k]), c[k]);
+            r2 = k == 0 ? vmul(z[k], z[k]) : vfma(z[k], z[k], r2);
+            if (DIV) pz = k == 0 ? vmul(c[D + k], z[k]) : vfma(c[D + k], z[k], pz);
         }
-        const float K = ex2_neg(r2);
+        const V K = vex2n(r2);
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            a[A_V + k] = fmaf(K, c[D + k], a[A_V + k]);
-            if (ETA) a[A_Z + k] = fmaf(K, z[k], a[A_Z + k]);
+            a[A_V + k] = vfma(K, c[D + k], a[A_V + k]);
+            if (ETA) a[A_Z + k] = vfma(K, z[k], a[A_Z + k]);
         }
-        if (DIV) a[A_DS] = fmaf(K, pz, a[A_DS]);
+        if (DIV) a[A_DS] = vfma(K, pz, a[A_DS]);
         if (ETA) {
-            a[A_S0] += K;
-            a[A_R2] = fmaf(K, r2, a[A_R2]);
+            a[A_S0] = vadd(a[A_S0], K);
+            a[A_R2] = vfma(K, r2, a[A_R2]);
         }
     }
     static DICP_HD void finish(const Params& P, int i, const Row& r, const float* a, float* scal) {
@@ -224,31 +255,13 @@ struct RhsXQ {
 // ------------------------------------------------------------------------------------------------
 template <int D, bool DIV, int R_ = DICP_RHS_R>
 struct AdjQQ {
-    using Params = RhsParams;
-    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
-    static constexpr int COLF4 = (4 * D + 3) / 4;
     static constexpr int A_GP = 0, A_GQ = D;
     static constexpr int NACC = 2 * D;
     static constexpr int NSCAL = 0;
+    DICP_RHS_COMMON(4 * D)
     struct Row { float q[D], p[D], a[D], u[D], gc; };
 
-    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) {
-#pragma unroll
-        for (int k = 0; k < COLF4 * 4; ++k) c[k] = 0.f;
-        if (j < N) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const size_t o = (size_t)j * D + k;
-                c[k] = (P.q[o] - P.origin[k]) * P.kappa;
-                c[D + k] = P.p[o];
-                c[2 * D + k] = P.a[o];
-                c[3 * D + k] = P.u[o];
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < D; ++k) c[k] = DICP_FAR;
-        }
-    }
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { pack_qpau<D>(P, j, N, c, COLF4 * 4); }
     static DICP_HD void load_row(const Params& P, int i, Row& r) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -260,46 +273,45 @@ struct AdjQQ {
         }
         r.gc = (DIV && P.gc != nullptr) ? P.gc[0] : 0.f;
     }
-    static DICP_HD void init(float* a) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
-    }
-    static DICP_HD void combine(float* a, const float* b) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] += b[k];
-    }
-    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* acc) {
-        float z[D], du[D];
-        float r2 = 0.f, w = 0.f, ap = 0.f, pa = 0.f, duz = 0.f, dpz = 0.f;
+    template <class V>
+    static DICP_HD void pair(const Params& P, const Row& r, const V* c, V* acc) {
+        V z[D], du[D], dp[D];
+        V r2, w, apa, duz, dpz;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            z[k] = r.q[k] - c[k];
-            r2 = fmaf(z[k], z[k], r2);
-            w = fmaf(r.p[k], c[D + k], w);
-            ap = fmaf(r.a[k], c[D + k], ap);          // a_i . p_j
-            pa = fmaf(r.p[k], c[2 * D + k], pa);      // p_i . a_j
-            du[k] = r.u[k] - c[3 * D + k];
-            duz = fmaf(du[k], z[k], duz);
-            if (DIV) dpz = fmaf(r.p[k] - c[D + k], z[k], dpz);
+            z[k] = vsub(vbc<V>(r.q[k]), c[k]);
+            du[k] = vsub(vbc<V>(r.u[k]), c[3 * D + k]);
+            if (DIV) dp[k] = vsub(vbc<V>(r.p[k]), c[D + k]);
+            r2 = k == 0 ? vmul(z[k], z[k]) : vfma(z[k], z[k], r2);
+            w = k == 0 ? vmul(vbc<V>(r.p[k]), c[D + k]) : vfma(vbc<V>(r.p[k]), c[D + k], w);
+            // (a_i . p_j) + (p_i . a_j)
+            apa = k == 0 ? vmul(vbc<V>(r.a[k]), c[D + k]) : vfma(vbc<V>(r.a[k]), c[D + k], apa);
+            apa = vfma(vbc<V>(r.p[k]), c[2 * D + k], apa);
+            duz = k == 0 ? vmul(du[k], z[k]) : vfma(du[k], z[k], duz);
+            if (DIV) dpz = k == 0 ? vmul(dp[k], z[k]) : vfma(dp[k], z[k], dpz);
         }
-        const float K = ex2_neg(r2);
-        // coefficient of z' in gq (sign folded: gq -= cz * z')
-        float cz = fmaf(P.alpha, ap + pa, P.s * P.beta * w * duz);
-        if (DIV) cz = fmaf(-r.gc * P.s * P.beta, dpz, cz);
-        const float Kcz = K * cz;
-        const float Ksw = K * P.s * w;
-        const float Kad = K * P.alpha * duz;
-        const float Kgz = DIV ? K * r.gc * P.alpha : 0.f;
-        const float Kgs = DIV ? K * r.gc * P.s : 0.f;
+        const V K = vex2n(r2);
+        // ncz = -(coefficient of z' in gq) = -[alpha (ap+pa) + s beta w (du.z')] (+ gc s beta (dp.z') if DIV)
+        const V swd = vmul(vmul(vbc<V>(-P.s * P.beta), w), duz);
+        V ncz = vfma(vbc<V>(-P.alpha), apa, swd);
+        if (DIV) ncz = vfma(vbc<V>(r.gc * P.s * P.beta), dpz, ncz);
+        const V Kncz = vmul(K, ncz);
+        const V Ksw = vmul(K, vmul(vbc<V>(P.s), w));
+        const V Kad = vmul(K, vmul(vbc<V>(P.alpha), duz));
+        V nKgz, nKgs;
+        if (DIV) {
+            nKgz = vmul(K, vbc<V>(-r.gc * P.alpha));
+            nKgs = vmul(K, vbc<V>(-r.gc * P.s));
+        }
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            float gp = fmaf(K, c[2 * D + k], acc[A_GP + k]);
-            gp = fmaf(Kad, c[D + k], gp);
-            float gq = fmaf(-Kcz, z[k], acc[A_GQ + k]);
-            gq = fmaf(Ksw, du[k], gq);
+            V gp = vfma(K, c[2 * D + k], acc[A_GP + k]);
+            gp = vfma(Kad, c[D + k], gp);
+            V gq = vfma(Kncz, z[k], acc[A_GQ + k]);
+            gq = vfma(Ksw, du[k], gq);
             if (DIV) {
-                gp = fmaf(-Kgz, z[k], gp);
-                gq = fmaf(-Kgs, r.p[k] - c[D + k], gq);
+                gp = vfma(nKgz, z[k], gp);
+                gq = vfma(nKgs, dp[k], gq);
             }
             acc[A_GP + k] = gp;
             acc[A_GQ + k] = gq;
@@ -326,13 +338,11 @@ struct AdjQQ {
 // ------------------------------------------------------------------------------------------------
 template <int D, bool DIV, int R_ = DICP_RHS_R>
 struct AdjXQx {
-    using Params = RhsParams;
-    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
-    static constexpr int COLF4 = (2 * D + 3) / 4;
     static constexpr int NACC = D, NSCAL = 0;
+    DICP_RHS_COMMON(2 * D)
     struct Row { float x[D], w[D], gc; };
 
-    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { RhsQQ<D, DIV, false, R_>::pack_col(P, j, N, c); }
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { pack_qp<D>(P, j, N, c, COLF4 * 4); }
     static DICP_HD void load_row(const Params& P, int i, Row& r) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -341,33 +351,27 @@ struct AdjXQx {
         }
         r.gc = (DIV && P.gc != nullptr) ? P.gc[0] : 0.f;
     }
-    static DICP_HD void init(float* a) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
-    }
-    static DICP_HD void combine(float* a, const float* b) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] += b[k];
-    }
-    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* acc) {
-        float z[D];
-        float r2 = 0.f, wp = 0.f, pz = 0.f;
+    template <class V>
+    static DICP_HD void pair(const Params& P, const Row& r, const V* c, V* acc) {
+        V z[D];
+        V r2, wp, pz;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            z[k] = r.x[k] - c[k];
-            r2 = fmaf(z[k], z[k], r2);
-            wp = fmaf(r.w[k], c[D + k], wp);
-            if (DIV) pz = fmaf(c[D + k], z[k], pz);
+            z[k] = vsub(vbc<V>(r.x[k]), c[k]);
+            r2 = k == 0 ? vmul(z[k], z[k]) : vfma(z[k], z[k], r2);
+            wp = k == 0 ? vmul(vbc<V>(r.w[k]), c[D + k]) : vfma(vbc<V>(r.w[k]), c[D + k], wp);
+            if (DIV) pz = k == 0 ? vmul(c[D + k], z[k]) : vfma(c[D + k], z[k], pz);
         }
-        const float K = ex2_neg(r2);
-        float cz = P.alpha * wp;
-        if (DIV) cz = fmaf(r.gc * P.s * P.beta, pz, cz);
-        const float Kcz = K * cz;
-        const float Kg = DIV ? K * r.gc * P.s : 0.f;
+        const V K = vex2n(r2);
+        V ncz = vmul(vbc<V>(-P.alpha), wp);
+        if (DIV) ncz = vfma(vbc<V>(-r.gc * P.s * P.beta), pz, ncz);
+        const V Kncz = vmul(K, ncz);
+        V Kg;
+        if (DIV) Kg = vmul(K, vbc<V>(r.gc * P.s));
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            float g = fmaf(-Kcz, z[k], acc[k]);
-            if (DIV) g = fmaf(Kg, c[D + k], g);
+            V g = vfma(Kncz, z[k], acc[k]);
+            if (DIV) g = vfma(Kg, c[D + k], g);
             acc[k] = g;
         }
     }
@@ -388,27 +392,12 @@ struct AdjXQx {
 // ------------------------------------------------------------------------------------------------
 template <int D, bool DIV, int R_ = DICP_RHS_R>
 struct AdjXQq {
-    using Params = RhsParams;
-    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
-    static constexpr int COLF4 = (2 * D + 3) / 4;
     static constexpr int A_GP = 0, A_GQ = D, A_S0 = 2 * D;
     static constexpr int NACC = 2 * D + (DIV ? 1 : 0), NSCAL = 0;
+    DICP_RHS_COMMON(2 * D)
     struct Row { float q[D], p[D], gc; };
 
-    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) {
-#pragma unroll
-        for (int k = 0; k < COLF4 * 4; ++k) c[k] = 0.f;
-        if (j < N) {
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                c[k] = (P.x[(size_t)j * D + k] - P.origin[k]) * P.kappa;
-                c[D + k] = P.wx[(size_t)j * D + k];
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < D; ++k) c[k] = DICP_FAR;
-        }
-    }
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { pack_xw<D>(P, j, N, c, COLF4 * 4); }
     static DICP_HD void load_row(const Params& P, int i, Row& r) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -417,37 +406,31 @@ struct AdjXQq {
         }
         r.gc = (DIV && P.gc != nullptr) ? P.gc[0] : 0.f;
     }
-    static DICP_HD void init(float* a) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
-    }
-    static DICP_HD void combine(float* a, const float* b) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] += b[k];
-    }
-    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* acc) {
-        float z[D];
-        float r2 = 0.f, wp = 0.f, pz = 0.f;
+    template <class V>
+    static DICP_HD void pair(const Params& P, const Row& r, const V* c, V* acc) {
+        V z[D];
+        V r2, wp, pz;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            z[k] = r.q[k] - c[k];
-            r2 = fmaf(z[k], z[k], r2);
-            wp = fmaf(c[D + k], r.p[k], wp);
-            if (DIV) pz = fmaf(r.p[k], z[k], pz);
+            z[k] = vsub(vbc<V>(r.q[k]), c[k]);
+            r2 = k == 0 ? vmul(z[k], z[k]) : vfma(z[k], z[k], r2);
+            wp = k == 0 ? vmul(c[D + k], vbc<V>(r.p[k])) : vfma(c[D + k], vbc<V>(r.p[k]), wp);
+            if (DIV) pz = k == 0 ? vmul(vbc<V>(r.p[k]), z[k]) : vfma(vbc<V>(r.p[k]), z[k], pz);
         }
-        const float K = ex2_neg(r2);
-        float cz = P.alpha * wp;
-        if (DIV) cz = fmaf(-r.gc * P.s * P.beta, pz, cz);
-        const float Kcz = K * cz;
-        const float Kg = DIV ? K * r.gc * P.alpha : 0.f;
+        const V K = vex2n(r2);
+        V ncz = vmul(vbc<V>(-P.alpha), wp);
+        if (DIV) ncz = vfma(vbc<V>(r.gc * P.s * P.beta), pz, ncz);
+        const V Kncz = vmul(K, ncz);
+        V nKg;
+        if (DIV) nKg = vmul(K, vbc<V>(-r.gc * P.alpha));
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            float gp = fmaf(K, c[D + k], acc[A_GP + k]);
-            if (DIV) gp = fmaf(-Kg, z[k], gp);
+            V gp = vfma(K, c[D + k], acc[A_GP + k]);
+            if (DIV) gp = vfma(nKg, z[k], gp);
             acc[A_GP + k] = gp;
-            acc[A_GQ + k] = fmaf(-Kcz, z[k], acc[A_GQ + k]);
+            acc[A_GQ + k] = vfma(Kncz, z[k], acc[A_GQ + k]);
         }
-        if (DIV) acc[A_S0] += K;
+        if (DIV) acc[A_S0] = vadd(acc[A_S0], K);
     }
     static DICP_HD void finish(const Params& P, int i, const Row& r, const float* acc, float*) {
 #pragma unroll
@@ -466,10 +449,8 @@ struct AdjXQq {
     }
 };
 
-
 // ================================================================================================================
-// Adjoint of the logdet model (eta = 1/lambda != 0).  Derivation in DESIGN.md §5.3; checked against torch autograd of
-// the oracle (tests/test_host_emulation.py).  Notation per pair (row m, column n), scaled z' = kappa (row - col):
+// Adjoint of the logdet model (eta = 1/lambda != 0).  Notation per pair (row m, column n), scaled z' = kappa (row - col):
 //   w = p_m.p_n, e = p_m - p_n, du = u_m - u_n, dA = a_m - a_n, t0 = beta r'^2 - D, t1 = beta r'^2 - (D+2), g = gc
 //   Phi  = (a_m.p_n + a_n.p_m) + eta alpha (dA.z') + alpha w (du.z') + eta s beta (z'.e)(du.z') - eta s (du.e)
 //          - eta^2 s alpha t1 (du.z') - g alpha (e.z') + 2 g eta s t0
@@ -479,14 +460,12 @@ struct AdjXQq {
 // ================================================================================================================
 template <int D, int R_ = DICP_RHS_R>
 struct AdjQQEta {
-    using Params = RhsParams;
-    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
-    static constexpr int COLF4 = (4 * D + 3) / 4;
     static constexpr int A_GP = 0, A_GQ = D;
     static constexpr int NACC = 2 * D, NSCAL = 0;
+    DICP_RHS_COMMON(4 * D)
     struct Row { float q[D], p[D], a[D], u[D], gc; };
 
-    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { AdjQQ<D, true, R_>::pack_col(P, j, N, c); }
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { pack_qpau<D>(P, j, N, c, COLF4 * 4); }
     static DICP_HD void load_row(const Params& P, int i, Row& r) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -498,48 +477,66 @@ struct AdjQQEta {
         }
         r.gc = (P.gc != nullptr && P.x == nullptr) ? P.gc[0] : 0.f;   // dcost comes from the (q,q) pass only when x is absent
     }
-    static DICP_HD void init(float* a) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
-    }
-    static DICP_HD void combine(float* a, const float* b) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] += b[k];
-    }
-    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* acc) {
-        const float eta = P.eta, s = P.s, al = P.alpha, be = P.beta, g = r.gc;
-        float z[D], e[D], du[D], dA[D];
-        float r2 = 0.f, w = 0.f, ze = 0.f, duz = 0.f, dAz = 0.f, due = 0.f, appa = 0.f;
+    template <class V>
+    static DICP_HD void pair(const Params& P, const Row& r, const V* c, V* acc) {
+        const float eta = P.eta, s = P.s, al = P.alpha, be = P.beta, g = r.gc, es = eta * s;
+        V z[D], e[D], du[D], dA[D];
+        V r2, w, ze, duz, dAz, due, appa;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            z[k] = r.q[k] - c[k];
-            e[k] = r.p[k] - c[D + k];
-            dA[k] = r.a[k] - c[2 * D + k];
-            du[k] = r.u[k] - c[3 * D + k];
-            r2 = fmaf(z[k], z[k], r2);
-            w = fmaf(r.p[k], c[D + k], w);
-            ze = fmaf(z[k], e[k], ze);
-            duz = fmaf(du[k], z[k], duz);
-            dAz = fmaf(dA[k], z[k], dAz);
-            due = fmaf(du[k], e[k], due);
-            appa = fmaf(r.a[k], c[D + k], fmaf(r.p[k], c[2 * D + k], appa));
+            z[k] = vsub(vbc<V>(r.q[k]), c[k]);
+            e[k] = vsub(vbc<V>(r.p[k]), c[D + k]);
+            dA[k] = vsub(vbc<V>(r.a[k]), c[2 * D + k]);
+            du[k] = vsub(vbc<V>(r.u[k]), c[3 * D + k]);
+            if (k == 0) {
+                r2 = vmul(z[k], z[k]);
+                w = vmul(vbc<V>(r.p[k]), c[D + k]);
+                ze = vmul(z[k], e[k]);
+                duz = vmul(du[k], z[k]);
+                dAz = vmul(dA[k], z[k]);
+                due = vmul(du[k], e[k]);
+                appa = vmul(vbc<V>(r.p[k]), c[2 * D + k]);
+            } else {
+                r2 = vfma(z[k], z[k], r2);
+                w = vfma(vbc<V>(r.p[k]), c[D + k], w);
+                ze = vfma(z[k], e[k], ze);
+                duz = vfma(du[k], z[k], duz);
+                dAz = vfma(dA[k], z[k], dAz);
+                due = vfma(du[k], e[k], due);
+                appa = vfma(vbc<V>(r.p[k]), c[2 * D + k], appa);
+            }
+            appa = vfma(vbc<V>(r.a[k]), c[D + k], appa);
         }
-        const float K = ex2_neg(r2);
-        const float t0 = fmaf(be, r2, -(float)D), t1 = fmaf(be, r2, -(float)(D + 2));
-        const float es = eta * s;
-        const float c_du = s * w + es * al * ze - es * es * t1;
-        const float c_e = es * al * duz - g * s;
-        const float Phi = appa + eta * al * dAz + al * w * duz + es * be * ze * duz - es * due - eta * es * al * t1 * duz
-                          - g * al * ze + 2.f * g * es * t0;
-        const float Cz = -2.f * es * es * be * duz + 4.f * g * es * al - al * Phi;
-        const float pz = es * be * duz - g * al;           // coefficient of z' in gp
-        const float pp = al * duz;                         // coefficient of p_n in gp
+        const V K = vex2n(r2);
+        const V t0 = vfma(vbc<V>(be), r2, vbc<V>(-(float)D));
+        const V t1 = vfma(vbc<V>(be), r2, vbc<V>(-(float)(D + 2)));
+        // c_du = s w + eta s alpha (z'.e) - (eta s)^2 t1
+        const V c_du = vfma(vbc<V>(s), w, vfma(vbc<V>(es * al), ze, vmul(vbc<V>(-es * es), t1)));
+        // c_e = eta s alpha (du.z') - g s
+        const V c_e = vfma(vbc<V>(es * al), duz, vbc<V>(-g * s));
+        // Phi
+        V Phi = vfma(vbc<V>(eta * al), dAz, appa);
+        Phi = vfma(vmul(vbc<V>(al), w), duz, Phi);
+        Phi = vfma(vmul(vbc<V>(es * be), ze), duz, Phi);
+        Phi = vfma(vbc<V>(-es), due, Phi);
+        Phi = vfma(vmul(vbc<V>(-eta * es * al), t1), duz, Phi);
+        Phi = vfma(vbc<V>(-g * al), ze, Phi);
+        Phi = vfma(vbc<V>(2.f * g * es), t0, Phi);
+        // Cz = -2 (eta s)^2 beta (du.z') + 4 g eta s alpha - alpha Phi
+        const V Cz = vfma(vbc<V>(-al), Phi, vfma(vbc<V>(-2.f * es * es * be), duz, vbc<V>(4.f * g * es * al)));
+        const V pz = vfma(vbc<V>(es * be), duz, vbc<V>(-g * al));       // coefficient of z' in gp
+        const V pp = vmul(vbc<V>(al), duz);                            // coefficient of p_n in gp
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            const float gq = es * dA[k] + c_du * du[k] + c_e * e[k] + Cz * z[k];
-            const float gp = c[2 * D + k] + pp * c[D + k] + pz * z[k] - es * du[k];
-            acc[A_GQ + k] = fmaf(K, gq, acc[A_GQ + k]);
-            acc[A_GP + k] = fmaf(K, gp, acc[A_GP + k]);
+            V gq = vmul(vbc<V>(es), dA[k]);
+            gq = vfma(c_du, du[k], gq);
+            gq = vfma(c_e, e[k], gq);
+            gq = vfma(Cz, z[k], gq);
+            V gp = vfma(pp, c[D + k], c[2 * D + k]);
+            gp = vfma(pz, z[k], gp);
+            gp = vfma(vbc<V>(-es), du[k], gp);
+            acc[A_GQ + k] = vfma(K, gq, acc[A_GQ + k]);
+            acc[A_GP + k] = vfma(K, gp, acc[A_GP + k]);
         }
     }
     static DICP_HD void finish(const Params& P, int i, const Row& r, const float* acc, float*) {
@@ -562,13 +559,11 @@ struct AdjQQEta {
 //   gx_k = sum_j K { eta s wx_k + g s p_j + (2 g eta s alpha - alpha psi) z' }
 template <int D, int R_ = DICP_RHS_R>
 struct AdjXQxEta {
-    using Params = RhsParams;
-    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
-    static constexpr int COLF4 = (2 * D + 3) / 4;
     static constexpr int NACC = D, NSCAL = 0;
+    DICP_RHS_COMMON(2 * D)
     struct Row { float x[D], w[D], gc; };
 
-    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { RhsQQ<D, true, true, R_>::pack_col(P, j, N, c); }
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { pack_qp<D>(P, j, N, c, COLF4 * 4); }
     static DICP_HD void load_row(const Params& P, int i, Row& r) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -577,32 +572,38 @@ struct AdjXQxEta {
         }
         r.gc = P.gc != nullptr ? P.gc[0] : 0.f;
     }
-    static DICP_HD void init(float* a) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
-    }
-    static DICP_HD void combine(float* a, const float* b) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] += b[k];
-    }
-    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* acc) {
+    template <class V>
+    static DICP_HD void pair(const Params& P, const Row& r, const V* c, V* acc) {
         const float es = P.eta * P.s, al = P.alpha, g = r.gc;
-        float z[D];
-        float r2 = 0.f, wp = 0.f, wz = 0.f, pz = 0.f;
+        V z[D];
+        V r2, wp, wz, pz;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            z[k] = r.x[k] - c[k];
-            r2 = fmaf(z[k], z[k], r2);
-            wp = fmaf(r.w[k], c[D + k], wp);
-            wz = fmaf(r.w[k], z[k], wz);
-            pz = fmaf(c[D + k], z[k], pz);
+            z[k] = vsub(vbc<V>(r.x[k]), c[k]);
+            if (k == 0) {
+                r2 = vmul(z[k], z[k]);
+                wp = vmul(vbc<V>(r.w[k]), c[D + k]);
+                wz = vmul(vbc<V>(r.w[k]), z[k]);
+                pz = vmul(c[D + k], z[k]);
+            } else {
+                r2 = vfma(z[k], z[k], r2);
+                wp = vfma(vbc<V>(r.w[k]), c[D + k], wp);
+                wz = vfma(vbc<V>(r.w[k]), z[k], wz);
+                pz = vfma(c[D + k], z[k], pz);
+            }
         }
-        const float K = ex2_neg(r2);
-        const float psi = wp + P.eta * al * wz + g * (al * pz + es * fmaf(P.beta, r2, -(float)D));
-        const float cz = 2.f * g * es * al - al * psi;
+        const V K = vex2n(r2);
+        // psi = wp + eta al wz + g al pz + g es (beta r2 - D)
+        V psi = vfma(vbc<V>(P.eta * al), wz, wp);
+        psi = vfma(vbc<V>(g * al), pz, psi);
+        psi = vfma(vbc<V>(g * es * P.beta), r2, vadd(psi, vbc<V>(-g * es * (float)D)));
+        const V cz = vfma(vbc<V>(-al), psi, vbc<V>(2.f * g * es * al));
 #pragma unroll
-        for (int k = 0; k < D; ++k)
-            acc[k] = fmaf(K, es * r.w[k] + g * P.s * c[D + k] + cz * z[k], acc[k]);
+        for (int k = 0; k < D; ++k) {
+            V t = vfma(vbc<V>(g * P.s), c[D + k], vbc<V>(es * r.w[k]));
+            t = vfma(cz, z[k], t);
+            acc[k] = vfma(K, t, acc[k]);
+        }
     }
     static DICP_HD void finish(const Params& P, int i, const Row&, const float* acc, float*) {
 #pragma unroll
@@ -619,14 +620,12 @@ struct AdjXQxEta {
 //   gp_j = sum_k K { wx_k - g alpha zeta' }
 template <int D, int R_ = DICP_RHS_R>
 struct AdjXQqEta {
-    using Params = RhsParams;
-    static constexpr int THREADS = DICP_RHS_THREADS, MINB = DICP_RHS_MINB, R = R_, TILE = DICP_RHS_TILE;
-    static constexpr int COLF4 = (2 * D + 3) / 4;
     static constexpr int A_GP = 0, A_GQ = D;
     static constexpr int NACC = 2 * D, NSCAL = 0;
+    DICP_RHS_COMMON(2 * D)
     struct Row { float q[D], p[D], gc; };
 
-    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { AdjXQq<D, true, R_>::pack_col(P, j, N, c); }
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { pack_xw<D>(P, j, N, c, COLF4 * 4); }
     static DICP_HD void load_row(const Params& P, int i, Row& r) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -635,33 +634,38 @@ struct AdjXQqEta {
         }
         r.gc = P.gc != nullptr ? P.gc[0] : 0.f;
     }
-    static DICP_HD void init(float* a) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] = 0.f;
-    }
-    static DICP_HD void combine(float* a, const float* b) {
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) a[k] += b[k];
-    }
-    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* acc) {
+    template <class V>
+    static DICP_HD void pair(const Params& P, const Row& r, const V* c, V* acc) {
         const float es = P.eta * P.s, al = P.alpha, g = r.gc;
-        float z[D];
-        float r2 = 0.f, wp = 0.f, wz = 0.f, pz = 0.f;
+        V z[D];
+        V r2, wp, wz, pz;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            z[k] = r.q[k] - c[k];
-            r2 = fmaf(z[k], z[k], r2);
-            wp = fmaf(c[D + k], r.p[k], wp);
-            wz = fmaf(c[D + k], z[k], wz);
-            pz = fmaf(r.p[k], z[k], pz);
+            z[k] = vsub(vbc<V>(r.q[k]), c[k]);
+            if (k == 0) {
+                r2 = vmul(z[k], z[k]);
+                wp = vmul(c[D + k], vbc<V>(r.p[k]));
+                wz = vmul(c[D + k], z[k]);
+                pz = vmul(vbc<V>(r.p[k]), z[k]);
+            } else {
+                r2 = vfma(z[k], z[k], r2);
+                wp = vfma(c[D + k], vbc<V>(r.p[k]), wp);
+                wz = vfma(c[D + k], z[k], wz);
+                pz = vfma(vbc<V>(r.p[k]), z[k], pz);
+            }
         }
-        const float K = ex2_neg(r2);
-        const float psi = wp - P.eta * al * wz + g * (-al * pz + es * fmaf(P.beta, r2, -(float)D));
-        const float cz = 2.f * g * es * al - al * psi;
+        const V K = vex2n(r2);
+        V psi = vfma(vbc<V>(-P.eta * al), wz, wp);
+        psi = vfma(vbc<V>(-g * al), pz, psi);
+        psi = vfma(vbc<V>(g * es * P.beta), r2, vadd(psi, vbc<V>(-g * es * (float)D)));
+        const V cz = vfma(vbc<V>(-al), psi, vbc<V>(2.f * g * es * al));
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            acc[A_GQ + k] = fmaf(K, -es * c[D + k] - g * P.s * r.p[k] + cz * z[k], acc[A_GQ + k]);
-            acc[A_GP + k] = fmaf(K, c[D + k] - g * al * z[k], acc[A_GP + k]);
+            V tq = vfma(vbc<V>(-es), c[D + k], vbc<V>(-g * P.s * r.p[k]));
+            tq = vfma(cz, z[k], tq);
+            acc[A_GQ + k] = vfma(K, tq, acc[A_GQ + k]);
+            const V tp = vfma(vbc<V>(-g * al), z[k], c[D + k]);
+            acc[A_GP + k] = vfma(K, tp, acc[A_GP + k]);
         }
     }
     static DICP_HD void finish(const Params& P, int i, const Row&, const float* acc, float*) {

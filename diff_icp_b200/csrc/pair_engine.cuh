@@ -30,6 +30,12 @@ namespace dicp {
 
 static constexpr int kStages = 3;
 
+#ifndef DICP_COL_UNROLL
+#define DICP_COL_UNROLL 2
+#endif
+#define DICP_STR2(x) #x
+#define DICP_STR(x) DICP_STR2(x)
+
 struct PairPlan {
     int M, N;
     int ntiles;      // column tiles of Op::TILE
@@ -99,7 +105,7 @@ pair_kernel(typename Op::Params prm, const float4* __restrict__ colpack, float* 
         const float4* sp = stage[s];
         const int left = N - (t0 + t) * TILE;            // the last tile may be partial: padded records are never visited
         const int ncol = left < TILE ? left : TILE;
-#pragma unroll 2
+_Pragma(DICP_STR(unroll DICP_COL_UNROLL))
         for (int j = 0; j < ncol; ++j) {
             float c[CF4 * 4];
 #pragma unroll
@@ -144,6 +150,147 @@ pair_kernel(typename Op::Params prm, const float4* __restrict__ colpack, float* 
                 float* dst = part + ((size_t)blockIdx.y * M + i) * NACC;
 #pragma unroll
                 for (int k = 0; k < NACC; ++k) dst[k] = acc[r][k];
+            }
+        }
+    }
+}
+
+// ---- packed variant: two columns per lane-pair (FFMA2 / FADD2 / FMUL2) -----------------------------------------
+// Column records are stored per PAIR of columns, interleaved: pair P holds NF float2 = (c_{2P}[k], c_{2P+1}[k]), so one
+// 64-bit register carries the same field of two columns and a float4 LDS delivers two such fields.
+template <class Op>
+__global__ void pack_kernel_p(typename Op::Params prm, float* __restrict__ colpack, int N, int Npad) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Npad) return;
+    float c[Op::COLF4 * 4];
+    Op::pack_col(prm, j, N, c);
+    float* dst = colpack + (size_t)(j >> 1) * (2 * Op::NF) + (j & 1);
+#pragma unroll
+    for (int k = 0; k < Op::NF; ++k) dst[2 * k] = c[k];
+}
+
+template <class Op>
+__global__ void __launch_bounds__(Op::THREADS, Op::MINB)
+pair_kernel_p(typename Op::Params prm, const float4* __restrict__ colpack, float* __restrict__ part,
+              float* __restrict__ blockscal, int M, int N, int ntiles) {
+    constexpr int R = Op::R, TILE = Op::TILE, NF = Op::NF, NACC = Op::NACC, NSCAL = Op::NSCAL;
+    static_assert(NF % 2 == 0 && TILE % 2 == 0, "packed records");
+    constexpr int TP = TILE / 2;              // column pairs per tile
+    constexpr int PF4 = NF / 2;               // float4 per column pair
+    constexpr uint32_t STAGE_BYTES = TP * PF4 * 16;
+    __shared__ __align__(128) float4 stage[kStages][TP * PF4];
+    __shared__ __align__(8) uint64_t full[kStages];
+    __shared__ float red[32];
+
+    const int tid = threadIdx.x;
+    const int nsplit = gridDim.y;
+    const int t0 = (int)(((long long)blockIdx.y * ntiles) / nsplit);
+    const int t1 = (int)(((long long)(blockIdx.y + 1) * ntiles) / nsplit);
+    const int nt = t1 - t0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s)
+            if (s < nt) {
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                bulk_g2s(stage[s], colpack + (size_t)(t0 + s) * TP * PF4, STAGE_BYTES, &full[s]);
+            }
+    }
+
+    typename Op::Row row[R];
+    F2 acc[R][NACC];
+    const int rbase = blockIdx.x * (Op::THREADS * R) + tid;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int i = rbase + r * Op::THREADS;
+        Op::load_row(prm, i < M ? i : M - 1, row[r]);
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[r][k] = f2(0.f, 0.f);
+    }
+
+    for (int t = 0; t < nt; ++t) {
+        const int s = t % kStages;
+        mbar_wait(&full[s], (uint32_t)((t / kStages) & 1));
+        const float4* sp = stage[s];
+        const int left = N - (t0 + t) * TILE;
+        const int ncol = left < TILE ? left : TILE;
+        const int npair = ncol >> 1;
+_Pragma(DICP_STR(unroll DICP_COL_UNROLL))
+        for (int P = 0; P < npair; ++P) {
+            F2 c[NF];
+#pragma unroll
+            for (int k = 0; k < PF4; ++k) {
+                float4 v = sp[P * PF4 + k];
+                c[2 * k] = f2(v.x, v.y);
+                c[2 * k + 1] = f2(v.z, v.w);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) Op::template pair<F2>(prm, row[r], c, acc[r]);
+        }
+        if (ncol & 1) {                       // odd trailing column of the whole problem: one-column form
+            float c[NF];
+#pragma unroll
+            for (int k = 0; k < PF4; ++k) {
+                float4 v = sp[npair * PF4 + k];
+                c[2 * k] = v.x;
+                c[2 * k + 1] = v.z;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float tmp[NACC];
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) tmp[k] = 0.f;
+                Op::template pair<float>(prm, row[r], c, tmp);
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) acc[r][k] = vadd(acc[r][k], f2(tmp[k], 0.f));
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && t + kStages < nt) {
+            mbar_expect_tx(&full[s], STAGE_BYTES);
+            bulk_g2s(stage[s], colpack + (size_t)(t0 + t + kStages) * TP * PF4, STAGE_BYTES, &full[s]);
+        }
+    }
+
+    float accf[R][NACC];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) accf[r][k] = f2_sum(acc[r][k]);
+
+    if (nsplit == 1) {
+        float scal[NSCAL > 0 ? NSCAL : 1];
+#pragma unroll
+        for (int k = 0; k < NSCAL; ++k) scal[k] = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int i = rbase + r * Op::THREADS;
+            if (i < M) {
+                float rs[NSCAL > 0 ? NSCAL : 1];
+                Op::finish(prm, i, row[r], accf[r], rs);
+#pragma unroll
+                for (int k = 0; k < NSCAL; ++k) scal[k] += rs[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NSCAL; ++k) {
+            float v = block_sum(scal[k], red);
+            if (tid == 0) blockscal[(size_t)blockIdx.x * NSCAL + k] = v;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int i = rbase + r * Op::THREADS;
+            if (i < M) {
+                float* dst = part + ((size_t)blockIdx.y * M + i) * NACC;
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) dst[k] = accf[r][k];
             }
         }
     }
@@ -220,7 +367,8 @@ template <class Op>
 inline int op_occupancy() {
     static int occ = [] {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, pair_kernel<Op>, Op::THREADS, 0);
+        if constexpr (Op::PACKED) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, pair_kernel_p<Op>, Op::THREADS, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, pair_kernel<Op>, Op::THREADS, 0);
         return o > 0 ? o : 1;
     }();
     return occ;
@@ -283,9 +431,14 @@ inline int run_pair(const typename Op::Params& prm, int M, int N, float* scal_ou
     float* part = (float*)(base + p.col_bytes);
     float* blockscal = (float*)(base + p.col_bytes + p.part_bytes);
     const int Npad = p.ntiles * Op::TILE;
-    pack_kernel<Op><<<(Npad + 255) / 256, 256, 0, st>>>(prm, colpack, N, Npad);
     dim3 grid(p.nrb, p.nsplit);
-    pair_kernel<Op><<<grid, Op::THREADS, 0, st>>>(prm, colpack, part, blockscal, M, N, p.ntiles);
+    if constexpr (Op::PACKED) {
+        pack_kernel_p<Op><<<(Npad + 255) / 256, 256, 0, st>>>(prm, (float*)colpack, N, Npad);
+        pair_kernel_p<Op><<<grid, Op::THREADS, 0, st>>>(prm, colpack, part, blockscal, M, N, p.ntiles);
+    } else {
+        pack_kernel<Op><<<(Npad + 255) / 256, 256, 0, st>>>(prm, colpack, N, Npad);
+        pair_kernel<Op><<<grid, Op::THREADS, 0, st>>>(prm, colpack, part, blockscal, M, N, p.ntiles);
+    }
     launch_counter() += 2;
     int nblk = p.nrb;
     if (p.nsplit > 1) {
@@ -315,7 +468,8 @@ inline void run_pair_host(const typename Op::Params& prm, int M, int N, float* s
         for (int j = 0; j < N; ++j) {
             float c[Op::COLF4 * 4];
             Op::pack_col(prm, j, N, c);
-            Op::pair(prm, row, c, acc);
+            if constexpr (Op::PACKED) Op::template pair<float>(prm, row, c, acc);
+            else Op::pair(prm, row, c, acc);
         }
         float rs[Op::NSCAL > 0 ? Op::NSCAL : 1] = {0};
         Op::finish(prm, i, row, acc, rs);
