@@ -33,7 +33,7 @@
 #define DICP_RHS_R 2
 #endif
 #ifndef DICP_RHS_THREADS
-#define DICP_RHS_THREADS 128
+#define DICP_RHS_THREADS 64
 #endif
 #ifndef DICP_RHS_TILE
 #define DICP_RHS_TILE 128

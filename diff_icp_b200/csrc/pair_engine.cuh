@@ -30,6 +30,9 @@ namespace dicp {
 
 static constexpr int kStages = 3;
 
+#ifndef DICP_WAVES
+#define DICP_WAVES 4          // column splits are chosen so that the grid is about this many waves of resident CTAs
+#endif
 #ifndef DICP_COL_UNROLL
 #define DICP_COL_UNROLL 2
 #endif
@@ -384,7 +387,7 @@ inline size_t pair_workspace_bound(long long M, long long N) {
     if (M < 1) M = 1;
     if (N < 1) N = 1;
     size_t col = align_up((size_t)(N + 256) * kMaxColF4 * 16, 256);
-    long long rows_a = 2 * sms * kMaxOcc * kMaxRowsPerCta + M;      // nsplit <= 2*slots/nrb
+    long long rows_a = (long long)DICP_WAVES * sms * kMaxOcc * kMaxRowsPerCta + M;      // nsplit <= waves*slots/nrb
     long long rows_b = M * ((N + 127) / 128);                        // nsplit <= number of column tiles
     long long rows = rows_a < rows_b ? rows_a : rows_b;
     size_t part = align_up((size_t)rows * kMaxAcc * 4, 256);
@@ -405,7 +408,7 @@ inline PairPlan make_plan(int M, int N) {
     int occ = op_occupancy<Op>();
     if (occ > kMaxOcc) occ = kMaxOcc;
     const long long slots = (long long)device_info().sms * occ;
-    long long s = (2 * slots) / p.nrb;
+    long long s = (DICP_WAVES * slots) / p.nrb;
     if (s < 1) s = 1;
     if (s > p.ntiles) s = p.ntiles;
     if ((long long)p.nrb >= slots) s = 1;
