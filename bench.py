@@ -378,9 +378,9 @@ def kernel_roofline(args, LM, q, p, dev, ops):
 
 # algorithmic FP32 instruction counts per pair, D = 3 (hand count of the formulas in csrc/ops_rhs.cuh)
 ALG_WORK = {
-    "classic": {"fwd_fp32": 16, "adj_fp32": 42},
-    "hybrid": {"fwd_fp32": 19, "adj_fp32": 58},
-    "logdet": {"fwd_fp32": 31, "adj_fp32": 88},
+    "classic": {"fwd_fp32": 16, "adj_fp32": 41},
+    "hybrid": {"fwd_fp32": 19, "adj_fp32": 56},
+    "logdet": {"fwd_fp32": 30, "adj_fp32": 83},
 }
 
 
