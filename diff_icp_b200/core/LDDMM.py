@@ -27,9 +27,10 @@ from ..tools.optim import LBFGS_optimization
 from ..tools.integrators import EulerIntegrator, RalstonIntegrator
 
 
-class ShootResult(list):
-    """The reference's "shoot" variable (list of nt+1 tuples (q, p, cost[, x])), plus the Hamiltonian at t = 0
-    as a differentiable 0-d tensor (``H0``) so that trajloss needs no extra kernel sum."""
+class ShootResult(shooting.LazyStates):
+    """The reference's "shoot" variable (sequence of nt+1 tuples (q, p, cost[, x]); len(), indexing, slicing and
+    iteration like the reference's list), plus the Hamiltonian at t = 0 as a differentiable 0-d tensor (``H0``) so that
+    trajloss needs no extra kernel sum."""
 
     H0 = None
 
@@ -178,9 +179,9 @@ class LDDMMModel:
             return self.Integrator(self.ODE, (q0, p0, cost0), self.nt)
         sp = self._spec_for(q0.shape[0], 0 if x0 is None else x0.shape[0], q0.device)
         states, H0 = shooting.shoot(sp, q0, p0, x0, use_graph=self.use_cuda_graph)
-        res = ShootResult(states)
-        res.H0 = H0
-        return res
+        states.__class__ = ShootResult
+        states.H0 = H0
+        return states
 
     def BasicQuadLossFunctor(self, y, cmul=1):
         """x -> cmul/2 |x-y|^2 (reference: core/LDDMM.py:303-314)."""

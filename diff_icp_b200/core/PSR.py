@@ -264,9 +264,10 @@ class DiffPSR(MultiPSR):
         return dataloss_func
 
     # number of frames registered concurrently (one Python thread + one CUDA stream each). Frames are independent
-    # (core/PSR.py:528), and every frame's computation is deterministic, so results do not depend on this setting;
-    # it only fills the GPU when single frames are too small to do so (SURVEY.md §7 "small-problem regime").
-    frame_workers = 16
+    # (core/PSR.py:528), and every frame's computation is deterministic, so results do not depend on this setting
+    # (asserted bit for bit in the tests).  Measured on B200 with 64 frames x 10k points it does NOT pay off: the
+    # per-frame L-BFGS is bound by host Python time, which threads serialise on the GIL -- hence the default of 1.
+    frame_workers = 1
 
     def _register_frame(self, k, nmax, tol):
         """Optimise a0[k] and collect everything Reg_opt's bookkeeping needs (no shared state is written here)."""

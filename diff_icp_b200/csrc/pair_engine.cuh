@@ -150,9 +150,9 @@ _Pragma(DICP_STR(unroll DICP_COL_UNROLL))
         for (int r = 0; r < R; ++r) {
             int i = rbase + r * Op::THREADS;
             if (i < M) {
-                float* dst = part + ((size_t)blockIdx.y * M + i) * NACC;
+                float* dst = part + (size_t)blockIdx.y * NACC * M + i;       // layout [split][k][row]: coalesced
 #pragma unroll
-                for (int k = 0; k < NACC; ++k) dst[k] = acc[r][k];
+                for (int k = 0; k < NACC; ++k) dst[(size_t)k * M] = acc[r][k];
             }
         }
     }
@@ -291,9 +291,9 @@ _Pragma(DICP_STR(unroll DICP_COL_UNROLL))
         for (int r = 0; r < R; ++r) {
             int i = rbase + r * Op::THREADS;
             if (i < M) {
-                float* dst = part + ((size_t)blockIdx.y * M + i) * NACC;
+                float* dst = part + (size_t)blockIdx.y * NACC * M + i;       // layout [split][k][row]: coalesced
 #pragma unroll
-                for (int k = 0; k < NACC; ++k) dst[k] = accf[r][k];
+                for (int k = 0; k < NACC; ++k) dst[(size_t)k * M] = accf[r][k];
             }
         }
     }
@@ -311,14 +311,14 @@ __global__ void finish_kernel(typename Op::Params prm, const float* __restrict__
     for (int k = 0; k < NSCAL; ++k) rs[k] = 0.f;
     if (i < M) {
         float acc[NACC];
-        const float* src = part + (size_t)i * NACC;
+        const float* src = part + i;
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) acc[k] = src[k];
+        for (int k = 0; k < NACC; ++k) acc[k] = src[(size_t)k * M];
         for (int s = 1; s < nsplit; ++s) {
-            src = part + ((size_t)s * M + i) * NACC;
+            src = part + (size_t)s * NACC * M + i;
             float b[NACC];
 #pragma unroll
-            for (int k = 0; k < NACC; ++k) b[k] = src[k];
+            for (int k = 0; k < NACC; ++k) b[k] = src[(size_t)k * M];
             Op::combine(acc, b);
         }
         typename Op::Row row;

@@ -257,14 +257,41 @@ class _ShootFn(torch.autograd.Function):
         return None, None, gq, gp, (gx if ctx.has_x else None)
 
 
+class LazyStates:
+    """The reference's "shoot" variable -- a list of nt+1 tuples (q, p, cost[, x]) -- whose tuples are views of the
+    trajectory tensor created on first access (most callers only read shoot[-1] and shoot[0])."""
+
+    def __init__(self, spec, traj, has_x):
+        self._spec, self._traj, self._has_x = spec, traj, has_x
+        self._cache = {}
+
+    def __len__(self):
+        return self._spec.nt + 1
+
+    def __getitem__(self, t):
+        if isinstance(t, slice):
+            return [self[i] for i in range(*t.indices(len(self)))]
+        n = len(self)
+        if t < 0:
+            t += n
+        if not 0 <= t < n:
+            raise IndexError("shoot index out of range")
+        st = self._cache.get(t)
+        if st is None:
+            q, p, x, cost = _views(self._spec, self._traj[t])
+            st = (q, p, cost, x) if self._has_x else (q, p, cost)
+            self._cache[t] = st
+        return st
+
+    def __iter__(self):
+        return (self[t] for t in range(len(self)))
+
+
 def shoot(spec: ShootSpec, q0, p0, x0=None, use_graph=False):
-    """Returns (list of nt+1 state tuples like the reference's Shoot, H(q0,p0)) with autograd attached."""
+    """Returns (states, H(q0,p0)): `states` behaves like the reference's list of nt+1 state tuples, with autograd
+    attached to every entry."""
     _lib.require_cuda(q0, p0, x0)
     q0c, p0c = q0.contiguous(), p0.contiguous()
     x0c = None if x0 is None else x0.contiguous()
     traj, H0 = _ShootFn.apply(spec, use_graph, q0c, p0c, x0c)
-    states = []
-    for t in range(spec.nt + 1):
-        q, p, x, cost = _views(spec, traj[t])
-        states.append((q, p, cost) if x0 is None else (q, p, cost, x))
-    return states, H0
+    return LazyStates(spec, traj, x0 is not None), H0

@@ -1,0 +1,107 @@
+"""GPU: the CUDA path at BASELINE.json's full sizes (20k x 20k, 3-D), checked through size-independent properties and
+row-subset comparisons with the oracle; plus a mid-size (5k) full gradient check that exercises the column-split grid."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+M_FULL = 20000
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def spec():
+    return {"device": dev(), "dtype": torch.float32}
+
+
+def test_kernel_sum_properties_at_20k():
+    from diff_icp_b200.tools.kernel import GaussKernel
+    from oracle.kernels import GaussOracle
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(M_FULL, 3, generator=g)
+    b1, b2 = torch.randn(M_FULL, 3, generator=g), torch.randn(M_FULL, 3, generator=g)
+    sig = 0.1
+    K = GaussKernel(sig, 3, spec=spec())
+    xd, b1d, b2d = x.to(dev()), b1.to(dev()), b2.to(dev())
+    r1, r2 = K.KRed(xd, xd, b1d), K.KRed(xd, xd, b2d)
+    r12 = K.KRed(xd, xd, 0.7 * b1d + b2d)
+    assert float((r12 - (0.7 * r1 + r2)).abs().max() / r12.abs().max()) < 1e-5                    # linearity in b
+    lhs, rhs = float((b2d * r1).sum()), float((b1d * r2).sum())
+    assert abs(lhs - rhs) < 1e-4 * max(abs(lhs), float((b2d.abs() * r1.abs()).sum()) * 1e-3)      # symmetry of K
+    rows = torch.arange(0, M_FULL, 313)                                                           # 64 rows vs all columns
+    ref = GaussOracle(sig, 3).KRed(x[rows].double(), x.double(), b1.double())
+    assert relerr(r1[rows.to(dev())].cpu().numpy(), ref.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("version", ["classic", "hybrid", "logdet"])
+def test_rhs_properties_at_20k(version):
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from oracle.lddmm import LDDMMOracle
+    g = torch.Generator().manual_seed(1)
+    q = torch.rand(M_FULL, 3, generator=g)
+    p = 1e-2 * torch.randn(M_FULL, 3, generator=g)
+    LM = LDDMMModel(sigma=0.1, D=3, lambd=50.0, spec=spec(), version=version, scheme="Euler", nt=4)
+    vq, dp, dcost = LM.ODE(q.to(dev()), p.to(dev()), torch.zeros(1, device=dev()))
+    if version != "logdet":
+        # Newton's third law of the classic interaction: sum_i dp_i = 0 (the pair term is antisymmetric)
+        assert float(dp.sum(0).abs().max()) < 1e-5 * float(dp.abs().sum(0).max())
+    # linearity of vq in p for eta = 0, affine for logdet: vq(2p) - vq(p) = KRed(q,q,p)
+    vq2, _, _ = LM.ODE(q.to(dev()), (2 * p).to(dev()), torch.zeros(1, device=dev()))
+    kr = LM.Kernel.KRed(q.to(dev()), q.to(dev()), p.to(dev()))
+    assert float((vq2 - vq - kr).abs().max() / kr.abs().max()) < 2e-5
+    # a row subset against the oracle evaluated on those rows (x = subset of q, same formulas as v / mdivsum)
+    rows = torch.arange(0, M_FULL, 625)
+    OR = LDDMMOracle(sigma=0.1, D=3, lambd=50.0, version=version)
+    ref_v = OR.v(q[rows].double(), q.double(), p.double())
+    assert relerr(vq[rows.to(dev())].cpu().numpy(), ref_v.numpy()) < 1e-5
+    ref_G = OR.K.GenDKRed(q[rows].double(), q.double(), p.double(), p[rows].double())
+    if version == "logdet":
+        ref_G = ref_G - OR.eta * OR.K.HessKRed(q[rows].double(), q.double(), p.double(), p[rows].double()) \
+            - OR.eta ** 2 * OR.K.GradLapKRed(q[rows].double(), q.double())
+    assert relerr(dp[rows.to(dev())].cpu().numpy(), (-ref_G).numpy()) < 1e-5
+
+
+def test_em_row_pass_at_20k_by_20k():
+    """E step of the two-set configuration (20k points x 20k frozen centroids): targets are convex combinations of the
+    centroids, sum_c gamma = 1, and a row subset matches the oracle."""
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    from oracle.gmm import GMMOracle
+    g = torch.Generator().manual_seed(2)
+    xB = torch.rand(M_FULL, 3, generator=g)
+    xA = xB[torch.randperm(M_FULL, generator=g)] + 0.02 * torch.randn(M_FULL, 3, generator=g)
+    G = GaussianMixtureUnif(xB.to(dev()), sigma=0.05, spec=spec())
+    G.to_optimize = {"mu": False, "sigma": True, "w": False, "eta0": False}
+    Y, Cfe, FE = G.EM_step(xA.to(dev()))
+    assert bool(((Y >= -1e-4) & (Y <= 1 + 1e-4)).all())
+    rows = torch.arange(0, M_FULL, 400)
+    O = GMMOracle(xB.double(), 0.05, to_optimize={"mu": False, "sigma": False, "w": False})
+    Yo, _, _ = O.em_step(xA[rows].double(), skip_M=True)
+    assert relerr(Y[rows.to(dev())].cpu().numpy(), Yo.numpy()) < 2e-5
+    assert 0.01 < G.sigma < 0.05
+
+
+@pytest.mark.parametrize("version,scheme", [("hybrid", "Ralston"), ("logdet", "Euler")])
+def test_midsize_gradient_vs_oracle(version, scheme):
+    """5000 support points (column-split grid, several tiles, odd count): loss and full gradient against the fp64 oracle."""
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from oracle.lddmm import LDDMMOracle
+    g = torch.Generator().manual_seed(3)
+    M = 4999
+    q = torch.rand(M, 3, generator=g)
+    p = 2e-3 * torch.randn(M, 3, generator=g)
+    y = q + 0.02 * torch.randn(M, 3, generator=g)
+    LM = LDDMMModel(sigma=0.15, D=3, lambd=20.0, spec=spec(), version=version, scheme=scheme, nt=3)
+    pd = p.to(dev()).requires_grad_(True)
+    sh = LM.Shoot(q.to(dev()), pd)
+    L = LM.trajloss(sh) + ((sh[-1][0] - y.to(dev())) ** 2).sum() * 50.0
+    L.backward()
+    OR = LDDMMOracle(sigma=0.15, D=3, lambd=20.0, version=version, scheme=scheme, nt=3, chunk=1024)
+    po = p.double().requires_grad_(True)
+    Lo, _ = OR.loss(q.double(), po, None, y.double(), 50.0)
+    (go,) = torch.autograd.grad(Lo, [po])
+    assert abs(float(L) - float(Lo)) < 2e-5 * abs(float(Lo))
+    assert relerr(pd.grad.cpu().numpy(), go.numpy()) < 2e-4
