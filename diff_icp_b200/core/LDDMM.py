@@ -37,6 +37,11 @@ class ShootResult(shooting.LazyStates):
 
 class LDDMMModel:
 
+    # B200-build switches (class-level defaults so that objects unpickled from older versions still work)
+    use_cuda_graph = False            # replay each shoot / adjoint sweep / closure as one CUDA graph
+    fused_closure = True              # run the L-BFGS closure of Optimize as one fused launch sequence (quadratic data loss)
+    host_lbfgs_max_numel = 100_000    # keep the L-BFGS vectors on the host below this many parameters
+
     def __init__(self, sigma=1.0, D=2, lambd=2.0,
                  spec=defspec, gradcomponent=True, withlogdet=True, version=None,
                  computversion="keops", scheme="Ralston", nonsupprev=False, nt=10):
@@ -60,6 +65,9 @@ class LDDMMModel:
         self.try_trajcost_optim = False
         # B200 build: replay each shoot / adjoint sweep as one CUDA graph (set False for eager launches)
         self.use_cuda_graph = False
+        # B200 build: run the L-BFGS closure of Optimize as one fused launch sequence when the data loss is quadratic
+        self.fused_closure = True
+        self.host_lbfgs_max_numel = 100_000      # keep the L-BFGS vectors on the host below this size
 
     def set_integration_scheme(self, scheme: str):
         if scheme == "Euler":
@@ -218,8 +226,29 @@ class LDDMMModel:
             moved = shoot[-1][-1] if is_x else shoot[-1][0]
             return self.trajloss(shoot) + dataloss(moved)
 
-        p0, _, nsteps, change = LBFGS_optimization([p0], lossfunc, nmax=nmax, tol=tol, errthresh=errthresh)
-        p0 = p0[0]
+        # Fast path (B200 build): when the data loss is DiffPSR's quadratic functor (it carries its targets and weights),
+        # the whole closure -- shoot, lambda*H + cost, data loss, adjoint -- is one captured launch sequence
+        # (shooting.ClosurePlan) and the L-BFGS vectors live on the host when they are small, so an optimiser step costs
+        # no tiny device launches.  Loss and gradient values are the ones `lossfunc` + backward() would produce.
+        lossgrad, host_side = None, False
+        targets, weights = getattr(dataloss, "targets", None), getattr(dataloss, "inv2sig2", None)
+        fused = targets is not None and weights is not None and self.fused_closure \
+            and not (self.withlogdet and self.gradcomponent and self.try_trajcost_optim and not is_x)
+        if fused:
+            sp = self._spec_for(q0.shape[0], x0.shape[0] if is_x else 0, q0.device)
+            cp = shooting.ClosurePlan.get(sp, self.use_cuda_graph, self.lam)
+            cp.set_problem(q0, x0, targets, weights)
+            host_side = p0.numel() <= self.host_lbfgs_max_numel
+
+            def lossgrad(p):
+                L, g = cp.evaluate(p)
+                return L, [g]
+
+        dev0 = p0.device
+        start = [p0.detach().cpu()] if (fused and host_side) else [p0]
+        p0, _, nsteps, change = LBFGS_optimization(start, lossfunc, nmax=nmax, tol=tol, errthresh=errthresh,
+                                                   lossgrad=lossgrad)
+        p0 = p0[0].to(dev0)
         with torch.no_grad():
             shoot = self.Shoot(q0, p0, x0)
             trajl = self.trajloss(shoot).item()

@@ -261,6 +261,7 @@ class DiffPSR(MultiPSR):
 
         def dataloss_func(x):
             return (((x - y) ** 2) * inv[:, None]).sum()
+        dataloss_func.targets, dataloss_func.inv2sig2 = y, inv       # lets LDDMMModel.Optimize fuse the whole closure
         return dataloss_func
 
     # number of frames registered concurrently (one Python thread + one CUDA stream each). Frames are independent

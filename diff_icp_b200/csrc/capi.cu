@@ -22,6 +22,24 @@ __global__ void rhs_scal_fix_kernel(float* scal, float eta, int withdiv) {
     if (threadIdx.x == 0) scal[0] = withdiv ? fmaf(eta, scal[3], scal[2]) : 0.f;
 }
 
+// Quadratic data loss of DiffPSR.QuadLossFunctor (core/PSR.py:498-516): loss = sum_n inv_n |x_n - y_n|^2 and its gradient
+// g_n = 2 inv_n (x_n - y_n); block partial sums in a fixed order (deterministic), summed by scalar_reduce_kernel.
+__global__ void quad_loss_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ inv,
+                                 long long n, int D, float* __restrict__ g, float* __restrict__ blocksum) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float w = inv[i];
+        for (int k = 0; k < D; ++k) {
+            const float r = x[i * D + k] - y[i * D + k];
+            g[i * D + k] = 2.f * w * r;
+            acc = fmaf(w * r, r, acc);
+        }
+    }
+    const float v = block_sum(acc, red);
+    if (threadIdx.x == 0) blocksum[blockIdx.x] = v;
+}
+
 struct DeviceExec {
     void* ws;
     size_t wsb;
@@ -188,6 +206,19 @@ int dicp_log_resp(int D, float sigma, const float* X, int64_t N, const float* mu
     if (D == 2) log_resp_kernel<2><<<blocks, 128, 0, (cudaStream_t)stream>>>(X, (int)N, mu, w, (int)C, den, lgam, argmax);
     else log_resp_kernel<3><<<blocks, 128, 0, (cudaStream_t)stream>>>(X, (int)N, mu, w, (int)C, den, lgam, argmax);
     launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
+int dicp_quad_loss(int D, const float* x, const float* y, const float* inv, int64_t n, float* g, float* loss,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+    if ((D != 2 && D != 3) || n < 1 || !x || !y || !inv || !g || !loss || !workspace) return DICP_EBADARG;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    if (workspace_bytes < (size_t)blocks * 4) return DICP_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    quad_loss_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, inv, n, D, g, (float*)workspace);
+    scalar_reduce_kernel<<<1, 256, 0, st>>>((const float*)workspace, (int)blocks, 1, loss, 0);
+    launch_counter() += 2;
     return last_error(DICP_OK);
 }
 

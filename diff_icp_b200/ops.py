@@ -79,6 +79,13 @@ def axpy(out, a, alpha, f1, beta=0.0, f2=None, n=None):
     check(rc, "dicp_axpy")
 
 
+def quad_loss(x, y, inv, g, loss, ws):
+    """loss[0] = sum_n inv[n]|x_n-y_n|^2, g = 2 inv (x-y); all preallocated contiguous fp32 CUDA tensors."""
+    n, D = x.shape
+    rc = load().dicp_quad_loss(D, ptr(x), ptr(y), ptr(inv), n, ptr(g), ptr(loss), ptr(ws), ws.numel(), stream_ptr())
+    check(rc, "dicp_quad_loss")
+
+
 def alloc_workspace(rows, cols, device):
     """A private workspace tensor for a long-lived plan (e.g. a CUDA-graph-captured shoot)."""
     return torch.empty(int(load().dicp_pair_workspace_bytes(int(rows), int(cols))), dtype=torch.uint8, device=device)

@@ -214,6 +214,92 @@ class ShootPlan:
             self._bwd_body()
 
 
+class ClosurePlan:
+    """One L-BFGS closure of the registration step -- shoot, trajectory loss lambda*H(q0,p0) + cost(1), quadratic data
+    loss sum_n inv_n |x_n(1) - y_n|^2 (core/LDDMM.py:363-371 with core/PSR.py:498-516) and the adjoint sweep -- as ONE
+    launch sequence on static buffers, replayed as a single CUDA graph.  Output: one contiguous buffer
+    [dcost(0), A, B, C, cost(1), data loss, -, - | d loss / d p0 (M*D)] so that the host reads loss and gradient with one
+    device-to-host copy (the reference synchronises once per closure too, tools/optim.py:39)."""
+
+    _cache = {}
+    NS = 8
+
+    def __init__(self, spec: ShootSpec, use_graph: bool, lam_reg: float):
+        self.spec, self.lam_reg, self.use_graph = spec, float(lam_reg), use_graph
+        self.plan = ShootPlan(spec, False)
+        dev = spec.device
+        self.n_data = spec.Nx if spec.Nx else spec.M
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.y = torch.zeros(self.n_data, spec.D, **f32)
+        self.inv = torch.zeros(self.n_data, **f32)
+        self.out = torch.zeros(self.NS + spec.M * spec.D, **f32)
+        self.out_host = torch.zeros(self.NS + spec.M * spec.D, dtype=torch.float32).pin_memory() if dev.type == "cuda" \
+            else torch.zeros(self.NS + spec.M * spec.D, dtype=torch.float32)
+        self.plan.gtraj[spec.nt][spec.S - 1] = 1.0            # d loss / d cost(1) = 1
+        self.graph = None
+
+    @classmethod
+    def get(cls, spec, use_graph, lam_reg):
+        key = spec.key() + (bool(use_graph), float(lam_reg), _plan_slot())
+        cp = cls._cache.get(key)
+        if cp is None:
+            with ShootPlan._lock:
+                cp = cls._cache.get(key)
+                if cp is None:
+                    if len(cls._cache) > 1024:
+                        cls._cache.clear()
+                    cp = cls(spec, use_graph, lam_reg)
+                    cls._cache[key] = cp
+        return cp
+
+    def set_problem(self, q0, x0, y, inv):
+        spec = self.spec
+        q, _, x, cost = _views(spec, self.plan.traj[0])
+        q.copy_(q0)
+        if x is not None:
+            x.copy_(x0)
+        cost.zero_()
+        self.y.copy_(y)
+        self.inv.copy_(inv)
+
+    def _body(self):
+        spec, plan = self.spec, self.plan
+        S, MD = spec.S, spec.M * spec.D
+        forward_sweep(spec, plan.traj, plan.mid, plan.F1, plan.F2, plan.F0, plan.ws)
+        end = plan.traj[spec.nt]
+        q1, _, x1, _ = _views(spec, end)
+        gq, _, gx, _ = _views(spec, plan.gtraj[spec.nt])
+        ops.quad_loss(x1 if spec.Nx else q1, self.y, self.inv, gx if spec.Nx else gq, self.out[5:6], plan.ws)
+        adjoint_sweep(spec, plan.traj, plan.mid, plan.gtraj, plan.lam, plan.mu, plan.G1, plan.G2, plan.ws)
+        # d/dp0 [lambda H(q0,p0)] = lambda vq(0)   (Hamilton's equations, core/LDDMM.py:156-158)
+        ops.axpy(self.out[self.NS:], plan.lam[MD:2 * MD], self.lam_reg, plan.F0[0:MD], n=MD)
+        self.out[0:4].copy_(plan.F0[S - 1:S + 3])
+        self.out[4:5].copy_(end[S - 1:S])
+
+    def evaluate(self, p0):
+        """p0: (M,D) tensor on any device.  Returns (loss as a Python float, gradient view into the host buffer)."""
+        spec = self.spec
+        _, p, _, _ = _views(spec, self.plan.traj[0])
+        p.copy_(p0)
+        if self.use_graph:
+            if self.graph is None:
+                with ShootPlan._lock:
+                    self._body()
+                    torch.cuda.current_stream().synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        self._body()
+                    self.graph = g
+            self.graph.replay()
+        else:
+            self._body()
+        self.out_host.copy_(self.out)                        # the one host synchronisation of this closure
+        s = self.out_host[:self.NS].tolist()
+        H0 = 0.5 * s[1] - spec.eta * s[2] - 0.5 * spec.eta ** 2 * s[3]
+        loss = self.lam_reg * H0 + s[4] + s[5]
+        return loss, self.out_host[self.NS:].view(spec.M, spec.D)
+
+
 class _ShootFn(torch.autograd.Function):
     """(q0, p0, x0) -> (trajectory (nt+1, S), H(q0,p0) as a 0-d tensor)."""
 

@@ -16,7 +16,10 @@ import math
 import torch
 
 
-def LBFGS_optimization(p0, lossfunc, nmax=10, tol=1e-3, errthresh=1e8):
+def LBFGS_optimization(p0, lossfunc, nmax=10, tol=1e-3, errthresh=1e8, lossgrad=None):
+    """`lossgrad` (optional, B200 build): callable returning (loss, [gradients]) directly -- used by LDDMMModel.Optimize when
+    the whole closure (shoot + quadratic loss + adjoint) runs as one captured launch sequence; the optimiser then sees
+    exactly the same loss / gradient values as through `lossfunc` + `.backward()`, without building an autograd graph."""
     params = [t.clone().contiguous().detach().requires_grad_(True) for t in p0]
 
     def new_optimizer(line_search):
@@ -28,13 +31,22 @@ def LBFGS_optimization(p0, lossfunc, nmax=10, tol=1e-3, errthresh=1e8):
 
     def closure():
         optimizer.zero_grad()
-        loss = lossfunc(*params)
-        val = loss.detach().item()
+        if lossgrad is not None:
+            val, grads = lossgrad(*[t.detach() for t in params])
+            val = float(val)
+            loss = torch.tensor(val)
+        else:
+            loss = lossfunc(*params)
+            val = loss.detach().item()
         history.append(val)
         if val < best["L"]:
             best["L"] = val
             best["p"] = [t.clone().detach() for t in params]
-        loss.backward()
+        if lossgrad is not None:
+            for t, g in zip(params, grads):
+                t.grad = g.to(device=t.device, dtype=t.dtype).clone()
+        else:
+            loss.backward()
         return loss
 
     step, go_on, L, change = 0, True, math.inf, None
@@ -58,7 +70,7 @@ def LBFGS_optimization(p0, lossfunc, nmax=10, tol=1e-3, errthresh=1e8):
             else:
                 rmod = 0.01
                 params = [t + rmod * t.std() * torch.randn(t.shape, dtype=t.dtype, device=t.device) for t in best["p"]]
-                L = lossfunc(*params)
+                L = lossfunc(*params) if lossgrad is None else lossgrad(*params)[0]
                 print(f"L-BFGS optimization. Trying a random perturbation of parameter from its current value, with relative strength {rmod}.")
             change = "None (divergent iteration step)"
             params = [t.requires_grad_(True) for t in params]

@@ -119,6 +119,11 @@ int dicp_em_colstats(int D, float sigma_old, const float* X, int64_t N, const fl
 int dicp_log_resp(int D, float sigma, const float* X, int64_t N, const float* mu, const float* w, int64_t C,
                   float* lgam, long long* argmax, void* stream);
 
+/* Quadratic data loss of the registration step (DiffPSR.QuadLossFunctor, core/PSR.py:498-516):
+ *   loss[0] = sum_n inv[n] |x_n - y_n|^2,   g[n,:] = 2 inv[n] (x_n - y_n)      (inv[n] = 1 / (2 sigma_s(n)^2)). */
+int dicp_quad_loss(int D, const float* x, const float* y, const float* inv, int64_t n, float* g, float* loss,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* out = a + alpha*f1 + beta*f2  (f2 may be null) over n floats: the Euler / Ralston state updates
  * (tools/integrators.py:27-29, 42-48) and the adjoint accumulations. */
 int dicp_axpy(int64_t n, float* out, const float* a, float alpha, const float* f1, float beta, const float* f2,

@@ -140,6 +140,18 @@ def install_all(monkeypatch):
     monkeypatch.setattr(ops, "rhs_forward", rhs_forward)
     monkeypatch.setattr(ops, "rhs_adjoint", rhs_adjoint)
     monkeypatch.setattr(ops, "axpy", axpy)
+    monkeypatch.setattr(ops, "quad_loss", quad_loss)
     monkeypatch.setattr(ops, "alloc_workspace", lambda r, c, dev: torch.empty(16, dtype=torch.uint8))
     monkeypatch.setattr(_lib, "require_cuda", lambda *t: torch.device("cpu"))
     monkeypatch.setattr(em_ops, "log_resp", None, raising=False)
+
+
+def quad_loss(x, y, inv, g, loss, ws):
+    r = x - y
+    g.copy_(2.0 * inv[:, None] * r)
+    loss[0] = float((inv[:, None].double() * r.double() ** 2).sum())
+
+
+def _install_quad(monkeypatch):
+    from diff_icp_b200 import ops
+    monkeypatch.setattr(ops, "quad_loss", quad_loss)
