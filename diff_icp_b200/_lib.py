@@ -38,6 +38,10 @@ SIGNATURES = {
     "dicp_em_rowpass": (_int, [_int, _int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dicp_em_colstats": (_int, [_int, _f, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "dicp_log_resp": (_int, [_int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "dicp_small_max_support": (_int, []),
+    "dicp_small_workspace_bytes": (_sz, [_i64, _i64]),
+    "dicp_small_rhs_step": (_int, [_int, _int, _f, _f, _i64, _i64, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "dicp_small_adj_step": (_int, [_int, _int, _f, _f, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "dicp_quad_loss": (_int, [_int, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dicp_axpy": (_int, [_i64, _vp, _vp, _f, _vp, _f, _vp, _vp]),
     "dicp_pipe_probe": (_int, [_int, _int, _int, _vp, _vp]),

@@ -1,6 +1,8 @@
 // extern "C" entry points of libdicp_b200.so (see include/dicp_b200.h).
 #include "../../include/dicp_b200.h"
 #include "dispatch.cuh"
+#include <type_traits>
+#include "small_step.cuh"
 
 using namespace dicp;
 
@@ -205,6 +207,61 @@ int dicp_log_resp(int D, float sigma, const float* X, int64_t N, const float* mu
     const int blocks = (int)((N + 127) / 128);
     if (D == 2) log_resp_kernel<2><<<blocks, 128, 0, (cudaStream_t)stream>>>(X, (int)N, mu, w, (int)C, den, lgam, argmax);
     else log_resp_kernel<3><<<blocks, 128, 0, (cudaStream_t)stream>>>(X, (int)N, mu, w, (int)C, den, lgam, argmax);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
+int dicp_small_max_support(void) { return kSmallMaxQ; }
+
+size_t dicp_small_workspace_bytes(int64_t M, int64_t Nx) { return small_workspace_bytes(M, Nx); }
+
+static int small_fill(SmallStep& S, int D, float sigma, float eta, int64_t M, int64_t Nx, void* ws, size_t wsb) {
+    if ((D != 2 && D != 3) || !(sigma > 0.f) || M < 1 || M > kSmallMaxQ || Nx < 0 || Nx > INT32_MAX) return DICP_EBADARG;
+    if (ws == nullptr || wsb < small_workspace_bytes(M, Nx)) return DICP_EWORKSPACE;
+    GaussConst g = gauss_const(sigma);
+    S.M = (int)M; S.Nx = (int)Nx;
+    S.kappa = g.kappa; S.s = g.s; S.alpha = g.alpha; S.beta = g.beta; S.eta = eta;
+    S.counters = (unsigned*)ws;
+    S.ws = (float*)((char*)ws + kSmallCounters * 4);
+    return DICP_OK;
+}
+
+int dicp_small_rhs_step(int D, int withlogdet, float sigma, float eta, int64_t M, int64_t Nx, const float* s_eval,
+                        const float* base, const float* other, float c_this, float c_other, float* out, float* F,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    SmallStep S{};
+    int rc = small_fill(S, D, sigma, eta, M, Nx, workspace, workspace_bytes);
+    if (rc != DICP_OK) return rc;
+    if (!s_eval || !F || (out && !base) || (eta != 0.f && !withlogdet)) return DICP_EBADARG;
+    S.s_eval = s_eval; S.base = base; S.other = other; S.out = out; S.This = F; S.c_this = c_this; S.c_other = c_other;
+    const unsigned grid = (unsigned)((Nx + kSmallThreads - 1) / kSmallThreads + (M + kSmallThreads - 1) / kSmallThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+#define DICP_LAUNCH(DD, W, E) small_rhs_step_kernel<DD, W, E><<<grid, kSmallThreads, 0, st>>>(S)
+    if (D == 2) { if (eta != 0.f) DICP_LAUNCH(2, true, true); else if (withlogdet) DICP_LAUNCH(2, true, false); else DICP_LAUNCH(2, false, false); }
+    else { if (eta != 0.f) DICP_LAUNCH(3, true, true); else if (withlogdet) DICP_LAUNCH(3, true, false); else DICP_LAUNCH(3, false, false); }
+#undef DICP_LAUNCH
+    launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
+int dicp_small_adj_step(int D, int withlogdet, float sigma, float eta, int64_t M, int64_t Nx, const float* s_eval,
+                        const float* lam, const float* base, const float* other, const float* add, float c_this,
+                        float c_other, float* out, float* G, void* workspace, size_t workspace_bytes, void* stream) {
+    SmallStep S{};
+    int rc = small_fill(S, D, sigma, eta, M, Nx, workspace, workspace_bytes);
+    if (rc != DICP_OK) return rc;
+    if (!s_eval || !lam || !G || (out && !base) || out == lam || (eta != 0.f && !withlogdet)) return DICP_EBADARG;
+    S.s_eval = s_eval; S.lam = lam; S.base = base; S.other = other; S.add = add; S.out = out; S.This = G;
+    S.c_this = c_this; S.c_other = c_other;
+    const int nsplit = small_adj_nsplit((int)Nx);
+    const unsigned nQB = (unsigned)((M + kSmallThreads - 1) / kSmallThreads);
+    if (1 + nQB > (unsigned)kSmallCounters) return DICP_EBADARG;
+    const unsigned grid = (unsigned)((Nx + kSmallThreads - 1) / kSmallThreads) + nQB * (unsigned)nsplit;
+    cudaStream_t st = (cudaStream_t)stream;
+#define DICP_LAUNCH(DD, W, E) small_adj_step_kernel<DD, W, E><<<grid, kSmallThreads, 0, st>>>(S, nsplit)
+    if (D == 2) { if (eta != 0.f) DICP_LAUNCH(2, true, true); else if (withlogdet) DICP_LAUNCH(2, true, false); else DICP_LAUNCH(2, false, false); }
+    else { if (eta != 0.f) DICP_LAUNCH(3, true, true); else if (withlogdet) DICP_LAUNCH(3, true, false); else DICP_LAUNCH(3, false, false); }
+#undef DICP_LAUNCH
     launch_counter() += 1;
     return last_error(DICP_OK);
 }

@@ -79,6 +79,34 @@ def axpy(out, a, alpha, f1, beta=0.0, f2=None, n=None):
     check(rc, "dicp_axpy")
 
 
+# ---- fused integrator stages for small supports ---------------------------------------------------------------------
+small_enabled = True
+
+
+def use_small_path(M):
+    """True when the support set is small enough for the one-launch-per-stage kernels (csrc/small_step.cuh)."""
+    return small_enabled and M <= load().dicp_small_max_support()
+
+
+def alloc_small_workspace(M, Nx, device):
+    """Zero-initialised (ticket counters) workspace for the small-support stage kernels."""
+    return torch.zeros(int(load().dicp_small_workspace_bytes(int(M), int(Nx))), dtype=torch.uint8, device=device)
+
+
+def small_rhs_step(D, withlogdet, sigma, eta, M, Nx, s_eval, base, other, c_this, c_other, out, F, ws):
+    rc = load().dicp_small_rhs_step(D, int(bool(withlogdet)), float(sigma), float(eta), M, Nx, ptr(s_eval), ptr(base),
+                                    ptr(other), float(c_this), float(c_other), ptr(out), ptr(F), ptr(ws), ws.numel(),
+                                    stream_ptr())
+    check(rc, "dicp_small_rhs_step")
+
+
+def small_adj_step(D, withlogdet, sigma, eta, M, Nx, s_eval, lam, base, other, add, c_this, c_other, out, G, ws):
+    rc = load().dicp_small_adj_step(D, int(bool(withlogdet)), float(sigma), float(eta), M, Nx, ptr(s_eval), ptr(lam),
+                                    ptr(base), ptr(other), ptr(add), float(c_this), float(c_other), ptr(out), ptr(G),
+                                    ptr(ws), ws.numel(), stream_ptr())
+    check(rc, "dicp_small_adj_step")
+
+
 def quad_loss(x, y, inv, g, loss, ws):
     """loss[0] = sum_n inv[n]|x_n-y_n|^2, g = 2 inv (x-y); all preallocated contiguous fp32 CUDA tensors."""
     n, D = x.shape

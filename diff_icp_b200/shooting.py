@@ -75,10 +75,21 @@ def _vjp(spec, state, lam, G, ws):
     ops.rhs_adjoint(spec.D, spec.withlogdet, spec.sigma, spec.eta, q, p, x, a, u, wx, gc, gq, gp, gx, ws)
 
 
-def forward_sweep(spec, traj, mid, F1, F2, F0, ws):
-    """traj[0] holds the initial state; fills traj[1..nt] (and mid[0..nt-1] for Ralston), F0 = rhs(traj[0])."""
+def forward_sweep(spec, traj, mid, F1, F2, F0, ws, sws=None):
+    """traj[0] holds the initial state; fills traj[1..nt] (and mid[0..nt-1] for Ralston), F0 = rhs(traj[0]).
+    With a small support (sws given) every stage is ONE fused launch (csrc/small_step.cuh)."""
     h = 1.0 / spec.nt
     S = spec.S
+    if sws is not None:
+        a = (spec.D, spec.withlogdet, spec.sigma, spec.eta, spec.M, spec.Nx)
+        for t in range(spec.nt):
+            Fa = F0 if t == 0 else F1
+            if spec.scheme == "Euler":
+                ops.small_rhs_step(*a, traj[t], traj[t], None, h, 0.0, traj[t + 1], Fa, sws)
+            else:
+                ops.small_rhs_step(*a, traj[t], traj[t], None, 2.0 * h / 3.0, 0.0, mid[t], Fa, sws)
+                ops.small_rhs_step(*a, mid[t], traj[t], Fa, 0.75 * h, 0.25 * h, traj[t + 1], F2, sws)
+        return
     for t in range(spec.nt):
         Fa = F0 if t == 0 else F1
         _rhs(spec, traj[t], Fa, ws)
@@ -90,10 +101,24 @@ def forward_sweep(spec, traj, mid, F1, F2, F0, ws):
             ops.axpy(traj[t + 1], traj[t], 0.25 * h, Fa, 0.75 * h, F2, n=S)
 
 
-def adjoint_sweep(spec, traj, mid, gtraj, lam, mu, G1, G2, ws):
-    """lam <- d(loss)/d(traj[0]) given gtraj[t] = d(loss)/d(traj[t]) (direct dependence on every stored state)."""
+def adjoint_sweep(spec, traj, mid, gtraj, lam, mu, G1, G2, ws, sws=None, lam2=None):
+    """lam <- d(loss)/d(traj[0]) given gtraj[t] = d(loss)/d(traj[t]) (direct dependence on every stored state).
+    With a small support (sws, lam2 given) every stage is ONE fused launch; lam / lam2 ping-pong so that the result
+    lands in lam."""
     h = 1.0 / spec.nt
     S = spec.S
+    if sws is not None:
+        a = (spec.D, spec.withlogdet, spec.sigma, spec.eta, spec.M, spec.Nx)
+        cur, nxt = (lam, lam2) if spec.nt % 2 == 0 else (lam2, lam)
+        cur.copy_(gtraj[spec.nt])
+        for t in range(spec.nt - 1, -1, -1):
+            if spec.scheme == "Euler":
+                ops.small_adj_step(*a, traj[t], cur, cur, None, gtraj[t], h, 0.0, nxt, G1, sws)
+            else:
+                ops.small_adj_step(*a, mid[t], cur, cur, None, None, 2.0 * h, 0.0, mu, G2, sws)
+                ops.small_adj_step(*a, traj[t], mu, cur, G2, gtraj[t], 0.25 * h, 0.75 * h, nxt, G1, sws)
+            cur, nxt = nxt, cur
+        return
     lam.copy_(gtraj[spec.nt])
     for t in range(spec.nt - 1, -1, -1):
         if spec.scheme == "Euler":
@@ -128,7 +153,14 @@ class ShootPlan:
         self.G1 = torch.zeros(S, **f32)
         self.G2 = torch.zeros(S, **f32)
         rows = max(spec.M, spec.Nx)
-        self.ws = ops.alloc_workspace(rows, rows, dev)
+        self.small = ops.use_small_path(spec.M)
+        if self.small:
+            self.sws = ops.alloc_small_workspace(spec.M, spec.Nx, dev)
+            self.lam2 = torch.zeros(S, **f32)
+            self.ws = torch.zeros(8192, dtype=torch.uint8, device=dev)       # quad-loss partials only
+        else:
+            self.sws, self.lam2 = None, None
+            self.ws = ops.alloc_workspace(rows, rows, dev)
         self.version = 0
         self.use_graph = use_graph
         self.fwd_graph = None
@@ -180,7 +212,7 @@ class ShootPlan:
 
     # -- forward ---------------------------------------------------------------------------------------
     def _fwd_body(self):
-        forward_sweep(self.spec, self.traj, self.mid, self.F1, self.F2, self.F0, self.ws)
+        forward_sweep(self.spec, self.traj, self.mid, self.F1, self.F2, self.F0, self.ws, self.sws)
 
     def run_forward(self, q0, p0, x0):
         spec = self.spec
@@ -201,7 +233,8 @@ class ShootPlan:
 
     # -- backward --------------------------------------------------------------------------------------
     def _bwd_body(self):
-        adjoint_sweep(self.spec, self.traj, self.mid, self.gtraj, self.lam, self.mu, self.G1, self.G2, self.ws)
+        adjoint_sweep(self.spec, self.traj, self.mid, self.gtraj, self.lam, self.mu, self.G1, self.G2, self.ws,
+                      self.sws, self.lam2)
 
     def run_backward(self, gtraj):
         self.gtraj.copy_(gtraj)
@@ -265,12 +298,13 @@ class ClosurePlan:
     def _body(self):
         spec, plan = self.spec, self.plan
         S, MD = spec.S, spec.M * spec.D
-        forward_sweep(spec, plan.traj, plan.mid, plan.F1, plan.F2, plan.F0, plan.ws)
+        forward_sweep(spec, plan.traj, plan.mid, plan.F1, plan.F2, plan.F0, plan.ws, plan.sws)
         end = plan.traj[spec.nt]
         q1, _, x1, _ = _views(spec, end)
         gq, _, gx, _ = _views(spec, plan.gtraj[spec.nt])
         ops.quad_loss(x1 if spec.Nx else q1, self.y, self.inv, gx if spec.Nx else gq, self.out[5:6], plan.ws)
-        adjoint_sweep(spec, plan.traj, plan.mid, plan.gtraj, plan.lam, plan.mu, plan.G1, plan.G2, plan.ws)
+        adjoint_sweep(spec, plan.traj, plan.mid, plan.gtraj, plan.lam, plan.mu, plan.G1, plan.G2, plan.ws,
+                      plan.sws, plan.lam2)
         # d/dp0 [lambda H(q0,p0)] = lambda vq(0)   (Hamilton's equations, core/LDDMM.py:156-158)
         ops.axpy(self.out[self.NS:], plan.lam[MD:2 * MD], self.lam_reg, plan.F0[0:MD], n=MD)
         self.out[0:4].copy_(plan.F0[S - 1:S + 3])

@@ -119,6 +119,28 @@ int dicp_em_colstats(int D, float sigma_old, const float* X, int64_t N, const fl
 int dicp_log_resp(int D, float sigma, const float* X, int64_t N, const float* mu, const float* w, int64_t C,
                   float* lgam, long long* argmax, void* stream);
 
+/* ---- Fused integrator stages for small supports (M <= dicp_small_max_support(); any number of data points) ----
+ * The grid / decimated support schemes of DiffPSR (core/PSR.py:430-493) give tens to hundreds of support points: one
+ * right-hand-side evaluation is then microseconds of arithmetic and launch latency dominates.  These entry points do a
+ * whole Euler / Ralston STAGE in one launch.  Flat vectors: state / cotangent [q (M,D) | p (M,D) | x (Nx,D) | cost],
+ * F = [vq | dp | vx | dcost, A, B, C] (S+3 floats), G = [gq | gp | gx | 0] (S floats).
+ * workspace: dicp_small_workspace_bytes(M, Nx) bytes, ZERO-initialised before its first use (it holds ticket counters
+ * that the kernels reset themselves), private to one launch sequence.
+ *
+ * forward stage:  F = rhs(s_eval);  out = base + c_this*F + c_other*other   (other, out nullable)
+ *   Euler step            s_eval = base = s_t, c_this = h
+ *   Ralston stage 1 / 2   (tools/integrators.py:42-48)  c_this = 2h/3  /  base = s_t, other = F1, c_this = 3h/4, c_other = h/4 */
+int dicp_small_max_support(void);
+size_t dicp_small_workspace_bytes(int64_t M, int64_t Nx);
+int dicp_small_rhs_step(int D, int withlogdet, float sigma, float eta, int64_t M, int64_t Nx, const float* s_eval,
+                        const float* base, const float* other, float c_this, float c_other, float* out, float* F,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* adjoint stage:  G = J_rhs(s_eval)^T lam;  out = base + c_this*G + c_other*other + add   (other, add, out nullable;
+ * out must not alias lam). */
+int dicp_small_adj_step(int D, int withlogdet, float sigma, float eta, int64_t M, int64_t Nx, const float* s_eval,
+                        const float* lam, const float* base, const float* other, const float* add, float c_this,
+                        float c_other, float* out, float* G, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Quadratic data loss of the registration step (DiffPSR.QuadLossFunctor, core/PSR.py:498-516):
  *   loss[0] = sum_n inv[n] |x_n - y_n|^2,   g[n,:] = 2 inv[n] (x_n - y_n)      (inv[n] = 1 / (2 sigma_s(n)^2)). */
 int dicp_quad_loss(int D, const float* x, const float* y, const float* inv, int64_t n, float* g, float* loss,

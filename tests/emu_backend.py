@@ -141,6 +141,7 @@ def install_all(monkeypatch):
     monkeypatch.setattr(ops, "rhs_adjoint", rhs_adjoint)
     monkeypatch.setattr(ops, "axpy", axpy)
     monkeypatch.setattr(ops, "quad_loss", quad_loss)
+    monkeypatch.setattr(ops, "small_enabled", False)        # the CPU emulation covers the general engine path
     monkeypatch.setattr(ops, "alloc_workspace", lambda r, c, dev: torch.empty(16, dtype=torch.uint8))
     monkeypatch.setattr(_lib, "require_cuda", lambda *t: torch.device("cpu"))
     monkeypatch.setattr(em_ops, "log_resp", None, raising=False)

@@ -108,7 +108,20 @@ def test_em_large_vs_oracle_both_variants():
     assert bool(((Y >= lo - 1e-4) & (Y <= hi + 1e-4)).all())
 
 
-def test_c1_single_set_registration_matches_reference(golden):
+@pytest.fixture(params=["small_support_stage_kernels", "general_pair_engine"])
+def shoot_path(request):
+    from diff_icp_b200 import ops, shooting
+    old = ops.small_enabled
+    ops.small_enabled = request.param == "small_support_stage_kernels"
+    shooting.ShootPlan._cache.clear()
+    shooting.ClosurePlan._cache.clear()
+    yield request.param
+    ops.small_enabled = old
+    shooting.ShootPlan._cache.clear()
+    shooting.ClosurePlan._cache.clear()
+
+
+def test_c1_single_set_registration_matches_reference(golden, shoot_path):
     """BASELINE configs[0]-like: one 2-D set registered to a known GMM (sigma optimised), classic LDDMM, grid support."""
     from diff_icp_b200.core.GMM import GaussianMixtureUnif
     from diff_icp_b200.core.LDDMM import LDDMMModel
@@ -139,7 +152,7 @@ def test_c1_single_set_registration_matches_reference(golden):
     assert np.abs(P.y[0, 0].cpu().numpy() - g["c1_gold_y"]).max() < 5e-3 * 0.2
 
 
-def test_atlas_api_matches_reference(golden):
+def test_atlas_api_matches_reference(golden, shoot_path):
     """Small groupwise atlas through ICP_atlas (3 frames, C = 6, hybrid, Euler, grid): L-BFGS paths of the reference's
     own fp32 and fp64 runs already differ by 0.17 % in FE here, so the bar is 'as close to gold as ref32 is'."""
     from diff_icp_b200.api.ICP_atlas import ICP_atlas

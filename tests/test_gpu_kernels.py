@@ -105,7 +105,22 @@ def test_check_coverage_bit_exact(GK):
     assert int((~safe).sum()) < 5
 
 
-def test_lddmm_shoot_and_gradients_match_reference_gold(golden):
+@pytest.fixture(params=["small_support_stage_kernels", "general_pair_engine"])
+def shoot_path(request):
+    """The golden cases have 37 support points, which the product routes to the one-launch-per-stage kernels
+    (csrc/small_step.cuh); the same cases are also forced through the general tiled engine."""
+    from diff_icp_b200 import ops, shooting
+    old = ops.small_enabled
+    ops.small_enabled = request.param == "small_support_stage_kernels"
+    shooting.ShootPlan._cache.clear()
+    shooting.ClosurePlan._cache.clear()
+    yield request.param
+    ops.small_enabled = old
+    shooting.ShootPlan._cache.clear()
+    shooting.ClosurePlan._cache.clear()
+
+
+def test_lddmm_shoot_and_gradients_match_reference_gold(golden, shoot_path):
     from diff_icp_b200.core.LDDMM import LDDMMModel
     g = golden("lddmm")
     spec = {"device": dev(), "dtype": torch.float32}
@@ -148,7 +163,7 @@ def test_lddmm_shoot_and_gradients_match_reference_gold(golden):
             assert relerr(x.grad.cpu().numpy(), g[f"{tag}_gold_gx0"]) < 2e-4, tag
 
 
-def test_cuda_graph_shoot_is_bit_identical_to_eager():
+def test_cuda_graph_shoot_is_bit_identical_to_eager(shoot_path):
     from diff_icp_b200.core.LDDMM import LDDMMModel
     spec = {"device": dev(), "dtype": torch.float32}
     g = torch.Generator().manual_seed(1)
@@ -166,7 +181,7 @@ def test_cuda_graph_shoot_is_bit_identical_to_eager():
         assert torch.equal(r[0], res[0][0]) and torch.equal(r[1], res[0][1]) and torch.equal(r[2], res[0][2])
 
 
-def test_hamiltonian_is_conserved_and_flow_inverts():
+def test_hamiltonian_is_conserved_and_flow_inverts(shoot_path):
     """Known-answer identities of SURVEY.md §4: H drift along a Ralston shoot, backward(apply(X)) = X for eta = 0."""
     from diff_icp_b200.core.LDDMM import LDDMMModel
     from diff_icp_b200.core.registrations import LDDMMRegistration
