@@ -187,15 +187,17 @@ __global__ void __launch_bounds__(kSmallThreads) small_rhs_step_kernel(SmallStep
         if (tid == 0) S.ws[(size_t)blockIdx.x * 4 + k] = v;
     }
     if (last_cta(&S.counters[0], gridDim.x)) {
-        if (tid < 4) {
+        // fixed-order parallel sum over CTAs (strided per thread, then the fixed block tree): deterministic
+        float tot[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
             float v = 0.f;
-            for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&S.ws[(size_t)b * 4 + tid]);
-            red[tid] = v;
+            for (unsigned b = tid; b < gridDim.x; b += kSmallThreads) v += __ldcg(&S.ws[(size_t)b * 4 + k]);
+            tot[k] = block_sum(v, red);
         }
-        __syncthreads();
         if (tid == 0) {
-            const float A = red[1], B = red[2], C = red[3];
-            const float dcost = Nx > 0 ? red[0] : (WLD ? fmaf(S.eta, C, B) : 0.f);
+            const float A = tot[1], B = tot[2], C = tot[3];
+            const float dcost = Nx > 0 ? tot[0] : (WLD ? fmaf(S.eta, C, B) : 0.f);
             S.This[Ssz - 1] = dcost; S.This[Ssz] = A; S.This[Ssz + 1] = B; S.This[Ssz + 2] = C;
             small_update(S, Ssz - 1);
             S.counters[0] = 0u;
@@ -306,15 +308,33 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
         for (int k = 0; k < NAX; ++k) part[((size_t)sp * NPART + NAQ + k) * M + i] = ax[k];
     }
     if (!last_cta(&S.counters[1 + rb], (unsigned)nsplit)) return;
+    // merge: every (row, accumulator) item of this row block is summed over the splits, in split order, by one of the 128
+    // threads (independent loads in flight), staged in shared memory, then each row thread finishes its row
+    {
+        float* merged = cols;                                     // reuse: kSmallThreads * NPART floats
+        const int rows_here = (M - rb * kSmallThreads < kSmallThreads) ? M - rb * kSmallThreads : kSmallThreads;
+        for (int item = tid; item < rows_here * NPART; item += kSmallThreads) {
+            const int rr = item / NPART, k = item - rr * NPART;
+            const size_t col = (size_t)k * M + (size_t)(rb * kSmallThreads + rr);
+            float v;
+            if (k < NAQ) {
+                v = __ldcg(&part[col]);                           // the (q,q) part lives in split 0
+            } else {
+                v = 0.f;
+                if (Nx > 0)
+                    for (int s2 = 0; s2 < nsplit; ++s2) v += __ldcg(&part[(size_t)s2 * NPART * M + col]);
+            }
+            merged[item] = v;
+        }
+        __syncthreads();
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < NAQ; ++k) aq[k] = merged[tid * NPART + k];
+#pragma unroll
+            for (int k = 0; k < NAX; ++k) ax[k] = merged[tid * NPART + NAQ + k];
+        }
+    }
     if (valid) {
-#pragma unroll
-        for (int k = 0; k < NAQ; ++k) aq[k] = __ldcg(&part[(size_t)k * M + i]);        // (q,q) part lives in split 0
-#pragma unroll
-        for (int k = 0; k < NAX; ++k) ax[k] = 0.f;
-        if (Nx > 0)
-            for (int s2 = 0; s2 < nsplit; ++s2)
-#pragma unroll
-                for (int k = 0; k < NAX; ++k) ax[k] += __ldcg(&part[((size_t)s2 * NPART + NAQ + k) * M + i]);
         P.accumulate = 0;
         if (Nx > 0) {
             typename OpQQx::Row row;
@@ -342,9 +362,14 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
     if (tid == 0) S.counters[1 + rb] = 0u;
 }
 
+// Column splits of the q-row CTAs: chunks of about sqrt(1.6 Nx) data points (clamped to [64, kSmallChunk]) balance the
+// serial sweep of a chunk against the serial merge of the splits.
 inline int small_adj_nsplit(int Nx) {
     if (Nx <= 0) return 1;
-    int n = (Nx + kSmallChunk - 1) / kSmallChunk;
+    int chunk = (int)sqrtf(1.6f * (float)Nx);
+    if (chunk < 64) chunk = 64;
+    if (chunk > kSmallChunk) chunk = kSmallChunk;
+    int n = (Nx + chunk - 1) / chunk;
     return n < 1 ? 1 : n;
 }
 
