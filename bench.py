@@ -276,6 +276,13 @@ def run_b200(args, rank, world, local_rank):
     ms_e2e_total = max(sum(e0.elapsed_time(e1) for e0, e1 in ev2), 0.0)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- second half of BASELINE.json's metric: groupwise PSR iteration time (frames sharded over the ranks) ----------
+    groupwise = None
+    if not args.no_groupwise:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        from groupwise_iteration import run_groupwise
+        groupwise = run_groupwise(rank, world, dev, GMM.comm, iters=3)
+
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e_total, wall_e2e * 1e3], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -306,6 +313,28 @@ def run_b200(args, rank, world, local_rank):
         cpu = {"value": pp_ / tt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"256 of {M} rows x {M} columns per evaluation (RHS + autograd backward + 1/{NT} E step), repeated for 10 s"}
 
+    if groupwise is not None and cpu is not None:
+        # CPU reference for the groupwise iteration: ONE closure evaluation of one frame (the reference's algorithm: separate
+        # reductions + autograd through the Euler loop), scaled by the measured ~23.5 closures per frame
+        from oracle.lddmm import LDDMMOracle
+        from groupwise_iteration import spiral_frames
+        torch.set_num_threads(threads)
+        fr = spiral_frames(1, groupwise["points_per_frame"])[0]
+        nq = groupwise["support_points"]
+        side = int(round(nq ** 0.5))
+        gx = torch.linspace(float(fr[:, 0].min()), float(fr[:, 0].max()), side)
+        gy = torch.linspace(float(fr[:, 1].min()), float(fr[:, 1].max()), max(1, nq // side))
+        qg = torch.stack(torch.meshgrid(gx, gy, indexing="ij"), -1).reshape(-1, 2)
+        OR = LDDMMOracle(sigma=0.2, D=2, lambd=500.0, version="hybrid", scheme="Euler", nt=10)
+        pc = (1e-3 * torch.randn(qg.shape)).requires_grad_(True)
+        t0 = time.perf_counter()
+        Lc, _ = OR.loss(qg, pc, fr, fr + 0.01, 50.0)
+        Lc.backward()
+        tc = time.perf_counter() - t0
+        groupwise["cpu_reference_estimate_ms"] = 1e3 * tc * 23.5 * groupwise["frames"]
+        groupwise["cpu_reference_note"] = (f"oracle port, {threads} threads: one closure evaluation of one frame took "
+                                           f"{1e3 * tc:.0f} ms; x 23.5 closures/frame x {groupwise['frames']} frames (EM excluded)")
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -314,6 +343,7 @@ def run_b200(args, rank, world, local_rank):
                 "ms_per_step": 1e3 * e2e_time / args.steps},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "cuda_graph": LM.use_cuda_graph, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "groupwise_psr_iteration": groupwise,
     }
     print(json.dumps(line), flush=True)
 
@@ -393,6 +423,7 @@ def main():
     ap.add_argument("--variant", default="logdet", choices=["classic", "hybrid", "logdet"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-groupwise", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -34,42 +34,26 @@ def spiral_frames(K, N, seed=1234):
     return frames
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=64)
-    ap.add_argument("--points", type=int, default=10000)
-    ap.add_argument("--iters", type=int, default=3)
-    ap.add_argument("--graph", type=int, default=1)
-    ap.add_argument("--C", type=int, default=50)
-    ap.add_argument("--workers", type=int, default=16)
-    args = ap.parse_args()
-    rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
-    dev = torch.device("cuda", lr)
-    torch.cuda.set_device(dev)
-    comm = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.distributed.init_process_group("nccl", device_id=dev)
-        from diff_icp_b200.dist import StatsComm
-        comm = StatsComm()
+def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, iters=3, graph=True, workers=1):
+    """Returns the dict reported as `groupwise_psr_iteration` (rank 0) -- times are the max over ranks."""
     from diff_icp_b200.core.GMM import GaussianMixtureUnif
     from diff_icp_b200.core.LDDMM import LDDMMModel
     from diff_icp_b200.core.PSR import DiffPSR
     from diff_icp_b200.dist import shard_frames
     spec = {"device": dev, "dtype": torch.float32}
-    frames = spiral_frames(args.frames, args.points)
-    mine = shard_frames(args.frames, rank, world)
+    frames = spiral_frames(n_frames, n_points)
+    mine = shard_frames(n_frames, rank, world)
     torch.manual_seed(1234)
-    G = GaussianMixtureUnif(torch.zeros(args.C, 2), spec=spec)
+    G = GaussianMixtureUnif(torch.zeros(C, 2), spec=spec)
     LM = LDDMMModel(sigma=0.2, D=2, lambd=500.0, version="hybrid", scheme="Euler", nt=10, spec=spec)
-    LM.use_cuda_graph = bool(args.graph)
+    LM.use_cuda_graph = bool(graph)
     P = DiffPSR([frames[k].to(dev) for k in mine], G, LM, dataspec=spec, compspec=spec, comm=comm)
     P.printstuff = False
-    P.frame_workers = args.workers
+    P.frame_workers = workers
     P.set_support_scheme("grid", rho=math.sqrt(2))
     P.reinitialize_GMM()
     times = []
-    for it in range(args.iters):
+    for it in range(iters):
         torch.cuda.synchronize()
         if comm is not None:
             torch.distributed.barrier()
@@ -87,12 +71,35 @@ def main():
         tt = torch.tensor(times, device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         times = tt.tolist()
+    return {"metric": "groupwise_psr_iteration_ms", "n_gpus": world, "frames": n_frames, "points_per_frame": n_points,
+            "C": C, "support_points": int(P.q0[0].shape[0]), "model": "hybrid, Euler nt=10, grid support rho=sqrt(2), 2-D",
+            "scaling": "strong (frames sharded over ranks)", "cuda_graph": bool(graph), "frame_workers": workers,
+            "FE": P.FE, "sigma": P.GMMi[0].sigma,
+            "gmm_opt_ms": [1e3 * a for a, _ in times], "reg_opt_ms": [1e3 * b for _, b in times],
+            "iteration_ms_steady": 1e3 * sum(times[-1])}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--points", type=int, default=10000)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--C", type=int, default=50)
+    ap.add_argument("--workers", type=int, default=1)
+    args = ap.parse_args()
+    rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    dev = torch.device("cuda", lr)
+    torch.cuda.set_device(dev)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+        from diff_icp_b200.dist import StatsComm
+        comm = StatsComm()
+    res = run_groupwise(rank, world, dev, comm, args.frames, args.points, args.C, args.iters, args.graph, args.workers)
     if rank == 0:
-        print(json.dumps({"metric": "groupwise_psr_iteration_ms", "n_gpus": world, "frames": args.frames,
-                          "points_per_frame": args.points, "C": args.C, "support_points": int(P.q0[0].shape[0]),
-                          "cuda_graph": bool(args.graph), "frame_workers": args.workers, "FE": P.FE, "sigma": P.GMMi[0].sigma,
-                          "gmm_opt_ms": [1e3 * a for a, _ in times], "reg_opt_ms": [1e3 * b for _, b in times],
-                          "iteration_ms_steady": 1e3 * sum(times[-1])}))
+        print(json.dumps(res))
     if comm is not None:
         torch.distributed.destroy_process_group()
 

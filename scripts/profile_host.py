@@ -20,4 +20,4 @@ torch.cuda.synchronize()
 pr = cProfile.Profile(); pr.enable()
 P.Reg_opt(tol=1e-3, nmax=1)
 torch.cuda.synchronize(); pr.disable()
-s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45); print(s.getvalue()[:9000])
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(28); print(s.getvalue()[:9000])
