@@ -281,7 +281,9 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_groupwise:
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         from groupwise_iteration import run_groupwise
-        groupwise = run_groupwise(rank, world, dev, GMM.comm, iters=3)
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):          # the algorithm's own progress / warning prints
+            groupwise = run_groupwise(rank, world, dev, GMM.comm, iters=3)
 
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e_total, wall_e2e * 1e3], device=dev, dtype=torch.float64)
