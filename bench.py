@@ -399,7 +399,9 @@ def kernel_roofline(args, LM, q, p, dev, ops):
     return {
         "bound": "fp32_pipe", "kernel": "pair_kernel<AdjQQ> (dicp_rhs_adjoint)",
         "achieved": 2 * fp_rate_adj / 1e12, "peak": 2 * peaks["ffma"] / 1e12, "unit": "TFLOP/s", "frac": frac_adj,
-        "traffic": None,
+        "traffic": NCU_DRAM_BYTES.get(args.variant),
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the adjoint pair kernel, ncu --set full "
+                        "(profiles/r01b_ncu_full_packed_kernels_20k.csv); algorithmic bytes = 2 x 20000 x 48 B = 1.92 MB",
         "note": "achieved = algorithmic FP32 instructions/pair x pairs / event time, x2 flop; peak = FFMA issue rate "
                 "measured live by dicp_pipe_probe (x2 flop), of measured; frac = binding-pipe utilisation",
         "adjoint": {"s_per_launch": t_adj, "pairs_per_s": pairs / t_adj, "fp32_per_pair": alg["adj_fp32"], "frac": frac_adj},
@@ -407,6 +409,9 @@ def kernel_roofline(args, LM, q, p, dev, ops):
         "measured_peaks": {"ffma_per_s": peaks["ffma"], "mufu_ex2_per_s": peaks["mufu_ex2"], "sms": sms},
     }
 
+
+# DRAM bytes per launch of the adjoint pair kernel at 20k x 20k (one ncu --set full capture, profiles/)
+NCU_DRAM_BYTES = {"classic": 1942528, "hybrid": 1945856, "logdet": 1949952}
 
 # algorithmic FP32 instruction counts per pair, D = 3 (hand count of the formulas in csrc/ops_rhs.cuh)
 ALG_WORK = {
