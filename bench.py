@@ -195,6 +195,7 @@ def run_b200(args, rank, world, local_rank):
     LM = LDDMMModel(sigma=SIGMA_LDDMM, D=DIM, lambd=LAMBDA_LDDMM, spec=spec, version=args.variant, scheme="Euler", nt=NT)
     LM.use_cuda_graph = not args.no_graph
     inv2s2 = 1.0 / (2 * SIGMA_GMM ** 2)
+    inv_w = torch.full((M,), inv2s2, device=dev)
     q_d, y_d, p_d = xA.to(dev), y.to(dev), p0.to(dev)
 
     from diff_icp_b200.core.GMM import GaussianMixtureUnif
@@ -205,14 +206,15 @@ def run_b200(args, rank, world, local_rank):
         GMM.comm = StatsComm()
 
     def closure(q, p_init, yy):
-        """(1) EM step on the current (warped) points -> targets; (2) shoot + loss + adjoint."""
+        """(1) EM step on the current points -> quadratic targets; (2) the L-BFGS closure exactly as DiffPSR.Reg_opt /
+        LDDMMModel.Optimize evaluate it: shoot + lambda*H + cost + quadratic data loss + adjoint, one captured launch
+        sequence, loss and gradient returned to the host."""
         GMM.sigma = SIGMA_GMM
         Y, Cfe, FE = GMM.EM_step(q)
-        p = p_init.detach().clone().requires_grad_(True)
-        sh = LM.Shoot(q, p)
-        L = LM.trajloss(sh) + ((sh[-1][0] - Y) ** 2).sum() * inv2s2
-        L.backward()
-        return L.detach(), p.grad
+        dataloss = lambda x: ((x - Y) ** 2).sum() * inv2s2
+        dataloss.targets, dataloss.inv2sig2 = Y, inv_w
+        evaluate = LM.closure_evaluator(dataloss, q)
+        return evaluate(p_init)
 
     def barrier():
         if world > 1:
@@ -259,9 +261,10 @@ def run_b200(args, rank, world, local_rank):
         q = q_h.to(dev, non_blocking=True)
         yy = y_h.to(dev, non_blocking=True)
         pp = p_h.to(dev, non_blocking=True)
-        L, g = closure(q, pp, yy)
-        g_h.copy_(g, non_blocking=True)
-        return float(L)                      # device -> host read of the loss (synchronises, like .item() in the reference)
+        GMM.mu = yy                          # the template (GMM centroids) also arrives from the host
+        L, g = closure(q, pp, yy)            # loss (float) and gradient (pinned host buffer): the D2H read of the step
+        g_h.copy_(g)
+        return float(L)
 
     e2e_step()
     barrier()

@@ -212,6 +212,23 @@ class LDDMMModel:
             H0 = self.Hamiltonian(q0, p0)
         return self.lam * H0 + cost
 
+    def closure_evaluator(self, dataloss, q0, x0=None):
+        """B200 build: if `dataloss` is a quadratic functor carrying `.targets` (N,D) and `.inv2sig2` (N,) -- what
+        DiffPSR.QuadLossFunctor returns -- give back a callable p0 -> (loss, d loss / d p0) that evaluates
+        trajloss(Shoot(q0,p0,x0)) + dataloss(arrival points) and its gradient as ONE captured launch sequence
+        (shooting.ClosurePlan); loss is a Python float, the gradient a host tensor view valid until the next call.
+        Returns None when the fused form does not apply (generic data loss, trajcost shortcut, fused_closure off)."""
+        targets, weights = getattr(dataloss, "targets", None), getattr(dataloss, "inv2sig2", None)
+        is_x = x0 is not None
+        if targets is None or weights is None or not self.fused_closure:
+            return None
+        if self.withlogdet and self.gradcomponent and self.try_trajcost_optim and not is_x:
+            return None
+        sp = self._spec_for(q0.shape[0], x0.shape[0] if is_x else 0, q0.device)
+        cp = shooting.ClosurePlan.get(sp, self.use_cuda_graph, self.lam)
+        cp.set_problem(q0, x0, targets, weights)
+        return cp.evaluate
+
     def Optimize(self, dataloss, q0, p0, x0=None, nmax=10, tol=1e-3, errthresh=1e8):
         """min_{p0} trajloss(p0) + dataloss(arrival points)  by L-BFGS (reference: core/LDDMM.py:338-398).
         Returns (p0, shoot, trajloss, dataloss, nsteps, change)."""
@@ -231,17 +248,13 @@ class LDDMMModel:
         # (shooting.ClosurePlan) and the L-BFGS vectors live on the host when they are small, so an optimiser step costs
         # no tiny device launches.  Loss and gradient values are the ones `lossfunc` + backward() would produce.
         lossgrad, host_side = None, False
-        targets, weights = getattr(dataloss, "targets", None), getattr(dataloss, "inv2sig2", None)
-        fused = targets is not None and weights is not None and self.fused_closure \
-            and not (self.withlogdet and self.gradcomponent and self.try_trajcost_optim and not is_x)
+        evaluator = self.closure_evaluator(dataloss, q0, x0)
+        fused = evaluator is not None
         if fused:
-            sp = self._spec_for(q0.shape[0], x0.shape[0] if is_x else 0, q0.device)
-            cp = shooting.ClosurePlan.get(sp, self.use_cuda_graph, self.lam)
-            cp.set_problem(q0, x0, targets, weights)
             host_side = p0.numel() <= self.host_lbfgs_max_numel
 
             def lossgrad(p):
-                L, g = cp.evaluate(p)
+                L, g = evaluator(p)
                 return L, [g]
 
         dev0 = p0.device
