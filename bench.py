@@ -277,7 +277,7 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     wall_e2e = time.perf_counter() - t0
     ms_e2e_total = max(sum(e0.elapsed_time(e1) for e0, e1 in ev2), 0.0)
-    if rank == 0:                            # short runs: keep the GPU under the same load until a few samples exist
+    if rank == 0 and world == 1:             # short runs: keep the GPU under the same load until a few samples exist
         t_wait = time.perf_counter()
         while len(sampler.rows) < 5 and time.perf_counter() - t_wait < 3.0:
             closure(q_d, p_d, y_d)
