@@ -42,6 +42,24 @@ SIGNATURES = {
     "dicp_small_workspace_bytes": (_sz, [_i64, _i64]),
     "dicp_small_rhs_step": (_int, [_int, _int, _f, _f, _i64, _i64, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "dicp_small_adj_step": (_int, [_int, _int, _f, _f, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "dicp_batch_rhs_step": (_int, [_int, _int, _f, _f, _int, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _f, _f, _vp, _vp,
+                                   _vp, _sz, _vp]),
+    "dicp_batch_adj_step": (_int, [_int, _int, _f, _f, _int, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _f, _f,
+                                   _vp, _vp, _vp, _sz, _vp]),
+    "dicp_batch_set_p": (_int, [_int, _int, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "dicp_batch_quad_workspace_bytes": (_sz, [_int]),
+    "dicp_batch_quad_loss": (_int, [_int, _int, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "dicp_batch_closure_out": (_int, [_int, _int, _vp, _vp, _i64, _i64, _f, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "dicp_batch_coverage": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _int, _f, _vp, _vp]),
+    "dicp_lbfgs_create": (_vp, [_int, _vp, _i64, _int, _int, _int, ctypes.c_double, ctypes.c_double]),
+    "dicp_lbfgs_destroy": (None, [_vp]),
+    "dicp_lbfgs_set_x": (_int, [_vp, _int, _vp]),
+    "dicp_lbfgs_get_x": (_int, [_vp, _int, _vp, _int]),
+    "dicp_lbfgs_reset": (_int, [_vp, _int, _int]),
+    "dicp_lbfgs_begin_step": (_int, [_vp, _vp]),
+    "dicp_lbfgs_pending": (_int, [_vp, _vp, _vp]),
+    "dicp_lbfgs_feed": (_int, [_vp, _vp, _vp]),
+    "dicp_lbfgs_stats": (_int, [_vp, _int, _vp]),
     "dicp_quad_loss": (_int, [_int, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dicp_axpy": (_int, [_i64, _vp, _vp, _f, _vp, _f, _vp, _vp]),
     "dicp_pipe_probe": (_int, [_int, _int, _int, _vp, _vp]),

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .GMM import GaussianMixtureUnif
-from .LDDMM import LDDMMModel
+from .LDDMM import LDDMMModel, ShootResult
 from .registrations import LDDMMRegistration
 from ..tools.in_out import read_point_sets
 from ..tools.point_sets import decimate
@@ -84,6 +84,9 @@ class MultiPSR:
     def __getstate__(self):
         state = dict(self.__dict__)
         state["comm"] = None
+        state.pop("_bplan", None)          # device buffers + captured CUDA graph of the batched registration
+        state.pop("_bplan_key", None)
+        state.pop("_a0_host", None)
         return state
 
     # ------------------------------------------------------------------------------------------------------
@@ -128,18 +131,27 @@ class MultiPSR:
         return self.GMMi[s].mu
 
     # ------------------------------------------------------------------------------------------------------
-    def _scatter_targets(self, allys, s):
+    def _scatter_targets(self, allys, s, allx1s=None):
+        """y[k,s] <- the frame's slice of the targets of structure s; quadloss[:, s] refreshed.  allx1s: the concatenated
+        warped points the targets were computed from (saves K small reductions: one segmented sum instead)."""
         last = 0
         for k in range(self.K):
             first, last = last, last + self.N[k, s]
             self.y[k, s] = allys[first:last].to(**self.dataspec)
-            self.update_quadloss(k, s)
+        n = int(self.N[0, s]) if self.K > 0 else 0
+        if allx1s is not None and n > 0 and all(int(self.N[k, s]) == n for k in range(self.K)):
+            d2 = ((allx1s - allys) ** 2).view(self.K, n * self.D).sum(1)        # equal-sized frames: one reduction
+            self.quadloss[:, s] = d2.to(**self.compspec) / (2 * self.GMMi[s].sigma ** 2)
+        else:
+            for k in range(self.K):
+                self.update_quadloss(k, s)
 
     def update_GMM_targets(self):
         """Recompute y, Cfe, quadloss, FE without any GMM parameter update (reference: core/PSR.py:197-213)."""
         for s in range(self.S):
-            allys, self.Cfe[s], _ = self.GMMi[s].EM_step(self._cat_structure(self.x1, s), skip_M=True)
-            self._scatter_targets(allys, s)
+            allx1s = self._cat_structure(self.x1, s)
+            allys, self.Cfe[s], _ = self.GMMi[s].EM_step(allx1s, skip_M=True)
+            self._scatter_targets(allys, s, allx1s)
         self.update_FE()
 
     def update_quadloss(self, k, s):
@@ -164,9 +176,9 @@ class MultiPSR:
         """GMM part of the alternation, one structure at a time on the points of all frames
         (reference: core/PSR.py:242-271)."""
         for s in range(self.S):
-            allys, self.Cfe[s], _, i = self.GMMi[s].EM_optimization(self._cat_structure(self.x1, s),
-                                                                    max_iterations=max_iterations, tol=tol)
-            self._scatter_targets(allys, s)
+            allx1s = self._cat_structure(self.x1, s)
+            allys, self.Cfe[s], _, i = self.GMMi[s].EM_optimization(allx1s, max_iterations=max_iterations, tol=tol)
+            self._scatter_targets(allys, s, allx1s)
             message = f"GMM optim (structure {s}) : {i} EM steps"
             if self.GMMi[s].outliers:
                 p0 = 1 / (1 + np.exp(-self.GMMi[s].outliers["eta0"]))
@@ -283,9 +295,77 @@ class DiffPSR(MultiPSR):
             counts = torch.stack([self.LMi.Kernel.check_coverage(st[-1], st[0], 2.0).sum() for st in shoot]).tolist()
         return dict(a0=a0, shoot=shoot, regloss=regloss, datal=datal, isteps=isteps, change=change, x1=allx1k, counts=counts)
 
+    # Lock-step registration of all frames: with a small support set (grid / decimated / custom
+    # scheme) one frame's closure is microseconds of device work, so the K independent L-BFGS runs of Reg_opt advance
+    # together and every round evaluates all pending closures with ONE launch sequence (shooting.BatchedClosurePlan +
+    # tools.optim.LBFGS_optimization_lockstep).  Per frame the algorithm is unchanged; iterates agree with the
+    # one-frame-at-a-time path up to floating-point rounding.  Set False for the sequential path.
+    batched_lbfgs = True
+
+    def _batched_plan(self):
+        """The BatchedClosurePlan of the current frames / support points, or None when the lock-step path does not
+        apply (dense or large supports, CPU tensors, generic model options)."""
+        from .. import ops, shooting
+        LM = self.LMi
+        dev = torch.device(self.compspec["device"])
+        if not (self.batched_lbfgs and LM.fused_closure and dev.type == "cuda" and self.K >= 1):
+            return None
+        has_x = self.support_scheme is not None
+        if LM.withlogdet and LM.gradcomponent and LM.try_trajcost_optim and not has_x:
+            return None
+        Ms = [int(q.shape[0]) for q in self.q0]
+        if min(Ms) < 1 or not ops.use_small_path(max(Ms), batched=True):
+            return None
+        Nxs = [int(x.shape[0]) if has_x else 0 for x in self.allx0]
+        key = (tuple(Ms), tuple(Nxs), LM.D, LM.nt, LM.scheme, LM.withlogdet, float(LM.Kernel.sigma), float(LM.eta),
+               float(LM.lam), str(dev), bool(LM.use_cuda_graph),
+               tuple((q.data_ptr(), q._version) for q in self.q0), tuple((x.data_ptr(), x._version) for x in self.allx0))
+        if getattr(self, "_bplan_key", None) != key:
+            plan = shooting.BatchedClosurePlan(LM.D, LM.nt, LM.scheme, LM.withlogdet, LM.Kernel.sigma, LM.eta, LM.lam, dev,
+                                               Ms, Nxs, use_graph=LM.use_cuda_graph)
+            plan.set_geometry(self.q0, self.allx0 if has_x else [None] * self.K)
+            self._bplan, self._bplan_key = plan, key
+        return self._bplan
+
+    def _register_all_lockstep(self, plan, nmax, tol):
+        from ..tools.optim import LBFGS_optimization_lockstep
+        K, D = self.K, self.D
+        # targets and weights of all frames' data points, concatenated in frame order (QuadLossFunctor, core/PSR.py:498-516)
+        y_cat = torch.cat([self.y[k, s] for k in range(K) for s in range(self.S)], dim=0).to(**self.compspec)
+        table = torch.tensor([1.0 / (2 * self.GMMi[s].sigma ** 2) for s in range(self.S)], **self.compspec)
+        if getattr(plan, "struct_id", None) is None:
+            plan.struct_id = torch.cat([torch.full((int(self.N[k, s]),), s, dtype=torch.long)
+                                        for k in range(K) for s in range(self.S)]).to(table.device)
+        plan.set_targets(y_cat, table[plan.struct_id])
+        # starting momenta on the host: the previous result of this path if a0[k] is still that tensor, else one download
+        cache = getattr(self, "_a0_host", None)
+        p0 = []
+        for k in range(K):
+            c = cache[k] if cache is not None else None
+            if c is not None and c[0] is self.a0[k] and c[1] == self.a0[k]._version:
+                p0.append(c[2])
+            else:
+                p0.append(self.a0[k].detach().cpu().numpy())
+        best_p, _, steps, change, _ = LBFGS_optimization_lockstep(p0, plan, nmax=nmax, tol=tol)
+        radius = 2.0 * self.LMi.Kernel.sigma if self.support_scheme is not None else None
+        traj, trajl, datal, counts = plan.finalize(best_p, coverage_radius=radius)
+        results, self._a0_host = [], [None] * K
+        for k in range(K):
+            shoot = plan.frame_states(traj, k)
+            shoot.__class__ = ShootResult
+            a0 = shoot[0][1]
+            self._a0_host[k] = (a0, a0._version, best_p[k])
+            results.append(dict(lockstep=True, a0=a0, shoot=shoot, regloss=float(trajl[k]), datal=float(datal[k]), isteps=steps[k],
+                                change=change[k], x1=shoot[-1][-1] if self.support_scheme is not None else shoot[-1][0],
+                                counts=None if counts is None else counts[k].tolist()))
+        return results
+
     def _register_all(self, nmax, tol):
         K = self.K
         dev = torch.device(self.compspec["device"])
+        plan = self._batched_plan()
+        if plan is not None:
+            return self._register_all_lockstep(plan, nmax, tol)
         W = min(int(self.frame_workers), K)
         if W <= 1 or dev.type != "cuda":
             return [self._register_frame(k, nmax, tol) for k in range(K)]
@@ -324,23 +404,31 @@ class DiffPSR(MultiPSR):
     def Reg_opt(self, nmax=10, tol=1e-3):
         """LDDMM registration of every (local) frame to its current targets (reference: core/PSR.py:521-569)."""
         results = self._register_all(nmax, tol)
+        lockstep = bool(results) and results[0].get("lockstep", False)
         for k, r in enumerate(results):
             self.a0[k], self.shoot[k], self.regloss[k] = r["a0"], r["shoot"], r["regloss"]
             last = 0
             for s in range(self.S):
                 first, last = last, last + self.N[k, s]
                 self.x1[k, s] = r["x1"][first:last].to(**self.dataspec)
-            for s in range(self.S):
-                self.update_quadloss(k, s)
+            if lockstep and self.S == 1:
+                # one structure: quadloss[k,0] is the frame's data loss sum_n |x1_n - y_n|^2 / (2 sigma^2), already
+                # reduced (deterministically) by the fused closure
+                self.quadloss[k, 0] = r["datal"]
+            else:
+                for s in range(self.S):
+                    self.update_quadloss(k, s)
             if r["counts"] is not None:
                 for t, c in enumerate(r["counts"]):
                     if c > 0:
                         print(f"WARNING : shooting, time step {t} : {c} uncovered points ({c / self.allx0[k].shape[0]:.2%})")
                         warnings.warn("Uncovered points during LDDMM shooting. Choose a smaller rho when defining the support scheme.", RuntimeWarning)
-            message = f"Frame {k} : {r['isteps']} optim steps, loss={r['regloss'] + r['datal']:.4}, change={r['change']:.4}."
-            if self.comm is None:
+            chg = r["change"]
+            chg = f"{chg:.4}" if isinstance(chg, float) else str(chg)
+            message = f"Frame {k} : {r['isteps']} optim steps, loss={r['regloss'] + r['datal']:.4}, change={chg}."
+            if self.comm is None and not lockstep:
                 self.update_FE(message=message)
             elif self.printstuff:
                 print(message)
-        if self.comm is not None:           # ranks hold different numbers of frames: ONE collective per Reg_opt
-            self.update_FE(message="Registration of all frames done.")
+        if self.comm is not None or lockstep:   # all frames were registered together: ONE free-energy update (and, with
+            self.update_FE(message="Registration of all frames done.")      # ranks, ONE collective) per Reg_opt

@@ -3,6 +3,7 @@
 #include "dispatch.cuh"
 #include <type_traits>
 #include "small_step.cuh"
+#include "batch_closure.cuh"
 
 using namespace dicp;
 
@@ -147,6 +148,55 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, float* out) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// launch the instantiation selected by (D, withlogdet, eta != 0) with `smem` bytes of dynamic shared memory
+template <int DD, bool W, bool E>
+static void launch_small_rhs(const SmallStep& S, int xpass, dim3 grid, size_t smem, cudaStream_t st) {
+    static const bool optin = [] {          // static + dynamic shared memory may exceed the 48 KB default: opt in once
+        return cudaFuncSetAttribute(small_rhs_step_kernel<DD, W, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)small_fwd_smem_bytes(kSmallMaxQ, DD)) == cudaSuccess;
+    }();
+    (void)optin;
+    small_rhs_step_kernel<DD, W, E><<<grid, kSmallThreads, smem, st>>>(S, xpass);
+}
+template <int DD, bool W, bool E>
+static void launch_small_adj(const SmallStep& S, int nsplit, int xpass, dim3 grid, size_t smem, cudaStream_t st) {
+    static const bool optin = [] {
+        return cudaFuncSetAttribute(small_adj_step_kernel<DD, W, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)small_adj_smem_bytes(kSmallMaxQ, DD)) == cudaSuccess;
+    }();
+    (void)optin;
+    small_adj_step_kernel<DD, W, E><<<grid, kSmallThreads, smem, st>>>(S, nsplit, xpass);
+}
+static void dispatch_small_rhs(int D, int withlogdet, float eta, const SmallStep& S, int xpass, dim3 grid, long long maxM,
+                               cudaStream_t st) {
+    const size_t smem = small_fwd_smem_bytes(maxM, D);
+    if (D == 2) {
+        if (eta != 0.f) launch_small_rhs<2, true, true>(S, xpass, grid, smem, st);
+        else if (withlogdet) launch_small_rhs<2, true, false>(S, xpass, grid, smem, st);
+        else launch_small_rhs<2, false, false>(S, xpass, grid, smem, st);
+    } else {
+        if (eta != 0.f) launch_small_rhs<3, true, true>(S, xpass, grid, smem, st);
+        else if (withlogdet) launch_small_rhs<3, true, false>(S, xpass, grid, smem, st);
+        else launch_small_rhs<3, false, false>(S, xpass, grid, smem, st);
+    }
+    launch_counter() += 1;
+}
+static void dispatch_small_adj(int D, int withlogdet, float eta, const SmallStep& S, int nsplit, int xpass, dim3 grid,
+                               long long maxM, cudaStream_t st) {
+    const size_t smem = small_adj_smem_bytes(maxM, D);
+    if (D == 2) {
+        if (eta != 0.f) launch_small_adj<2, true, true>(S, nsplit, xpass, grid, smem, st);
+        else if (withlogdet) launch_small_adj<2, true, false>(S, nsplit, xpass, grid, smem, st);
+        else launch_small_adj<2, false, false>(S, nsplit, xpass, grid, smem, st);
+    } else {
+        if (eta != 0.f) launch_small_adj<3, true, true>(S, nsplit, xpass, grid, smem, st);
+        else if (withlogdet) launch_small_adj<3, true, false>(S, nsplit, xpass, grid, smem, st);
+        else launch_small_adj<3, false, false>(S, nsplit, xpass, grid, smem, st);
+    }
+    launch_counter() += 1;
+}
+
+
 }  // namespace
 
 extern "C" {
@@ -234,13 +284,10 @@ int dicp_small_rhs_step(int D, int withlogdet, float sigma, float eta, int64_t M
     if (rc != DICP_OK) return rc;
     if (!s_eval || !F || (out && !base) || (eta != 0.f && !withlogdet)) return DICP_EBADARG;
     S.s_eval = s_eval; S.base = base; S.other = other; S.out = out; S.This = F; S.c_this = c_this; S.c_other = c_other;
-    const unsigned grid = (unsigned)((Nx + kSmallThreads - 1) / kSmallThreads + (M + kSmallThreads - 1) / kSmallThreads);
+    const int xpass = small_xpass(1, Nx, device_info().sms);
+    const unsigned grid = (unsigned)((Nx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass) + (M + kSmallThreads - 1) / kSmallThreads);
     cudaStream_t st = (cudaStream_t)stream;
-#define DICP_LAUNCH(DD, W, E) small_rhs_step_kernel<DD, W, E><<<grid, kSmallThreads, 0, st>>>(S)
-    if (D == 2) { if (eta != 0.f) DICP_LAUNCH(2, true, true); else if (withlogdet) DICP_LAUNCH(2, true, false); else DICP_LAUNCH(2, false, false); }
-    else { if (eta != 0.f) DICP_LAUNCH(3, true, true); else if (withlogdet) DICP_LAUNCH(3, true, false); else DICP_LAUNCH(3, false, false); }
-#undef DICP_LAUNCH
-    launch_counter() += 1;
+    dispatch_small_rhs(D, withlogdet, eta, S, xpass, dim3(grid), M, st);
     return last_error(DICP_OK);
 }
 
@@ -256,12 +303,128 @@ int dicp_small_adj_step(int D, int withlogdet, float sigma, float eta, int64_t M
     const int nsplit = small_adj_nsplit((int)Nx);
     const unsigned nQB = (unsigned)((M + kSmallThreads - 1) / kSmallThreads);
     if (1 + nQB > (unsigned)kSmallCounters) return DICP_EBADARG;
-    const unsigned grid = (unsigned)((Nx + kSmallThreads - 1) / kSmallThreads) + nQB * (unsigned)nsplit;
+    const int xpass = small_xpass(1, Nx, device_info().sms);
+    const unsigned grid = (unsigned)((Nx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass)) + nQB * (unsigned)nsplit;
     cudaStream_t st = (cudaStream_t)stream;
-#define DICP_LAUNCH(DD, W, E) small_adj_step_kernel<DD, W, E><<<grid, kSmallThreads, 0, st>>>(S, nsplit)
-    if (D == 2) { if (eta != 0.f) DICP_LAUNCH(2, true, true); else if (withlogdet) DICP_LAUNCH(2, true, false); else DICP_LAUNCH(2, false, false); }
-    else { if (eta != 0.f) DICP_LAUNCH(3, true, true); else if (withlogdet) DICP_LAUNCH(3, true, false); else DICP_LAUNCH(3, false, false); }
-#undef DICP_LAUNCH
+    dispatch_small_adj(D, withlogdet, eta, S, nsplit, xpass, dim3(grid), M, st);
+    return last_error(DICP_OK);
+}
+
+// ---- batched (multi-frame) closure for small supports ----------------------------------------------------------------
+static int batch_fill(SmallStep& S, int D, float sigma, float eta, int K, const int* dims, const int* active,
+                      int64_t maxM, int64_t maxNx, int64_t fstride, void* ws, size_t ws_frame_bytes) {
+    if ((D != 2 && D != 3) || !(sigma > 0.f) || K < 1 || K > 65535 || !dims || maxM < 1 || maxM > kSmallMaxQ ||
+        maxNx < 0 || maxNx > INT32_MAX || fstride < 2 * maxM * D + maxNx * D + 4)
+        return DICP_EBADARG;
+    if (ws == nullptr || ws_frame_bytes < small_workspace_bytes(maxM, maxNx) || (ws_frame_bytes & 15)) return DICP_EWORKSPACE;
+    GaussConst g = gauss_const(sigma);
+    S.M = (int)maxM; S.Nx = (int)maxNx;
+    S.kappa = g.kappa; S.s = g.s; S.alpha = g.alpha; S.beta = g.beta; S.eta = eta;
+    S.counters = (unsigned*)ws;
+    S.ws = (float*)((char*)ws + kSmallCounters * 4);
+    S.dims = dims; S.active = active; S.fstride = fstride; S.ws_fstride = (long long)ws_frame_bytes;
+    return DICP_OK;
+}
+
+int dicp_batch_rhs_step(int D, int withlogdet, float sigma, float eta, int K, const int* dims, const int* active,
+                        int64_t maxM, int64_t maxNx, int64_t fstride, const float* s_eval, const float* base,
+                        const float* other, float c_this, float c_other, float* out, float* F, void* workspace,
+                        size_t ws_frame_bytes, void* stream) {
+    SmallStep S{};
+    int rc = batch_fill(S, D, sigma, eta, K, dims, active, maxM, maxNx, fstride, workspace, ws_frame_bytes);
+    if (rc != DICP_OK) return rc;
+    if (!s_eval || !F || (out && !base) || (eta != 0.f && !withlogdet)) return DICP_EBADARG;
+    S.s_eval = s_eval; S.base = base; S.other = other; S.out = out; S.This = F; S.c_this = c_this; S.c_other = c_other;
+    const int xpass = small_xpass(K, maxNx, device_info().sms);
+    const dim3 grid((unsigned)((maxNx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass) +
+                               (maxM + kSmallThreads - 1) / kSmallThreads), (unsigned)K);
+    cudaStream_t st = (cudaStream_t)stream;
+    dispatch_small_rhs(D, withlogdet, eta, S, xpass, grid, maxM, st);
+    return last_error(DICP_OK);
+}
+
+int dicp_batch_adj_step(int D, int withlogdet, float sigma, float eta, int K, const int* dims, const int* active,
+                        int64_t maxM, int64_t maxNx, int64_t fstride, const float* s_eval, const float* lam,
+                        const float* base, const float* other, const float* add, float c_this, float c_other, float* out,
+                        float* G, void* workspace, size_t ws_frame_bytes, void* stream) {
+    SmallStep S{};
+    int rc = batch_fill(S, D, sigma, eta, K, dims, active, maxM, maxNx, fstride, workspace, ws_frame_bytes);
+    if (rc != DICP_OK) return rc;
+    if (!s_eval || !lam || !G || (out && !base) || out == lam || (eta != 0.f && !withlogdet)) return DICP_EBADARG;
+    S.s_eval = s_eval; S.lam = lam; S.base = base; S.other = other; S.add = add; S.out = out; S.This = G;
+    S.c_this = c_this; S.c_other = c_other;
+    // grid.x bounds every frame's CTA count: x-row CTAs + q-row blocks x splits are both monotone in Nx and M
+    const int nsplit = small_adj_nsplit((int)maxNx);
+    const unsigned nQB = (unsigned)((maxM + kSmallThreads - 1) / kSmallThreads);
+    if (1 + nQB > (unsigned)kSmallCounters) return DICP_EBADARG;
+    const int xpass = small_xpass(K, maxNx, device_info().sms);
+    const dim3 grid((unsigned)((maxNx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass)) + nQB * (unsigned)nsplit,
+                    (unsigned)K);
+    cudaStream_t st = (cudaStream_t)stream;
+    dispatch_small_adj(D, withlogdet, eta, S, nsplit, xpass, grid, maxM, st);
+    return last_error(DICP_OK);
+}
+
+static inline bool batch_dims_ok(int D, int K, const int* dims, int64_t fstride) {
+    return (D == 2 || D == 3) && K >= 1 && K <= 65535 && dims != nullptr && fstride >= 1;
+}
+
+int dicp_batch_set_p(int D, int K, const int* dims, const int* active, int64_t maxM, int64_t fstride, const float* X,
+                     int64_t xstride, float* state0, void* stream) {
+    if (!batch_dims_ok(D, K, dims, fstride) || !X || !state0 || maxM < 1 || xstride < maxM * D) return DICP_EBADARG;
+    BatchDims B{dims, active, fstride};
+    const dim3 grid((unsigned)((maxM * D + 127) / 128), (unsigned)K);
+    batch_set_p_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(B, D, X, xstride, state0);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
+size_t dicp_batch_quad_workspace_bytes(int K) { return (size_t)K * (64 + 1) * 4 + 256; }
+
+int dicp_batch_quad_loss(int D, int K, const int* dims, const int* active, int64_t max_points, int64_t fstride,
+                         const float* state_end, const float* y, const float* inv, int64_t ystride, float* g_end,
+                         float* loss, int64_t lstride, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!batch_dims_ok(D, K, dims, fstride) || !state_end || !y || !inv || !g_end || !loss || max_points < 1 ||
+        ystride < max_points || lstride < 1)
+        return DICP_EBADARG;
+    if (!workspace || workspace_bytes < dicp_batch_quad_workspace_bytes(K)) return DICP_EWORKSPACE;
+    BatchDims B{dims, active, fstride};
+    long long blocks = (max_points + 255) / 256;
+    if (blocks > 64) blocks = 64;
+    unsigned* counters = (unsigned*)workspace;                      // K words, zero before the first use
+    float* partials = (float*)workspace + ((K + 63) / 64) * 64;   // K x 64 floats
+    if ((size_t)(((K + 63) / 64) * 64 + (size_t)K * 64) * 4 > workspace_bytes) return DICP_EWORKSPACE;
+    const dim3 grid((unsigned)blocks, (unsigned)K);
+    batch_quad_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, D, state_end, y, inv, ystride, g_end, loss, lstride,
+                                                                   partials, 64, counters);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
+int dicp_batch_closure_out(int D, int K, const int* dims, const int* active, int64_t maxM, int64_t fstride,
+                           float lam_reg, const float* lam, const float* F0, const float* state_end, float* out,
+                           int64_t ostride, int nscal, void* stream) {
+    if (!batch_dims_ok(D, K, dims, fstride) || !F0 || !state_end || !out || nscal < 6 || maxM < 1 ||
+        ostride < nscal + (lam ? maxM * D : 0))
+        return DICP_EBADARG;
+    BatchDims B{dims, active, fstride};
+    const dim3 grid((unsigned)((maxM * D + 127) / 128), (unsigned)K);
+    batch_closure_out_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(B, D, lam_reg, lam, F0, state_end, out, ostride, nscal);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
+int dicp_batch_coverage(int D, int K, const int* dims, const int* active, int64_t maxM, int64_t maxNx, int64_t fstride,
+                        const float* traj, int64_t tstride, int ntimes, float radius, int* counts, void* stream) {
+    if (!batch_dims_ok(D, K, dims, fstride) || !traj || !counts || ntimes < 1 || ntimes > 65535 || maxM < 1 ||
+        maxM > kSmallMaxQ || maxNx < 0 || !(radius >= 0.f))
+        return DICP_EBADARG;
+    if (maxNx == 0) return DICP_OK;
+    BatchDims B{dims, active, fstride};
+    const dim3 grid((unsigned)((maxNx + 127) / 128), (unsigned)ntimes, (unsigned)K);
+    const float thr2 = radius * radius;
+    if (D == 2) batch_coverage_kernel<2><<<grid, 128, 0, (cudaStream_t)stream>>>(B, traj, tstride, thr2, counts, ntimes);
+    else batch_coverage_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(B, traj, tstride, thr2, counts, ntimes);
     launch_counter() += 1;
     return last_error(DICP_OK);
 }

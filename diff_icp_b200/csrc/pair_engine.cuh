@@ -299,28 +299,53 @@ _Pragma(DICP_STR(unroll DICP_COL_UNROLL))
     }
 }
 
-// Merge the column-split partials of each row in split order, then run the Op's finish.
+// Merge the column-split partials of each row, then run the Op's finish.  A CTA of 128 threads handles 128 / G rows with
+// G thread groups per row: group g merges splits g, g+G, g+2G, ... in that order, the G group results are merged in group
+// order through shared memory (fixed order => deterministic).  G = 1 is the plain serial merge in split order; G = 16 is
+// used when a few rows face many splits (column statistics of the EM step: 50 rows x thousands of splits).
 template <class Op>
 __global__ void finish_kernel(typename Op::Params prm, const float* __restrict__ part,
-                              float* __restrict__ blockscal, int M, int nsplit) {
+                              float* __restrict__ blockscal, int M, int nsplit, int G) {
     constexpr int NACC = Op::NACC, NSCAL = Op::NSCAL;
     __shared__ float red[32];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float xch[128 * NACC];
+    const int FR = 128 / G;                            // rows per CTA
+    const int r = threadIdx.x % FR, g = threadIdx.x / FR;
+    const int i = blockIdx.x * FR + r;
     float rs[NSCAL > 0 ? NSCAL : 1];
 #pragma unroll
     for (int k = 0; k < NSCAL; ++k) rs[k] = 0.f;
-    if (i < M) {
-        float acc[NACC];
-        const float* src = part + i;
+    float acc[NACC];
+    const bool have = i < M && g < nsplit;
+    if (have) {
+        const float* src = part + (size_t)g * NACC * M + i;
 #pragma unroll
         for (int k = 0; k < NACC; ++k) acc[k] = src[(size_t)k * M];
-        for (int s = 1; s < nsplit; ++s) {
+        for (int s = g + G; s < nsplit; s += G) {
             src = part + (size_t)s * NACC * M + i;
             float b[NACC];
 #pragma unroll
             for (int k = 0; k < NACC; ++k) b[k] = src[(size_t)k * M];
             Op::combine(acc, b);
         }
+    }
+    if (G > 1) {
+        if (have && g > 0) {
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) xch[(g * NACC + k) * FR + r] = acc[k];
+        }
+        __syncthreads();
+        if (have && g == 0) {
+            const int ng = nsplit < G ? nsplit : G;
+            for (int g2 = 1; g2 < ng; ++g2) {
+                float b[NACC];
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) b[k] = xch[(g2 * NACC + k) * FR + r];
+                Op::combine(acc, b);
+            }
+        }
+    }
+    if (have && g == 0) {
         typename Op::Row row;
         Op::load_row(prm, i, row);
         Op::finish(prm, i, row, acc, rs);
@@ -331,6 +356,9 @@ __global__ void finish_kernel(typename Op::Params prm, const float* __restrict__
         if (threadIdx.x == 0) blockscal[(size_t)blockIdx.x * NSCAL + k] = v;
     }
 }
+
+// thread groups per row of finish_kernel
+DICP_HD int finish_groups(int M, int nsplit) { return (nsplit >= 32 && M <= 4096) ? 16 : 1; }
 
 // out[k] (+)= scale * sum_b blockscal[b][k]   -- single CTA, fixed order.
 __global__ void scalar_reduce_kernel(const float* __restrict__ blockscal, int nblocks, int nscal,
@@ -391,7 +419,7 @@ inline size_t pair_workspace_bound(long long M, long long N) {
     long long rows_b = M * ((N + 127) / 128);                        // nsplit <= number of column tiles
     long long rows = rows_a < rows_b ? rows_a : rows_b;
     size_t part = align_up((size_t)rows * kMaxAcc * 4, 256);
-    size_t scal = align_up((size_t)((M + 127) / 128 + 1) * kMaxScal * 4, 256);
+    size_t scal = align_up((size_t)((M + 127) / 128 + 1 + 4096 / 8) * kMaxScal * 4, 256);    // finish CTAs: <= M/8 when M <= 4096
     return col + part + scal + 1024;
 }
 
@@ -415,7 +443,8 @@ inline PairPlan make_plan(int M, int N) {
     p.nsplit = (int)s;
     p.col_bytes = align_up((size_t)p.ntiles * Op::TILE * Op::COLF4 * 16, 256);
     p.part_bytes = p.nsplit > 1 ? align_up((size_t)p.nsplit * M * Op::NACC * 4, 256) : 0;
-    int nfin = p.nsplit > 1 ? (M + 127) / 128 : p.nrb;
+    const int fr = 128 / finish_groups(M, p.nsplit);
+    int nfin = p.nsplit > 1 ? (M + fr - 1) / fr : p.nrb;
     p.scal_bytes = align_up((size_t)(nfin > p.nrb ? nfin : p.nrb) * (Op::NSCAL > 0 ? Op::NSCAL : 1) * 4, 256);
     return p;
 }
@@ -445,8 +474,9 @@ inline int run_pair(const typename Op::Params& prm, int M, int N, float* scal_ou
     launch_counter() += 2;
     int nblk = p.nrb;
     if (p.nsplit > 1) {
-        nblk = (M + 127) / 128;
-        finish_kernel<Op><<<nblk, 128, 0, st>>>(prm, part, blockscal, M, p.nsplit);
+        const int G = finish_groups(M, p.nsplit);
+        nblk = (M + 128 / G - 1) / (128 / G);
+        finish_kernel<Op><<<nblk, 128, 0, st>>>(prm, part, blockscal, M, p.nsplit, G);
         launch_counter() += 1;
     }
     if (Op::NSCAL > 0 && scal_out != nullptr) {

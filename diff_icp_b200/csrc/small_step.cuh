@@ -16,10 +16,11 @@
 // State / cotangent layout: flat [ q (M,D) | p (M,D) | x (Nx,D) | cost ];  F layout: [ vq | dp | vx | dcost, A, B, C ].
 #pragma once
 #include "ops_rhs.cuh"
+#include <cstdlib>
 
 namespace dicp {
 
-static constexpr int kSmallMaxQ = 512;        // support points staged entirely in shared memory
+static constexpr int kSmallMaxQ = 1024;       // support points staged entirely in (dynamic) shared memory
 static constexpr int kSmallThreads = 128;     // rows per CTA (one row per thread)
 static constexpr int kSmallChunk = 512;       // data-point columns per q-row CTA in the adjoint
 static constexpr int kSmallCounters = 64;     // uint32 counters at the head of the workspace
@@ -37,7 +38,50 @@ struct SmallStep {
     float kappa, s, alpha, beta, eta;
     float* ws;               // workspace after the counters: block scalars / partials
     unsigned* counters;
+    // Batched form (dims != nullptr; see batch_closure.cuh): blockIdx.y = frame k.  Every pointer above addresses frame 0
+    // and advances by `fstride` floats per frame, the workspace (counters included) by `ws_fstride` bytes; M / Nx above
+    // are replaced by the frame's own sizes.  Frames with active[k] == 0 are skipped.
+    const int* dims;         // (K,2): M_k, Nx_k
+    const int* active;       // (K), nullable
+    long long fstride;
+    long long ws_fstride;
 };
+
+// Selects the frame of this CTA in the batched form; false => nothing to do for this CTA's frame.
+DICP_D bool small_select_frame(SmallStep& S) {
+    if (S.dims == nullptr) return true;
+    const int k = blockIdx.y;
+    if (S.active != nullptr && S.active[k] == 0) return false;
+    S.M = S.dims[2 * k];
+    S.Nx = S.dims[2 * k + 1];
+    const long long o = (long long)k * S.fstride;
+    S.s_eval += o;
+    S.This += o;
+    if (S.lam) S.lam += o;
+    if (S.base) S.base += o;
+    if (S.other) S.other += o;
+    if (S.add) S.add += o;
+    if (S.out) S.out += o;
+    S.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(S.ws) + (long long)k * S.ws_fstride);
+    S.counters = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(S.counters) + (long long)k * S.ws_fstride);
+    return true;
+}
+
+// Column splits of the q-row CTAs: chunks of about sqrt(1.6 Nx) data points (clamped to [64, kSmallChunk]) balance the
+// serial sweep of a chunk against the serial merge of the splits.  Integer arithmetic only: host (grid size, workspace)
+// and device (batched form) must agree exactly.
+DICP_HD int small_adj_nsplit(int Nx) {
+    if (Nx <= 0) return 1;
+    const long long v = ((long long)Nx * 16) / 10;
+    long long r = (long long)sqrtf((float)v);      // floor(sqrt(v)) made exact by the two integer corrections
+    while (r * r > v) --r;
+    while ((r + 1) * (r + 1) <= v) ++r;
+    int chunk = (int)r;
+    if (chunk < 64) chunk = 64;
+    if (chunk > kSmallChunk) chunk = kSmallChunk;
+    const int n = (Nx + chunk - 1) / chunk;
+    return n < 1 ? 1 : n;
+}
 
 // ---- shared helpers ------------------------------------------------------------------------------------------------
 template <int D>
@@ -62,14 +106,15 @@ DICP_D void stage_cols(const RhsParams& P, int j0, int n, int Ntotal, float* sme
     }
 }
 
-// acc (packed, NACC) += sum over the n staged columns of Op::pair(row, col)
+// acc (packed, NACC) += sum over the staged column pairs [P0, P1) of Op::pair(row, col); with `tail`, also the odd last
+// column (stored alone in pair slot `tailpair`).
 template <class Op>
-DICP_D void sweep_cols(const RhsParams& P, const typename Op::Row& row, const float* smem, int n, F2* acc) {
+DICP_D void sweep_range(const RhsParams& P, const typename Op::Row& row, const float* smem, int P0, int P1, bool tail,
+                        int tailpair, F2* acc) {
     constexpr int NF = Op::NF, PF4 = NF / 2;
     const float4* sp = reinterpret_cast<const float4*>(smem);
-    const int npair = n >> 1;
 #pragma unroll 2
-    for (int Pp = 0; Pp < npair; ++Pp) {
+    for (int Pp = P0; Pp < P1; ++Pp) {
         F2 c[NF];
 #pragma unroll
         for (int k = 0; k < PF4; ++k) {
@@ -79,11 +124,11 @@ DICP_D void sweep_cols(const RhsParams& P, const typename Op::Row& row, const fl
         }
         Op::template pair<F2>(P, row, c, acc);
     }
-    if (n & 1) {
+    if (tail) {
         float c[NF], tmp[Op::NACC];
 #pragma unroll
         for (int k = 0; k < PF4; ++k) {
-            const float4 v = sp[npair * PF4 + k];
+            const float4 v = sp[tailpair * PF4 + k];
             c[2 * k] = v.x;
             c[2 * k + 1] = v.z;
         }
@@ -93,6 +138,20 @@ DICP_D void sweep_cols(const RhsParams& P, const typename Op::Row& row, const fl
 #pragma unroll
         for (int k = 0; k < Op::NACC; ++k) acc[k] = vadd(acc[k], f2(tmp[k], 0.f));
     }
+}
+
+// all n staged columns
+template <class Op>
+DICP_D void sweep_cols(const RhsParams& P, const typename Op::Row& row, const float* smem, int n, F2* acc) {
+    sweep_range<Op>(P, row, smem, 0, n >> 1, (n & 1) != 0, n >> 1, acc);
+}
+
+// group g of G: an even share of the n staged columns (whole pairs; the odd last column goes to the last group)
+template <class Op>
+DICP_D void sweep_share(const RhsParams& P, const typename Op::Row& row, const float* smem, int n, int g, int G, F2* acc) {
+    const int npair = n >> 1;
+    sweep_range<Op>(P, row, smem, (int)(((long long)npair * g) / G), (int)(((long long)npair * (g + 1)) / G),
+                    (n & 1) != 0 && g == G - 1, npair, acc);
 }
 
 DICP_D void small_update(const SmallStep& S, size_t idx) {
@@ -116,37 +175,46 @@ DICP_D bool last_cta(unsigned* counter, unsigned total) {
 }
 
 // ---- forward stage -------------------------------------------------------------------------------------------------
+// CTAs [0, nXB): x rows, `xpass` consecutive blocks of 128 rows each (more rows per CTA amortise the staging of the support
+// set, the block reductions and the ticket when many frames / data points make the grid large); then the q-row CTAs.
 template <int D, bool WLD, bool ETA>
-__global__ void __launch_bounds__(kSmallThreads) small_rhs_step_kernel(SmallStep S) {
+__global__ void __launch_bounds__(kSmallThreads) small_rhs_step_kernel(SmallStep S, int xpass) {
     using OpQQx = RhsQQ<D, false, ETA, 1>;       // x present: the divergence cost comes from the (x,q) pass
     using OpQQn = RhsQQ<D, WLD, ETA, 1>;         // x absent
     using OpXQ = RhsXQ<D, WLD, ETA, 1>;
-    __shared__ __align__(16) float cols[kSmallMaxQ * 2 * D];
+    extern __shared__ __align__(16) float cols[];                // small_fwd_smem_bytes(max M, D)
     __shared__ float red[32];
+    if (!small_select_frame(S)) return;
     const int tid = threadIdx.x, M = S.M, Nx = S.Nx;
+    const int nXB = (Nx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass);
+    const unsigned nblk = (unsigned)(nXB + (M + kSmallThreads - 1) / kSmallThreads);    // CTAs of this frame
+    if (blockIdx.x >= nblk) return;
     const size_t MD = (size_t)M * D, Ssz = 2 * MD + (size_t)Nx * D + 1;
     RhsParams P = small_params<D>(S);
     P.vq = S.This; P.dp = S.This + MD; P.vx = S.This + 2 * MD;
     stage_cols<OpXQ>(P, 0, M, M, cols);
     __syncthreads();
 
-    const int nXB = (Nx + kSmallThreads - 1) / kSmallThreads;
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     if ((int)blockIdx.x < nXB) {
-        const int i = blockIdx.x * kSmallThreads + tid;
-        if (i < Nx) {
-            typename OpXQ::Row row;
-            OpXQ::load_row(P, i, row);
-            F2 acc[OpXQ::NACC];
+        for (int ps = 0; ps < xpass; ++ps) {
+            const int i = ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid;
+            if (i < Nx) {
+                typename OpXQ::Row row;
+                OpXQ::load_row(P, i, row);
+                F2 acc[OpXQ::NACC];
 #pragma unroll
-            for (int k = 0; k < OpXQ::NACC; ++k) acc[k] = f2(0.f, 0.f);
-            sweep_cols<OpXQ>(P, row, cols, M, acc);
-            float a[OpXQ::NACC];
+                for (int k = 0; k < OpXQ::NACC; ++k) acc[k] = f2(0.f, 0.f);
+                sweep_cols<OpXQ>(P, row, cols, M, acc);
+                float a[OpXQ::NACC];
 #pragma unroll
-            for (int k = 0; k < OpXQ::NACC; ++k) a[k] = f2_sum(acc[k]);
-            OpXQ::finish(P, i, row, a, &rs[0]);
+                for (int k = 0; k < OpXQ::NACC; ++k) a[k] = f2_sum(acc[k]);
+                float dc = 0.f;                     // finish ASSIGNS the row's dcost contribution
+                OpXQ::finish(P, i, row, a, &dc);
+                rs[0] += dc;
 #pragma unroll
-            for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)i * D + k);
+                for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)i * D + k);
+            }
         }
     } else {
         const int i = ((int)blockIdx.x - nXB) * kSmallThreads + tid;
@@ -186,13 +254,13 @@ __global__ void __launch_bounds__(kSmallThreads) small_rhs_step_kernel(SmallStep
         const float v = block_sum(rs[k], red);
         if (tid == 0) S.ws[(size_t)blockIdx.x * 4 + k] = v;
     }
-    if (last_cta(&S.counters[0], gridDim.x)) {
+    if (last_cta(&S.counters[0], nblk)) {
         // fixed-order parallel sum over CTAs (strided per thread, then the fixed block tree): deterministic
         float tot[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float v = 0.f;
-            for (unsigned b = tid; b < gridDim.x; b += kSmallThreads) v += __ldcg(&S.ws[(size_t)b * 4 + k]);
+            for (unsigned b = tid; b < nblk; b += kSmallThreads) v += __ldcg(&S.ws[(size_t)b * 4 + k]);
             tot[k] = block_sum(v, red);
         }
         if (tid == 0) {
@@ -206,41 +274,52 @@ __global__ void __launch_bounds__(kSmallThreads) small_rhs_step_kernel(SmallStep
 }
 
 // ---- adjoint stage ---------------------------------------------------------------------------------------------------
-// CTA kinds: [0, nXB) x rows (columns = support set);  then nQB * nsplit q-row CTAs: row block rb, column split sp over
-// the data points (plus, for sp == 0, the support-set columns of the (q,q) interaction).
+// CTA kinds: [0, nXB) x rows (columns = support set), `xpass` blocks of 128 rows each;  then nQB * nsplit q-row CTAs: row
+// block rb, column split sp over the data points (plus, for sp == 0, the support-set columns of the (q,q) interaction).
+// In a q-row CTA with Mr <= 64 rows the 128 threads form G = 128 / Mr groups; every group sweeps its own share of the
+// staged columns for all Mr rows and the group results are added in group order through shared memory, so that all lanes
+// work even when the support set is tiny (25 points: G = 5).
 template <int D, bool WLD, bool ETA>
-__global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep S, int nsplit) {
+__global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep S, int nsplit, int xpass) {
     using OpX = typename std::conditional<ETA, AdjXQxEta<D, 1>, AdjXQx<D, WLD, 1>>::type;       // rows x, cols (q,p)
     using OpQx = typename std::conditional<ETA, AdjXQqEta<D, 1>, AdjXQq<D, WLD, 1>>::type;      // rows q, cols (x,wx)
     using OpQQx = typename std::conditional<ETA, AdjQQEta<D, 1>, AdjQQ<D, false, 1>>::type;     // rows q, cols q; x present
     using OpQQn = typename std::conditional<ETA, AdjQQEta<D, 1>, AdjQQ<D, WLD, 1>>::type;       // x absent
     constexpr int NAQ = OpQQn::NACC, NAX = OpQx::NACC, NPART = NAQ + NAX;
-    __shared__ __align__(16) float cols[kSmallMaxQ * 4 * D];      // >= kSmallChunk * 2 * D as well
+    extern __shared__ __align__(16) float cols[];                // small_adj_smem_bytes(max M, D)
+    __shared__ float xch[kSmallThreads * NPART];
+    if (!small_select_frame(S)) return;
     const int tid = threadIdx.x, M = S.M, Nx = S.Nx;
+    const int nXB = (Nx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass);
+    if (S.dims != nullptr) {                          // batched form: this frame's own split count and CTA count
+        nsplit = small_adj_nsplit(Nx);
+        if (blockIdx.x >= (unsigned)(nXB + ((M + kSmallThreads - 1) / kSmallThreads) * nsplit)) return;
+    }
     const size_t MD = (size_t)M * D, Ssz = 2 * MD + (size_t)Nx * D + 1;
     RhsParams P = small_params<D>(S);
     P.a = S.lam; P.u = S.lam + MD; P.wx = S.lam + 2 * MD; P.gc = S.lam + (Ssz - 1);
     P.gq = S.This; P.gp = S.This + MD; P.gx = S.This + 2 * MD;
-    const int nXB = (Nx + kSmallThreads - 1) / kSmallThreads;
 
     if ((int)blockIdx.x < nXB) {
         stage_cols<OpX>(P, 0, M, M, cols);
         __syncthreads();
-        const int i = blockIdx.x * kSmallThreads + tid;
-        if (i < Nx) {
-            typename OpX::Row row;
-            OpX::load_row(P, i, row);
-            F2 acc[OpX::NACC];
+        P.accumulate = 0;
+        for (int ps = 0; ps < xpass; ++ps) {
+            const int i = ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid;
+            if (i < Nx) {
+                typename OpX::Row row;
+                OpX::load_row(P, i, row);
+                F2 acc[OpX::NACC];
 #pragma unroll
-            for (int k = 0; k < OpX::NACC; ++k) acc[k] = f2(0.f, 0.f);
-            sweep_cols<OpX>(P, row, cols, M, acc);
-            float a[OpX::NACC];
+                for (int k = 0; k < OpX::NACC; ++k) acc[k] = f2(0.f, 0.f);
+                sweep_cols<OpX>(P, row, cols, M, acc);
+                float a[OpX::NACC];
 #pragma unroll
-            for (int k = 0; k < OpX::NACC; ++k) a[k] = f2_sum(acc[k]);
-            P.accumulate = 0;
-            OpX::finish(P, i, row, a, nullptr);
+                for (int k = 0; k < OpX::NACC; ++k) a[k] = f2_sum(acc[k]);
+                OpX::finish(P, i, row, a, nullptr);
 #pragma unroll
-            for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)i * D + k);
+                for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)i * D + k);
+            }
         }
         if (blockIdx.x == 0 && tid == 0) {          // cost entry: the right-hand side does not depend on cost
             S.This[Ssz - 1] = 0.f;
@@ -251,8 +330,13 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
 
     const int qb = (int)blockIdx.x - nXB;
     const int rb = qb / nsplit, sp = qb % nsplit;
-    const int i = rb * kSmallThreads + tid;
-    const bool valid = i < M;
+    // thread -> (column group g, row r)
+    const int Mr = (M <= kSmallThreads / 2) ? M : kSmallThreads;        // rows handled by this CTA's groups
+    const int G = kSmallThreads / Mr;
+    const int g = tid / Mr, r = tid - g * Mr;
+    const int i = rb * kSmallThreads + r;
+    const bool work = g < G && i < M;                // sweeps columns
+    const bool valid = work && g == 0;               // owns the row's results
     float aq[NAQ], ax[NAX];
 #pragma unroll
     for (int k = 0; k < NAQ; ++k) aq[k] = 0.f;
@@ -262,18 +346,18 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
     if (sp == 0) {                                   // (q,q) interaction
         if (Nx > 0) stage_cols<OpQQx>(P, 0, M, M, cols); else stage_cols<OpQQn>(P, 0, M, M, cols);
         __syncthreads();
-        if (valid) {
+        if (work) {
             F2 acc[NAQ];
 #pragma unroll
             for (int k = 0; k < NAQ; ++k) acc[k] = f2(0.f, 0.f);
             if (Nx > 0) {
                 typename OpQQx::Row row;
                 OpQQx::load_row(P, i, row);
-                sweep_cols<OpQQx>(P, row, cols, M, acc);
+                sweep_share<OpQQx>(P, row, cols, M, g, G, acc);
             } else {
                 typename OpQQn::Row row;
                 OpQQn::load_row(P, i, row);
-                sweep_cols<OpQQn>(P, row, cols, M, acc);
+                sweep_share<OpQQn>(P, row, cols, M, g, G, acc);
             }
 #pragma unroll
             for (int k = 0; k < NAQ; ++k) aq[k] = f2_sum(acc[k]);
@@ -284,7 +368,7 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
         const int per = (Nx + nsplit - 1) / nsplit;
         const int c0 = sp * per, c1 = (c0 + per < Nx) ? c0 + per : Nx;
         typename OpQx::Row row;
-        if (valid) OpQx::load_row(P, i, row);
+        if (work) OpQx::load_row(P, i, row);
         F2 acc[NAX];
 #pragma unroll
         for (int k = 0; k < NAX; ++k) acc[k] = f2(0.f, 0.f);
@@ -292,11 +376,28 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
             const int n = (c1 - j0 < kSmallChunk) ? c1 - j0 : kSmallChunk;
             stage_cols<OpQx>(P, j0, n, Nx, cols);
             __syncthreads();
-            if (valid) sweep_cols<OpQx>(P, row, cols, n, acc);
+            if (work) sweep_share<OpQx>(P, row, cols, n, g, G, acc);
             __syncthreads();
         }
 #pragma unroll
         for (int k = 0; k < NAX; ++k) ax[k] = f2_sum(acc[k]);
+    }
+    if (G > 1) {                                     // add the groups' results in group order
+        if (work && g > 0) {
+#pragma unroll
+            for (int k = 0; k < NAQ; ++k) xch[(g * NPART + k) * Mr + r] = aq[k];
+#pragma unroll
+            for (int k = 0; k < NAX; ++k) xch[(g * NPART + NAQ + k) * Mr + r] = ax[k];
+        }
+        __syncthreads();
+        if (valid) {
+            for (int g2 = 1; g2 < G; ++g2) {
+#pragma unroll
+                for (int k = 0; k < NAQ; ++k) aq[k] += xch[(g2 * NPART + k) * Mr + r];
+#pragma unroll
+                for (int k = 0; k < NAX; ++k) ax[k] += xch[(g2 * NPART + NAQ + k) * Mr + r];
+            }
+        }
     }
 
     // partials -> workspace [split][k][row]; the last CTA of this row block merges them in split order
@@ -329,9 +430,9 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
         __syncthreads();
         if (valid) {
 #pragma unroll
-            for (int k = 0; k < NAQ; ++k) aq[k] = merged[tid * NPART + k];
+            for (int k = 0; k < NAQ; ++k) aq[k] = merged[r * NPART + k];
 #pragma unroll
-            for (int k = 0; k < NAX; ++k) ax[k] = merged[tid * NPART + NAQ + k];
+            for (int k = 0; k < NAX; ++k) ax[k] = merged[r * NPART + NAQ + k];
         }
     }
     if (valid) {
@@ -362,15 +463,31 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
     if (tid == 0) S.counters[1 + rb] = 0u;
 }
 
-// Column splits of the q-row CTAs: chunks of about sqrt(1.6 Nx) data points (clamped to [64, kSmallChunk]) balance the
-// serial sweep of a chunk against the serial merge of the splits.
-inline int small_adj_nsplit(int Nx) {
-    if (Nx <= 0) return 1;
-    int chunk = (int)sqrtf(1.6f * (float)Nx);
-    if (chunk < 64) chunk = 64;
-    if (chunk > kSmallChunk) chunk = kSmallChunk;
-    int n = (Nx + chunk - 1) / chunk;
-    return n < 1 ? 1 : n;
+// Row passes of the x-row CTAs: one block of 128 rows per CTA until the x-row CTAs of all frames exceed ~8 resident CTAs
+// per SM, then proportionally more (at most 8).  DICP_SMALL_XPASS overrides (tuning sweeps only).
+inline int small_xpass(long long frames, long long maxNx, int sms) {
+    static const int forced = [] {
+        const char* e = getenv("DICP_SMALL_XPASS");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 1 && v <= 64) ? v : 0;
+    }();
+    if (forced) return forced;
+    const long long ctas = frames * ((maxNx + kSmallThreads - 1) / kSmallThreads);
+    long long r = ctas / ((long long)sms * 8);
+    if (r < 1) r = 1;
+    if (r > 8) r = 8;
+    return (int)r;
+}
+
+// dynamic shared memory of the two kernels: the staged column records (pair-interleaved, so an even number of columns)
+inline size_t small_fwd_smem_bytes(long long M, int D) { return (size_t)((M + 1) / 2 * 2) * 2 * D * 4; }
+inline size_t small_adj_smem_bytes(long long M, int D) {
+    size_t a = (size_t)((M + 1) / 2 * 2) * 4 * D * 4;            // (q,q) records: 4D floats
+    const size_t b = (size_t)kSmallChunk * 2 * D * 4;            // data-point chunk: 2D floats
+    const size_t c = (size_t)kSmallThreads * 16 * 4;             // merge staging: 128 x NPART floats
+    if (b > a) a = b;
+    if (c > a) a = c;
+    return a;
 }
 
 // workspace bytes: counters + max(forward block scalars, adjoint partials)

@@ -83,9 +83,14 @@ def axpy(out, a, alpha, f1, beta=0.0, f2=None, n=None):
 small_enabled = True
 
 
-def use_small_path(M):
-    """True when the support set is small enough for the one-launch-per-stage kernels (csrc/small_step.cuh)."""
-    return small_enabled and M <= load().dicp_small_max_support()
+SMALL_SINGLE_MAX = 512        # one frame at a time: above this the general tiled engine is at least as fast
+
+
+def use_small_path(M, batched=False):
+    """True when the support set is small enough for the one-launch-per-stage kernels (csrc/small_step.cuh): up to
+    dicp_small_max_support() points when many frames are evaluated together, SMALL_SINGLE_MAX for a single frame."""
+    cap = load().dicp_small_max_support()
+    return small_enabled and M <= (cap if batched else min(cap, SMALL_SINGLE_MAX))
 
 
 def alloc_small_workspace(M, Nx, device):
@@ -122,3 +127,48 @@ def alloc_workspace(rows, cols, device):
 def pipe_probe(which: int, blocks: int, iters: int, out):
     rc = load().dicp_pipe_probe(which, blocks, iters, ptr(out), stream_ptr())
     check(rc, "dicp_pipe_probe")
+
+
+# ---- batched (multi-frame) closure for small supports: blockIdx.y = frame (csrc/batch_closure.cuh) -------------------
+def batch_frame_ws_bytes(maxM, maxNx):
+    b = int(load().dicp_small_workspace_bytes(int(maxM), int(maxNx)))
+    return (b + 255) // 256 * 256
+
+
+def batch_rhs_step(D, withlogdet, sigma, eta, K, dims, active, maxM, maxNx, fstride, s_eval, base, other, c_this, c_other,
+                   out, F, ws, ws_frame):
+    rc = load().dicp_batch_rhs_step(D, int(bool(withlogdet)), float(sigma), float(eta), K, ptr(dims), ptr(active), maxM,
+                                    maxNx, fstride, ptr(s_eval), ptr(base), ptr(other), float(c_this), float(c_other),
+                                    ptr(out), ptr(F), ptr(ws), ws_frame, stream_ptr())
+    check(rc, "dicp_batch_rhs_step")
+
+
+def batch_adj_step(D, withlogdet, sigma, eta, K, dims, active, maxM, maxNx, fstride, s_eval, lam, base, other, add,
+                   c_this, c_other, out, G, ws, ws_frame):
+    rc = load().dicp_batch_adj_step(D, int(bool(withlogdet)), float(sigma), float(eta), K, ptr(dims), ptr(active), maxM,
+                                    maxNx, fstride, ptr(s_eval), ptr(lam), ptr(base), ptr(other), ptr(add), float(c_this),
+                                    float(c_other), ptr(out), ptr(G), ptr(ws), ws_frame, stream_ptr())
+    check(rc, "dicp_batch_adj_step")
+
+
+def batch_set_p(D, K, dims, active, maxM, fstride, X, xstride, state0):
+    rc = load().dicp_batch_set_p(D, K, ptr(dims), ptr(active), maxM, fstride, ptr(X), xstride, ptr(state0), stream_ptr())
+    check(rc, "dicp_batch_set_p")
+
+
+def batch_quad_loss(D, K, dims, active, max_points, fstride, state_end, y, inv, ystride, g_end, loss, lstride, ws):
+    rc = load().dicp_batch_quad_loss(D, K, ptr(dims), ptr(active), max_points, fstride, ptr(state_end), ptr(y), ptr(inv),
+                                     ystride, ptr(g_end), ptr(loss), lstride, ptr(ws), ws.numel(), stream_ptr())
+    check(rc, "dicp_batch_quad_loss")
+
+
+def batch_closure_out(D, K, dims, active, maxM, fstride, lam_reg, lam, F0, state_end, out, ostride, nscal):
+    rc = load().dicp_batch_closure_out(D, K, ptr(dims), ptr(active), maxM, fstride, float(lam_reg), ptr(lam), ptr(F0),
+                                       ptr(state_end), ptr(out), ostride, nscal, stream_ptr())
+    check(rc, "dicp_batch_closure_out")
+
+
+def batch_coverage(D, K, dims, active, maxM, maxNx, fstride, traj, tstride, ntimes, radius, counts):
+    rc = load().dicp_batch_coverage(D, K, ptr(dims), ptr(active), maxM, maxNx, fstride, ptr(traj), tstride, ntimes,
+                                    float(radius), ptr(counts), stream_ptr())
+    check(rc, "dicp_batch_coverage")

@@ -415,3 +415,182 @@ def shoot(spec: ShootSpec, q0, p0, x0=None, use_graph=False):
     x0c = None if x0 is None else x0.contiguous()
     traj, H0 = _ShootFn.apply(spec, use_graph, q0c, p0c, x0c)
     return LazyStates(spec, traj, x0 is not None), H0
+
+
+class BatchedClosurePlan:
+    """The L-BFGS closures of K independent frames -- shoot, lambda*H(q0,p0) + cost(1), quadratic data loss, adjoint sweep
+    (what ClosurePlan does for one frame) -- evaluated by ONE launch sequence with the frame index on blockIdx.y, replayed
+    as a single CUDA graph that also contains the host->device copy of the trial momenta and the device->host copy of
+    losses and gradients.  Small supports only (M_k <= dicp_small_max_support()).  It is the `evaluator` of
+    tools.optim.LBFGS_optimization_lockstep: numpy views `X`, `active`, `losses`, `grads` of its pinned host buffers.
+
+    Frame k's buffers are rows of (K, fstride) arrays, with the frame's own sizes (ragged frames are fine).
+    Every frame's arithmetic is independent of which other frames are active, and deterministic."""
+
+    NS = 8
+
+    def __init__(self, D, nt, scheme, withlogdet, sigma, eta, lam_reg, device, Ms, Nxs, use_graph=True):
+        import numpy as np
+        self.D, self.nt, self.scheme, self.withlogdet = int(D), int(nt), scheme, bool(withlogdet)
+        self.sigma, self.eta, self.lam_reg, self.device = float(sigma), float(eta), float(lam_reg), device
+        self.Ms, self.Nxs = [int(m) for m in Ms], [int(n) for n in Nxs]
+        self.K = K = len(self.Ms)
+        self.maxM, self.maxNx = max(self.Ms), max(self.Nxs)
+        if self.maxM > _lib.load().dicp_small_max_support():
+            raise ValueError("BatchedClosurePlan: support sets are too large for the small-support kernels")
+        self.specs = [ShootSpec(D, m, n, nt, scheme, withlogdet, sigma, eta, device) for m, n in zip(self.Ms, self.Nxs)]
+        self.ndata = [n if n > 0 else m for m, n in zip(self.Ms, self.Nxs)]
+        self.maxNd = max(self.ndata)
+        self.fstride = (2 * self.maxM * D + self.maxNx * D + 4 + 3) // 4 * 4
+        self.pstride = (self.maxM * D + 3) // 4 * 4
+        self.ostride = self.NS + self.pstride
+        f32 = dict(dtype=torch.float32, device=device)
+        fs = self.fstride
+        self.traj = torch.zeros(nt + 1, K, fs, **f32)
+        self.mid = torch.zeros(nt, K, fs, **f32) if scheme == "Ralston" else None
+        self.F0, self.F1, self.F2 = (torch.zeros(K, fs, **f32) for _ in range(3))
+        self.gend, self.lamA, self.lamB, self.mu, self.G1, self.G2 = (torch.zeros(K, fs, **f32) for _ in range(6))
+        self.dims = torch.tensor([[m, n] for m, n in zip(self.Ms, self.Nxs)], dtype=torch.int32).to(device)
+        # d loss / d cost(1) = 1
+        idx = torch.tensor([k * fs + sp.S - 1 for k, sp in enumerate(self.specs)], dtype=torch.long, device=device)
+        self.gend.view(-1)[idx] = 1.0
+        self.y = torch.zeros(K, self.maxNd, D, **f32)
+        self.inv = torch.zeros(K, self.maxNd, **f32)
+        # destination rows of the frames' data points in the padded (K * maxNd) layout
+        self.rows = torch.cat([k * self.maxNd + torch.arange(n) for k, n in enumerate(self.ndata)]).to(device)
+        self.ws_frame = ops.batch_frame_ws_bytes(self.maxM, self.maxNx)
+        self.ws = torch.zeros(K * self.ws_frame, dtype=torch.uint8, device=device)
+        self.qws = torch.zeros(int(_lib.load().dicp_batch_quad_workspace_bytes(K)), dtype=torch.uint8, device=device)
+        self.counts = torch.zeros(K, nt + 1, dtype=torch.int32, device=device)
+        # host <-> device staging: [ active (K int32, stored in a float32 buffer) | X (K, ostride) ] and out (K, ostride)
+        pin = device.type == "cuda"
+        self.h_in = torch.zeros(K + K * self.ostride, dtype=torch.float32)
+        self.h_out = torch.zeros(K, self.ostride, dtype=torch.float32)
+        if pin:
+            self.h_in, self.h_out = self.h_in.pin_memory(), self.h_out.pin_memory()
+        self.d_in = torch.zeros(K + K * self.ostride, **f32)
+        self.d_out = torch.zeros(K, self.ostride, **f32)
+        self.d_active = self.d_in[:K].view(torch.int32)
+        self.d_X = self.d_in[K:].view(K, self.ostride)
+        self._h_active = self.h_in[:K].view(torch.int32).numpy()
+        self.X = self.h_in[K:].view(K, self.ostride).numpy()
+        self.active = np.zeros(K, dtype=np.uint8)
+        self.losses = np.zeros(K, dtype=np.float32)
+        self._out_np = self.h_out.numpy()
+        self.grads = self._out_np.reshape(-1)[self.NS:]
+        self.use_graph = bool(use_graph) and device.type == "cuda"
+        self.graph = None
+        self.evaluations = 0
+
+    # ---- problem data -------------------------------------------------------------------------------------------------
+    def set_geometry(self, q0_list, x0_list):
+        """Support points and data points of every frame (constant over the outer iterations of DiffPSR)."""
+        t0 = self.traj[0]
+        for k, sp in enumerate(self.specs):
+            q, _, x, _ = _views(sp, t0[k])
+            q.copy_(q0_list[k])
+            if x is not None:
+                x.copy_(x0_list[k])
+
+    def set_targets(self, y_cat, inv_cat):
+        """y_cat (sum_k n_k, D), inv_cat (sum_k n_k): targets / weights 1/(2 sigma_s^2) of all frames' data points,
+        concatenated in frame order."""
+        self.y.view(-1, self.D).index_copy_(0, self.rows, y_cat)
+        self.inv.view(-1).index_copy_(0, self.rows, inv_cat)
+
+    # ---- launch sequences ---------------------------------------------------------------------------------------------
+    def _args(self):
+        return (self.D, self.withlogdet, self.sigma, self.eta, self.K, self.dims, self.d_active, self.maxM, self.maxNx,
+                self.fstride)
+
+    def _forward(self):
+        a, h, nt = self._args(), 1.0 / self.nt, self.nt
+        ops.batch_set_p(self.D, self.K, self.dims, self.d_active, self.maxM, self.fstride, self.d_X, self.ostride,
+                        self.traj[0])
+        for t in range(nt):
+            Fa = self.F0 if t == 0 else self.F1
+            if self.scheme == "Euler":
+                ops.batch_rhs_step(*a, self.traj[t], self.traj[t], None, h, 0.0, self.traj[t + 1], Fa, self.ws, self.ws_frame)
+            else:
+                ops.batch_rhs_step(*a, self.traj[t], self.traj[t], None, 2.0 * h / 3.0, 0.0, self.mid[t], Fa, self.ws,
+                                   self.ws_frame)
+                ops.batch_rhs_step(*a, self.mid[t], self.traj[t], Fa, 0.75 * h, 0.25 * h, self.traj[t + 1], self.F2,
+                                   self.ws, self.ws_frame)
+        ops.batch_quad_loss(self.D, self.K, self.dims, self.d_active, self.maxNd, self.fstride, self.traj[nt], self.y,
+                            self.inv, self.maxNd, self.gend, self.d_out[:, 5], self.ostride, self.qws)
+
+    def _adjoint(self):
+        a, h, nt = self._args(), 1.0 / self.nt, self.nt
+        cur = self.gend
+        for t in range(nt - 1, -1, -1):
+            nxt = self.lamA if cur is not self.lamA else self.lamB
+            if self.scheme == "Euler":
+                ops.batch_adj_step(*a, self.traj[t], cur, cur, None, None, h, 0.0, nxt, self.G1, self.ws, self.ws_frame)
+            else:
+                ops.batch_adj_step(*a, self.mid[t], cur, cur, None, None, 2.0 * h, 0.0, self.mu, self.G2, self.ws,
+                                   self.ws_frame)
+                ops.batch_adj_step(*a, self.traj[t], self.mu, cur, self.G2, None, 0.25 * h, 0.75 * h, nxt, self.G1,
+                                   self.ws, self.ws_frame)
+            cur = nxt
+        return cur
+
+    def _body(self):
+        self.d_in.copy_(self.h_in, non_blocking=True)
+        self._forward()
+        lam = self._adjoint()
+        ops.batch_closure_out(self.D, self.K, self.dims, self.d_active, self.maxM, self.fstride, self.lam_reg, lam,
+                              self.F0, self.traj[self.nt], self.d_out, self.ostride, self.NS)
+        self.h_out.copy_(self.d_out, non_blocking=True)
+
+    def _losses(self):
+        s = self._out_np[:, :self.NS].astype("float64")
+        H0 = 0.5 * s[:, 1] - self.eta * s[:, 2] - 0.5 * self.eta ** 2 * s[:, 3]
+        return self.lam_reg * H0 + s[:, 4], s[:, 5]
+
+    def evaluate(self):
+        """Closure values of the frames flagged in `active` at the rows of `X` -> `losses`, `grads` (one host
+        synchronisation for all frames)."""
+        self._h_active[:] = self.active
+        if self.use_graph:
+            if self.graph is None:
+                with ShootPlan._lock:
+                    self._body()
+                    torch.cuda.current_stream().synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        self._body()
+                    self.graph = g
+            self.graph.replay()
+        else:
+            self._body()
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        trajl, datal = self._losses()
+        self.losses[:] = trajl + datal
+        self.evaluations += 1
+
+    def finalize(self, p_list, coverage_radius=None):
+        """Shoot every frame from the given momenta (forward only).  Returns (traj, trajloss (K,), dataloss (K,), counts):
+        traj is a private (nt+1, K, fstride) copy of the trajectories; counts (K, nt+1) numbers of data points farther
+        than coverage_radius from every support point at each stored time (None without data points / radius)."""
+        for k, p in enumerate(p_list):
+            self.X[k, :self.Ms[k] * self.D] = p.reshape(-1)
+        self.active[:] = 1
+        self._h_active[:] = 1
+        self.d_in.copy_(self.h_in, non_blocking=True)
+        self._forward()
+        ops.batch_closure_out(self.D, self.K, self.dims, self.d_active, self.maxM, self.fstride, self.lam_reg, None,
+                              self.F0, self.traj[self.nt], self.d_out, self.ostride, self.NS)
+        counts = None
+        if coverage_radius is not None and self.maxNx > 0:
+            self.counts.zero_()
+            ops.batch_coverage(self.D, self.K, self.dims, self.d_active, self.maxM, self.maxNx, self.fstride, self.traj,
+                               self.K * self.fstride, self.nt + 1, coverage_radius, self.counts)
+            counts = self.counts.cpu().numpy()             # synchronises
+        self.h_out.copy_(self.d_out)
+        trajl, datal = self._losses()
+        return self.traj.clone(), trajl.copy(), datal.copy(), counts
+
+    def frame_states(self, traj, k):
+        """The reference's "shoot" variable of frame k (list-like of nt+1 tuples) as views into `traj`."""
+        return LazyStates(self.specs[k], traj[:, k, :], self.Nxs[k] > 0)

@@ -82,3 +82,146 @@ def LBFGS_optimization(p0, lossfunc, nmax=10, tol=1e-3, errthresh=1e8, lossgrad=
             change = max(deltas)
 
     return [t.detach() for t in best["p"]], best["L"], step, change
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Lock-step form for K independent problems (B200 build)
+
+class LockstepLBFGS:
+    """K independent torch.optim.LBFGS-like optimisers (max_iter=20, max_eval=100, history_size=100, strong-Wolfe line
+    search: the settings of tools/optim.py:26) advanced together: each round, every optimiser that needs a closure value
+    writes its trial point into row k of `X`, ONE call of `evaluate` serves all of them, and every optimiser consumes its
+    own (loss, gradient).  The per-frame state machines are native host code (csrc/lbfgs_batch.cu, C ABI
+    dicp_lbfgs_*); this class only owns the buffers."""
+
+    def __init__(self, sizes, stride=None, max_iter=20, max_eval=100, history_size=100,
+                 tolerance_grad=1e-7, tolerance_change=1e-9):
+        import ctypes
+        import numpy as np
+        from .._lib import load
+        self._lib = load()
+        self.K = len(sizes)
+        self.sizes = [int(n) for n in sizes]
+        self.stride = int(stride) if stride is not None else max(self.sizes)
+        arr = (ctypes.c_int64 * self.K)(*self.sizes)
+        self._h = self._lib.dicp_lbfgs_create(self.K, arr, self.stride, max_iter, max_eval, history_size,
+                                              float(tolerance_grad), float(tolerance_change))
+        if not self._h:
+            raise ValueError("LockstepLBFGS: bad sizes")
+        self._np = np
+        self._ct = ctypes
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.dicp_lbfgs_destroy(h)
+
+    def _fp(self, a):
+        return a.ctypes.data_as(self._ct.c_void_p)
+
+    def set_x(self, k, x):
+        a = self._np.ascontiguousarray(x, dtype=self._np.float32).reshape(-1)
+        assert a.size == self.sizes[k]
+        self._lib.dicp_lbfgs_set_x(self._h, k, self._fp(a))
+
+    def get_x(self, k, best=False):
+        a = self._np.empty(self.sizes[k], dtype=self._np.float32)
+        if self._lib.dicp_lbfgs_get_x(self._h, k, self._fp(a), int(best)) != 0:
+            raise RuntimeError("LockstepLBFGS.get_x: no value")
+        return a
+
+    def reset(self, k, line_search=True):
+        """A fresh optimiser for frame k (tools/optim.py:77 restarts without line search after a divergent step)."""
+        self._lib.dicp_lbfgs_reset(self._h, k, int(bool(line_search)))
+
+    def stats(self, k):
+        out = (self._ct.c_double * 4)()
+        self._lib.dicp_lbfgs_stats(self._h, k, out)
+        return {"last": out[0], "best": out[1], "func_evals": int(out[2]), "n_iter": int(out[3])}
+
+    def step(self, mask, evaluate, X, active, losses, grads):
+        """One optimizer.step(closure) of every frame selected by `mask` (uint8 (K,)).  X / grads: (K, stride) fp32 numpy
+        arrays, active: (K,) uint8, losses: (K,) fp32 -- the caller's (pinned) buffers; `evaluate()` must fill losses and
+        grads for the frames flagged in `active` from the rows of X.  Returns the number of evaluation rounds."""
+        m = self._np.ascontiguousarray(mask, dtype=self._np.uint8)
+        if self._lib.dicp_lbfgs_begin_step(self._h, self._fp(m)) < 0:
+            raise RuntimeError("LockstepLBFGS.step: an optimiser step is already in progress")
+        rounds = 0
+        while self._lib.dicp_lbfgs_pending(self._h, self._fp(X), self._fp(active)) > 0:
+            evaluate()
+            rounds += 1
+            self._lib.dicp_lbfgs_feed(self._h, self._fp(losses), self._fp(grads))
+        return rounds
+
+
+def LBFGS_optimization_lockstep(p0, evaluator, nmax=10, tol=1e-3, errthresh=1e8):
+    """`LBFGS_optimization` (tools/optim.py:10-110) for K independent problems advanced in lock step.
+
+    p0: list of K host arrays (any shape).  evaluator: object with numpy buffers `X` (K, stride) fp32, `active` (K,)
+    uint8, `losses` (K,) fp32, `grads` (K, stride) fp32 and a method `evaluate()` that fills losses / grads for the active
+    frames.  Per frame, same control flow as the sequential driver: at most nmax optimiser steps, stop when the RMS change
+    is below tol x RMS, divergence guard with fall-back to the best point / a 1 % perturbation and a restart without line
+    search, and the BEST parameters over all closure evaluations are returned.
+    Returns (list of best parameter arrays, list of best losses, list of step counts, list of changes, rounds)."""
+    import numpy as np
+    K = len(p0)
+    shapes = [np.shape(p) for p in p0]
+    sizes = [int(np.prod(s)) for s in shapes]
+    opt = LockstepLBFGS(sizes, stride=evaluator.X.shape[1])
+    for k in range(K):
+        opt.set_x(k, np.asarray(p0[k], dtype=np.float32))
+        opt.reset(k, True)
+    steps = [0] * K
+    go_on = [True] * K
+    L = [math.inf] * K
+    change = [None] * K
+    rounds = 0
+    while True:
+        mask = np.array([1 if (go_on[k] and steps[k] < nmax) else 0 for k in range(K)], dtype=np.uint8)
+        if not mask.any():
+            break
+        before = {k: opt.get_x(k) for k in range(K) if mask[k]}
+        rounds += opt.step(mask, evaluator.evaluate, evaluator.X, evaluator.active, evaluator.losses, evaluator.grads)
+        redo = []
+        for k in before:
+            steps[k] += 1
+            st = opt.stats(k)
+            L_before, L[k] = L[k], st["last"]
+            if L[k] > L_before or L[k] > errthresh or math.isnan(L[k]):
+                if math.isnan(L[k]):
+                    print("WARNING: NaN value for loss L during L-BFGS optimization.")
+                elif L[k] > errthresh:
+                    print("WARNING: Aberrantly large value for loss L during L-BFGS optimization.")
+                else:
+                    print("WARNING: Increase of loss L during L-BGFS optimization.")
+                best = opt.get_x(k, best=True)
+                if st["best"] < L_before:
+                    opt.set_x(k, best)
+                    L[k] = st["best"]
+                    print("L-BFGS optimization. Found an intermediate 'best_p' value for this iteration.")
+                else:
+                    rmod = 0.01
+                    t = torch.from_numpy(best)
+                    opt.set_x(k, (t + rmod * t.std() * torch.randn(t.shape)).numpy())
+                    redo.append(k)
+                    print(f"L-BFGS optimization. Trying a random perturbation of parameter from its current value, with relative strength {rmod}.")
+                change[k] = "None (divergent iteration step)"
+                opt.reset(k, False)
+            else:
+                now = opt.get_x(k)
+                delta = float(np.sqrt(np.mean((now - before[k]) ** 2)))
+                scale = float(np.sqrt(np.mean(before[k] ** 2)))
+                go_on[k] = delta > tol * scale
+                change[k] = delta
+        if redo:                                   # loss at the perturbed points (tools/optim.py:73), outside the optimisers
+            evaluator.active[:] = 0
+            for k in redo:
+                evaluator.active[k] = 1
+                evaluator.X[k, :sizes[k]] = opt.get_x(k)
+            evaluator.evaluate()
+            rounds += 1
+            for k in redo:
+                L[k] = float(evaluator.losses[k])
+    best_p = [opt.get_x(k, best=True).reshape(shapes[k]) for k in range(K)]
+    best_L = [opt.stats(k)["best"] for k in range(K)]
+    return best_p, best_L, steps, change, rounds

@@ -141,6 +141,63 @@ int dicp_small_adj_step(int D, int withlogdet, float sigma, float eta, int64_t M
                         const float* lam, const float* base, const float* other, const float* add, float c_this,
                         float c_other, float* out, float* G, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Batched (multi-frame) registration closure for small supports -------------------------------------------------
+ * DiffPSR.Reg_opt (core/PSR.py:521-569) optimises K independent frames, each through LDDMMModel.Optimize
+ * (core/LDDMM.py:338-398).  These entry points evaluate the closure of ALL frames with the same launches
+ * (blockIdx.y = frame).  Frame k owns floats [k*fstride, (k+1)*fstride) of every state-like buffer (state, cotangent, F,
+ * G: same flat layouts as above, with the frame's own sizes); dims = (K,2) int32 device array {M_k, Nx_k};
+ * active = (K) int32 device array or null: frames with active[k] == 0 are skipped.  maxM / maxNx bound the frames' sizes
+ * (maxM <= dicp_small_max_support()); fstride >= 2*maxM*D + maxNx*D + 4.
+ * workspace of the two stage calls: K * ws_frame_bytes bytes, ws_frame_bytes >= dicp_small_workspace_bytes(maxM, maxNx)
+ * and a multiple of 16, ZERO-initialised before its first use. */
+int dicp_batch_rhs_step(int D, int withlogdet, float sigma, float eta, int K, const int* dims, const int* active,
+                        int64_t maxM, int64_t maxNx, int64_t fstride, const float* s_eval, const float* base,
+                        const float* other, float c_this, float c_other, float* out, float* F, void* workspace,
+                        size_t ws_frame_bytes, void* stream);
+int dicp_batch_adj_step(int D, int withlogdet, float sigma, float eta, int K, const int* dims, const int* active,
+                        int64_t maxM, int64_t maxNx, int64_t fstride, const float* s_eval, const float* lam,
+                        const float* base, const float* other, const float* add, float c_this, float c_other, float* out,
+                        float* G, void* workspace, size_t ws_frame_bytes, void* stream);
+/* p part of state0[k] <- X[k*xstride : k*xstride + M_k*D], cost entry <- 0 (the trial momenta of one L-BFGS round). */
+int dicp_batch_set_p(int D, int K, const int* dims, const int* active, int64_t maxM, int64_t fstride, const float* X,
+                     int64_t xstride, float* state0, void* stream);
+/* Quadratic data loss of every frame on its arrival state (x part if Nx_k > 0, else q part):
+ * loss[k*lstride] = sum_n inv[k*ystride+n] |z_n - y[(k*ystride+n)*D ..]|^2, g_end data part = 2 inv (z - y).
+ * workspace: dicp_batch_quad_workspace_bytes(K) bytes, zero before the first use. */
+size_t dicp_batch_quad_workspace_bytes(int K);
+int dicp_batch_quad_loss(int D, int K, const int* dims, const int* active, int64_t max_points, int64_t fstride,
+                         const float* state_end, const float* y, const float* inv, int64_t ystride, float* g_end,
+                         float* loss, int64_t lstride, void* workspace, size_t workspace_bytes, void* stream);
+/* out[k*ostride ..] = { dcost(0), A, B, C, cost(1), (untouched: data loss), -, - | lam_p + lam_reg * vq(0) } with nscal
+ * leading scalars (>= 6); lam == null: scalars only (forward-only evaluation). */
+int dicp_batch_closure_out(int D, int K, const int* dims, const int* active, int64_t maxM, int64_t fstride,
+                           float lam_reg, const float* lam, const float* F0, const float* state_end, float* out,
+                           int64_t ostride, int nscal, void* stream);
+/* counts[k*ntimes + t] += #{data points of frame k farther than `radius` from every support point at stored time t}
+ * (GaussKernel.check_coverage over a whole trajectory, tools/kernel.py:324-329 as used in core/PSR.py:559-566);
+ * traj: time-major, time point t of frame k at traj + t*tstride + k*fstride.  counts must be zeroed by the caller. */
+int dicp_batch_coverage(int D, int K, const int* dims, const int* active, int64_t maxM, int64_t maxNx, int64_t fstride,
+                        const float* traj, int64_t tstride, int ntimes, float radius, int* counts, void* stream);
+
+/* ---- Lock-step L-BFGS over K independent problems (HOST arithmetic; pointers below are HOST pointers) ---------------
+ * One optimiser per frame with the settings and the algorithm of torch.optim.LBFGS(line_search_fn="strong_wolfe") as
+ * used by LBFGS_optimization (tools/optim.py:26): state persists over steps, strong-Wolfe line search with cubic
+ * interpolation (c1 = 1e-4, c2 = 0.9, at most 25 trials), or a fixed unit step when line_search == 0 (:77).
+ * Protocol:  begin_step(mask) ; loop { n = pending(X, active) ; if n == 0 break ; <evaluate the active frames at the
+ * rows of X> ; feed(losses, grads) }.  X and grads are (K, stride) fp32 row-major, losses (K); only rows of frames that
+ * were pending are read.  The best closure value seen by a frame and its parameters are tracked (tools/optim.py:42-44). */
+void* dicp_lbfgs_create(int K, const int64_t* n, int64_t stride, int max_iter, int max_eval, int history,
+                        double tolerance_grad, double tolerance_change);
+void dicp_lbfgs_destroy(void* h);
+int dicp_lbfgs_set_x(void* h, int k, const float* x);
+int dicp_lbfgs_get_x(void* h, int k, float* x, int best);
+int dicp_lbfgs_reset(void* h, int k, int line_search);
+int dicp_lbfgs_begin_step(void* h, const uint8_t* mask);
+int dicp_lbfgs_pending(void* h, float* X, uint8_t* active);
+int dicp_lbfgs_feed(void* h, const float* losses, const float* grads);
+/* out4 = { last closure value, best closure value, closure evaluations, L-BFGS iterations } of frame k */
+int dicp_lbfgs_stats(void* h, int k, double* out4);
+
 /* Quadratic data loss of the registration step (DiffPSR.QuadLossFunctor, core/PSR.py:498-516):
  *   loss[0] = sum_n inv[n] |x_n - y_n|^2,   g[n,:] = 2 inv[n] (x_n - y_n)      (inv[n] = 1 / (2 sigma_s(n)^2)). */
 int dicp_quad_loss(int D, const float* x, const float* y, const float* inv, int64_t n, float* g, float* loss,

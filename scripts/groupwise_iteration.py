@@ -34,7 +34,8 @@ def spiral_frames(K, N, seed=1234):
     return frames
 
 
-def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, iters=3, graph=True, workers=1):
+def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, iters=3, graph=True, workers=1,
+                  lockstep=True):
     """Returns the dict reported as `groupwise_psr_iteration` (rank 0) -- times are the max over ranks."""
     from diff_icp_b200.core.GMM import GaussianMixtureUnif
     from diff_icp_b200.core.LDDMM import LDDMMModel
@@ -50,6 +51,7 @@ def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, ite
     P = DiffPSR([frames[k].to(dev) for k in mine], G, LM, dataspec=spec, compspec=spec, comm=comm)
     P.printstuff = False
     P.frame_workers = workers
+    P.batched_lbfgs = bool(lockstep)
     P.set_support_scheme("grid", rho=math.sqrt(2))
     P.reinitialize_GMM()
     times = []
@@ -73,7 +75,7 @@ def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, ite
         times = tt.tolist()
     return {"metric": "groupwise_psr_iteration_ms", "n_gpus": world, "frames": n_frames, "points_per_frame": n_points,
             "C": C, "support_points": int(P.q0[0].shape[0]), "model": "hybrid, Euler nt=10, grid support rho=sqrt(2), 2-D",
-            "scaling": "strong (frames sharded over ranks)", "cuda_graph": bool(graph), "frame_workers": workers,
+            "scaling": "strong (frames sharded over ranks)", "cuda_graph": bool(graph), "frame_workers": workers, "lockstep_lbfgs": bool(lockstep),
             "FE": P.FE, "sigma": P.GMMi[0].sigma,
             "gmm_opt_ms": [1e3 * a for a, _ in times], "reg_opt_ms": [1e3 * b for _, b in times],
             "iteration_ms_steady": 1e3 * sum(times[-1])}
@@ -87,6 +89,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--C", type=int, default=50)
     ap.add_argument("--workers", type=int, default=1)
+    ap.add_argument("--lockstep", type=int, default=1)
     args = ap.parse_args()
     rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     dev = torch.device("cuda", lr)
@@ -97,7 +100,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
         from diff_icp_b200.dist import StatsComm
         comm = StatsComm()
-    res = run_groupwise(rank, world, dev, comm, args.frames, args.points, args.C, args.iters, args.graph, args.workers)
+    res = run_groupwise(rank, world, dev, comm, args.frames, args.points, args.C, args.iters, args.graph, args.workers, args.lockstep)
     if rank == 0:
         print(json.dumps(res))
     if comm is not None:

