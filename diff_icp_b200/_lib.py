@@ -60,6 +60,10 @@ SIGNATURES = {
     "dicp_lbfgs_pending": (_int, [_vp, _vp, _vp]),
     "dicp_lbfgs_feed": (_int, [_vp, _vp, _vp]),
     "dicp_lbfgs_stats": (_int, [_vp, _int, _vp]),
+    "dicp_min2_sqdist": (_int, [_int, _vp, _i64, _vp, _vp]),
+    "dicp_decimate_workspace_bytes": (_sz, [_i64]),
+    "dicp_decimate_steps": (_int, [_int, _vp, _i64, _f, _int, _int, _vp, _vp, _sz, _vp]),
+    "dicp_decimate_status": (_int, [_vp, _i64, _vp, _vp]),
     "dicp_quad_loss": (_int, [_int, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dicp_axpy": (_int, [_i64, _vp, _vp, _f, _vp, _f, _vp, _vp]),
     "dicp_pipe_probe": (_int, [_int, _int, _int, _vp, _vp]),

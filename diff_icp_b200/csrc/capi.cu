@@ -4,6 +4,7 @@
 #include <type_traits>
 #include "small_step.cuh"
 #include "batch_closure.cuh"
+#include "pointset.cuh"
 
 using namespace dicp;
 
@@ -427,6 +428,58 @@ int dicp_batch_coverage(int D, int K, const int* dims, const int* active, int64_
     else batch_coverage_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(B, traj, tstride, thr2, counts, ntimes);
     launch_counter() += 1;
     return last_error(DICP_OK);
+}
+
+// ---- set-up helpers on point sets ----------------------------------------------------------------------------------------
+int dicp_min2_sqdist(int D, const float* x, int64_t N, float* out, void* stream) {
+    if ((D != 2 && D != 3) || N < 0 || N > INT32_MAX) return DICP_EBADARG;
+    if (N == 0) return DICP_OK;
+    if (!x || !out) return DICP_EBADARG;
+    const unsigned blocks = (unsigned)((N + kPsThreads - 1) / kPsThreads);
+    if (D == 2) min2_sqdist_kernel<2><<<blocks, kPsThreads, 0, (cudaStream_t)stream>>>(x, (int)N, out);
+    else min2_sqdist_kernel<3><<<blocks, kPsThreads, 0, (cudaStream_t)stream>>>(x, (int)N, out);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
+size_t dicp_decimate_workspace_bytes(int64_t N) {
+    if (N < 1) N = 1;
+    const size_t blocks = (size_t)((N + kPsThreads - 1) / kPsThreads);
+    return align_up((size_t)N, 256) + 256 + align_up(blocks * 8, 256);          // flags | ctrl | cand
+}
+
+int dicp_decimate_steps(int D, const float* x, int64_t N, float radius, int restart, int nsteps, int* kept, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    if ((D != 2 && D != 3) || N < 1 || N > INT32_MAX || !(radius >= 0.f) || nsteps < 0 || !x || !kept) return DICP_EBADARG;
+    if (!workspace || workspace_bytes < dicp_decimate_workspace_bytes(N)) return DICP_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    DecimState S{};
+    S.x = x; S.N = (int)N;
+    S.thr2 = (float)((double)radius * (double)radius);       // R**2 in double, compared in fp32 like the reference
+    S.flags = (unsigned char*)workspace;
+    S.ctrl = (int*)((char*)workspace + align_up((size_t)N, 256));
+    S.cand = S.ctrl + 64;
+    S.kept = kept;
+    if (restart) {
+        static const int init[4] = {0, 0, -1, 0};
+        cudaMemsetAsync(S.flags, 1, (size_t)N, st);
+        cudaMemcpyAsync(S.ctrl, init, sizeof(init), cudaMemcpyHostToDevice, st);
+    }
+    const unsigned blocks = (unsigned)((N + kPsThreads - 1) / kPsThreads);
+    for (int it = 0; it < nsteps; ++it) {
+        if (D == 2) decim_step_kernel<2><<<blocks, kPsThreads, 0, st>>>(S);
+        else decim_step_kernel<3><<<blocks, kPsThreads, 0, st>>>(S);
+    }
+    launch_counter() += (unsigned long long)nsteps;
+    return last_error(DICP_OK);
+}
+
+int dicp_decimate_status(const void* workspace, int64_t N, int* nkept_done, void* stream) {
+    if (!workspace || !nkept_done || N < 1) return DICP_EBADARG;
+    const int* ctrl = (const int*)((const char*)workspace + align_up((size_t)N, 256));
+    cudaError_t e = cudaMemcpyAsync(nkept_done, ctrl, 2 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? DICP_OK : (int)e;
 }
 
 int dicp_quad_loss(int D, const float* x, const float* y, const float* inv, int64_t n, float* g, float* loss,

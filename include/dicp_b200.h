@@ -198,6 +198,22 @@ int dicp_lbfgs_feed(void* h, const float* losses, const float* grads);
 /* out4 = { last closure value, best closure value, closure evaluations, L-BFGS iterations } of frame k */
 int dicp_lbfgs_stats(void* h, int k, double* out4);
 
+/* ---- Set-up helpers on point sets (not on the per-iteration path) ---------------------------
+ * out[i] = second smallest squared distance from x_i to the points of x (the smallest is x_i itself): the Kmin(2)
+ * reduction of intrinsic_scale (tools/point_sets.py:13-26); intrinsic scale = sqrt(mean(out)). */
+int dicp_min2_sqdist(int D, const float* x, int64_t N, float* out, void* stream);
+/* Greedy decimation with radius R (tools/point_sets.py:102-133): repeatedly keep the uncovered point with most uncovered
+ * neighbours within R (smallest index on ties) and cover its neighbours.  One pick = one launch; nothing N x N is stored.
+ * dicp_decimate_steps enqueues `nsteps` picks (restart != 0 first resets the state: all points uncovered); picks after
+ * completion are no-ops.  kept (N int32, device) receives the kept indices in pick order.
+ * dicp_decimate_status copies { number kept so far, done flag } to the HOST array nkept_done and synchronises the
+ * stream (the only synchronising entry point of this library; the caller loops steps / status until done).
+ * workspace: dicp_decimate_workspace_bytes(N) bytes, private to one decimation. */
+size_t dicp_decimate_workspace_bytes(int64_t N);
+int dicp_decimate_steps(int D, const float* x, int64_t N, float radius, int restart, int nsteps, int* kept, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int dicp_decimate_status(const void* workspace, int64_t N, int* nkept_done, void* stream);
+
 /* Quadratic data loss of the registration step (DiffPSR.QuadLossFunctor, core/PSR.py:498-516):
  *   loss[0] = sum_n inv[n] |x_n - y_n|^2,   g[n,:] = 2 inv[n] (x_n - y_n)      (inv[n] = 1 / (2 sigma_s(n)^2)). */
 int dicp_quad_loss(int D, const float* x, const float* y, const float* inv, int64_t n, float* g, float* loss,

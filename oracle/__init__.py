@@ -22,4 +22,4 @@ where it coincides with the executable torch twin ("parity unpinned" for the
 M-step ordering difference of the KeOps variant).
 """
 
-from . import kernels, lddmm, gmm  # noqa: F401
+from . import kernels, lddmm, gmm, pointsets  # noqa: F401

@@ -300,10 +300,62 @@ def gen_psr():
     print("psr.npz", len(out))
 
 
+def reference_function(relpath, name, namespace):
+    """Compile ONE function of a reference module from its source text (for modules that cannot be imported here because
+    they import pykeops at the top) and return it; nothing of the source is written anywhere."""
+    import ast
+    path = os.path.join(REF_ROOT, relpath)
+    tree = ast.parse(open(path).read(), filename=path)
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = dict(namespace)
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def gen_pointsets(rk):
+    """decimate and point_set_distance of the reference itself (tools/point_sets.py:102-133, :46-95)."""
+    import math
+    ref_decimate = reference_function("diffICP/tools/point_sets.py", "decimate", {"np": np, "torch": torch})
+
+    def kmin2_scale(x):        # the one KeOps call (Kmin(2)) that cannot run here: dense equivalent
+        d2 = ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+        return float(d2.topk(2, dim=1, largest=False).values[:, 1].mean().sqrt())
+    ref_psd = reference_function("diffICP/tools/point_sets.py", "point_set_distance",
+                                 {"math": math, "warnings": warnings, "torch": torch, "intrinsic_scale": kmin2_scale,
+                                  "GaussKernel": lambda s, D: rk.GaussKernel(s, D, computversion="torch")})
+    out, cases = {}, []
+    g = torch.Generator().manual_seed(99)
+    sets = {
+        "u2": (torch.rand(700, 2, generator=g), 0.08),
+        "u3": (torch.rand(900, 3, generator=g), 0.17),
+        "clustered2": (torch.cat([0.03 * torch.randn(250, 2, generator=g) + c for c in torch.rand(4, 2, generator=g)]), 0.05),
+        # exact ties in the neighbour counts and distances exactly equal to R^2 (0.25^2 = 0.0625 is exact in fp32)
+        "lattice2": (torch.stack(torch.meshgrid(torch.arange(12.) * 0.25, torch.arange(9.) * 0.25, indexing="ij"), -1).reshape(-1, 2), 0.25),
+        "lattice3": (torch.stack(torch.meshgrid(*[torch.arange(6.) * 0.5] * 3, indexing="ij"), -1).reshape(-1, 3), 0.5),
+    }
+    for tag, (x, R) in sets.items():
+        kept, rej = ref_decimate(x, R)
+        out[f"{tag}_x"], out[f"{tag}_R"] = x.numpy(), np.array(R)
+        out[f"{tag}_kept"], out[f"{tag}_rejected"] = np.array(kept, dtype=np.int64), np.array(rej, dtype=np.int64)
+        cases.append(tag)
+    X, Y = sets["u3"][0][:500], sets["u3"][0][400:] + 0.05
+    for tag, kw in (("auto", {}), ("fixed", {"sigma_X": 0.2, "sigma_Y": 0.15})):
+        out[f"psd_{tag}_ref32"] = np.array(float(ref_psd(X, Y, **kw)))
+        out[f"psd_{tag}_gold"] = np.array(float(ref_psd(X.double(), Y.double(), **kw)))
+    out["psd_X"], out["psd_Y"] = X.numpy(), Y.numpy()
+    out["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(OUT, "pointsets.npz"), **out)
+    print("pointsets.npz", len(out))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     rk, rl, rg = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "pointsets":
+        gen_pointsets(rk)
+        sys.exit(0)
     gen_kernels(rk)
     gen_lddmm(rl)
     gen_gmm(rg)
     gen_psr()
+    gen_pointsets(rk)
