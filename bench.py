@@ -403,6 +403,7 @@ def kernel_roofline(args, LM, q, p, dev, ops):
     frac_adj = max(fp_rate_adj / peaks["ffma"], sfu_rate_adj / peaks["mufu_ex2"])
     fp_rate_fwd = alg["fwd_fp32"] * pairs / t_fwd
     frac_fwd = max(fp_rate_fwd / peaks["ffma"], pairs / t_fwd / peaks["mufu_ex2"])
+    em = em_roofline(dev, timeit, peaks)
     return {
         "bound": "fp32_pipe", "kernel": "pair_kernel<AdjQQ> (dicp_rhs_adjoint)",
         "achieved": 2 * fp_rate_adj / 1e12, "peak": 2 * peaks["ffma"] / 1e12, "unit": "TFLOP/s", "frac": frac_adj,
@@ -414,7 +415,51 @@ def kernel_roofline(args, LM, q, p, dev, ops):
         "adjoint": {"s_per_launch": t_adj, "pairs_per_s": pairs / t_adj, "fp32_per_pair": alg["adj_fp32"], "frac": frac_adj},
         "forward": {"s_per_launch": t_fwd, "pairs_per_s": pairs / t_fwd, "fp32_per_pair": alg["fwd_fp32"], "frac": frac_fwd},
         "measured_peaks": {"ffma_per_s": peaks["ffma"], "mufu_ex2_per_s": peaks["mufu_ex2"], "sms": sms},
+        "em_step": em,
     }
+
+
+def em_roofline(dev, timeit, peaks):
+    """E step at the atlas size of configs[2] (640k points x 50 components, 2-D): the three fused passes timed alone.
+    north_star asks for the achieved HBM GB/s of the E step next to its FP32 / SFU fraction: at C = 50 the passes are
+    pipe-bound, HBM-bound only below C ~ 9 -- both fractions are reported, against the measured HBM peak of
+    MEASURED_PEAKS.json (fallback 6549 GB/s = the same file's value on this pool) and the live FFMA / MUFU probes."""
+    import math
+    from diff_icp_b200 import em_ops
+    hbm = 6549.4
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        src = "MEASURED_PEAKS.json"
+    except Exception:
+        src = "fallback (MEASURED_PEAKS.json absent)"
+    N, C, D, sig = 640000, 50, 2, 0.05
+    g = torch.Generator().manual_seed(7)
+    X = torch.rand(N, D, generator=g).to(dev)
+    mu = torch.rand(C, D, generator=g).to(dev)
+    w = torch.zeros(C, device=dev)
+    lgn = D * (math.log(sig) + 0.5 * math.log(2 * math.pi))
+    wl2 = ((w - torch.logsumexp(w, 0) - lgn) * 1.4426950408889634).contiguous()
+    lpi = (w - torch.logsumexp(w, 0)).contiguous()
+    T2 = em_ops.rowpass(sig, X, mu, wl2)
+    out = {"workload": f"{N} points x {C} components, D={D}", "hbm_peak_gbs": hbm, "hbm_peak_source": src}
+    # name: (callable, algorithmic FP32 instr / pair, algorithmic HBM bytes / point)
+    passes = {
+        "row_lite": (lambda: em_ops.rowpass(sig, X, mu, wl2), 8, 4 * D + 4),
+        "col_stats": (lambda: em_ops.colstats(sig, X, T2, mu, wl2), 14, 4 * D + 4),
+        "row_full": (lambda: em_ops.rowpass(sig, X, mu, wl2, mu, lpi), 17, 4 * D + 4 + 4 * D),
+    }
+    total = 0.0
+    for name, (fn, fp, nbytes) in passes.items():
+        t = timeit(fn, n=10)
+        total += t
+        pairs = float(N) * C
+        out[name] = {"s_per_call": t, "pairs_per_s": pairs / t, "fp32_per_pair": fp,
+                     "frac_fp32": fp * pairs / t / peaks["ffma"], "frac_sfu": pairs / t / peaks["mufu_ex2"],
+                     "hbm_gbs": nbytes * N / t / 1e9, "frac_hbm": nbytes * N / t / 1e9 / hbm}
+    out["em_step_s"] = total
+    out["note"] = ("each call = pack + pair kernel (+ split merge / scalar reduction); algorithmic bytes per point: "
+                   "12D+8 per EM step (SURVEY.md 8d)")
+    return out
 
 
 # DRAM bytes per launch of the adjoint pair kernel at 20k x 20k (one ncu --set full capture, profiles/)

@@ -317,6 +317,8 @@ class DiffPSR(MultiPSR):
         if min(Ms) < 1 or not ops.use_small_path(max(Ms), batched=True):
             return None
         Nxs = [int(x.shape[0]) if has_x else 0 for x in self.allx0]
+        if has_x and min(Nxs) < 1:                 # a frame without data points: leave it to the per-frame path
+            return None
         key = (tuple(Ms), tuple(Nxs), LM.D, LM.nt, LM.scheme, LM.withlogdet, float(LM.Kernel.sigma), float(LM.eta),
                float(LM.lam), str(dev), bool(LM.use_cuda_graph),
                tuple((q.data_ptr(), q._version) for q in self.q0), tuple((x.data_ptr(), x._version) for x in self.allx0))

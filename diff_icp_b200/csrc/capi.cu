@@ -301,7 +301,7 @@ int dicp_small_adj_step(int D, int withlogdet, float sigma, float eta, int64_t M
     if (!s_eval || !lam || !G || (out && !base) || out == lam || (eta != 0.f && !withlogdet)) return DICP_EBADARG;
     S.s_eval = s_eval; S.lam = lam; S.base = base; S.other = other; S.add = add; S.out = out; S.This = G;
     S.c_this = c_this; S.c_other = c_other;
-    const int nsplit = small_adj_nsplit((int)Nx);
+    const int nsplit = small_adj_nsplit((int)Nx, small_adj_groups((int)M));
     const unsigned nQB = (unsigned)((M + kSmallThreads - 1) / kSmallThreads);
     if (1 + nQB > (unsigned)kSmallCounters) return DICP_EBADARG;
     const int xpass = small_xpass(1, Nx, device_info().sms);
@@ -355,7 +355,7 @@ int dicp_batch_adj_step(int D, int withlogdet, float sigma, float eta, int K, co
     S.s_eval = s_eval; S.lam = lam; S.base = base; S.other = other; S.add = add; S.out = out; S.This = G;
     S.c_this = c_this; S.c_other = c_other;
     // grid.x bounds every frame's CTA count: x-row CTAs + q-row blocks x splits are both monotone in Nx and M
-    const int nsplit = small_adj_nsplit((int)maxNx);
+    const int nsplit = small_adj_nsplit((int)maxNx, small_adj_groups((int)maxM));
     const unsigned nQB = (unsigned)((maxM + kSmallThreads - 1) / kSmallThreads);
     if (1 + nQB > (unsigned)kSmallCounters) return DICP_EBADARG;
     const int xpass = small_xpass(K, maxNx, device_info().sms);

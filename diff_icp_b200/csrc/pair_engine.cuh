@@ -409,6 +409,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 // Upper bound of the workspace any Op needs for an (M rows, N columns) launch on this device.
 // The Ops are held to these limits by static_asserts in make_plan.
+static constexpr int kMaxSplit = 1024;
 static constexpr int kMaxColF4 = 4, kMaxAcc = 16, kMaxScal = 8, kMaxRowsPerCta = 512, kMaxOcc = 16;
 inline size_t pair_workspace_bound(long long M, long long N) {
     const long long sms = device_info().sms;
@@ -439,6 +440,8 @@ inline PairPlan make_plan(int M, int N) {
     long long s = (DICP_WAVES * slots) / p.nrb;
     if (s < 1) s = 1;
     if (s > p.ntiles) s = p.ntiles;
+    if (s > kMaxSplit) s = kMaxSplit;          // few rows x very many columns (EM column statistics): the serial part of the
+                                               // split merge grows with s while the grid is already > 1 wave
     if ((long long)p.nrb >= slots) s = 1;
     p.nsplit = (int)s;
     p.col_bytes = align_up((size_t)p.ntiles * Op::TILE * Op::COLF4 * 16, 256);

@@ -67,12 +67,12 @@ DICP_D bool small_select_frame(SmallStep& S) {
     return true;
 }
 
-// Column splits of the q-row CTAs: chunks of about sqrt(1.6 Nx) data points (clamped to [64, kSmallChunk]) balance the
-// serial sweep of a chunk against the serial merge of the splits.  Integer arithmetic only: host (grid size, workspace)
+// Column splits of the q-row CTAs: chunks of about sqrt(1.6 Nx G) data points (clamped to [64, kSmallChunk]) balance the
+// serial sweep of a chunk (by G column groups) against the serial merge of the splits.  Integer arithmetic only: host (grid size, workspace)
 // and device (batched form) must agree exactly.
-DICP_HD int small_adj_nsplit(int Nx) {
+DICP_HD int small_adj_nsplit(int Nx, int G = 1) {
     if (Nx <= 0) return 1;
-    const long long v = ((long long)Nx * 16) / 10;
+    const long long v = ((long long)Nx * 16 * G) / 10;
     long long r = (long long)sqrtf((float)v);      // floor(sqrt(v)) made exact by the two integer corrections
     while (r * r > v) --r;
     while ((r + 1) * (r + 1) <= v) ++r;
@@ -82,6 +82,9 @@ DICP_HD int small_adj_nsplit(int Nx) {
     const int n = (Nx + chunk - 1) / chunk;
     return n < 1 ? 1 : n;
 }
+// column groups of a q-row CTA: with M <= 64 support points the 128 threads form 128 / M groups, each sweeping its own share
+// of the staged columns (G times faster sweeps => G times longer chunks in small_adj_nsplit)
+DICP_HD int small_adj_groups(int M) { return M <= kSmallThreads / 2 ? kSmallThreads / (M < 1 ? 1 : M) : 1; }
 
 // ---- shared helpers ------------------------------------------------------------------------------------------------
 template <int D>
@@ -197,11 +200,16 @@ __global__ void __launch_bounds__(kSmallThreads) small_rhs_step_kernel(SmallStep
 
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     if ((int)blockIdx.x < nXB) {
+        typename OpXQ::Row row, nextrow;
+        {
+            const int i0 = (int)blockIdx.x * xpass * kSmallThreads + tid;
+            if (i0 < Nx) OpXQ::load_row(P, i0, nextrow);
+        }
         for (int ps = 0; ps < xpass; ++ps) {
             const int i = ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid;
+            row = nextrow;
+            if (ps + 1 < xpass && i + kSmallThreads < Nx) OpXQ::load_row(P, i + kSmallThreads, nextrow);   // prefetch
             if (i < Nx) {
-                typename OpXQ::Row row;
-                OpXQ::load_row(P, i, row);
                 F2 acc[OpXQ::NACC];
 #pragma unroll
                 for (int k = 0; k < OpXQ::NACC; ++k) acc[k] = f2(0.f, 0.f);
@@ -288,11 +296,12 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
     constexpr int NAQ = OpQQn::NACC, NAX = OpQx::NACC, NPART = NAQ + NAX;
     extern __shared__ __align__(16) float cols[];                // small_adj_smem_bytes(max M, D)
     __shared__ float xch[kSmallThreads * NPART];
+    const int maxM = S.M;                             // batched form: bound of the frames' support sizes
     if (!small_select_frame(S)) return;
     const int tid = threadIdx.x, M = S.M, Nx = S.Nx;
     const int nXB = (Nx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass);
     if (S.dims != nullptr) {                          // batched form: this frame's own split count and CTA count
-        nsplit = small_adj_nsplit(Nx);
+        nsplit = small_adj_nsplit(Nx, small_adj_groups(maxM));
         if (blockIdx.x >= (unsigned)(nXB + ((M + kSmallThreads - 1) / kSmallThreads) * nsplit)) return;
     }
     const size_t MD = (size_t)M * D, Ssz = 2 * MD + (size_t)Nx * D + 1;
@@ -304,11 +313,16 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
         stage_cols<OpX>(P, 0, M, M, cols);
         __syncthreads();
         P.accumulate = 0;
+        typename OpX::Row row, nextrow;
+        {
+            const int i0 = (int)blockIdx.x * xpass * kSmallThreads + tid;
+            if (i0 < Nx) OpX::load_row(P, i0, nextrow);
+        }
         for (int ps = 0; ps < xpass; ++ps) {
             const int i = ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid;
+            row = nextrow;
+            if (ps + 1 < xpass && i + kSmallThreads < Nx) OpX::load_row(P, i + kSmallThreads, nextrow);      // prefetch
             if (i < Nx) {
-                typename OpX::Row row;
-                OpX::load_row(P, i, row);
                 F2 acc[OpX::NACC];
 #pragma unroll
                 for (int k = 0; k < OpX::NACC; ++k) acc[k] = f2(0.f, 0.f);
@@ -422,8 +436,17 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep
                 v = __ldcg(&part[col]);                           // the (q,q) part lives in split 0
             } else {
                 v = 0.f;
-                if (Nx > 0)
-                    for (int s2 = 0; s2 < nsplit; ++s2) v += __ldcg(&part[(size_t)s2 * NPART * M + col]);
+                if (Nx > 0) {
+                    int s2 = 0;
+                    for (; s2 + 8 <= nsplit; s2 += 8) {           // 8 independent loads in flight, added in split order
+                        float t[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t[u] = __ldcg(&part[(size_t)(s2 + u) * NPART * M + col]);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v += t[u];
+                    }
+                    for (; s2 < nsplit; ++s2) v += __ldcg(&part[(size_t)s2 * NPART * M + col]);
+                }
             }
             merged[item] = v;
         }
