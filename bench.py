@@ -291,6 +291,12 @@ def run_b200(args, rank, world, local_rank):
         import contextlib
         with contextlib.redirect_stdout(sys.stderr):          # the algorithm's own progress / warning prints
             groupwise = run_groupwise(rank, world, dev, GMM.comm, iters=3)
+            if world > 1:       # the 64-frame atlas is latency-bound once sharded: also report it at 64 frames PER rank
+                weak = run_groupwise(rank, world, dev, GMM.comm, iters=3, weak=True)
+                if groupwise is not None and weak is not None:
+                    groupwise["weak_scaling_64_frames_per_gpu"] = {k: weak[k] for k in
+                                                                   ("frames", "scaling", "gmm_opt_ms", "reg_opt_ms",
+                                                                    "iteration_ms_steady", "FE", "sigma")}
 
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e_total, wall_e2e * 1e3], device=dev, dtype=torch.float64)

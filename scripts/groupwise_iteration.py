@@ -35,8 +35,11 @@ def spiral_frames(K, N, seed=1234):
 
 
 def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, iters=3, graph=True, workers=1,
-                  lockstep=True):
-    """Returns the dict reported as `groupwise_psr_iteration` (rank 0) -- times are the max over ranks."""
+                  lockstep=True, weak=False):
+    """Returns the dict reported as `groupwise_psr_iteration` (rank 0) -- times are the max over ranks.
+    weak=True: `n_frames` frames PER RANK (atlas of n_frames * world frames) instead of n_frames in total."""
+    if weak:
+        n_frames = n_frames * world
     from diff_icp_b200.core.GMM import GaussianMixtureUnif
     from diff_icp_b200.core.LDDMM import LDDMMModel
     from diff_icp_b200.core.PSR import DiffPSR
@@ -75,7 +78,7 @@ def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, ite
         times = tt.tolist()
     return {"metric": "groupwise_psr_iteration_ms", "n_gpus": world, "frames": n_frames, "points_per_frame": n_points,
             "C": C, "support_points": int(P.q0[0].shape[0]), "model": "hybrid, Euler nt=10, grid support rho=sqrt(2), 2-D",
-            "scaling": "strong (frames sharded over ranks)", "cuda_graph": bool(graph), "frame_workers": workers, "lockstep_lbfgs": bool(lockstep),
+            "scaling": "weak (frames per rank fixed)" if weak else "strong (frames sharded over ranks)", "cuda_graph": bool(graph), "frame_workers": workers, "lockstep_lbfgs": bool(lockstep),
             "FE": P.FE, "sigma": P.GMMi[0].sigma,
             "gmm_opt_ms": [1e3 * a for a, _ in times], "reg_opt_ms": [1e3 * b for _, b in times],
             "iteration_ms_steady": 1e3 * sum(times[-1])}
@@ -90,6 +93,7 @@ def main():
     ap.add_argument("--C", type=int, default=50)
     ap.add_argument("--workers", type=int, default=1)
     ap.add_argument("--lockstep", type=int, default=1)
+    ap.add_argument("--weak", type=int, default=0, help="1: --frames is the number of frames per rank")
     args = ap.parse_args()
     rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     dev = torch.device("cuda", lr)
@@ -100,7 +104,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
         from diff_icp_b200.dist import StatsComm
         comm = StatsComm()
-    res = run_groupwise(rank, world, dev, comm, args.frames, args.points, args.C, args.iters, args.graph, args.workers, args.lockstep)
+    res = run_groupwise(rank, world, dev, comm, args.frames, args.points, args.C, args.iters, args.graph, args.workers, args.lockstep, bool(args.weak))
     if rank == 0:
         print(json.dumps(res))
     if comm is not None:
