@@ -426,10 +426,13 @@ def kernel_roofline(args, LM, q, p, dev, ops):
 
 
 def em_roofline(dev, timeit, peaks):
-    """E step at the atlas size of configs[2] (640k points x 50 components, 2-D): the three fused passes timed alone.
-    north_star asks for the achieved HBM GB/s of the E step next to its FP32 / SFU fraction: at C = 50 the passes are
-    pipe-bound, HBM-bound only below C ~ 9 -- both fractions are reported, against the measured HBM peak of
-    MEASURED_PEAKS.json (fallback 6549 GB/s = the same file's value on this pool) and the live FFMA / MUFU probes."""
+    """E step: the three fused passes timed alone as device time (each pass captured 10x in a CUDA graph, so host launch
+    latency does not pollute these ~10-100 us calls), at three shapes:
+      atlas   640k points x 50 components, 2-D  (configs[2]): pipe-bound, small => partly latency-bound
+      two_set 20k points x 20k components, 3-D  (configs[1], the E step inside this bench's step): pipe-bound, large
+      few_components  4M points x 8 components, 3-D: the regime (C <~ 9) where HBM binds
+    north_star asks for the achieved HBM GB/s of the E step next to its FP32 / SFU fraction: both are reported, against the
+    measured HBM peak of MEASURED_PEAKS.json (fallback: the same pool's 6549 GB/s) and the live FFMA / MUFU probes."""
     import math
     from diff_icp_b200 import em_ops
     hbm = 6549.4
@@ -438,33 +441,50 @@ def em_roofline(dev, timeit, peaks):
         src = "MEASURED_PEAKS.json"
     except Exception:
         src = "fallback (MEASURED_PEAKS.json absent)"
-    N, C, D, sig = 640000, 50, 2, 0.05
-    g = torch.Generator().manual_seed(7)
-    X = torch.rand(N, D, generator=g).to(dev)
-    mu = torch.rand(C, D, generator=g).to(dev)
-    w = torch.zeros(C, device=dev)
-    lgn = D * (math.log(sig) + 0.5 * math.log(2 * math.pi))
-    wl2 = ((w - torch.logsumexp(w, 0) - lgn) * 1.4426950408889634).contiguous()
-    lpi = (w - torch.logsumexp(w, 0)).contiguous()
-    T2 = em_ops.rowpass(sig, X, mu, wl2)
-    out = {"workload": f"{N} points x {C} components, D={D}", "hbm_peak_gbs": hbm, "hbm_peak_source": src}
-    # name: (callable, algorithmic FP32 instr / pair, algorithmic HBM bytes / point)
-    passes = {
-        "row_lite": (lambda: em_ops.rowpass(sig, X, mu, wl2), 8, 4 * D + 4),
-        "col_stats": (lambda: em_ops.colstats(sig, X, T2, mu, wl2), 14, 4 * D + 4),
-        "row_full": (lambda: em_ops.rowpass(sig, X, mu, wl2, mu, lpi), 17, 4 * D + 4 + 4 * D),
-    }
-    total = 0.0
-    for name, (fn, fp, nbytes) in passes.items():
-        t = timeit(fn, n=10)
-        total += t
-        pairs = float(N) * C
-        out[name] = {"s_per_call": t, "pairs_per_s": pairs / t, "fp32_per_pair": fp,
-                     "frac_fp32": fp * pairs / t / peaks["ffma"], "frac_sfu": pairs / t / peaks["mufu_ex2"],
-                     "hbm_gbs": nbytes * N / t / 1e9, "frac_hbm": nbytes * N / t / 1e9 / hbm}
-    out["em_step_s"] = total
-    out["note"] = ("each call = pack + pair kernel (+ split merge / scalar reduction); algorithmic bytes per point: "
-                   "12D+8 per EM step (SURVEY.md 8d)")
+
+    def graph_time(fn, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        return timeit(g.replay, n=10) / reps
+
+    out = {"hbm_peak_gbs": hbm, "hbm_peak_source": src,
+           "note": "device time per call = pack + pair kernel (+ split merge / scalar reduction), 10 calls per CUDA-graph "
+                   "replay; algorithmic bytes per point: 12D+8 per EM step (SURVEY.md 8d): pass 1 reads 4D and writes 4, "
+                   "the column pass reads 4D+4, pass 2 reads 4D+4 and writes 4D"}
+    for tag, (N, C, D, sig) in {"atlas": (640000, 50, 2, 0.05), "two_set": (20000, 20000, 3, 0.1),
+                                "few_components": (4000000, 8, 3, 0.2)}.items():
+        g = torch.Generator().manual_seed(7)
+        X = torch.rand(N, D, generator=g).to(dev)
+        mu = torch.rand(C, D, generator=g).to(dev)
+        w = torch.zeros(C, device=dev)
+        lgn = D * (math.log(sig) + 0.5 * math.log(2 * math.pi))
+        wl2 = ((w - torch.logsumexp(w, 0) - lgn) * 1.4426950408889634).contiguous()
+        lpi = (w - torch.logsumexp(w, 0)).contiguous()
+        T2 = em_ops.rowpass(sig, X, mu, wl2)
+        res = {"workload": f"{N} points x {C} components, D={D}"}
+        # name: (callable, algorithmic FP32 instr / pair, algorithmic HBM bytes / point)
+        passes = {
+            "row_lite": (lambda: em_ops.rowpass(sig, X, mu, wl2), 8, 4 * D + 4),
+            "col_stats": (lambda: em_ops.colstats(sig, X, T2, mu, wl2), 14, 4 * D + 4),
+            "row_full": (lambda: em_ops.rowpass(sig, X, mu, wl2, mu, lpi), 17, 4 * D + 4 + 4 * D),
+        }
+        total = 0.0
+        for name, (fn, fp, nbytes) in passes.items():
+            t = graph_time(fn)
+            total += t
+            pairs = float(N) * C
+            res[name] = {"s_per_call": t, "pairs_per_s": pairs / t, "fp32_per_pair": fp,
+                         "frac_fp32": fp * pairs / t / peaks["ffma"], "frac_sfu": pairs / t / peaks["mufu_ex2"],
+                         "hbm_gbs": nbytes * N / t / 1e9, "frac_hbm": nbytes * N / t / 1e9 / hbm}
+        res["em_step_s"] = total
+        res["binding"] = max(("fp32", max(res[k]["frac_fp32"] for k in passes)), ("sfu", max(res[k]["frac_sfu"] for k in passes)),
+                             ("hbm", max(res[k]["frac_hbm"] for k in passes)), key=lambda kv: kv[1])[0]
+        out[tag] = res
+        del X, T2
     return out
 
 

@@ -37,6 +37,7 @@ SIGNATURES = {
                                 _vp, _sz, _vp]),
     "dicp_em_rowpass": (_int, [_int, _int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dicp_em_colstats": (_int, [_int, _f, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "dicp_em_mstep": (_int, [_int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "dicp_log_resp": (_int, [_int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "dicp_small_max_support": (_int, []),
     "dicp_small_workspace_bytes": (_sz, [_i64, _i64]),
@@ -109,7 +110,12 @@ def ptr(t):
 
 
 def stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream on the current device (raw handle: ~20x cheaper than building a
+    torch.cuda.Stream object for every launch)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:          # private binding renamed: the public, slower way
+        return torch.cuda.current_stream().cuda_stream
 
 
 def require_cuda(*tensors):

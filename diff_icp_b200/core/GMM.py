@@ -108,6 +108,7 @@ class GaussianMixtureUnif(Module):
     def __getstate__(self):
         state = dict(self.__dict__)
         state.pop("EM_step", None)            # bound method: rebuilt on load
+        state.pop("_lpi_cache", None)
         state["comm"] = None
         return state
 
@@ -151,31 +152,32 @@ class GaussianMixtureUnif(Module):
         sigma_old = float(self.sigma)
         lgn_old = self._lgn(sigma_old)
         mu_old = self.mu.contiguous()
-        wl2 = ((self.w - torch.logsumexp(self.w, 0) - lgn_old) * _LOG2E).contiguous()
+        w_old = self.w.contiguous()
+        # log pi of the current weights: kept from the previous M step when self.w is still that tensor
+        cache = getattr(self, "_lpi_cache", None)
+        if cache is not None and cache[0] is self.w and cache[1] == self.w._version:
+            lpi_old = cache[2]
+        else:
+            lpi_old = w_old - torch.logsumexp(w_old, 0)
+        wl2 = ((lpi_old - lgn_old) * _LOG2E).contiguous()
 
-        # ---- M step for mu / w (and the column form of sigma) from log-domain column statistics ------------
-        nds2 = None
-        mu_new, w_new = mu_old, self.w
+        # ---- M step for mu / w (and the column form of sigma) from log-domain column statistics, ONE launch --
+        ms = None
+        mu_new, w_new, lpi_new = mu_old, w_old, lpi_old
         if do_mu or do_w:
             T2 = em_ops.rowpass(sigma_old, X, mu_old, wl2)
             stats = em_ops.colstats(sigma_old, X, T2, mu_old, wl2) if N_local > 0 else _empty_stats(C, D, X.device)
             if comm is not None:
                 stats = comm.merge_colstats(stats)
-            m, S0, B, A = stats[:, 0], stats[:, 1], stats[:, 2:2 + D], stats[:, 2 + D]
-            if do_mu:
-                mu_new = (mu_old + B / S0[:, None]).contiguous()
-            if do_w:
-                w_new = (m + torch.log2(S0)) * _LN2
-            if do_sig:
-                if keops_sem and do_mu:
-                    nds2 = (torch.exp2(m) * (A - (B * B).sum(-1) / S0)).sum()
-                else:
-                    nds2 = (torch.exp2(m) * A).sum()
-        lpi_new = (w_new - torch.logsumexp(w_new, 0)).contiguous()
+            sig_mode = 0 if not do_sig else (1 if (keops_sem and do_mu) else 2)
+            mu_new, w_new, lpi_new, ms = em_ops.mstep(stats, mu_old, w_old, do_mu, do_w, sig_mode)
+        nds2 = ms[0] if (ms is not None and do_sig) else None
+        lpi_new = lpi_new.contiguous()
 
         # ---- full row pass: old responsibilities, new centroids / weights ------------------------------------
         T2, Y, scal, rowP, rowQ, sq = em_ops.rowpass(sigma_old, X, mu_old, wl2, mu_new, lpi_new, per_point=use_out)
-        parts = [scal, torch.tensor([float(N_local)], device=scal.device)]
+        parts = [scal, torch.tensor([float(N_local)]).to(scal.device, non_blocking=True) if comm is not None
+                 else scal.new_zeros(1)]
         if nds2 is not None:
             parts.append(nds2.reshape(1))
         if use_out:
@@ -196,6 +198,8 @@ class GaussianMixtureUnif(Module):
             vec = torch.cat((head, vec[5:]))
         vals = vec.tolist()                                     # the ONE host synchronisation of this EM step
         P, Q, SQ, DS, N = vals[:5]
+        if comm is None:
+            N = float(N_local)
         k = 5
         if do_sig:
             nd = vals[k] if nds2 is not None else DS
@@ -209,6 +213,7 @@ class GaussianMixtureUnif(Module):
             self.mu = mu_new
         if do_w:
             self.w = w_new
+        self._lpi_cache = (self.w, self.w._version, lpi_new)
 
         sig = float(self.sigma)
         lgn = self._lgn(sig) if keops_sem else lgn_old
@@ -216,8 +221,10 @@ class GaussianMixtureUnif(Module):
         if not use_out:
             Cfe_val = P * inv2s2 + Q + N * lgn
             FE_val = Cfe_val + SQ * inv2s2
-            Cfe = torch.tensor(Cfe_val, **self.spec)
-            FE = torch.tensor(FE_val, **self.spec)
+            # 0-d fp32 tensors like the reference's return values; kept on the host (they are only ever read back as
+            # Python numbers -- EM_optimization's stop test, MultiPSR.update_FE -- and a device copy costs a transfer each)
+            Cfe = torch.tensor(Cfe_val, dtype=self.spec["dtype"])
+            FE = torch.tensor(FE_val, dtype=self.spec["dtype"])
             return Y, Cfe, FE
         g0, gT = lg0.exp(), lgT.exp()
         lpi0, lpiT = self.log_ratio_to_proba(self.outliers["eta0"])

@@ -5,6 +5,7 @@
 #include "small_step.cuh"
 #include "batch_closure.cuh"
 #include "pointset.cuh"
+#include "em_col_small.cuh"
 
 using namespace dicp;
 
@@ -245,8 +246,38 @@ int dicp_em_rowpass(int D, int lite, float sigma_old, const float* X, int64_t N,
 
 int dicp_em_colstats(int D, float sigma_old, const float* X, int64_t N, const float* T2, const float* mu_old,
                      const float* wl2, int64_t C, float* stats, void* workspace, size_t workspace_bytes, void* stream) {
+    if (C >= 1 && C <= kEmColMaxC && (D == 2 || D == 3) && sigma_old > 0.f && N >= 1 && N <= INT32_MAX && X && T2 && mu_old &&
+        wl2 && stats && workspace && workspace_bytes >= em_col_small_workspace(N, (int)C, device_info().sms)) {
+        // few components: dedicated one-launch kernel with all lanes busy (em_col_small.cuh)
+        EmParams prm{};
+        prm.X = X; prm.T2 = T2; prm.mu_old = mu_old; prm.wl2 = wl2; prm.origin = mu_old;
+        prm.kappa = gauss_const(sigma_old).kappa;
+        prm.o_stats = stats;
+        cudaStream_t st = (cudaStream_t)stream;
+        unsigned* counter = (unsigned*)workspace;
+        const size_t cbytes = em_col_small_counter_bytes(N, device_info().sms);
+        float* part = (float*)((char*)workspace + cbytes);
+        cudaMemsetAsync(counter, 0, cbytes, st);
+        const int nsplit = em_col_small_splits(N, device_info().sms);
+        if (D == 2) em_col_small_kernel<2><<<nsplit, 128, 0, st>>>(prm, (int)N, (int)C, part, counter);
+        else em_col_small_kernel<3><<<nsplit, 128, 0, st>>>(prm, (int)N, (int)C, part, counter);
+        launch_counter() += 1;
+        return last_error(DICP_OK);
+    }
     DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream};
     return last_error(em_colstats_entry(ex, D, sigma_old, X, N, T2, mu_old, wl2, C, stats));
+}
+
+int dicp_em_mstep(int D, const float* stats, const float* mu_old, const float* w_old, int64_t C, int do_mu, int do_w,
+                  int sig_mode, float* mu_new, float* w_new, float* lpi_new, float* out_scal, void* stream) {
+    if ((D != 2 && D != 3) || C < 1 || C > INT32_MAX || sig_mode < 0 || sig_mode > 2 || !mu_old || !w_old || !mu_new ||
+        !w_new || !lpi_new || !out_scal || ((do_mu || do_w || sig_mode) && !stats))
+        return DICP_EBADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (D == 2) em_mstep_kernel<2><<<1, 256, 0, st>>>(stats, mu_old, w_old, (int)C, do_mu, do_w, sig_mode, mu_new, w_new, lpi_new, out_scal);
+    else em_mstep_kernel<3><<<1, 256, 0, st>>>(stats, mu_old, w_old, (int)C, do_mu, do_w, sig_mode, mu_new, w_new, lpi_new, out_scal);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
 }
 
 int dicp_log_resp(int D, float sigma, const float* X, int64_t N, const float* mu, const float* w, int64_t C,

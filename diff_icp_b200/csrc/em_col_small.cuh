@@ -1,0 +1,210 @@
+// Column statistics of the EM step for FEW components (C <= 64): one launch, all lanes busy.
+//
+// The M step (/root/reference/diffICP/core/GMM.py:432-458; torch twin :286-297) needs, per component c, the log-domain
+// sums over ALL points n of gamma_nc, gamma_nc (x_n - mu_c), gamma_nc |x_n - mu_c|^2 (EmCol in ops_em.cuh).  Through the
+// general pair engine this is "C rows x N columns": with C = 50 (atlas) or 8 only 50 / 8 of the 128 threads of a CTA hold a
+// row, and the result needs three launches (pack, pair, split merge).  Here a CTA takes a contiguous range of points, its
+// 128 threads form G = 128 / C groups of C lanes; the points are staged chunk by chunk in shared memory and every group
+// sweeps its own share of the chunk for all C components (same EmCol::pair arithmetic, same online-max rescaling); the
+// groups are merged in group order (EmCol::combine, the log-sum-exp merge), the CTA's partial goes to the workspace, and
+// the CTAs' partials are merged in two levels by "last CTA to finish" tickets (groups of 16 CTAs, then the groups) and the
+// statistics written.  Fixed orders everywhere: deterministic, no floating-point atomics.
+#pragma once
+#include "ops_em.cuh"
+#include "small_step.cuh"     // last_cta
+
+namespace dicp {
+
+static constexpr int kEmColMaxC = 64;
+static constexpr int kEmColChunk = 512;      // points staged per step
+
+static constexpr int kEmColGroup = 16;     // CTAs per level-1 merge group
+
+// acc <- merge (in a fixed order) of the partials s in [s0, s1) of component c: thread group g takes s0+g, s0+g+G, ...
+// (loads of a batch of 8 issued before they are combined), then the groups are merged in group order through `xch`.
+// Valid result in the threads with g == 0.  All threads of the CTA must call it.
+template <int D>
+DICP_D void em_col_merge(const float* part, int s0, int s1, int g, int G, int c, int C, bool work, float* xch, float* acc) {
+    using Op = EmCol<D>;
+    constexpr int NACC = Op::NACC;
+    Op::init(acc);
+    if (work) {
+        for (int s = s0 + g; s < s1; s += 8 * G) {
+            float b[8][NACC];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int ss = s + u * G;
+                if (ss < s1) {
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) b[u][k] = __ldcg(&part[((size_t)ss * NACC + k) * C + c]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (s + u * G < s1) Op::combine(acc, b[u]);
+        }
+    }
+    __syncthreads();
+    if (work && g > 0) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) xch[(g * NACC + k) * C + c] = acc[k];
+    }
+    __syncthreads();
+    if (work && g == 0) {
+        for (int g2 = 1; g2 < G; ++g2) {
+            float b[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) b[k] = xch[(g2 * NACC + k) * C + c];
+            Op::combine(acc, b);
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) em_col_small_kernel(EmParams P, int N, int C, float* __restrict__ part,
+                                                           unsigned* __restrict__ counter) {
+    using Op = EmCol<D>;
+    constexpr int NACC = Op::NACC, CF = D + 1;                // staged record: x' (D), T2
+    __shared__ __align__(16) float pts[kEmColChunk * CF];
+    __shared__ float xch[128 * NACC];
+    const int tid = threadIdx.x;
+    const int G = 128 / C;
+    const int g = tid / C, c = tid - g * C;
+    const bool work = g < G;
+    const int nsplit = gridDim.x;
+    const int per = (N + nsplit - 1) / nsplit;
+    const int n0 = blockIdx.x * per, n1 = (n0 + per < N) ? n0 + per : N;
+
+    typename Op::Row row;
+    if (work) Op::load_row(P, c, row);
+    float acc[NACC];
+    Op::init(acc);
+    for (int j0 = n0; j0 < n1; j0 += kEmColChunk) {
+        const int n = (n1 - j0 < kEmColChunk) ? n1 - j0 : kEmColChunk;
+        __syncthreads();
+        for (int t = tid; t < n; t += 128) {
+            float rec[Op::COLF4 * 4];
+            Op::pack_col(P, j0 + t, N, rec);
+#pragma unroll
+            for (int k = 0; k < CF; ++k) pts[t * CF + k] = rec[k];
+        }
+        __syncthreads();
+        if (work) {
+            const int a = (int)(((long long)n * g) / G), b = (int)(((long long)n * (g + 1)) / G);
+            for (int t = a; t < b; ++t) {
+                float rec[CF];
+#pragma unroll
+                for (int k = 0; k < CF; ++k) rec[k] = pts[t * CF + k];
+                Op::pair(P, row, rec, acc);
+            }
+        }
+    }
+    // groups -> one partial per component, in group order
+    if (work && g > 0) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) xch[(g * NACC + k) * C + c] = acc[k];
+    }
+    __syncthreads();
+    if (work && g == 0) {
+        for (int g2 = 1; g2 < G; ++g2) {
+            float b[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) b[k] = xch[(g2 * NACC + k) * C + c];
+            Op::combine(acc, b);
+        }
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) part[((size_t)blockIdx.x * NACC + k) * C + c] = acc[k];
+    }
+    // Two-level merge of the CTAs' partials (a single serial merge of hundreds of partials by one CTA is a chain of
+    // dependent L2 round trips): the last CTA of every group of kEmColGroup consecutive CTAs merges that group's partials
+    // into a level-2 partial, and the last of those mergers merges the level-2 partials and writes the statistics.
+    const int ngroups = (nsplit + kEmColGroup - 1) / kEmColGroup;
+    const int grp = blockIdx.x / kEmColGroup;
+    const int s0 = grp * kEmColGroup, s1 = (s0 + kEmColGroup < nsplit) ? s0 + kEmColGroup : nsplit;
+    if (!last_cta(&counter[1 + grp], (unsigned)(s1 - s0))) return;
+    float* part2 = part + (size_t)nsplit * NACC * C;
+    em_col_merge<D>(part, s0, s1, g, G, c, C, work, xch, acc);
+    if (work && g == 0) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) part2[((size_t)grp * NACC + k) * C + c] = acc[k];
+    }
+    if (tid == 0) counter[1 + grp] = 0u;
+    if (!last_cta(&counter[0], (unsigned)ngroups)) return;
+    em_col_merge<D>(part2, 0, ngroups, g, G, c, C, work, xch, acc);
+    if (work && g == 0) Op::finish(P, c, row, acc, nullptr);
+    if (tid == 0) counter[0] = 0u;
+}
+
+// M step on the column statistics (/root/reference/diffICP/core/GMM.py:286-297 torch twin, :442-456 KeOps formulation):
+//   w'_c = (m_c + log2 S0_c) ln 2,  mu'_c = mu_c + B_c / S0_c,  log pi'_c = w'_c - LSE(w'),
+//   nds2 = N D sigma'^2 = sum_c 2^m_c (A_c - |B_c|^2 / S0_c)   [sig_mode 1: distances to the NEW centroids]
+//                       = sum_c 2^m_c A_c                        [sig_mode 2: distances to the OLD centroids],  0: not wanted.
+// One CTA; reductions over c with the fixed block tree (deterministic).  out_scal = { nds2, LSE(w') }.
+template <int D>
+__global__ void __launch_bounds__(256) em_mstep_kernel(const float* __restrict__ stats, const float* __restrict__ mu_old,
+                                                       const float* __restrict__ w_old, int C, int do_mu, int do_w,
+                                                       int sig_mode, float* __restrict__ mu_new, float* __restrict__ w_new,
+                                                       float* __restrict__ lpi_new, float* __restrict__ out_scal) {
+    __shared__ float red[32];
+    __shared__ float bc;
+    const int tid = threadIdx.x;
+    float wmax = -INFINITY, nd = 0.f;
+    for (int c = tid; c < C; c += 256) {
+        const float* st = stats + (size_t)c * (D + 3);
+        const float m = st[0], S0 = st[1], A = st[2 + D];
+        float b2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float B = st[2 + k];
+            b2 = fmaf(B, B, b2);
+            mu_new[(size_t)c * D + k] = do_mu ? mu_old[(size_t)c * D + k] + B / S0 : mu_old[(size_t)c * D + k];
+        }
+        const float w = do_w ? (m + log2f(S0)) * kLn2 : w_old[c];
+        w_new[c] = w;
+        wmax = fmaxf(wmax, w);
+        if (sig_mode == 1) nd += exp2f(m) * (A - b2 / S0);
+        else if (sig_mode == 2) nd += exp2f(m) * A;
+    }
+    // max over c
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if ((tid & 31) == 0) red[tid >> 5] = wmax;
+    __syncthreads();
+    if (tid == 0) {
+        float v = red[0];
+        for (int k = 1; k < 8; ++k) v = fmaxf(v, red[k]);
+        bc = v;
+    }
+    __syncthreads();
+    wmax = bc;
+    __syncthreads();
+    float se = 0.f;
+    for (int c = tid; c < C; c += 256) se += expf(w_new[c] - wmax);
+    se = block_sum(se, red);
+    if (tid == 0) bc = wmax + logf(se);
+    __syncthreads();
+    const float lse = bc;
+    for (int c = tid; c < C; c += 256) lpi_new[c] = w_new[c] - lse;
+    __syncthreads();
+    nd = block_sum(nd, red);
+    if (tid == 0) { out_scal[0] = nd; out_scal[1] = lse; }
+}
+
+// number of point ranges (CTAs): about 4 per SM, at least one chunk of points each
+inline int em_col_small_splits(long long N, int sms) {
+    long long s = (N + kEmColChunk - 1) / kEmColChunk;
+    const long long cap = (long long)sms * 4;
+    if (s > cap) s = cap;
+    return s < 1 ? 1 : (int)s;
+}
+// workspace: counters (1 + groups words, zeroed before every launch) | level-1 partials | level-2 partials
+inline size_t em_col_small_counter_bytes(long long N, int sms) {
+    const size_t words = 1 + (size_t)(em_col_small_splits(N, sms) + kEmColGroup - 1) / kEmColGroup;
+    return (words * 4 + 255) / 256 * 256;
+}
+inline size_t em_col_small_workspace(long long N, int C, int sms) {
+    const size_t ns = (size_t)em_col_small_splits(N, sms);
+    return em_col_small_counter_bytes(N, sms) + (ns + (ns + kEmColGroup - 1) / kEmColGroup) * 8 * (size_t)C * 4;
+}
+
+}  // namespace dicp

@@ -50,6 +50,19 @@ def colstats(sigma_old, X, T2, mu_old, wl2):
     return stats
 
 
+def mstep(stats, mu_old, w_old, do_mu, do_w, sig_mode):
+    """M step on the (merged) column statistics in one launch.  Returns (mu_new (C,D), w_new (C,), lpi_new (C,),
+    scal (2,) = [N D sigma'^2 or 0, LSE(w_new)]); sig_mode: 0 none, 1 distances to the new centroids, 2 to the old ones."""
+    dev = require_cuda(stats, mu_old, w_old)
+    C, D = mu_old.shape
+    f32 = dict(dtype=torch.float32, device=dev)
+    mu_new, w_new, lpi_new, scal = torch.empty(C, D, **f32), torch.empty(C, **f32), torch.empty(C, **f32), torch.empty(2, **f32)
+    rc = load().dicp_em_mstep(D, ptr(stats), ptr(mu_old), ptr(w_old), C, int(bool(do_mu)), int(bool(do_w)), int(sig_mode),
+                              ptr(mu_new), ptr(w_new), ptr(lpi_new), ptr(scal), stream_ptr())
+    check(rc, "dicp_em_mstep")
+    return mu_new, w_new, lpi_new, scal
+
+
 def log_resp(sigma, X, mu, w, want_lgam=True, want_argmax=False):
     dev = require_cuda(X, mu, w)
     N, D = X.shape

@@ -114,6 +114,13 @@ int dicp_em_rowpass(int D, int lite, float sigma_old, const float* X, int64_t N,
 int dicp_em_colstats(int D, float sigma_old, const float* X, int64_t N, const float* T2, const float* mu_old,
                      const float* wl2, int64_t C, float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* M step on the column statistics, one launch (core/GMM.py:286-297 / :442-456):
+ *   mu_new = do_mu ? mu_old + B/S0 : mu_old;   w_new = do_w ? (m + log2 S0) ln 2 : w_old;   lpi_new = w_new - LSE(w_new);
+ *   out_scal = { N D sigma'^2 (sig_mode 1: sum_c 2^m_c (A_c - |B_c|^2/S0_c), 2: sum_c 2^m_c A_c, 0: 0), LSE(w_new) }.
+ * With do_mu = do_w = sig_mode = 0 (frozen mixture) `stats` may be null. */
+int dicp_em_mstep(int D, const float* stats, const float* mu_old, const float* w_old, int64_t C, int do_mu, int do_w,
+                  int sig_mode, float* mu_new, float* w_new, float* lpi_new, float* out_scal, void* stream);
+
 /* lgam (N,C) = log_softmax_c(w_c - |x_n-mu_c|^2/(2 sigma^2)) (core/GMM.py:221-232) and/or argmax (N) int64
  * (first index wins ties, core/GMM.py:677-680); either output may be null. */
 int dicp_log_resp(int D, float sigma, const float* X, int64_t N, const float* mu, const float* w, int64_t C,

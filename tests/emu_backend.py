@@ -62,10 +62,27 @@ def colstats(sigma_old, X, T2, mu_old, wl2):
     return torch.from_numpy(stats)
 
 
+def mstep(stats, mu_old, w_old, do_mu, do_w, sig_mode):
+    """CPU stand-in of dicp_em_mstep: the same formulas with torch ops (csrc/em_col_small.cuh, em_mstep_kernel)."""
+    D = mu_old.shape[1]
+    m, S0, B, A = stats[:, 0], stats[:, 1], stats[:, 2:2 + D], stats[:, 2 + D]
+    mu_new = (mu_old + B / S0[:, None]).contiguous() if do_mu else mu_old.clone()
+    w_new = (m + torch.log2(S0)) * 0.6931471805599453 if do_w else w_old.clone()
+    lse = torch.logsumexp(w_new, 0)
+    if sig_mode == 1:
+        nd = (torch.exp2(m) * (A - (B * B).sum(-1) / S0)).sum()
+    elif sig_mode == 2:
+        nd = (torch.exp2(m) * A).sum()
+    else:
+        nd = torch.zeros(())
+    return mu_new, w_new, w_new - lse, torch.stack((nd, lse)).float()
+
+
 def install(monkeypatch):
     from diff_icp_b200 import em_ops
     monkeypatch.setattr(em_ops, "rowpass", rowpass)
     monkeypatch.setattr(em_ops, "colstats", colstats)
+    monkeypatch.setattr(em_ops, "mstep", mstep)
 
 
 # ---- kernel sums / LDDMM right-hand side on the CPU emulation -------------------------------------------------------
