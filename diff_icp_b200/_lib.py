@@ -61,6 +61,8 @@ SIGNATURES = {
     "dicp_lbfgs_pending": (_int, [_vp, _vp, _vp]),
     "dicp_lbfgs_feed": (_int, [_vp, _vp, _vp]),
     "dicp_lbfgs_stats": (_int, [_vp, _int, _vp]),
+    "dicp_lbfgs_get_all": (_int, [_vp, _vp, _int]),
+    "dicp_lbfgs_stats_all": (_int, [_vp, _vp]),
     "dicp_min2_sqdist": (_int, [_int, _vp, _i64, _vp, _vp]),
     "dicp_decimate_workspace_bytes": (_sz, [_i64]),
     "dicp_decimate_steps": (_int, [_int, _vp, _i64, _f, _int, _int, _vp, _vp, _sz, _vp]),

@@ -353,13 +353,14 @@ class DiffPSR(MultiPSR):
         traj, trajl, datal, counts = plan.finalize(best_p, coverage_radius=radius)
         results, self._a0_host = [], [None] * K
         for k in range(K):
-            shoot = plan.frame_states(traj, k)
+            shoot = plan.frame_states(traj, k)              # lazy: state tuples are built on first access
             shoot.__class__ = ShootResult
-            a0 = shoot[0][1]
+            M, MD, Nx = plan.Ms[k], plan.Ms[k] * D, plan.Nxs[k]
+            a0 = traj[0, k, MD:2 * MD].view(M, D)
+            x1 = traj[-1, k, 2 * MD:2 * MD + Nx * D].view(Nx, D) if Nx else traj[-1, k, :MD].view(M, D)
             self._a0_host[k] = (a0, a0._version, best_p[k])
             results.append(dict(lockstep=True, a0=a0, shoot=shoot, regloss=float(trajl[k]), datal=float(datal[k]), isteps=steps[k],
-                                change=change[k], x1=shoot[-1][-1] if self.support_scheme is not None else shoot[-1][0],
-                                counts=None if counts is None else counts[k].tolist()))
+                                change=change[k], x1=x1, counts=None if counts is None else counts[k].tolist()))
         return results
 
     def _register_all(self, nmax, tol):
@@ -414,9 +415,7 @@ class DiffPSR(MultiPSR):
                 first, last = last, last + self.N[k, s]
                 self.x1[k, s] = r["x1"][first:last].to(**self.dataspec)
             if lockstep and self.S == 1:
-                # one structure: quadloss[k,0] is the frame's data loss sum_n |x1_n - y_n|^2 / (2 sigma^2), already
-                # reduced (deterministically) by the fused closure
-                self.quadloss[k, 0] = r["datal"]
+                pass        # one structure: quadloss[:, 0] = the frames' fused data losses, set for all frames below
             else:
                 for s in range(self.S):
                     self.update_quadloss(k, s)
@@ -432,5 +431,9 @@ class DiffPSR(MultiPSR):
                 self.update_FE(message=message)
             elif self.printstuff:
                 print(message)
+        if lockstep and self.S == 1:
+            # one structure: quadloss[k,0] is the frame's data loss sum_n |x1_n - y_n|^2 / (2 sigma^2), already reduced
+            # (deterministically) by the fused closure -- one host-to-device copy for all frames
+            self.quadloss[:, 0] = torch.tensor([r["datal"] for r in results], dtype=self.quadloss.dtype).to(self.quadloss.device)
         if self.comm is not None or lockstep:   # all frames were registered together: ONE free-energy update (and, with
             self.update_FE(message="Registration of all frames done.")      # ranks, ONE collective) per Reg_opt

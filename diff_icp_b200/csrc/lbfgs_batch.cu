@@ -423,6 +423,35 @@ int dicp_lbfgs_feed(void* h, const float* losses, const float* grads) {
     return cnt;
 }
 
+int dicp_lbfgs_get_all(void* h, float* X, int best) {
+    Batch* B = as_batch(h);
+    if (!B || !X) return DICP_EBADARG;
+    for (int k = 0; k < B->K; ++k) {
+        const Frame& F = B->f[k];
+        float* dst = X + (size_t)k * (size_t)B->stride;
+        if (best) {
+            if (!F.has_best) return DICP_EBADARG;
+            std::memcpy(dst, F.best_x.data(), sizeof(float) * (size_t)F.n);
+        } else {
+            for (int i = 0; i < F.n; ++i) dst[i] = (float)F.x[i];
+        }
+    }
+    return DICP_OK;
+}
+
+int dicp_lbfgs_stats_all(void* h, double* out) {
+    Batch* B = as_batch(h);
+    if (!B || !out) return DICP_EBADARG;
+    for (int k = 0; k < B->K; ++k) {
+        const Frame& F = B->f[k];
+        out[4 * k] = F.last_eval;
+        out[4 * k + 1] = F.best_loss;
+        out[4 * k + 2] = (double)F.func_evals;
+        out[4 * k + 3] = (double)F.n_iter_total;
+    }
+    return DICP_OK;
+}
+
 int dicp_lbfgs_stats(void* h, int k, double* out4) {
     Batch* B = as_batch(h);
     if (!B || k < 0 || k >= B->K || !out4) return DICP_EBADARG;

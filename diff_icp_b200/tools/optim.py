@@ -139,6 +139,19 @@ class LockstepLBFGS:
         self._lib.dicp_lbfgs_stats(self._h, k, out)
         return {"last": out[0], "best": out[1], "func_evals": int(out[2]), "n_iter": int(out[3])}
 
+    def get_all(self, best=False):
+        """(K, stride) fp32 array of every frame's current (or best-so-far) parameters; row k is valid in [:sizes[k]]."""
+        X = self._np.zeros((self.K, self.stride), dtype=self._np.float32)
+        if self._lib.dicp_lbfgs_get_all(self._h, self._fp(X), int(best)) != 0:
+            raise RuntimeError("LockstepLBFGS.get_all: no value")
+        return X
+
+    def stats_all(self):
+        """(K, 4) fp64 array: last closure value, best closure value, closure evaluations, L-BFGS iterations."""
+        out = self._np.zeros((self.K, 4), dtype=self._np.float64)
+        self._lib.dicp_lbfgs_stats_all(self._h, self._fp(out))
+        return out
+
     def step(self, mask, evaluate, X, active, losses, grads):
         """One optimizer.step(closure) of every frame selected by `mask` (uint8 (K,)).  X / grads: (K, stride) fp32 numpy
         arrays, active: (K,) uint8, losses: (K,) fp32 -- the caller's (pinned) buffers; `evaluate()` must fill losses and
@@ -180,12 +193,14 @@ def LBFGS_optimization_lockstep(p0, evaluator, nmax=10, tol=1e-3, errthresh=1e8)
         mask = np.array([1 if (go_on[k] and steps[k] < nmax) else 0 for k in range(K)], dtype=np.uint8)
         if not mask.any():
             break
-        before = {k: opt.get_x(k) for k in range(K) if mask[k]}
+        before = opt.get_all()
         rounds += opt.step(mask, evaluator.evaluate, evaluator.X, evaluator.active, evaluator.losses, evaluator.grads)
         redo = []
-        for k in before:
+        st_all, now_all = opt.stats_all(), opt.get_all()
+        for k in np.flatnonzero(mask):
+            k = int(k)
             steps[k] += 1
-            st = opt.stats(k)
+            st = {"last": float(st_all[k, 0]), "best": float(st_all[k, 1])}
             L_before, L[k] = L[k], st["last"]
             if L[k] > L_before or L[k] > errthresh or math.isnan(L[k]):
                 if math.isnan(L[k]):
@@ -208,9 +223,9 @@ def LBFGS_optimization_lockstep(p0, evaluator, nmax=10, tol=1e-3, errthresh=1e8)
                 change[k] = "None (divergent iteration step)"
                 opt.reset(k, False)
             else:
-                now = opt.get_x(k)
-                delta = float(np.sqrt(np.mean((now - before[k]) ** 2)))
-                scale = float(np.sqrt(np.mean(before[k] ** 2)))
+                n = sizes[k]
+                delta = float(np.sqrt(np.mean((now_all[k, :n] - before[k, :n]) ** 2)))
+                scale = float(np.sqrt(np.mean(before[k, :n] ** 2)))
                 go_on[k] = delta > tol * scale
                 change[k] = delta
         if redo:                                   # loss at the perturbed points (tools/optim.py:73), outside the optimisers
@@ -222,6 +237,7 @@ def LBFGS_optimization_lockstep(p0, evaluator, nmax=10, tol=1e-3, errthresh=1e8)
             rounds += 1
             for k in redo:
                 L[k] = float(evaluator.losses[k])
-    best_p = [opt.get_x(k, best=True).reshape(shapes[k]) for k in range(K)]
-    best_L = [opt.stats(k)["best"] for k in range(K)]
+    best_all, st_all = opt.get_all(best=True), opt.stats_all()
+    best_p = [best_all[k, :sizes[k]].reshape(shapes[k]) for k in range(K)]
+    best_L = [float(st_all[k, 1]) for k in range(K)]
     return best_p, best_L, steps, change, rounds

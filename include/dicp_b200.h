@@ -204,6 +204,9 @@ int dicp_lbfgs_pending(void* h, float* X, uint8_t* active);
 int dicp_lbfgs_feed(void* h, const float* losses, const float* grads);
 /* out4 = { last closure value, best closure value, closure evaluations, L-BFGS iterations } of frame k */
 int dicp_lbfgs_stats(void* h, int k, double* out4);
+/* all frames at once: X (K, stride) <- current (best == 0) or best-so-far parameters; out (K, 4) <- the statistics above */
+int dicp_lbfgs_get_all(void* h, float* X, int best);
+int dicp_lbfgs_stats_all(void* h, double* out);
 
 /* ---- Set-up helpers on point sets (not on the per-iteration path) ---------------------------
  * out[i] = second smallest squared distance from x_i to the points of x (the smallest is x_i itself): the Kmin(2)
