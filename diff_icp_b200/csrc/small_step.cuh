@@ -22,6 +22,12 @@ namespace dicp {
 
 static constexpr int kSmallMaxQ = 1024;       // support points staged entirely in (dynamic) shared memory
 static constexpr int kSmallThreads = 128;     // rows per CTA (one row per thread)
+#ifndef DICP_SMALL_MINB_FWD
+#define DICP_SMALL_MINB_FWD 12                // minimum resident CTAs per SM asked of the compiler (register cap); swept on B200
+#endif
+#ifndef DICP_SMALL_MINB_ADJ
+#define DICP_SMALL_MINB_ADJ 8
+#endif
 static constexpr int kSmallChunk = 512;       // data-point columns per q-row CTA in the adjoint
 static constexpr int kSmallCounters = 64;     // uint32 counters at the head of the workspace
 
@@ -181,7 +187,7 @@ DICP_D bool last_cta(unsigned* counter, unsigned total) {
 // CTAs [0, nXB): x rows, `xpass` consecutive blocks of 128 rows each (more rows per CTA amortise the staging of the support
 // set, the block reductions and the ticket when many frames / data points make the grid large); then the q-row CTAs.
 template <int D, bool WLD, bool ETA>
-__global__ void __launch_bounds__(kSmallThreads) small_rhs_step_kernel(SmallStep S, int xpass) {
+__global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_FWD) small_rhs_step_kernel(SmallStep S, int xpass) {
     using OpQQx = RhsQQ<D, false, ETA, 1>;       // x present: the divergence cost comes from the (x,q) pass
     using OpQQn = RhsQQ<D, WLD, ETA, 1>;         // x absent
     using OpXQ = RhsXQ<D, WLD, ETA, 1>;
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(kSmallThreads) small_rhs_step_kernel(SmallStep
 // staged columns for all Mr rows and the group results are added in group order through shared memory, so that all lanes
 // work even when the support set is tiny (25 points: G = 5).
 template <int D, bool WLD, bool ETA>
-__global__ void __launch_bounds__(kSmallThreads) small_adj_step_kernel(SmallStep S, int nsplit, int xpass) {
+__global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_ADJ) small_adj_step_kernel(SmallStep S, int nsplit, int xpass) {
     using OpX = typename std::conditional<ETA, AdjXQxEta<D, 1>, AdjXQx<D, WLD, 1>>::type;       // rows x, cols (q,p)
     using OpQx = typename std::conditional<ETA, AdjXQqEta<D, 1>, AdjXQq<D, WLD, 1>>::type;      // rows q, cols (x,wx)
     using OpQQx = typename std::conditional<ETA, AdjQQEta<D, 1>, AdjQQ<D, false, 1>>::type;     // rows q, cols q; x present
