@@ -29,6 +29,7 @@ _sz = ctypes.c_size_t
 SIGNATURES = {
     "dicp_version": (_int, []),
     "dicp_sm_count": (_int, []),
+    "dicp_sym_mode": (_int, [_int]),
     "dicp_launch_count": (ctypes.c_ulonglong, []),
     "dicp_pair_workspace_bytes": (_sz, [_i64, _i64]),
     "dicp_ksum": (_int, [_int, _u, _f, _vp, _i64, _vp, _i64, _vp, _vp, _vp] + [_vp] * 11 + [_vp, _sz, _vp]),

@@ -3,6 +3,7 @@
 #include "dispatch.cuh"
 #include <type_traits>
 #include "small_step.cuh"
+#include "sym_engine.cuh"
 #include "batch_closure.cuh"
 #include "pointset.cuh"
 #include "em_col_small.cuh"
@@ -45,6 +46,16 @@ __global__ void quad_loss_kernel(const float* __restrict__ x, const float* __res
     if (threadIdx.x == 0) blocksum[blockIdx.x] = v;
 }
 
+// symmetric engine switch: default on; DICP_SYM=0 in the environment or dicp_sym_mode(0) disable it (A/B measurements, tests)
+inline int& sym_mode_ref() {
+    static int mode = [] {
+        const char* e = getenv("DICP_SYM");
+        return e ? atoi(e) : 1;
+    }();
+    return mode;
+}
+inline int sym_mode() { return sym_mode_ref(); }
+
 struct DeviceExec {
     void* ws;
     size_t wsb;
@@ -53,6 +64,10 @@ struct DeviceExec {
     int run(const typename Op::Params& prm, int M, int N, float* scal_out, int accumulate) {
         return run_pair<Op>(prm, M, N, scal_out, accumulate, ws, wsb, st);
     }
+    // (q,q) adjoint passes through the symmetric engine (sym_engine.cuh): every unordered pair once
+    bool use_sym(int M) const { return sym_mode() != 0 && sym_applicable(M); }
+    template <class Op>
+    int run_sym(const typename Op::Params& prm, int M) { return run_pair_sym<Op>(prm, M, ws, wsb, st); }
     void scal_fix(float* scal, float eta, int withdiv) {
         rhs_scal_fix_kernel<<<1, 32, 0, st>>>(scal, eta, withdiv);
         launch_counter() += 1;
@@ -207,9 +222,23 @@ int dicp_version(void) { return 100; }
 
 int dicp_sm_count(void) { return device_info().sms; }
 
+int dicp_sym_mode(int mode) {
+    const int prev = sym_mode_ref();
+    if (mode >= 0) sym_mode_ref() = mode;
+    return prev;
+}
+
 unsigned long long dicp_launch_count(void) { return launch_counter(); }
 
-size_t dicp_pair_workspace_bytes(int64_t rows, int64_t cols) { return pair_workspace_bound(rows, cols); }
+size_t dicp_pair_workspace_bytes(int64_t rows, int64_t cols) {
+    size_t b = pair_workspace_bound(rows, cols);
+    if (rows == cols && sym_applicable(rows)) {          // symmetric (q,q) adjoint: packed columns + row / column partials
+        const size_t col = align_up((size_t)(rows + 256) * kMaxColF4 * 16, 256);
+        const size_t s = col + sym_workspace_bound(rows, device_info().sms) + 1024;
+        if (s > b) b = s;
+    }
+    return b;
+}
 
 int dicp_ksum(int D, unsigned mask, float sigma, const float* x, int64_t M, const float* y, int64_t N,
               const float* b, const float* c, const float* d,

@@ -108,7 +108,7 @@ int rhs_adjoint_d(Exec& ex, int withlogdet, RhsParams prm, int M, int Nx) {
     int rc;
     prm.accumulate = 0;
     if (prm.eta != 0.f) {                           // logdet model (withlogdet is implied)
-        rc = ex.template run<AdjQQEta<D>>(prm, M, M, nullptr, 0);
+        rc = ex.use_sym(M) ? ex.template run_sym<AdjQQEta<D>>(prm, M) : ex.template run<AdjQQEta<D>>(prm, M, M, nullptr, 0);
         if (rc != DICP_OK || !hasx) return rc;
         rc = ex.template run<AdjXQxEta<D>>(prm, Nx, M, nullptr, 0);
         if (rc != DICP_OK) return rc;
@@ -116,8 +116,13 @@ int rhs_adjoint_d(Exec& ex, int withlogdet, RhsParams prm, int M, int Nx) {
         return ex.template run<AdjXQqEta<D>>(prm, M, Nx, nullptr, 0);
     }
     const bool div_qq = withlogdet && !hasx;
-    if (div_qq) rc = ex.template run<AdjQQ<D, true>>(prm, M, M, nullptr, 0);
-    else rc = ex.template run<AdjQQ<D, false>>(prm, M, M, nullptr, 0);
+    if (ex.use_sym(M)) {
+        if (div_qq) rc = ex.template run_sym<AdjQQ<D, true>>(prm, M);
+        else rc = ex.template run_sym<AdjQQ<D, false>>(prm, M);
+    } else {
+        if (div_qq) rc = ex.template run<AdjQQ<D, true>>(prm, M, M, nullptr, 0);
+        else rc = ex.template run<AdjQQ<D, false>>(prm, M, M, nullptr, 0);
+    }
     if (rc != DICP_OK) return rc;
     if (hasx) {
         if (withlogdet) rc = ex.template run<AdjXQx<D, true>>(prm, Nx, M, nullptr, 0);
@@ -181,6 +186,13 @@ int em_colstats_entry(Exec& ex, int D, float sigma_old, const float* X, int64_t 
 
 // CPU executor: tests only (tests/hostemu).  Never part of libdicp_b200.so.
 struct HostExec {
+    bool sym = false;                       // evaluate the (q,q) adjoint pass through Op::pair_sym (tests of the formulas)
+    bool use_sym(int) const { return sym; }
+    template <class Op>
+    int run_sym(const typename Op::Params& prm, int M) {
+        run_pair_host_sym<Op>(prm, M);
+        return DICP_OK;
+    }
     template <class Op>
     int run(const typename Op::Params& prm, int M, int N, float* scal_out, int accumulate) {
         float tmp[8] = {0};

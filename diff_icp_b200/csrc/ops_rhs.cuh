@@ -317,6 +317,59 @@ struct AdjQQ {
             acc[A_GQ + k] = gq;
         }
     }
+    // Both orientations of an unordered pair from ONE evaluation (symmetric engine, sym_engine.cuh): `acc` receives the
+    // row's term (row m, column n) exactly as `pair` does, `cacc` the column's term (row n, column m).  Under the swap
+    // z', du, dp change sign while K, w, (a.p)+(p.a), (du.z'), (dp.z') do not, so the gq increment is antisymmetric and the
+    // gp increment only exchanges (a_n, p_n) for (a_m, p_m) and flips the z' term.
+    template <class V, bool MASKED = false>
+    static DICP_HD void pair_sym(const Params& P, const Row& r, const V* c, V* acc, V* cacc, V km = V()) {
+        V z[D], du[D], dp[D];
+        V r2, w, apa, duz, dpz;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            z[k] = vsub(vbc<V>(r.q[k]), c[k]);
+            du[k] = vsub(vbc<V>(r.u[k]), c[3 * D + k]);
+            if (DIV) dp[k] = vsub(vbc<V>(r.p[k]), c[D + k]);
+            r2 = k == 0 ? vmul(z[k], z[k]) : vfma(z[k], z[k], r2);
+            w = k == 0 ? vmul(vbc<V>(r.p[k]), c[D + k]) : vfma(vbc<V>(r.p[k]), c[D + k], w);
+            apa = k == 0 ? vmul(vbc<V>(r.a[k]), c[D + k]) : vfma(vbc<V>(r.a[k]), c[D + k], apa);
+            apa = vfma(vbc<V>(r.p[k]), c[2 * D + k], apa);
+            duz = k == 0 ? vmul(du[k], z[k]) : vfma(du[k], z[k], duz);
+            if (DIV) dpz = k == 0 ? vmul(dp[k], z[k]) : vfma(dp[k], z[k], dpz);
+        }
+        V K = vex2n(r2);
+        if (MASKED) K = vmul(K, km);                          // padded rows / columns of a ragged tail: K = 0
+        const V swd = vmul(vmul(vbc<V>(-P.s * P.beta), w), duz);
+        V ncz = vfma(vbc<V>(-P.alpha), apa, swd);
+        if (DIV) ncz = vfma(vbc<V>(r.gc * P.s * P.beta), dpz, ncz);
+        const V Kncz = vmul(K, ncz);
+        const V Ksw = vmul(K, vmul(vbc<V>(P.s), w));
+        const V Kad = vmul(K, vmul(vbc<V>(P.alpha), duz));
+        V nKgz, nKgs;
+        if (DIV) {
+            nKgz = vmul(K, vbc<V>(-r.gc * P.alpha));
+            nKgs = vmul(K, vbc<V>(-r.gc * P.s));
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            V inc = vmul(Kncz, z[k]);                         // gq increment of the row; the column gets its negative
+            inc = vfma(Ksw, du[k], inc);
+            if (DIV) inc = vfma(nKgs, dp[k], inc);
+            acc[A_GQ + k] = vadd(acc[A_GQ + k], inc);
+            cacc[A_GQ + k] = vsub(cacc[A_GQ + k], inc);
+            V gp = vfma(K, c[2 * D + k], acc[A_GP + k]);
+            gp = vfma(Kad, c[D + k], gp);
+            V gpc = vfma(K, vbc<V>(r.a[k]), cacc[A_GP + k]);
+            gpc = vfma(Kad, vbc<V>(r.p[k]), gpc);
+            if (DIV) {
+                const V gz = vmul(nKgz, z[k]);
+                gp = vadd(gp, gz);
+                gpc = vsub(gpc, gz);
+            }
+            acc[A_GP + k] = gp;
+            cacc[A_GP + k] = gpc;
+        }
+    }
     static DICP_HD void finish(const Params& P, int i, const Row& r, const float* acc, float*) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -537,6 +590,71 @@ struct AdjQQEta {
             gp = vfma(vbc<V>(-es), du[k], gp);
             acc[A_GQ + k] = vfma(K, gq, acc[A_GQ + k]);
             acc[A_GP + k] = vfma(K, gp, acc[A_GP + k]);
+        }
+    }
+    // Both orientations of an unordered pair from ONE evaluation (symmetric engine).  Under the swap m <-> n the vectors
+    // z', e, du, dA change sign and every scalar (w, z'.e, du.z', dA.z', du.e, t0, t1, Phi) is unchanged: the gq term is
+    // antisymmetric; the gp term is  a_m + alpha (du.z') p_m - [eta s beta (du.z') z' - eta s du - g alpha z'].
+    template <class V, bool MASKED = false>
+    static DICP_HD void pair_sym(const Params& P, const Row& r, const V* c, V* acc, V* cacc, V km = V()) {
+        const float eta = P.eta, s = P.s, al = P.alpha, be = P.beta, g = r.gc, es = eta * s;
+        V z[D], e[D], du[D], dA[D];
+        V r2, w, ze, duz, dAz, due, appa;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            z[k] = vsub(vbc<V>(r.q[k]), c[k]);
+            e[k] = vsub(vbc<V>(r.p[k]), c[D + k]);
+            dA[k] = vsub(vbc<V>(r.a[k]), c[2 * D + k]);
+            du[k] = vsub(vbc<V>(r.u[k]), c[3 * D + k]);
+            if (k == 0) {
+                r2 = vmul(z[k], z[k]);
+                w = vmul(vbc<V>(r.p[k]), c[D + k]);
+                ze = vmul(z[k], e[k]);
+                duz = vmul(du[k], z[k]);
+                dAz = vmul(dA[k], z[k]);
+                due = vmul(du[k], e[k]);
+                appa = vmul(vbc<V>(r.p[k]), c[2 * D + k]);
+            } else {
+                r2 = vfma(z[k], z[k], r2);
+                w = vfma(vbc<V>(r.p[k]), c[D + k], w);
+                ze = vfma(z[k], e[k], ze);
+                duz = vfma(du[k], z[k], duz);
+                dAz = vfma(dA[k], z[k], dAz);
+                due = vfma(du[k], e[k], due);
+                appa = vfma(vbc<V>(r.p[k]), c[2 * D + k], appa);
+            }
+            appa = vfma(vbc<V>(r.a[k]), c[D + k], appa);
+        }
+        V K = vex2n(r2);
+        if (MASKED) K = vmul(K, km);                          // padded rows / columns of a ragged tail: K = 0
+        const V nK = vmul(K, vbc<V>(-1.f));
+        const V t0 = vfma(vbc<V>(be), r2, vbc<V>(-(float)D));
+        const V t1 = vfma(vbc<V>(be), r2, vbc<V>(-(float)(D + 2)));
+        const V c_du = vfma(vbc<V>(s), w, vfma(vbc<V>(es * al), ze, vmul(vbc<V>(-es * es), t1)));
+        const V c_e = vfma(vbc<V>(es * al), duz, vbc<V>(-g * s));
+        V Phi = vfma(vbc<V>(eta * al), dAz, appa);
+        Phi = vfma(vmul(vbc<V>(al), w), duz, Phi);
+        Phi = vfma(vmul(vbc<V>(es * be), ze), duz, Phi);
+        Phi = vfma(vbc<V>(-es), due, Phi);
+        Phi = vfma(vmul(vbc<V>(-eta * es * al), t1), duz, Phi);
+        Phi = vfma(vbc<V>(-g * al), ze, Phi);
+        Phi = vfma(vbc<V>(2.f * g * es), t0, Phi);
+        const V Cz = vfma(vbc<V>(-al), Phi, vfma(vbc<V>(-2.f * es * es * be), duz, vbc<V>(4.f * g * es * al)));
+        const V pz = vfma(vbc<V>(es * be), duz, vbc<V>(-g * al));
+        const V pp = vmul(vbc<V>(al), duz);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            V gq = vmul(vbc<V>(es), dA[k]);
+            gq = vfma(c_du, du[k], gq);
+            gq = vfma(c_e, e[k], gq);
+            gq = vfma(Cz, z[k], gq);
+            acc[A_GQ + k] = vfma(K, gq, acc[A_GQ + k]);
+            cacc[A_GQ + k] = vfma(nK, gq, cacc[A_GQ + k]);
+            const V t = vfma(pz, z[k], vmul(vbc<V>(-es), du[k]));            // odd part of the gp term
+            const V gpr = vadd(vfma(pp, c[D + k], c[2 * D + k]), t);
+            const V gpc = vsub(vfma(pp, vbc<V>(r.p[k]), vbc<V>(r.a[k])), t);
+            acc[A_GP + k] = vfma(K, gpr, acc[A_GP + k]);
+            cacc[A_GP + k] = vfma(K, gpc, cacc[A_GP + k]);
         }
     }
     static DICP_HD void finish(const Params& P, int i, const Row& r, const float* acc, float*) {

@@ -24,6 +24,7 @@
 // order (deterministic, no float atomics).  Row-scalars (dcost, Hamiltonian pieces, ...) are block-reduced
 // with a fixed tree and summed over blocks by `scalar_reduce_kernel`, also deterministic.
 #pragma once
+#include <vector>
 #include "common.cuh"
 
 namespace dicp {
@@ -513,6 +514,30 @@ inline void run_pair_host(const typename Op::Params& prm, int M, int N, float* s
     }
     if (scal_out)
         for (int k = 0; k < Op::NSCAL; ++k) scal_out[k] = (float)scal[k];
+}
+
+// Symmetric evaluation (tests only): every unordered pair {i, j}, i < j, visited ONCE with Op::pair_sym, the diagonal
+// pairs with Op::pair -- what the device's symmetric engine (sym_engine.cuh) computes, in a simple order.
+template <class Op>
+inline void run_pair_host_sym(const typename Op::Params& prm, int M) {
+    std::vector<float> acc((size_t)M * Op::NACC, 0.f);
+    for (int i = 0; i < M; ++i) {
+        typename Op::Row row;
+        Op::load_row(prm, i, row);
+        float c[Op::COLF4 * 4];
+        Op::pack_col(prm, i, M, c);
+        Op::template pair<float>(prm, row, c, &acc[(size_t)i * Op::NACC]);
+        for (int j = i + 1; j < M; ++j) {
+            Op::pack_col(prm, j, M, c);
+            Op::template pair_sym<float>(prm, row, c, &acc[(size_t)i * Op::NACC], &acc[(size_t)j * Op::NACC]);
+        }
+    }
+    for (int i = 0; i < M; ++i) {
+        typename Op::Row row;
+        Op::load_row(prm, i, row);
+        float rs[Op::NSCAL > 0 ? Op::NSCAL : 1] = {0};
+        Op::finish(prm, i, row, &acc[(size_t)i * Op::NACC], rs);
+    }
 }
 
 }  // namespace dicp

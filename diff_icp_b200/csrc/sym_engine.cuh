@@ -1,0 +1,281 @@
+// Symmetric pair engine for the (q,q) adjoint passes: every UNORDERED pair of support points is evaluated once.
+//
+// In the (q,q) passes rows and columns are the same point set and the pair term of (row n, column m) follows from the one
+// of (row m, column n) by sign flips of the odd quantities (Op::pair_sym, ops_rhs.cuh): the exponential, the dot products
+// and the scalar coefficients -- most of the 41 / 56 / 83 FP32 operations of a pair -- are shared.  The general engine
+// (pair_engine.cuh) cannot exploit this: it keeps ROW accumulators in registers and streams columns, so a column-side
+// contribution would need a cross-thread reduction per column.  Here a warp works as a ring:
+//
+//   * lane l owns R = 2 rows (register-resident data and accumulators, as before);
+//   * the columns come in groups of 64 = 32 column PAIRS (packed fp32: one 64-bit register carries the same field of two
+//     columns), staged in shared memory; at step s (0..31) lane l evaluates its rows against column pair (l + s) mod 32
+//     and adds the column-side terms to a set of accumulators that TRAVELS with the column pair: after each step the
+//     column accumulators move one lane down the ring (SHFL), so after 32 steps every column pair has met all 64 rows of
+//     the warp and its accumulators are back in lane l = pair index;
+//   * the four warps of a CTA (256 rows) then add their column sums in warp order through shared memory and write them
+//     to the column-partial array [row block][k][column]; row accumulators are written once per work item to
+//     [item][k][row].  A finish kernel adds, for row i, its items' row partials (item order) and the column partials of the
+//     row blocks above it (block order), then runs Op::finish.  Fixed orders everywhere: deterministic, no atomics.
+//
+// Work items: for row block I (256 rows) one DIAGONAL item -- its own 256 columns, all ordered pairs, plain Op::pair --
+// and the columns beyond it in chunks of Lc columns, symmetric.  Ragged tails (rows / columns >= M) are evaluated on
+// zero-filled records with K multiplied by a 0/1 mask (a separate instantiation of the inner loop).
+#pragma once
+#include "ops_rhs.cuh"
+
+namespace dicp {
+
+static constexpr int kSymThreads = 128, kSymR = 2, kSymRows = (kSymThreads / 32) * 32 * kSymR;      // 256 rows per CTA
+static constexpr int kSymGroup = 64;                                                                 // columns per ring round
+static constexpr int kSymMaxBlocks = 256;                                                            // row blocks (M <= 65536)
+static constexpr int kSymMinM = 2048;
+
+struct SymPlan {
+    int M, nrb, Lc, ngroups_total;      // points, row blocks, chunk length (columns), column groups (ceil(M/64))
+    int items;
+    int prefix[kSymMaxBlocks + 1];      // first item of every row block
+};
+
+inline SymPlan sym_make_plan(int M, int sms) {
+    SymPlan p{};
+    p.M = M;
+    p.nrb = (M + kSymRows - 1) / kSymRows;
+    p.ngroups_total = (M + kSymGroup - 1) / kSymGroup;
+    const long long target = (long long)sms * 6;                    // symmetric items wanted
+    long long lc = ((long long)M * M / 2) / ((long long)kSymRows * target);
+    lc = (lc + kSymGroup - 1) / kSymGroup * kSymGroup;
+    if (lc < kSymGroup) lc = kSymGroup;
+    p.Lc = (int)lc;
+    const int mpad = p.ngroups_total * kSymGroup;
+    int n = 0;
+    for (int I = 0; I < p.nrb; ++I) {
+        p.prefix[I] = n;
+        const int beyond = mpad - (I + 1) * kSymRows;
+        n += 1 + (beyond > 0 ? (beyond + p.Lc - 1) / p.Lc : 0);
+    }
+    p.prefix[p.nrb] = n;
+    p.items = n;
+    return p;
+}
+inline bool sym_applicable(long long M) { return M >= kSymMinM && M <= (long long)kSymMaxBlocks * kSymRows; }
+inline size_t sym_rowpart_floats(const SymPlan& p, int nacc) { return (size_t)p.items * nacc * kSymRows; }
+inline size_t sym_colpart_floats(const SymPlan& p, int nacc) {
+    return (size_t)p.nrb * nacc * (size_t)p.ngroups_total * kSymGroup;
+}
+// upper bound of the extra workspace (beyond the packed columns) for any Op (NACC <= 16) at M points
+inline size_t sym_workspace_bound(long long M, int sms) {
+    if (!sym_applicable(M)) return 0;
+    const SymPlan p = sym_make_plan((int)M, sms);
+    return (sym_rowpart_floats(p, 16) + sym_colpart_floats(p, 16)) * 4 + 1024;
+}
+
+#if defined(__CUDACC__)
+
+DICP_D F2 f2_shfl(F2 v, int src) {
+    unsigned lo = (unsigned)(v.v & 0xffffffffull), hi = (unsigned)(v.v >> 32);
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    F2 r;
+    r.v = ((unsigned long long)hi << 32) | lo;
+    return r;
+}
+
+// one ring round: 32 steps over the 32 staged column pairs
+template <class Op, bool MASKED>
+DICP_D void sym_ring_round(const typename Op::Params& prm, const typename Op::Row (&row)[kSymR], const float* tile,
+                           int stride, int lane, const float (&rmask)[kSymR], int col0, int M, F2 (&acc)[kSymR][Op::NACC],
+                           F2 (&cacc)[Op::NACC]) {
+    constexpr int NF = Op::NF, PF4 = NF / 2;
+#pragma unroll 2
+    for (int s = 0; s < 32; ++s) {
+        const int pr = (lane + s) & 31;
+        const float4* rec = reinterpret_cast<const float4*>(tile + pr * stride);
+        F2 c[NF];
+#pragma unroll
+        for (int k = 0; k < PF4; ++k) {
+            const float4 v = rec[k];
+            c[2 * k] = f2(v.x, v.y);
+            c[2 * k + 1] = f2(v.z, v.w);
+        }
+        if (MASKED) {
+            const int j = col0 + 2 * pr;
+            const float m0 = j < M ? 1.f : 0.f, m1 = j + 1 < M ? 1.f : 0.f;
+#pragma unroll
+            for (int r = 0; r < kSymR; ++r)
+                Op::template pair_sym<F2, true>(prm, row[r], c, acc[r], cacc, f2(m0 * rmask[r], m1 * rmask[r]));
+        } else {
+#pragma unroll
+            for (int r = 0; r < kSymR; ++r) Op::template pair_sym<F2, false>(prm, row[r], c, acc[r], cacc);
+        }
+        // the column accumulators follow their column pair: lane l next handles pair (l + s + 1) mod 32, held by lane l + 1
+#pragma unroll
+        for (int k = 0; k < Op::NACC; ++k) cacc[k] = f2_shfl(cacc[k], (lane + 1) & 31);
+    }
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kSymThreads) sym_pair_kernel(typename Op::Params prm, const float* __restrict__ colpack,
+                                                               float* __restrict__ rowpart, float* __restrict__ colpart,
+                                                               SymPlan plan) {
+    constexpr int NF = Op::NF, NACC = Op::NACC, REC = 2 * NF, STRIDE = REC + 4;      // padded: conflict-free LDS.128
+    __shared__ __align__(16) float tile[32 * STRIDE];
+    __shared__ float xch[(kSymThreads / 32) * 32 * 2 * NACC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = plan.M;
+    // item -> (row block I, chunk)
+    int lo = 0, hi = plan.nrb;
+    const int item = blockIdx.x;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (plan.prefix[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int I = lo, chunk = item - plan.prefix[I];
+    const int mpad = plan.ngroups_total * kSymGroup;
+
+    // rows of this lane (zero-filled beyond M: masked wherever they could matter)
+    typename Op::Row row[kSymR];
+    float rmask[kSymR];
+    int ri[kSymR];
+#pragma unroll
+    for (int r = 0; r < kSymR; ++r) {
+        ri[r] = I * kSymRows + warp * (32 * kSymR) + r * 32 + lane;
+        rmask[r] = ri[r] < M ? 1.f : 0.f;
+        Op::load_row(prm, ri[r] < M ? ri[r] : M - 1, row[r]);
+    }
+    F2 acc[kSymR][NACC];
+#pragma unroll
+    for (int r = 0; r < kSymR; ++r)
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[r][k] = f2(0.f, 0.f);
+
+    const bool rows_ragged = (I + 1) * kSymRows > M;
+    int j0, j1;
+    if (chunk == 0) { j0 = I * kSymRows; j1 = j0 + kSymRows; }
+    else { j0 = (I + 1) * kSymRows + (chunk - 1) * plan.Lc; j1 = j0 + plan.Lc; }
+    if (j1 > mpad) j1 = mpad;
+
+    for (int g0 = j0; g0 < j1; g0 += kSymGroup) {
+        __syncthreads();
+        {   // stage 32 pair records (contiguous in the packed array) with the padded stride
+            const float4* src = reinterpret_cast<const float4*>(colpack + (size_t)(g0 >> 1) * REC);
+            constexpr int F4 = REC / 4;
+            for (int t = tid; t < 32 * F4; t += kSymThreads) {
+                const int rec = t / F4, f = t - rec * F4;
+                reinterpret_cast<float4*>(tile + rec * STRIDE)[f] = src[t];
+            }
+        }
+        __syncthreads();
+        if (chunk == 0) {
+            // diagonal block: every ORDERED pair, row side only (plain Op::pair, broadcast reads); columns >= M skipped
+            const int nvalid = (M - g0 < kSymGroup) ? (M - g0 > 0 ? M - g0 : 0) : kSymGroup;
+            const int npair = nvalid >> 1;
+            for (int pr = 0; pr < npair; ++pr) {
+                const float4* rec = reinterpret_cast<const float4*>(tile + pr * STRIDE);
+                F2 c[NF];
+#pragma unroll
+                for (int k = 0; k < NF / 2; ++k) {
+                    const float4 v = rec[k];
+                    c[2 * k] = f2(v.x, v.y);
+                    c[2 * k + 1] = f2(v.z, v.w);
+                }
+#pragma unroll
+                for (int r = 0; r < kSymR; ++r) Op::template pair<F2>(prm, row[r], c, acc[r]);
+            }
+            if (nvalid & 1) {
+                const float* rec = tile + npair * STRIDE;
+                float c[NF], tmp[NACC];
+#pragma unroll
+                for (int k = 0; k < NF; ++k) c[k] = rec[2 * k];
+#pragma unroll
+                for (int r = 0; r < kSymR; ++r) {
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) tmp[k] = 0.f;
+                    Op::template pair<float>(prm, row[r], c, tmp);
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) acc[r][k] = vadd(acc[r][k], f2(tmp[k], 0.f));
+                }
+            }
+            continue;
+        }
+        F2 cacc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) cacc[k] = f2(0.f, 0.f);
+        if (rows_ragged || g0 + kSymGroup > M) sym_ring_round<Op, true>(prm, row, tile, STRIDE, lane, rmask, g0, M, acc, cacc);
+        else sym_ring_round<Op, false>(prm, row, tile, STRIDE, lane, rmask, g0, M, acc, cacc);
+        // lane l holds the sums of column pair l over this warp's 64 rows: add the four warps in warp order
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+            float a, b;
+            f2_unpack(cacc[k], a, b);
+            xch[((warp * NACC + k) * 32 + lane) * 2] = a;
+            xch[((warp * NACC + k) * 32 + lane) * 2 + 1] = b;
+        }
+        __syncthreads();
+        for (int t = tid; t < NACC * kSymGroup; t += kSymThreads) {
+            const int k = t / kSymGroup, cc = t - k * kSymGroup;            // column cc of the group = pair cc/2, half cc&1
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kSymThreads / 32; ++w) v += xch[((w * NACC + k) * 32 + (cc >> 1)) * 2 + (cc & 1)];
+            colpart[((size_t)I * NACC + k) * mpad + g0 + cc] = v;
+        }
+    }
+    // row partials of this item
+    float* rp = rowpart + (size_t)item * NACC * kSymRows;
+#pragma unroll
+    for (int r = 0; r < kSymR; ++r)
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) rp[k * kSymRows + warp * (32 * kSymR) + r * 32 + lane] = f2_sum(acc[r][k]);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(128) sym_finish_kernel(typename Op::Params prm, const float* __restrict__ rowpart,
+                                                         const float* __restrict__ colpart, SymPlan plan) {
+    constexpr int NACC = Op::NACC;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= plan.M) return;
+    const int I = i / kSymRows, rl = i - I * kSymRows;
+    const int mpad = plan.ngroups_total * kSymGroup;
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    for (int it = plan.prefix[I]; it < plan.prefix[I + 1]; ++it) {
+        const float* rp = rowpart + (size_t)it * NACC * kSymRows + rl;
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] += rp[k * kSymRows];
+    }
+    for (int J = 0; J < I; ++J) {
+        const float* cp = colpart + (size_t)J * NACC * mpad + i;
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] += cp[(size_t)k * mpad];
+    }
+    typename Op::Row row;
+    Op::load_row(prm, i, row);
+    Op::finish(prm, i, row, acc, nullptr);
+}
+
+// packed columns (same layout as the general engine) + symmetric kernel + finish
+template <class Op>
+inline int run_pair_sym(const typename Op::Params& prm, int M, void* ws, size_t ws_bytes, cudaStream_t st) {
+    static_assert(Op::PACKED && Op::NSCAL == 0, "symmetric engine: packed Ops without row scalars");
+    const SymPlan plan = sym_make_plan(M, device_info().sms);
+    const int mpad = plan.ngroups_total * kSymGroup;
+    const int npadcol = (mpad + 127) / 128 * 128;
+    const size_t col_bytes = align_up((size_t)npadcol * Op::NF * 4, 256);
+    const size_t row_bytes = align_up(sym_rowpart_floats(plan, Op::NACC) * 4, 256);
+    const size_t cpart_bytes = align_up(sym_colpart_floats(plan, Op::NACC) * 4, 256);
+    if (ws == nullptr || col_bytes + row_bytes + cpart_bytes > ws_bytes) return DICP_EWORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(ws) & 127) != 0) return DICP_EBADARG;
+    float* colpack = (float*)ws;
+    float* rowpart = (float*)((char*)ws + col_bytes);
+    float* colpart = (float*)((char*)ws + col_bytes + row_bytes);
+    pack_kernel_p<Op><<<(npadcol + 255) / 256, 256, 0, st>>>(prm, colpack, M, npadcol);
+    sym_pair_kernel<Op><<<plan.items, kSymThreads, 0, st>>>(prm, colpack, rowpart, colpart, plan);
+    sym_finish_kernel<Op><<<(M + 127) / 128, 128, 0, st>>>(prm, rowpart, colpart, plan);
+    launch_counter() += 3;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DICP_OK : (int)e;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace dicp

@@ -49,6 +49,11 @@ int dicp_version(void);
 /* number of SMs of the current device (148 on B200) */
 int dicp_sm_count(void);
 
+/* The (q,q) passes of dicp_rhs_adjoint run on the symmetric engine (every unordered pair evaluated once) for
+ * 2048 <= M <= 65536.  mode 0 / 1 switches it off / on (process-wide; default 1, or the DICP_SYM environment variable),
+ * mode < 0 only queries.  Returns the previous mode.  Results of the two engines agree to fp32 rounding. */
+int dicp_sym_mode(int mode);
+
 /* number of kernel launches this library has issued so far in this process (launches recorded into a CUDA graph
  * are counted once, at capture) */
 unsigned long long dicp_launch_count(void);

@@ -26,6 +26,14 @@ int emu_rhs_forward(int D, int withlogdet, float sigma, float eta, const float* 
     return rhs_forward_entry(ex, D, withlogdet, sigma, eta, q, p, M, x, Nx, vq, dp, vx, scal);
 }
 
+int emu_rhs_adjoint_sym(int D, int withlogdet, float sigma, float eta, const float* q, const float* p, int64_t M,
+                        const float* x, int64_t Nx, const float* a, const float* u, const float* wx, const float* gc,
+                        float* gq, float* gp, float* gx) {
+    HostExec ex;
+    ex.sym = true;
+    return rhs_adjoint_entry(ex, D, withlogdet, sigma, eta, q, p, M, x, Nx, a, u, wx, gc, gq, gp, gx);
+}
+
 int emu_rhs_adjoint(int D, int withlogdet, float sigma, float eta, const float* q, const float* p, int64_t M,
                     const float* x, int64_t Nx, const float* a, const float* u, const float* wx, const float* gc,
                     float* gq, float* gp, float* gx) {

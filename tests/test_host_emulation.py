@@ -145,11 +145,14 @@ def test_emulated_rhs_adjoint_matches_autograd(emu, D, version, with_x):
     gq, gp = np.zeros_like(qa), np.zeros_like(pa)
     gx = np.zeros_like(xa) if with_x else None
     gca = np.array([gc], dtype=np.float32)
-    rc = emu.emu_rhs_adjoint(D, int(LM.withlogdet), ctypes.c_float(sig), ctypes.c_float(LM.eta), fp(qa), fp(pa),
-                             ctypes.c_int64(Nq), fp(xa), ctypes.c_int64(Nx), fp(aa), fp(ua), fp(wa), fp(gca),
-                             fp(gq), fp(gp), fp(gx))
-    assert rc == 0
-    assert relerr(gq, grads[0].numpy()) < 3e-5, relerr(gq, grads[0].numpy())
-    assert relerr(gp, grads[1].numpy()) < 3e-5, relerr(gp, grads[1].numpy())
-    if with_x:
-        assert relerr(gx, grads[2].numpy()) < 3e-5, relerr(gx, grads[2].numpy())
+    # plain evaluation (every ordered pair) and symmetric evaluation (every unordered (q,q) pair once, Op::pair_sym)
+    for fn in (emu.emu_rhs_adjoint, emu.emu_rhs_adjoint_sym):
+        gq[:], gp[:] = 0, 0
+        rc = fn(D, int(LM.withlogdet), ctypes.c_float(sig), ctypes.c_float(LM.eta), fp(qa), fp(pa),
+                ctypes.c_int64(Nq), fp(xa), ctypes.c_int64(Nx), fp(aa), fp(ua), fp(wa), fp(gca),
+                fp(gq), fp(gp), fp(gx))
+        assert rc == 0
+        assert relerr(gq, grads[0].numpy()) < 3e-5, relerr(gq, grads[0].numpy())
+        assert relerr(gp, grads[1].numpy()) < 3e-5, relerr(gp, grads[1].numpy())
+        if with_x:
+            assert relerr(gx, grads[2].numpy()) < 3e-5, relerr(gx, grads[2].numpy())
