@@ -402,22 +402,29 @@ def kernel_roofline(args, LM, q, p, dev, ops):
         peaks[name] = blocks * 256 * iters * 8 * per / t
 
     # algorithmic FP32 instructions / MUFU per pair of the adjoint and forward kernels (DESIGN.md §6, D = 3)
-    alg = ALG_WORK[args.variant]
+    alg = dict(ALG_WORK[args.variant])
+    symmetric = bool(ops.load().dicp_sym_mode(-1)) and 4096 <= M <= 65536
+    if not symmetric:
+        alg["adj_fp32"] = alg["adj_fp32_ordered"]
     pairs = float(M) * M
     fp_rate_adj = alg["adj_fp32"] * pairs / t_adj
-    sfu_rate_adj = pairs / t_adj
+    sfu_rate_adj = (0.5 if symmetric else 1.0) * pairs / t_adj          # one MUFU.EX2 per evaluated pair
     frac_adj = max(fp_rate_adj / peaks["ffma"], sfu_rate_adj / peaks["mufu_ex2"])
     fp_rate_fwd = alg["fwd_fp32"] * pairs / t_fwd
     frac_fwd = max(fp_rate_fwd / peaks["ffma"], pairs / t_fwd / peaks["mufu_ex2"])
     em = em_roofline(dev, timeit, peaks)
     return {
-        "bound": "fp32_pipe", "kernel": "pair_kernel<AdjQQ> (dicp_rhs_adjoint)",
+        "bound": "fp32_pipe",
+        "kernel": ("sym_pair_kernel<AdjQQ*> (dicp_rhs_adjoint, symmetric engine)" if symmetric
+                   else "pair_kernel_p<AdjQQ*> (dicp_rhs_adjoint)"),
         "achieved": 2 * fp_rate_adj / 1e12, "peak": 2 * peaks["ffma"] / 1e12, "unit": "TFLOP/s", "frac": frac_adj,
         "traffic": NCU_DRAM_BYTES.get(args.variant),
-        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the adjoint pair kernel, ncu --set full "
-                        "(profiles/r01b_ncu_full_packed_kernels_20k.csv); algorithmic bytes = 2 x 20000 x 48 B = 1.92 MB",
-        "note": "achieved = algorithmic FP32 instructions/pair x pairs / event time, x2 flop; peak = FFMA issue rate "
-                "measured live by dicp_pipe_probe (x2 flop), of measured; frac = binding-pipe utilisation",
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the adjoint kernel, ncu --set full "
+                        "(profiles/r01c_ncu_full_sym_adjoint_20k.csv); algorithmic bytes = 2 x 20000 x 48 B = 1.92 MB",
+        "note": "achieved = algorithmic FP32 instructions per ordered pair x M^2 pairs / event time, x2 flop; the adjoint "
+                "evaluates every UNORDERED pair once (symmetric engine), its per-ordered-pair count is half the unordered "
+                "one; peak = FFMA issue rate measured live by dicp_pipe_probe (x2 flop), of measured; frac = binding-pipe "
+                "utilisation",
         "adjoint": {"s_per_launch": t_adj, "pairs_per_s": pairs / t_adj, "fp32_per_pair": alg["adj_fp32"], "frac": frac_adj},
         "forward": {"s_per_launch": t_fwd, "pairs_per_s": pairs / t_fwd, "fp32_per_pair": alg["fwd_fp32"], "frac": frac_fwd},
         "measured_peaks": {"ffma_per_s": peaks["ffma"], "mufu_ex2_per_s": peaks["mufu_ex2"], "sms": sms},
@@ -488,14 +495,18 @@ def em_roofline(dev, timeit, peaks):
     return out
 
 
-# DRAM bytes per launch of the adjoint pair kernel at 20k x 20k (one ncu --set full capture, profiles/)
-NCU_DRAM_BYTES = {"classic": 1942528, "hybrid": 1945856, "logdet": 1949952}
+# DRAM bytes per launch of the adjoint kernel at 20k x 20k (one ncu --set full capture per variant, profiles/):
+# dram__bytes_read.sum + dram__bytes_write.sum; the row / column partials of the symmetric engine (~40 MB) stay in L2
+NCU_DRAM_BYTES = {"classic": None, "hybrid": None, "logdet": 1953792}
 
-# algorithmic FP32 instruction counts per pair, D = 3 (hand count of the formulas in csrc/ops_rhs.cuh)
+# algorithmic FP32 instruction counts per ORDERED pair, D = 3 (hand count of the formulas in csrc/ops_rhs.cuh).
+# The adjoint (q,q) pass runs on the symmetric engine: an unordered pair costs the shared part once plus both sides'
+# accumulations -- 53 / 74 / 99 operations (classic / hybrid / logdet) instead of 2 x 41 / 56 / 83 -- i.e. 26.5 / 37 / 49.5
+# per ordered pair.  With DICP_SYM=0 (general engine) the counts are the ordered ones.
 ALG_WORK = {
-    "classic": {"fwd_fp32": 16, "adj_fp32": 41},
-    "hybrid": {"fwd_fp32": 19, "adj_fp32": 56},
-    "logdet": {"fwd_fp32": 30, "adj_fp32": 83},
+    "classic": {"fwd_fp32": 16, "adj_fp32": 26.5, "adj_fp32_ordered": 41},
+    "hybrid": {"fwd_fp32": 19, "adj_fp32": 37.0, "adj_fp32_ordered": 56},
+    "logdet": {"fwd_fp32": 30, "adj_fp32": 49.5, "adj_fp32_ordered": 83},
 }
 
 

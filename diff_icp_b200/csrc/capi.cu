@@ -66,8 +66,11 @@ struct DeviceExec {
     }
     // (q,q) adjoint passes through the symmetric engine (sym_engine.cuh): every unordered pair once
     bool use_sym(int M) const { return sym_mode() != 0 && sym_applicable(M); }
+    bool use_sym_forward(int M) const { return sym_mode() == 2 && sym_applicable(M); }
     template <class Op>
-    int run_sym(const typename Op::Params& prm, int M) { return run_pair_sym<Op>(prm, M, ws, wsb, st); }
+    int run_sym(const typename Op::Params& prm, int M, float* scal_out) {
+        return run_pair_sym<Op>(prm, M, scal_out, ws, wsb, st);
+    }
     void scal_fix(float* scal, float eta, int withdiv) {
         rhs_scal_fix_kernel<<<1, 32, 0, st>>>(scal, eta, withdiv);
         launch_counter() += 1;

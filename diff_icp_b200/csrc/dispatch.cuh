@@ -72,7 +72,12 @@ int rhs_forward_d(Exec& ex, int withlogdet, const RhsParams& prm, int M, int Nx,
     const bool div_qq = withlogdet && !hasx;
     int rc;
     // (q,q) pass: scal[1..3] = A, B, C
-    if (eta) rc = ex.template run<RhsQQ<D, true, true>>(prm, M, M, scal + 1, 0);
+    if (ex.use_sym_forward(M)) {                    // every unordered pair once (symmetric engine; measured SLOWER than the
+                                                    // general engine for the forward pass on B200: off unless mode 2)
+        if (eta) rc = ex.template run_sym<RhsQQ<D, true, true>>(prm, M, scal + 1);
+        else if (div_qq) rc = ex.template run_sym<RhsQQ<D, true, false>>(prm, M, scal + 1);
+        else rc = ex.template run_sym<RhsQQ<D, false, false>>(prm, M, scal + 1);
+    } else if (eta) rc = ex.template run<RhsQQ<D, true, true>>(prm, M, M, scal + 1, 0);
     else if (div_qq) rc = ex.template run<RhsQQ<D, true, false>>(prm, M, M, scal + 1, 0);
     else rc = ex.template run<RhsQQ<D, false, false>>(prm, M, M, scal + 1, 0);
     if (rc != DICP_OK) return rc;
@@ -108,7 +113,7 @@ int rhs_adjoint_d(Exec& ex, int withlogdet, RhsParams prm, int M, int Nx) {
     int rc;
     prm.accumulate = 0;
     if (prm.eta != 0.f) {                           // logdet model (withlogdet is implied)
-        rc = ex.use_sym(M) ? ex.template run_sym<AdjQQEta<D>>(prm, M) : ex.template run<AdjQQEta<D>>(prm, M, M, nullptr, 0);
+        rc = ex.use_sym(M) ? ex.template run_sym<AdjQQEta<D>>(prm, M, nullptr) : ex.template run<AdjQQEta<D>>(prm, M, M, nullptr, 0);
         if (rc != DICP_OK || !hasx) return rc;
         rc = ex.template run<AdjXQxEta<D>>(prm, Nx, M, nullptr, 0);
         if (rc != DICP_OK) return rc;
@@ -117,8 +122,8 @@ int rhs_adjoint_d(Exec& ex, int withlogdet, RhsParams prm, int M, int Nx) {
     }
     const bool div_qq = withlogdet && !hasx;
     if (ex.use_sym(M)) {
-        if (div_qq) rc = ex.template run_sym<AdjQQ<D, true>>(prm, M);
-        else rc = ex.template run_sym<AdjQQ<D, false>>(prm, M);
+        if (div_qq) rc = ex.template run_sym<AdjQQ<D, true>>(prm, M, nullptr);
+        else rc = ex.template run_sym<AdjQQ<D, false>>(prm, M, nullptr);
     } else {
         if (div_qq) rc = ex.template run<AdjQQ<D, true>>(prm, M, M, nullptr, 0);
         else rc = ex.template run<AdjQQ<D, false>>(prm, M, M, nullptr, 0);
@@ -188,9 +193,10 @@ int em_colstats_entry(Exec& ex, int D, float sigma_old, const float* X, int64_t 
 struct HostExec {
     bool sym = false;                       // evaluate the (q,q) adjoint pass through Op::pair_sym (tests of the formulas)
     bool use_sym(int) const { return sym; }
+    bool use_sym_forward(int) const { return sym; }
     template <class Op>
-    int run_sym(const typename Op::Params& prm, int M) {
-        run_pair_host_sym<Op>(prm, M);
+    int run_sym(const typename Op::Params& prm, int M, float* scal_out) {
+        run_pair_host_sym<Op>(prm, M, scal_out);
         return DICP_OK;
     }
     template <class Op>

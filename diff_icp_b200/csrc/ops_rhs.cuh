@@ -166,6 +166,54 @@ struct RhsQQ {
             if (NEEDZ) a[A_Z + k] = vfma(K, z[k], a[A_Z + k]);
         }
     }
+    // Both orientations of an unordered pair from ONE evaluation (symmetric engine): K, r'^2, w and the z' coefficient are
+    // even under the swap of the two points, z' is odd: the column's sums get K p_i, -Kc z', -K z', K, K r'^2.
+    template <class V, bool MASKED = false>
+    static DICP_HD void pair_sym(const Params& P, const Row& r, const V* c, V* a, V* ca, V km = V()) {
+        V z[D];
+        V r2, w;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            z[k] = vsub(vbc<V>(r.q[k]), c[k]);
+            r2 = k == 0 ? vmul(z[k], z[k]) : vfma(z[k], z[k], r2);
+            w = k == 0 ? vmul(vbc<V>(r.p[k]), c[D + k]) : vfma(vbc<V>(r.p[k]), c[D + k], w);
+        }
+        V K = vex2n(r2);
+        if (MASKED) K = vmul(K, km);
+        V coef;
+        if (ETA) {
+            V ze;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const V ek = vsub(vbc<V>(r.p[k]), c[D + k]);
+                ze = k == 0 ? vmul(z[k], ek) : vfma(z[k], ek, ze);
+            }
+            const float c1 = P.eta * P.s * P.beta, c2 = P.eta * P.eta * P.s * P.alpha;
+            const V t1 = vfma(vbc<V>(-c2 * P.beta), r2, vbc<V>(c2 * (float)(D + 2)));
+            coef = vfma(vbc<V>(P.alpha), w, vfma(vbc<V>(c1), ze, t1));
+            a[A_S0] = vadd(a[A_S0], K);
+            ca[A_S0] = vadd(ca[A_S0], K);
+            a[A_R2] = vfma(K, r2, a[A_R2]);
+            ca[A_R2] = vfma(K, r2, ca[A_R2]);
+        } else {
+            coef = w;
+        }
+        const V Kc = vmul(K, coef);
+        const V nKc = vmul(Kc, vbc<V>(-1.f));
+        V nK;
+        if (NEEDZ) nK = vmul(K, vbc<V>(-1.f));
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            a[A_V + k] = vfma(K, c[D + k], a[A_V + k]);
+            ca[A_V + k] = vfma(K, vbc<V>(r.p[k]), ca[A_V + k]);
+            a[A_T + k] = vfma(Kc, z[k], a[A_T + k]);
+            ca[A_T + k] = vfma(nKc, z[k], ca[A_T + k]);
+            if (NEEDZ) {
+                a[A_Z + k] = vfma(K, z[k], a[A_Z + k]);
+                ca[A_Z + k] = vfma(nK, z[k], ca[A_Z + k]);
+            }
+        }
+    }
     static DICP_HD void finish(const Params& P, int i, const Row& r, const float* a, float* scal) {
         float A = 0.f, B = 0.f, C = 0.f;
 #pragma unroll

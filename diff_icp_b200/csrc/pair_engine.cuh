@@ -519,7 +519,7 @@ inline void run_pair_host(const typename Op::Params& prm, int M, int N, float* s
 // Symmetric evaluation (tests only): every unordered pair {i, j}, i < j, visited ONCE with Op::pair_sym, the diagonal
 // pairs with Op::pair -- what the device's symmetric engine (sym_engine.cuh) computes, in a simple order.
 template <class Op>
-inline void run_pair_host_sym(const typename Op::Params& prm, int M) {
+inline void run_pair_host_sym(const typename Op::Params& prm, int M, float* scal_out = nullptr) {
     std::vector<float> acc((size_t)M * Op::NACC, 0.f);
     for (int i = 0; i < M; ++i) {
         typename Op::Row row;
@@ -532,12 +532,16 @@ inline void run_pair_host_sym(const typename Op::Params& prm, int M) {
             Op::template pair_sym<float>(prm, row, c, &acc[(size_t)i * Op::NACC], &acc[(size_t)j * Op::NACC]);
         }
     }
+    double scal[Op::NSCAL > 0 ? Op::NSCAL : 1] = {0};
     for (int i = 0; i < M; ++i) {
         typename Op::Row row;
         Op::load_row(prm, i, row);
         float rs[Op::NSCAL > 0 ? Op::NSCAL : 1] = {0};
         Op::finish(prm, i, row, &acc[(size_t)i * Op::NACC], rs);
+        for (int k = 0; k < Op::NSCAL; ++k) scal[k] += rs[k];
     }
+    if (scal_out)
+        for (int k = 0; k < Op::NSCAL; ++k) scal_out[k] = (float)scal[k];
 }
 
 }  // namespace dicp

@@ -1,4 +1,7 @@
-// Symmetric pair engine for the (q,q) adjoint passes: every UNORDERED pair of support points is evaluated once.
+// Symmetric pair engine for the (q,q) passes: every UNORDERED pair of support points is evaluated once.  Used for the
+// ADJOINT pass (6 travelling accumulators, 41-83 operations per pair: 1.3-1.5x faster than the general engine on B200);
+// the forward pass (up to 11 travelling accumulators, 16-30 operations per pair) is SHFL / shared-memory bound in this
+// form and measured slower, so it stays on the general engine (dicp_sym_mode(2) routes it here for experiments).
 //
 // In the (q,q) passes rows and columns are the same point set and the pair term of (row n, column m) follows from the one
 // of (row m, column n) by sign flips of the odd quantities (Op::pair_sym, ops_rhs.cuh): the exponential, the dot products
@@ -28,7 +31,7 @@ namespace dicp {
 static constexpr int kSymThreads = 128, kSymR = 2, kSymRows = (kSymThreads / 32) * 32 * kSymR;      // 256 rows per CTA
 static constexpr int kSymGroup = 64;                                                                 // columns per ring round
 static constexpr int kSymMaxBlocks = 256;                                                            // row blocks (M <= 65536)
-static constexpr int kSymMinM = 2048;
+static constexpr int kSymMinM = 4096;                // below this the general engine is as fast (measured)
 
 struct SymPlan {
     int M, nrb, Lc, ngroups_total;      // points, row blocks, chunk length (columns), column groups (ceil(M/64))
@@ -41,7 +44,7 @@ inline SymPlan sym_make_plan(int M, int sms) {
     p.M = M;
     p.nrb = (M + kSymRows - 1) / kSymRows;
     p.ngroups_total = (M + kSymGroup - 1) / kSymGroup;
-    const long long target = (long long)sms * 6;                    // symmetric items wanted
+    const long long target = (long long)sms * 16;                   // symmetric items wanted: short items => short tail
     long long lc = ((long long)M * M / 2) / ((long long)kSymRows * target);
     lc = (lc + kSymGroup - 1) / kSymGroup * kSymGroup;
     if (lc < kSymGroup) lc = kSymGroup;
@@ -66,7 +69,7 @@ inline size_t sym_colpart_floats(const SymPlan& p, int nacc) {
 inline size_t sym_workspace_bound(long long M, int sms) {
     if (!sym_applicable(M)) return 0;
     const SymPlan p = sym_make_plan((int)M, sms);
-    return (sym_rowpart_floats(p, 16) + sym_colpart_floats(p, 16)) * 4 + 1024;
+    return (sym_rowpart_floats(p, 16) + sym_colpart_floats(p, 16)) * 4 + (size_t)((M + 31) / 32) * 8 * 4 + 2048;
 }
 
 #if defined(__CUDACC__)
@@ -227,51 +230,109 @@ __global__ void __launch_bounds__(kSymThreads) sym_pair_kernel(typename Op::Para
         for (int k = 0; k < NACC; ++k) rp[k * kSymRows + warp * (32 * kSymR) + r * 32 + lane] = f2_sum(acc[r][k]);
 }
 
+// Finish: 32 rows per CTA, 4 thread groups per row.  Group g adds the row's item partials it, it+4, ... and the column
+// partials of the row blocks J = g, g+4, ... (4 independent loads in flight per step), the groups are added in group order
+// through shared memory, group 0 runs Op::finish.  Fixed order => deterministic.
 template <class Op>
 __global__ void __launch_bounds__(128) sym_finish_kernel(typename Op::Params prm, const float* __restrict__ rowpart,
-                                                         const float* __restrict__ colpart, SymPlan plan) {
-    constexpr int NACC = Op::NACC;
-    const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= plan.M) return;
-    const int I = i / kSymRows, rl = i - I * kSymRows;
-    const int mpad = plan.ngroups_total * kSymGroup;
+                                                         const float* __restrict__ colpart, float* __restrict__ blockscal,
+                                                         SymPlan plan) {
+    constexpr int NACC = Op::NACC, NSCAL = Op::NSCAL, FR = 32, G = 4;
+    __shared__ float red[32];
+    __shared__ float xch[G * NACC * FR];
+    const int r = threadIdx.x & (FR - 1), g = threadIdx.x / FR;
+    const int i = blockIdx.x * FR + r;
+    float rs[NSCAL > 0 ? NSCAL : 1];
+#pragma unroll
+    for (int k = 0; k < NSCAL; ++k) rs[k] = 0.f;
     float acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-    for (int it = plan.prefix[I]; it < plan.prefix[I + 1]; ++it) {
-        const float* rp = rowpart + (size_t)it * NACC * kSymRows + rl;
+    const bool valid = i < plan.M;
+    if (valid) {
+        const int I = i / kSymRows, rl = i - I * kSymRows;
+        const int mpad = plan.ngroups_total * kSymGroup;
+        const int it1 = plan.prefix[I + 1];
+        for (int it = plan.prefix[I] + g; it < it1; it += 4 * G) {
+            float v[4][NACC];
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) acc[k] += rp[k * kSymRows];
-    }
-    for (int J = 0; J < I; ++J) {
-        const float* cp = colpart + (size_t)J * NACC * mpad + i;
+            for (int u = 0; u < 4; ++u) {
+                const int t = it + u * G;
+                const float* rp = rowpart + (size_t)(t < it1 ? t : it) * NACC * kSymRows + rl;
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) acc[k] += cp[(size_t)k * mpad];
+                for (int k = 0; k < NACC; ++k) v[u][k] = rp[k * kSymRows];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (it + u * G < it1) {
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) acc[k] += v[u][k];
+                }
+        }
+        for (int J = g; J < I; J += 4 * G) {
+            float v[4][NACC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = J + u * G;
+                const float* cp = colpart + (size_t)(t < I ? t : J) * NACC * mpad + i;
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) v[u][k] = cp[(size_t)k * mpad];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (J + u * G < I) {
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k) acc[k] += v[u][k];
+                }
+        }
     }
-    typename Op::Row row;
-    Op::load_row(prm, i, row);
-    Op::finish(prm, i, row, acc, nullptr);
+    if (g > 0) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) xch[(g * NACC + k) * FR + r] = acc[k];
+    }
+    __syncthreads();
+    if (valid && g == 0) {
+        for (int g2 = 1; g2 < G; ++g2) {
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[k] += xch[(g2 * NACC + k) * FR + r];
+        }
+        typename Op::Row row;
+        Op::load_row(prm, i, row);
+        Op::finish(prm, i, row, acc, rs);
+    }
+#pragma unroll
+    for (int k = 0; k < NSCAL; ++k) {           // row scalars: block partials in a fixed tree, summed by scalar_reduce_kernel
+        const float v = block_sum(rs[k], red);
+        if (threadIdx.x == 0) blockscal[(size_t)blockIdx.x * NSCAL + k] = v;
+    }
 }
 
 // packed columns (same layout as the general engine) + symmetric kernel + finish
 template <class Op>
-inline int run_pair_sym(const typename Op::Params& prm, int M, void* ws, size_t ws_bytes, cudaStream_t st) {
-    static_assert(Op::PACKED && Op::NSCAL == 0, "symmetric engine: packed Ops without row scalars");
+inline int run_pair_sym(const typename Op::Params& prm, int M, float* scal_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    static_assert(Op::PACKED, "symmetric engine: packed Ops");
     const SymPlan plan = sym_make_plan(M, device_info().sms);
     const int mpad = plan.ngroups_total * kSymGroup;
     const int npadcol = (mpad + 127) / 128 * 128;
     const size_t col_bytes = align_up((size_t)npadcol * Op::NF * 4, 256);
     const size_t row_bytes = align_up(sym_rowpart_floats(plan, Op::NACC) * 4, 256);
     const size_t cpart_bytes = align_up(sym_colpart_floats(plan, Op::NACC) * 4, 256);
-    if (ws == nullptr || col_bytes + row_bytes + cpart_bytes > ws_bytes) return DICP_EWORKSPACE;
+    const int nfin = (M + 31) / 32;
+    const size_t scal_bytes = align_up((size_t)nfin * (Op::NSCAL > 0 ? Op::NSCAL : 1) * 4, 256);
+    if (ws == nullptr || col_bytes + row_bytes + cpart_bytes + scal_bytes > ws_bytes) return DICP_EWORKSPACE;
     if ((reinterpret_cast<uintptr_t>(ws) & 127) != 0) return DICP_EBADARG;
     float* colpack = (float*)ws;
     float* rowpart = (float*)((char*)ws + col_bytes);
     float* colpart = (float*)((char*)ws + col_bytes + row_bytes);
+    float* blockscal = (float*)((char*)ws + col_bytes + row_bytes + cpart_bytes);
     pack_kernel_p<Op><<<(npadcol + 255) / 256, 256, 0, st>>>(prm, colpack, M, npadcol);
     sym_pair_kernel<Op><<<plan.items, kSymThreads, 0, st>>>(prm, colpack, rowpart, colpart, plan);
-    sym_finish_kernel<Op><<<(M + 127) / 128, 128, 0, st>>>(prm, rowpart, colpart, plan);
+    sym_finish_kernel<Op><<<nfin, 128, 0, st>>>(prm, rowpart, colpart, blockscal, plan);
     launch_counter() += 3;
+    if (Op::NSCAL > 0 && scal_out != nullptr) {
+        scalar_reduce_kernel<<<1, 256, 0, st>>>(blockscal, nfin, Op::NSCAL, scal_out, 0);
+        launch_counter() += 1;
+    }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DICP_OK : (int)e;
 }

@@ -26,6 +26,13 @@ int emu_rhs_forward(int D, int withlogdet, float sigma, float eta, const float* 
     return rhs_forward_entry(ex, D, withlogdet, sigma, eta, q, p, M, x, Nx, vq, dp, vx, scal);
 }
 
+int emu_rhs_forward_sym(int D, int withlogdet, float sigma, float eta, const float* q, const float* p, int64_t M,
+                        const float* x, int64_t Nx, float* vq, float* dp, float* vx, float* scal) {
+    HostExec ex;
+    ex.sym = true;
+    return rhs_forward_entry(ex, D, withlogdet, sigma, eta, q, p, M, x, Nx, vq, dp, vx, scal);
+}
+
 int emu_rhs_adjoint_sym(int D, int withlogdet, float sigma, float eta, const float* q, const float* p, int64_t M,
                         const float* x, int64_t Nx, const float* a, const float* u, const float* wx, const float* gc,
                         float* gq, float* gp, float* gx) {

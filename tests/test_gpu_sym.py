@@ -22,9 +22,48 @@ def adjoint(D, withlogdet, sigma, eta, q, p, a, u, gc, mode):
         lib.dicp_sym_mode(prev)
 
 
+def forward(D, withlogdet, sigma, eta, q, p, mode):
+    from diff_icp_b200 import ops
+    lib = ops.load()
+    prev = lib.dicp_sym_mode(mode)
+    try:
+        M = q.shape[0]
+        vq, dp, scal = torch.zeros_like(q), torch.zeros_like(q), torch.zeros(4, device=q.device)
+        ws = ops.alloc_workspace(M, M, q.device)
+        ops.rhs_forward(D, withlogdet, sigma, eta, q, p, None, vq, dp, None, scal, ws)
+        torch.cuda.synchronize()
+        return vq, dp, scal
+    finally:
+        lib.dicp_sym_mode(prev)
+
+
 @pytest.mark.parametrize("D", [2, 3])
 @pytest.mark.parametrize("model", ["classic", "hybrid", "logdet"])
-@pytest.mark.parametrize("M", [2048, 2049, 4999, 20000])
+@pytest.mark.parametrize("M", [4096, 4097, 6999, 20000])
+def test_symmetric_forward_matches_general_engine(D, model, M):
+    if M == 20000 and D == 2:
+        pytest.skip("large case once per model")
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + D)
+    q = torch.rand(M, D, generator=g).to(dev)
+    p = torch.randn(M, D, generator=g).to(dev)
+    sigma = 0.2 if M > 10000 else 0.3
+    eta = 0.02 if model == "logdet" else 0.0
+    wld = model != "classic"
+    ref = forward(D, wld, sigma, eta, q, p, 0)
+    got = forward(D, wld, sigma, eta, q, p, 2)          # mode 2: the forward (q,q) pass on the symmetric engine too
+    for r, s in zip(ref[:2], got[:2]):
+        scale = float(r.abs().max())
+        assert torch.isfinite(s).all()
+        assert float((r - s).abs().max()) <= 2e-5 * scale, (float((r - s).abs().max()), scale)
+    assert float((ref[2] - got[2]).abs().max()) <= 2e-5 * float(ref[2].abs().max()) + 1e-6       # dcost, A, B, C
+    again = forward(D, wld, sigma, eta, q, p, 2)
+    assert all(torch.equal(a, b) for a, b in zip(again, got))
+
+
+@pytest.mark.parametrize("D", [2, 3])
+@pytest.mark.parametrize("model", ["classic", "hybrid", "logdet"])
+@pytest.mark.parametrize("M", [4096, 4097, 6999, 20000])
 def test_symmetric_engine_matches_general_engine(D, model, M):
     if M == 20000 and D == 2:
         pytest.skip("large case once per model")
@@ -33,7 +72,7 @@ def test_symmetric_engine_matches_general_engine(D, model, M):
     q = torch.rand(M, D, generator=g).to(dev)
     p, a, u = (torch.randn(M, D, generator=g).to(dev) for _ in range(3))
     gc = torch.tensor([0.7], device=dev)
-    sigma = 0.2 if M > 5000 else 0.35
+    sigma = 0.2 if M > 10000 else 0.3
     eta = 0.02 if model == "logdet" else 0.0
     wld = model != "classic"
     ref = adjoint(D, wld, sigma, eta, q, p, a, u, gc, 0)
@@ -54,4 +93,4 @@ def test_small_and_huge_sizes_use_the_general_engine():
     p, a, u = (torch.randn(500, 3, device=dev) for _ in range(3))
     r0 = adjoint(3, True, 0.3, 0.0, q, p, a, u, torch.ones(1, device=dev), 0)
     r1 = adjoint(3, True, 0.3, 0.0, q, p, a, u, torch.ones(1, device=dev), 1)
-    assert torch.equal(r0[0], r1[0]) and torch.equal(r0[1], r1[1])          # below 2048 points: same engine, same bits
+    assert torch.equal(r0[0], r1[0]) and torch.equal(r0[1], r1[1])          # below 4096 points: same engine, same bits

@@ -104,18 +104,21 @@ def test_emulated_rhs_forward_matches_oracle(emu, D, version, with_x):
     vq, dp = np.zeros_like(qa), np.zeros_like(pa)
     vx = np.zeros_like(xa) if with_x else None
     scal = np.zeros(4, dtype=np.float32)
-    rc = emu.emu_rhs_forward(D, int(LM.withlogdet), ctypes.c_float(sig), ctypes.c_float(LM.eta), fp(qa), fp(pa),
-                             ctypes.c_int64(Nq), fp(xa), ctypes.c_int64(Nx), fp(vq), fp(dp), fp(vx), fp(scal))
-    assert rc == 0
-    assert relerr(vq, ode[0].numpy()) < 2e-5
-    assert relerr(dp, ode[1].numpy()) < 2e-5
-    dc = float(ode[2].sum())
-    assert abs(scal[0] - dc) < 2e-5 * max(1.0, abs(dc)), (scal[0], dc)
-    if with_x:
-        assert relerr(vx, ode[3].numpy()) < 2e-5
-    H = float(LM.hamiltonian(q.double(), p.double()))
-    Hk = 0.5 * scal[1] - LM.eta * scal[2] - 0.5 * LM.eta ** 2 * scal[3]
-    assert abs(Hk - H) < 2e-5 * max(1.0, abs(H)), (Hk, H)
+    # plain evaluation (every ordered pair) and symmetric evaluation (every unordered (q,q) pair once, Op::pair_sym)
+    for fn in (emu.emu_rhs_forward, emu.emu_rhs_forward_sym):
+        vq[:], dp[:], scal[:] = 0, 0, 0
+        rc = fn(D, int(LM.withlogdet), ctypes.c_float(sig), ctypes.c_float(LM.eta), fp(qa), fp(pa),
+                ctypes.c_int64(Nq), fp(xa), ctypes.c_int64(Nx), fp(vq), fp(dp), fp(vx), fp(scal))
+        assert rc == 0
+        assert relerr(vq, ode[0].numpy()) < 2e-5
+        assert relerr(dp, ode[1].numpy()) < 2e-5
+        dc = float(ode[2].sum())
+        assert abs(scal[0] - dc) < 2e-5 * max(1.0, abs(dc)), (scal[0], dc)
+        if with_x:
+            assert relerr(vx, ode[3].numpy()) < 2e-5
+        H = float(LM.hamiltonian(q.double(), p.double()))
+        Hk = 0.5 * scal[1] - LM.eta * scal[2] - 0.5 * LM.eta ** 2 * scal[3]
+        assert abs(Hk - H) < 2e-5 * max(1.0, abs(H)), (Hk, H)
 
 
 @pytest.mark.parametrize("D", [2, 3])
