@@ -67,6 +67,14 @@ struct DeviceExec {
     // (q,q) adjoint passes through the symmetric engine (sym_engine.cuh): every unordered pair once
     bool use_sym(int M) const { return sym_mode() != 0 && sym_applicable(M); }
     bool use_sym_forward(int M) const { return sym_mode() == 2 && sym_applicable(M); }
+    // (x,q) adjoint: both sides from ONE ring pass (rect_pair_kernel) when the sets are large enough and the workspace fits
+    bool use_rect(int Nx, int M) const {
+        if (sym_mode() == 0 || M < 256 || Nx < 2048) return false;
+        const RectPlan p = rect_make_plan(Nx, M, 4, device_info().sms);
+        return ws != nullptr && rect_workspace_bytes(p, 8, 4, 8) <= wsb;
+    }
+    template <class Op>
+    int run_rect(const typename Op::Params& prm, int Nx, int M) { return run_pair_rect<Op>(prm, Nx, M, ws, wsb, st); }
     template <class Op>
     int run_sym(const typename Op::Params& prm, int M, float* scal_out) {
         return run_pair_sym<Op>(prm, M, scal_out, ws, wsb, st);

@@ -129,6 +129,10 @@ int rhs_adjoint_d(Exec& ex, int withlogdet, RhsParams prm, int M, int Nx) {
         else rc = ex.template run<AdjQQ<D, false>>(prm, M, M, nullptr, 0);
     }
     if (rc != DICP_OK) return rc;
+    if (hasx && ex.use_rect(Nx, M)) {               // both sides of the (x,q) pass from one evaluation of every pair
+        if (withlogdet) return ex.template run_rect<AdjXQ<D, true>>(prm, Nx, M);
+        return ex.template run_rect<AdjXQ<D, false>>(prm, Nx, M);
+    }
     if (hasx) {
         if (withlogdet) rc = ex.template run<AdjXQx<D, true>>(prm, Nx, M, nullptr, 0);
         else rc = ex.template run<AdjXQx<D, false>>(prm, Nx, M, nullptr, 0);
@@ -194,6 +198,12 @@ struct HostExec {
     bool sym = false;                       // evaluate the (q,q) adjoint pass through Op::pair_sym (tests of the formulas)
     bool use_sym(int) const { return sym; }
     bool use_sym_forward(int) const { return sym; }
+    bool use_rect(int, int) const { return sym; }
+    template <class Op>
+    int run_rect(const typename Op::Params& prm, int Mrows, int Ncols) {
+        run_rect_host<Op>(prm, Mrows, Ncols);
+        return DICP_OK;
+    }
     template <class Op>
     int run_sym(const typename Op::Params& prm, int M, float* scal_out) {
         run_pair_host_sym<Op>(prm, M, scal_out);

@@ -118,6 +118,7 @@ struct RhsQQ {
     static constexpr int A_S0 = A_Z + (NEEDZ ? D : 0);
     static constexpr int A_R2 = A_S0 + (ETA ? 1 : 0);
     static constexpr int NACC = A_R2 + (ETA ? 1 : 0);
+    static constexpr int NACC_COL = NACC;
     static constexpr int NSCAL = 3;   // A, B, C
     DICP_RHS_COMMON(2 * D)
     struct Row { float q[D], p[D]; };
@@ -305,6 +306,7 @@ template <int D, bool DIV, int R_ = DICP_RHS_R>
 struct AdjQQ {
     static constexpr int A_GP = 0, A_GQ = D;
     static constexpr int NACC = 2 * D;
+    static constexpr int NACC_COL = NACC;
     static constexpr int NSCAL = 0;
     DICP_RHS_COMMON(4 * D)
     struct Row { float q[D], p[D], a[D], u[D], gc; };
@@ -550,6 +552,90 @@ struct AdjXQq {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// adjoint of the (x,q) pass, BOTH sides from one evaluation of the pair (rectangular ring engine, sym_engine.cuh):
+// rows = (x_k, wx_k), cols = (q_j, p_j), z' = kappa (x_k - q_j) = -zeta'.  With wp = wx_k.p_j, pz = p_j.z',
+// c = -alpha wp - gc s beta pz (the SAME coefficient in AdjXQx and AdjXQq, because p_j.zeta' = -pz):
+//   row side    gx_k += K c z' + gc s K p_j                      (= AdjXQx)
+//   column side gq_j -= K c z' ;  gp_j += K wx_k + gc alpha K z' ;  S0_j += K        (= AdjXQq; finish adds -gc s S0_j p_j)
+// 36 operations per pair instead of 22 + 26 in two passes (D = 3, with the divergence cost).
+// ------------------------------------------------------------------------------------------------
+template <int D, bool DIV>
+struct AdjXQ {
+    using Params = RhsParams;
+    static constexpr bool PACKED = true;
+    static constexpr int NF = 2 * D, COLF4 = (NF + 3) / 4;
+    static constexpr int NACC = D;                                   // row side: gx
+    static constexpr int C_GP = 0, C_GQ = D, C_S0 = 2 * D;
+    static constexpr int NACC_COL = 2 * D + (DIV ? 1 : 0);           // column side: gp, gq, S0
+    static constexpr int NSCAL = 0;
+    static constexpr int RECT_R = 4;                                 // rows per lane in the ring engine (light rows)
+    struct Row { float x[D], w[D], gc; };
+
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { pack_qp<D>(P, j, N, c, COLF4 * 4); }
+    static DICP_HD void load_row(const Params& P, int i, Row& r) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            r.x[k] = (P.x[(size_t)i * D + k] - P.origin[k]) * P.kappa;
+            r.w[k] = P.wx[(size_t)i * D + k];
+        }
+        r.gc = (DIV && P.gc != nullptr) ? P.gc[0] : 0.f;
+    }
+    template <class V, bool MASKED = false>
+    static DICP_HD void pair_sym(const Params& P, const Row& r, const V* c, V* acc, V* cacc, V km = V()) {
+        V z[D];
+        V r2, wp, pz;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            z[k] = vsub(vbc<V>(r.x[k]), c[k]);
+            r2 = k == 0 ? vmul(z[k], z[k]) : vfma(z[k], z[k], r2);
+            wp = k == 0 ? vmul(vbc<V>(r.w[k]), c[D + k]) : vfma(vbc<V>(r.w[k]), c[D + k], wp);
+            if (DIV) pz = k == 0 ? vmul(c[D + k], z[k]) : vfma(c[D + k], z[k], pz);
+        }
+        V K = vex2n(r2);
+        if (MASKED) K = vmul(K, km);
+        V ncz = vmul(vbc<V>(-P.alpha), wp);
+        if (DIV) ncz = vfma(vbc<V>(-r.gc * P.s * P.beta), pz, ncz);
+        const V Kncz = vmul(K, ncz);
+        V Kg, Kga;
+        if (DIV) {
+            Kg = vmul(K, vbc<V>(r.gc * P.s));
+            Kga = vmul(K, vbc<V>(r.gc * P.alpha));
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const V inc = vmul(Kncz, z[k]);
+            V gx = vadd(acc[k], inc);
+            V gp = vfma(K, vbc<V>(r.w[k]), cacc[C_GP + k]);
+            if (DIV) {
+                gx = vfma(Kg, c[D + k], gx);
+                gp = vfma(Kga, z[k], gp);
+            }
+            acc[k] = gx;
+            cacc[C_GP + k] = gp;
+            cacc[C_GQ + k] = vsub(cacc[C_GQ + k], inc);
+        }
+        if (DIV) cacc[C_S0] = vadd(cacc[C_S0], K);
+    }
+    // row side: gx_k
+    static DICP_HD void finish(const Params& P, int i, const Row&, const float* acc, float*) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) P.gx[(size_t)i * D + k] = acc[k];
+    }
+    // column side: ADDED to gq_j, gp_j (which hold the (q,q) pass)
+    static DICP_HD void finish_col(const Params& P, int j, const float* cacc) {
+        const float gc = (DIV && P.gc != nullptr) ? P.gc[0] : 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const size_t o = (size_t)j * D + k;
+            float gq = cacc[C_GQ + k];
+            if (DIV) gq = fmaf(-gc * P.s * cacc[C_S0], P.p[o], gq);
+            P.gp[o] += cacc[C_GP + k];
+            P.gq[o] += gq;
+        }
+    }
+};
+
 // ================================================================================================================
 // Adjoint of the logdet model (eta = 1/lambda != 0).  Notation per pair (row m, column n), scaled z' = kappa (row - col):
 //   w = p_m.p_n, e = p_m - p_n, du = u_m - u_n, dA = a_m - a_n, t0 = beta r'^2 - D, t1 = beta r'^2 - (D+2), g = gc
@@ -562,7 +648,7 @@ struct AdjXQq {
 template <int D, int R_ = DICP_RHS_R>
 struct AdjQQEta {
     static constexpr int A_GP = 0, A_GQ = D;
-    static constexpr int NACC = 2 * D, NSCAL = 0;
+    static constexpr int NACC = 2 * D, NACC_COL = NACC, NSCAL = 0;
     DICP_RHS_COMMON(4 * D)
     struct Row { float q[D], p[D], a[D], u[D], gc; };
 

@@ -322,12 +322,18 @@ __global__ void finish_kernel(typename Op::Params prm, const float* __restrict__
         const float* src = part + (size_t)g * NACC * M + i;
 #pragma unroll
         for (int k = 0; k < NACC; ++k) acc[k] = src[(size_t)k * M];
-        for (int s = g + G; s < nsplit; s += G) {
-            src = part + (size_t)s * NACC * M + i;
-            float b[NACC];
+        for (int s = g + G; s < nsplit; s += 4 * G) {          // 4 splits' loads in flight, combined in split order
+            float b[4][NACC];
 #pragma unroll
-            for (int k = 0; k < NACC; ++k) b[k] = src[(size_t)k * M];
-            Op::combine(acc, b);
+            for (int u = 0; u < 4; ++u) {
+                const int ss = s + u * G;
+                src = part + (size_t)(ss < nsplit ? ss : s) * NACC * M + i;
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) b[u][k] = src[(size_t)k * M];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (s + u * G < nsplit) Op::combine(acc, b[u]);
         }
     }
     if (G > 1) {
@@ -359,7 +365,7 @@ __global__ void finish_kernel(typename Op::Params prm, const float* __restrict__
 }
 
 // thread groups per row of finish_kernel
-DICP_HD int finish_groups(int M, int nsplit) { return (nsplit >= 32 && M <= 4096) ? 16 : 1; }
+DICP_HD int finish_groups(int M, int nsplit) { return (nsplit >= 8 && M <= 4096) ? 16 : 1; }
 
 // out[k] (+)= scale * sum_b blockscal[b][k]   -- single CTA, fixed order.
 __global__ void scalar_reduce_kernel(const float* __restrict__ blockscal, int nblocks, int nscal,
@@ -514,6 +520,25 @@ inline void run_pair_host(const typename Op::Params& prm, int M, int N, float* s
     }
     if (scal_out)
         for (int k = 0; k < Op::NSCAL; ++k) scal_out[k] = (float)scal[k];
+}
+
+// Rectangular both-sides evaluation (tests only): every (row, column) pair once with Op::pair_sym; rows finished with
+// Op::finish, columns with Op::finish_col -- what the device's rectangular ring engine computes, in a simple order.
+template <class Op>
+inline void run_rect_host(const typename Op::Params& prm, int Mrows, int Ncols) {
+    std::vector<float> cacc((size_t)Ncols * Op::NACC_COL, 0.f);
+    for (int i = 0; i < Mrows; ++i) {
+        typename Op::Row row;
+        Op::load_row(prm, i, row);
+        float acc[Op::NACC] = {0};
+        for (int j = 0; j < Ncols; ++j) {
+            float c[Op::COLF4 * 4];
+            Op::pack_col(prm, j, Ncols, c);
+            Op::template pair_sym<float>(prm, row, c, acc, &cacc[(size_t)j * Op::NACC_COL]);
+        }
+        Op::finish(prm, i, row, acc, nullptr);
+    }
+    for (int j = 0; j < Ncols; ++j) Op::finish_col(prm, j, &cacc[(size_t)j * Op::NACC_COL]);
 }
 
 // Symmetric evaluation (tests only): every unordered pair {i, j}, i < j, visited ONCE with Op::pair_sym, the diagonal

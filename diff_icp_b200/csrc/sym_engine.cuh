@@ -72,6 +72,36 @@ inline size_t sym_workspace_bound(long long M, int sms) {
     return (sym_rowpart_floats(p, 16) + sym_colpart_floats(p, 16)) * 4 + (size_t)((M + 31) / 32) * 8 * 4 + 2048;
 }
 
+// ---- rectangular form: rows and columns are DIFFERENT point sets (data points x, support points q) -------------------------
+// The adjoint of the (x,q) pass needs sums over the columns for every row (gx_k) AND sums over the rows for every column
+// (gq_j, gp_j) of terms built from the same K, z', dot products: the general engine makes two passes over the same pairs
+// (AdjXQx with rows = x, AdjXQq with rows = q).  Here ONE ring pass does both: rows = x (2 per lane), column pairs of q
+// travelling round the warp with their accumulators (Op::pair_sym of AdjXQ).  Items = (256-row block) x (column chunk).
+struct RectPlan {
+    int Mrows, Ncols, rpc, nrb, ngroups_total, Lc, nchunks, items;       // rpc: rows per CTA (128 x rows per lane)
+};
+inline RectPlan rect_make_plan(int Mrows, int Ncols, int rows_per_lane, int sms) {
+    RectPlan p{};
+    p.Mrows = Mrows; p.Ncols = Ncols;
+    p.rpc = kSymThreads * rows_per_lane;
+    p.nrb = (Mrows + p.rpc - 1) / p.rpc;
+    p.ngroups_total = (Ncols + kSymGroup - 1) / kSymGroup;
+    long long want = ((long long)sms * 16 + p.nrb - 1) / p.nrb;            // column chunks per row block
+    if (want < 1) want = 1;
+    if (want > p.ngroups_total) want = p.ngroups_total;
+    const int gpc = (int)((p.ngroups_total + want - 1) / want);              // groups per chunk
+    p.Lc = gpc * kSymGroup;
+    p.nchunks = (p.ngroups_total + gpc - 1) / gpc;
+    p.items = p.nrb * p.nchunks;
+    return p;
+}
+inline size_t rect_workspace_bytes(const RectPlan& p, int nf, int nacc_row, int nacc_col) {
+    const size_t mpad = (size_t)p.ngroups_total * kSymGroup;
+    const size_t npadcol = (mpad + 127) / 128 * 128;
+    return align_up(npadcol * nf * 4, 256) + align_up((size_t)p.items * nacc_row * p.rpc * 4, 256) +
+           align_up((size_t)p.nrb * nacc_col * mpad * 4, 256);
+}
+
 #if defined(__CUDACC__)
 
 DICP_D F2 f2_shfl(F2 v, int src) {
@@ -84,10 +114,10 @@ DICP_D F2 f2_shfl(F2 v, int src) {
 }
 
 // one ring round: 32 steps over the 32 staged column pairs
-template <class Op, bool MASKED>
-DICP_D void sym_ring_round(const typename Op::Params& prm, const typename Op::Row (&row)[kSymR], const float* tile,
-                           int stride, int lane, const float (&rmask)[kSymR], int col0, int M, F2 (&acc)[kSymR][Op::NACC],
-                           F2 (&cacc)[Op::NACC]) {
+template <class Op, bool MASKED, int R>
+DICP_D void sym_ring_round(const typename Op::Params& prm, const typename Op::Row (&row)[R], const float* tile,
+                           int stride, int lane, const float (&rmask)[R], int col0, int M, F2 (&acc)[R][Op::NACC],
+                           F2 (&cacc)[Op::NACC_COL]) {
     constexpr int NF = Op::NF, PF4 = NF / 2;
 #pragma unroll 2
     for (int s = 0; s < 32; ++s) {
@@ -104,15 +134,15 @@ DICP_D void sym_ring_round(const typename Op::Params& prm, const typename Op::Ro
             const int j = col0 + 2 * pr;
             const float m0 = j < M ? 1.f : 0.f, m1 = j + 1 < M ? 1.f : 0.f;
 #pragma unroll
-            for (int r = 0; r < kSymR; ++r)
+            for (int r = 0; r < R; ++r)
                 Op::template pair_sym<F2, true>(prm, row[r], c, acc[r], cacc, f2(m0 * rmask[r], m1 * rmask[r]));
         } else {
 #pragma unroll
-            for (int r = 0; r < kSymR; ++r) Op::template pair_sym<F2, false>(prm, row[r], c, acc[r], cacc);
+            for (int r = 0; r < R; ++r) Op::template pair_sym<F2, false>(prm, row[r], c, acc[r], cacc);
         }
         // the column accumulators follow their column pair: lane l next handles pair (l + s + 1) mod 32, held by lane l + 1
 #pragma unroll
-        for (int k = 0; k < Op::NACC; ++k) cacc[k] = f2_shfl(cacc[k], (lane + 1) & 31);
+        for (int k = 0; k < Op::NACC_COL; ++k) cacc[k] = f2_shfl(cacc[k], (lane + 1) & 31);
     }
 }
 
@@ -203,8 +233,8 @@ __global__ void __launch_bounds__(kSymThreads) sym_pair_kernel(typename Op::Para
         F2 cacc[NACC];
 #pragma unroll
         for (int k = 0; k < NACC; ++k) cacc[k] = f2(0.f, 0.f);
-        if (rows_ragged || g0 + kSymGroup > M) sym_ring_round<Op, true>(prm, row, tile, STRIDE, lane, rmask, g0, M, acc, cacc);
-        else sym_ring_round<Op, false>(prm, row, tile, STRIDE, lane, rmask, g0, M, acc, cacc);
+        if (rows_ragged || g0 + kSymGroup > M) sym_ring_round<Op, true, kSymR>(prm, row, tile, STRIDE, lane, rmask, g0, M, acc, cacc);
+        else sym_ring_round<Op, false, kSymR>(prm, row, tile, STRIDE, lane, rmask, g0, M, acc, cacc);
         // lane l holds the sums of column pair l over this warp's 64 rows: add the four warps in warp order
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
@@ -333,6 +363,163 @@ inline int run_pair_sym(const typename Op::Params& prm, int M, float* scal_out, 
         scalar_reduce_kernel<<<1, 256, 0, st>>>(blockscal, nfin, Op::NSCAL, scal_out, 0);
         launch_counter() += 1;
     }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? DICP_OK : (int)e;
+}
+
+template <class Op, int R>
+__global__ void __launch_bounds__(kSymThreads) rect_pair_kernel(typename Op::Params prm, const float* __restrict__ colpack,
+                                                                float* __restrict__ rowpart, float* __restrict__ colpart,
+                                                                RectPlan plan) {
+    constexpr int NF = Op::NF, NACC = Op::NACC, NACC_COL = Op::NACC_COL, REC = 2 * NF, STRIDE = REC + 4;
+    __shared__ __align__(16) float tile[32 * STRIDE];
+    __shared__ float xch[(kSymThreads / 32) * 32 * 2 * NACC_COL];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int item = blockIdx.x, I = item / plan.nchunks, chunk = item - I * plan.nchunks;
+    const int Mrows = plan.Mrows, Ncols = plan.Ncols, mpad = plan.ngroups_total * kSymGroup;
+    typename Op::Row row[R];
+    float rmask[R];
+    const int RPC = plan.rpc;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int ri = I * RPC + warp * (32 * R) + r * 32 + lane;
+        rmask[r] = ri < Mrows ? 1.f : 0.f;
+        Op::load_row(prm, ri < Mrows ? ri : Mrows - 1, row[r]);
+    }
+    F2 acc[R][NACC];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[r][k] = f2(0.f, 0.f);
+    const bool rows_ragged = (I + 1) * RPC > Mrows;
+    const int j0 = chunk * plan.Lc;
+    int j1 = j0 + plan.Lc;
+    if (j1 > mpad) j1 = mpad;
+    for (int g0 = j0; g0 < j1; g0 += kSymGroup) {
+        __syncthreads();
+        {
+            const float4* src = reinterpret_cast<const float4*>(colpack + (size_t)(g0 >> 1) * REC);
+            constexpr int F4 = REC / 4;
+            for (int t = tid; t < 32 * F4; t += kSymThreads) {
+                const int rec = t / F4, f = t - rec * F4;
+                reinterpret_cast<float4*>(tile + rec * STRIDE)[f] = src[t];
+            }
+        }
+        __syncthreads();
+        F2 cacc[NACC_COL];
+#pragma unroll
+        for (int k = 0; k < NACC_COL; ++k) cacc[k] = f2(0.f, 0.f);
+        if (rows_ragged || g0 + kSymGroup > Ncols) sym_ring_round<Op, true, R>(prm, row, tile, STRIDE, lane, rmask, g0, Ncols, acc, cacc);
+        else sym_ring_round<Op, false, R>(prm, row, tile, STRIDE, lane, rmask, g0, Ncols, acc, cacc);
+#pragma unroll
+        for (int k = 0; k < NACC_COL; ++k) {
+            float a, b;
+            f2_unpack(cacc[k], a, b);
+            xch[((warp * NACC_COL + k) * 32 + lane) * 2] = a;
+            xch[((warp * NACC_COL + k) * 32 + lane) * 2 + 1] = b;
+        }
+        __syncthreads();
+        for (int t = tid; t < NACC_COL * kSymGroup; t += kSymThreads) {
+            const int k = t / kSymGroup, cc = t - k * kSymGroup;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kSymThreads / 32; ++w) v += xch[((w * NACC_COL + k) * 32 + (cc >> 1)) * 2 + (cc & 1)];
+            colpart[((size_t)I * NACC_COL + k) * mpad + g0 + cc] = v;
+        }
+    }
+    float* rp = rowpart + (size_t)item * NACC * RPC;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) rp[k * RPC + warp * (32 * R) + r * 32 + lane] = f2_sum(acc[r][k]);
+}
+
+// rows: add the chunks' partials in chunk order, Op::finish
+template <class Op>
+__global__ void __launch_bounds__(128) rect_finish_rows_kernel(typename Op::Params prm, const float* __restrict__ rowpart,
+                                                               RectPlan plan) {
+    constexpr int NACC = Op::NACC;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= plan.Mrows) return;
+    const int I = i / plan.rpc, rl = i - I * plan.rpc;
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    for (int c = 0; c < plan.nchunks; ++c) {
+        const float* rp = rowpart + (size_t)(I * plan.nchunks + c) * NACC * plan.rpc + rl;
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] += rp[k * plan.rpc];
+    }
+    typename Op::Row row;
+    Op::load_row(prm, i, row);
+    Op::finish(prm, i, row, acc, nullptr);
+}
+
+// columns: 32 columns x 4 thread groups per CTA; group g adds row blocks g, g+4, ... (4 loads in flight), groups in order
+template <class Op>
+__global__ void __launch_bounds__(128) rect_finish_cols_kernel(typename Op::Params prm, const float* __restrict__ colpart,
+                                                               RectPlan plan) {
+    constexpr int NC = Op::NACC_COL, FR = 32, G = 4;
+    __shared__ float xch[G * NC * FR];
+    const int r = threadIdx.x & (FR - 1), g = threadIdx.x / FR;
+    const int j = blockIdx.x * FR + r;
+    const int mpad = plan.ngroups_total * kSymGroup;
+    const bool valid = j < plan.Ncols;
+    float acc[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) acc[k] = 0.f;
+    if (valid) {
+        for (int J = g; J < plan.nrb; J += 4 * G) {
+            float v[4][NC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = J + u * G;
+                const float* cp = colpart + (size_t)(t < plan.nrb ? t : J) * NC * mpad + j;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) v[u][k] = cp[(size_t)k * mpad];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (J + u * G < plan.nrb) {
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) acc[k] += v[u][k];
+                }
+        }
+    }
+    if (g > 0) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) xch[(g * NC + k) * FR + r] = acc[k];
+    }
+    __syncthreads();
+    if (valid && g == 0) {
+        for (int g2 = 1; g2 < G; ++g2) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) acc[k] += xch[(g2 * NC + k) * FR + r];
+        }
+        Op::finish_col(prm, j, acc);
+    }
+}
+
+// packed columns + rectangular ring kernel + the two finish kernels.  DICP_EWORKSPACE if `ws` is too small (the caller
+// then falls back to the two-pass path).
+template <class Op>
+inline int run_pair_rect(const typename Op::Params& prm, int Mrows, int Ncols, void* ws, size_t ws_bytes, cudaStream_t st) {
+    constexpr int R = Op::RECT_R;
+    const RectPlan plan = rect_make_plan(Mrows, Ncols, R, device_info().sms);
+    if (ws == nullptr || rect_workspace_bytes(plan, Op::NF, Op::NACC, Op::NACC_COL) > ws_bytes) return DICP_EWORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(ws) & 127) != 0) return DICP_EBADARG;
+    const int mpad = plan.ngroups_total * kSymGroup;
+    const int npadcol = (mpad + 127) / 128 * 128;
+    const size_t col_bytes = align_up((size_t)npadcol * Op::NF * 4, 256);
+    const size_t row_bytes = align_up((size_t)plan.items * Op::NACC * plan.rpc * 4, 256);
+    float* colpack = (float*)ws;
+    float* rowpart = (float*)((char*)ws + col_bytes);
+    float* colpart = (float*)((char*)ws + col_bytes + row_bytes);
+    pack_kernel_p<Op><<<(npadcol + 255) / 256, 256, 0, st>>>(prm, colpack, Ncols, npadcol);
+    rect_pair_kernel<Op, R><<<plan.items, kSymThreads, 0, st>>>(prm, colpack, rowpart, colpart, plan);
+    rect_finish_rows_kernel<Op><<<(Mrows + 127) / 128, 128, 0, st>>>(prm, rowpart, plan);
+    rect_finish_cols_kernel<Op><<<(Ncols + 31) / 32, 128, 0, st>>>(prm, colpart, plan);
+    launch_counter() += 4;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? DICP_OK : (int)e;
 }

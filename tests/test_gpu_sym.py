@@ -94,3 +94,41 @@ def test_small_and_huge_sizes_use_the_general_engine():
     r0 = adjoint(3, True, 0.3, 0.0, q, p, a, u, torch.ones(1, device=dev), 0)
     r1 = adjoint(3, True, 0.3, 0.0, q, p, a, u, torch.ones(1, device=dev), 1)
     assert torch.equal(r0[0], r1[0]) and torch.equal(r0[1], r1[1])          # below 4096 points: same engine, same bits
+
+
+def adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, mode):
+    from diff_icp_b200 import ops
+    lib = ops.load()
+    prev = lib.dicp_sym_mode(mode)
+    try:
+        M, Nx = q.shape[0], x.shape[0]
+        gq, gp, gx = torch.zeros_like(q), torch.zeros_like(q), torch.zeros_like(x)
+        ws = ops.alloc_workspace(max(M, Nx), max(M, Nx), q.device)
+        ops.rhs_adjoint(D, withlogdet, sigma, 0.0, q, p, x, a, u, wx, gc, gq, gp, gx, ws)
+        torch.cuda.synchronize()
+        return gq, gp, gx
+    finally:
+        lib.dicp_sym_mode(prev)
+
+
+@pytest.mark.parametrize("D", [2, 3])
+@pytest.mark.parametrize("withlogdet", [False, True])
+@pytest.mark.parametrize("M,Nx", [(256, 2048), (257, 2049), (1584, 50000), (5000, 7001), (300, 100000)])
+def test_fused_xq_adjoint_matches_two_pass_path(D, withlogdet, M, Nx):
+    """(x,q) adjoint from ONE ring pass (rect_pair_kernel, Op AdjXQ) vs the two passes AdjXQx + AdjXQq of the general engine."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + Nx + D)
+    q = torch.rand(M, D, generator=g).to(dev)
+    x = torch.rand(Nx, D, generator=g).to(dev)
+    p, a, u = (torch.randn(M, D, generator=g).to(dev) for _ in range(3))
+    wx = torch.randn(Nx, D, generator=g).to(dev)
+    gc = torch.tensor([-0.4], device=dev)
+    sigma = 0.25
+    ref = adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, 0)
+    got = adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, 1)
+    for r, s in zip(ref, got):
+        scale = float(r.abs().max())
+        assert torch.isfinite(s).all()
+        assert float((r - s).abs().max()) <= 3e-5 * scale, (float((r - s).abs().max()), scale)
+    again = adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, 1)
+    assert all(torch.equal(a_, b_) for a_, b_ in zip(again, got))
