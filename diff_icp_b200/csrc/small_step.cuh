@@ -492,6 +492,179 @@ __global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_ADJ) small_adj_
     if (tid == 0) S.counters[1 + rb] = 0u;
 }
 
+// ---- adjoint stage, ring form (eta = 0, data points present, M <= 64) -------------------------------------------------------
+// The x rows need sum_j over the support points (gx_k) and the support points need sum_k over the x rows (gq_j, gp_j) of terms
+// built from the SAME K, z', dot products: small_adj_step_kernel evaluates every (x_k, q_j) pair twice (x-row CTAs with
+// AdjXQx, q-row CTAs with AdjXQq over column splits of the data).  Here every pair is evaluated ONCE (Op AdjXQ, both sides):
+// a lane owns 4 x rows; the support points -- at most 32 column pairs -- travel round a ring of W = 16 or 32 lanes together
+// with their accumulators (see sym_engine.cuh), so after W steps lane l holds column pair l summed over the ring's rows; the
+// rings of a CTA are added in ring order through shared memory and the CTA's column sums go to the workspace.  One more CTA
+// does the (q,q) interaction.  The last CTA of the frame (ticket) adds the CTAs' column sums in CTA order, finishes the
+// support points' gradients and applies their cotangent update.  Deterministic, no atomics.
+static constexpr int kRingR = 4;                                   // x rows per lane
+static constexpr int kRingRows = kSmallThreads * kRingR;           // x rows per CTA
+static constexpr int kRingMaxQ = 64;                               // support points (one ring round)
+
+template <int D, bool WLD>
+__global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep S) {
+    using OpX = AdjXQ<D, WLD>;
+    using OpQQ = AdjQQ<D, false, 1>;                               // x present: no divergence term in the (q,q) pass
+    constexpr int NF = OpX::NF, REC = 2 * NF, STRIDE = (REC % 8 == 4) ? REC : REC + 4, NC = OpX::NACC_COL;
+    constexpr int NAQ = OpQQ::NACC;
+    __shared__ __align__(16) float cols[32 * STRIDE > kRingMaxQ * 4 * D ? 32 * STRIDE : kRingMaxQ * 4 * D];
+    __shared__ float xch[kSmallThreads * (2 * NC > NAQ ? 2 * NC : NAQ)];
+    if (!small_select_frame(S)) return;
+    const int tid = threadIdx.x, lane = tid & 31, M = S.M, Nx = S.Nx;
+    const int nXB = (Nx + kRingRows - 1) / kRingRows;
+    const unsigned nblk = (unsigned)nXB + 1u;
+    if (blockIdx.x >= nblk) return;
+    const size_t MD = (size_t)M * D, Ssz = 2 * MD + (size_t)Nx * D + 1;
+    RhsParams P = small_params<D>(S);
+    P.a = S.lam; P.u = S.lam + MD; P.wx = S.lam + 2 * MD; P.gc = S.lam + (Ssz - 1);
+    P.gq = S.This; P.gp = S.This + MD; P.gx = S.This + 2 * MD;
+    P.accumulate = 0;
+    float* part = S.ws;                                            // [x CTA][k][2W columns]
+    const int W = M <= 32 ? 16 : 32;
+
+    if ((int)blockIdx.x < nXB) {
+        // stage the support points as zero-padded pair records
+        for (int t = tid; t < 32 * STRIDE; t += kSmallThreads) cols[t] = 0.f;
+        __syncthreads();
+        for (int j = tid; j < M; j += kSmallThreads) {
+            float c[OpX::COLF4 * 4];
+            OpX::pack_col(P, j, M, c);
+            float* dst = cols + (j >> 1) * STRIDE + (j & 1);
+#pragma unroll
+            for (int k = 0; k < NF; ++k) dst[2 * k] = c[k];
+        }
+        __syncthreads();
+        typename OpX::Row row[kRingR];
+        float rmask[kRingR];
+        int ri[kRingR];
+#pragma unroll
+        for (int r = 0; r < kRingR; ++r) {
+            ri[r] = blockIdx.x * kRingRows + (tid >> 5) * (32 * kRingR) + r * 32 + lane;
+            rmask[r] = ri[r] < Nx ? 1.f : 0.f;
+            OpX::load_row(P, ri[r] < Nx ? ri[r] : Nx - 1, row[r]);
+        }
+        F2 acc[kRingR][OpX::NACC], cacc[NC];
+#pragma unroll
+        for (int r = 0; r < kRingR; ++r)
+#pragma unroll
+            for (int k = 0; k < OpX::NACC; ++k) acc[r][k] = f2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) cacc[k] = f2(0.f, 0.f);
+        const int lr = lane & (W - 1);
+        for (int s = 0; s < W; ++s) {
+            const int pr = (lr + s) & (W - 1);
+            const float4* rec = reinterpret_cast<const float4*>(cols + pr * STRIDE);
+            F2 c[NF];
+#pragma unroll
+            for (int k = 0; k < NF / 2; ++k) {
+                const float4 v = rec[k];
+                c[2 * k] = f2(v.x, v.y);
+                c[2 * k + 1] = f2(v.z, v.w);
+            }
+            const float m0 = 2 * pr < M ? 1.f : 0.f, m1 = 2 * pr + 1 < M ? 1.f : 0.f;
+#pragma unroll
+            for (int r = 0; r < kRingR; ++r)
+                OpX::template pair_sym<F2, true>(P, row[r], c, acc[r], cacc, f2(m0 * rmask[r], m1 * rmask[r]));
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                unsigned lo = (unsigned)(cacc[k].v & 0xffffffffull), hi = (unsigned)(cacc[k].v >> 32);
+                lo = __shfl_sync(0xffffffffu, lo, (lr + 1) & (W - 1), W);
+                hi = __shfl_sync(0xffffffffu, hi, (lr + 1) & (W - 1), W);
+                cacc[k].v = ((unsigned long long)hi << 32) | lo;
+            }
+        }
+        // rows: gx and the cotangent update of the x entries
+#pragma unroll
+        for (int r = 0; r < kRingR; ++r) {
+            if (ri[r] < Nx) {
+                float a[OpX::NACC];
+#pragma unroll
+                for (int k = 0; k < OpX::NACC; ++k) a[k] = f2_sum(acc[r][k]);
+                OpX::finish(P, ri[r], row[r], a, nullptr);
+#pragma unroll
+                for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)ri[r] * D + k);
+            }
+        }
+        // columns: lane lr of every ring holds pair lr; add the CTA's rings in ring order
+        const int ring = tid / W, nring = kSmallThreads / W;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            float a, b;
+            f2_unpack(cacc[k], a, b);
+            xch[((ring * NC + k) * W + lr) * 2] = a;
+            xch[((ring * NC + k) * W + lr) * 2 + 1] = b;
+        }
+        __syncthreads();
+        for (int t = tid; t < NC * 2 * W; t += kSmallThreads) {
+            const int k = t / (2 * W), cc = t - k * 2 * W;
+            float v = 0.f;
+            for (int g2 = 0; g2 < nring; ++g2) v += xch[((g2 * NC + k) * W + (cc >> 1)) * 2 + (cc & 1)];
+            part[((size_t)blockIdx.x * NC + k) * kRingMaxQ + cc] = v;
+        }
+        if (blockIdx.x == 0 && tid == 0) {            // cost entry: the right-hand side does not depend on cost
+            S.This[Ssz - 1] = 0.f;
+            small_update(S, Ssz - 1);
+        }
+    } else {
+        // (q,q) interaction: rows = support points, column groups as in small_adj_step_kernel
+        const int Mr = (M <= kSmallThreads / 2) ? M : kSmallThreads;
+        const int G = kSmallThreads / Mr;
+        const int g = tid / Mr, r = tid - g * Mr;
+        const bool work = g < G && r < M;
+        stage_cols<OpQQ>(P, 0, M, M, cols);
+        __syncthreads();
+        float aq[NAQ];
+#pragma unroll
+        for (int k = 0; k < NAQ; ++k) aq[k] = 0.f;
+        if (work) {
+            F2 acc[NAQ];
+#pragma unroll
+            for (int k = 0; k < NAQ; ++k) acc[k] = f2(0.f, 0.f);
+            typename OpQQ::Row row;
+            OpQQ::load_row(P, r, row);
+            sweep_share<OpQQ>(P, row, cols, M, g, G, acc);
+#pragma unroll
+            for (int k = 0; k < NAQ; ++k) aq[k] = f2_sum(acc[k]);
+        }
+        if (work && g > 0) {
+#pragma unroll
+            for (int k = 0; k < NAQ; ++k) xch[(g * NAQ + k) * Mr + r] = aq[k];
+        }
+        __syncthreads();
+        if (work && g == 0) {
+            for (int g2 = 1; g2 < G; ++g2) {
+#pragma unroll
+                for (int k = 0; k < NAQ; ++k) aq[k] += xch[(g2 * NAQ + k) * Mr + r];
+            }
+            typename OpQQ::Row row;
+            OpQQ::load_row(P, r, row);
+            OpQQ::finish(P, r, row, aq, nullptr);
+        }
+    }
+    if (!last_cta(&S.counters[0], nblk)) return;
+    // last CTA of the frame: column sums of the x CTAs in CTA order, then the support points' gradients and update
+    for (int j = tid; j < M; j += kSmallThreads) {
+        float cs[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) cs[k] = 0.f;
+        for (int b = 0; b < nXB; ++b) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) cs[k] += __ldcg(&part[((size_t)b * NC + k) * kRingMaxQ + j]);
+        }
+        OpX::finish_col(P, j, cs);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            small_update(S, (size_t)j * D + k);
+            small_update(S, MD + (size_t)j * D + k);
+        }
+    }
+    if (tid == 0) S.counters[0] = 0u;
+}
+
 // Row passes of the x-row CTAs: one block of 128 rows per CTA until the x-row CTAs of all frames exceed ~8 resident CTAs
 // per SM, then proportionally more (at most 8).  DICP_SMALL_XPASS overrides (tuning sweeps only).
 inline int small_xpass(long long frames, long long maxNx, int sms) {
@@ -523,7 +696,9 @@ inline size_t small_adj_smem_bytes(long long M, int D) {
 inline size_t small_workspace_bytes(long long M, long long Nx) {
     const long long nXB = (Nx + kSmallThreads - 1) / kSmallThreads, nQB = (M + kSmallThreads - 1) / kSmallThreads;
     const size_t fwd = (size_t)(nXB + nQB) * 4 * 4;
-    const size_t adj = (size_t)small_adj_nsplit((int)Nx) * 16 * (size_t)M * 4;
+    size_t adj = (size_t)small_adj_nsplit((int)Nx) * 16 * (size_t)M * 4;
+    const size_t ringb = (size_t)((Nx + kSmallThreads * 4 - 1) / (kSmallThreads * 4)) * 8 * 64 * 4;      // ring form: x CTAs x 8 x 64
+    if (ringb > adj) adj = ringb;
     return kSmallCounters * 4 + (fwd > adj ? fwd : adj) + 256;
 }
 

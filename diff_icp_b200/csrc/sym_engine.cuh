@@ -33,6 +33,10 @@ static constexpr int kSymGroup = 64;                                            
 static constexpr int kSymMaxBlocks = 256;                                                            // row blocks (M <= 65536)
 static constexpr int kSymMinM = 4096;                // below this the general engine is as fast (measured)
 
+// Record stride (floats) in shared memory such that the 8 lanes of an LDS.128 wavefront, reading consecutive records, hit 8
+// different bank quads: the stride must be 4 mod 8 (REC is a multiple of 4).
+template <int REC> struct SymStride { static constexpr int value = REC % 8 == 4 ? REC : REC + 4; };
+
 struct SymPlan {
     int M, nrb, Lc, ngroups_total;      // points, row blocks, chunk length (columns), column groups (ceil(M/64))
     int items;
@@ -150,7 +154,7 @@ template <class Op>
 __global__ void __launch_bounds__(kSymThreads) sym_pair_kernel(typename Op::Params prm, const float* __restrict__ colpack,
                                                                float* __restrict__ rowpart, float* __restrict__ colpart,
                                                                SymPlan plan) {
-    constexpr int NF = Op::NF, NACC = Op::NACC, REC = 2 * NF, STRIDE = REC + 4;      // padded: conflict-free LDS.128
+    constexpr int NF = Op::NF, NACC = Op::NACC, REC = 2 * NF, STRIDE = SymStride<REC>::value;   // conflict-free per-lane LDS.128
     __shared__ __align__(16) float tile[32 * STRIDE];
     __shared__ float xch[(kSymThreads / 32) * 32 * 2 * NACC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -371,7 +375,7 @@ template <class Op, int R>
 __global__ void __launch_bounds__(kSymThreads) rect_pair_kernel(typename Op::Params prm, const float* __restrict__ colpack,
                                                                 float* __restrict__ rowpart, float* __restrict__ colpart,
                                                                 RectPlan plan) {
-    constexpr int NF = Op::NF, NACC = Op::NACC, NACC_COL = Op::NACC_COL, REC = 2 * NF, STRIDE = REC + 4;
+    constexpr int NF = Op::NF, NACC = Op::NACC, NACC_COL = Op::NACC_COL, REC = 2 * NF, STRIDE = SymStride<REC>::value;
     __shared__ __align__(16) float tile[32 * STRIDE];
     __shared__ float xch[(kSymThreads / 32) * 32 * 2 * NACC_COL];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

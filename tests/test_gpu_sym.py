@@ -132,3 +132,36 @@ def test_fused_xq_adjoint_matches_two_pass_path(D, withlogdet, M, Nx):
         assert float((r - s).abs().max()) <= 3e-5 * scale, (float((r - s).abs().max()), scale)
     again = adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, 1)
     assert all(torch.equal(a_, b_) for a_, b_ in zip(again, got))
+
+
+@pytest.mark.parametrize("D", [2, 3])
+@pytest.mark.parametrize("withlogdet", [False, True])
+@pytest.mark.parametrize("M,Nx", [(25, 10000), (7, 300), (33, 5111), (64, 2048), (1, 129)])
+def test_small_support_ring_adjoint_matches_two_sided_kernel(D, withlogdet, M, Nx):
+    """One-launch adjoint stage for small supports: ring form (every (x,q) pair once) vs the x-row / q-row form."""
+    from diff_icp_b200 import ops
+    dev = torch.device("cuda:0")
+    lib = ops.load()
+    g = torch.Generator().manual_seed(M * 7 + Nx + D)
+    S = 2 * M * D + Nx * D + 1
+    state = torch.rand(S, generator=g).to(dev)
+    state[M * D:2 * M * D] = 0.3 * torch.randn(M * D, generator=g).to(dev)
+    lam = torch.randn(S, generator=g).to(dev)
+    base = torch.randn(S, generator=g).to(dev)
+    add = torch.randn(S, generator=g).to(dev)
+    outs = []
+    for mode in (0, 1):
+        prev = lib.dicp_sym_mode(mode)
+        try:
+            out, G = torch.zeros(S, device=dev), torch.zeros(S, device=dev)
+            ws = ops.alloc_small_workspace(M, Nx, dev)
+            for _ in range(2):                                   # twice: the ticket counters must reset themselves
+                ops.small_adj_step(D, withlogdet, 0.3, 0.0, M, Nx, state, lam, base, None, add, 0.1, 0.0, out, G, ws)
+            torch.cuda.synchronize()
+            outs.append((out, G))
+        finally:
+            lib.dicp_sym_mode(prev)
+    for a, b in zip(outs[0], outs[1]):
+        scale = float(a.abs().max())
+        assert torch.isfinite(b).all()
+        assert float((a - b).abs().max()) <= 3e-5 * scale, (float((a - b).abs().max()), scale)
