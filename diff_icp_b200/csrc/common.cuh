@@ -105,6 +105,11 @@ DICP_F2_OP2(vsub, "sub.rn.f32x2", -)
 DICP_HD F2 vex2n(F2 a) { float x, y; f2_unpack(a, x, y); return f2(ex2_neg(x), ex2_neg(y)); }
 template <> DICP_HD F2 vbc<F2>(float a) { return f2(a, a); }
 DICP_HD float f2_sum(F2 a) { float x, y; f2_unpack(a, x, y); return x + y; }
+// lane helpers for Ops that keep a per-row scalar state (running maximum) next to packed sums
+DICP_HD float vlane0(float a) { return a; }
+DICP_HD float vlane0(F2 a) { float x, y; f2_unpack(a, x, y); return x; }
+DICP_HD float vhmax(float a) { return a; }
+DICP_HD float vhmax(F2 a) { float x, y; f2_unpack(a, x, y); return fmaxf(x, y); }
 
 #if defined(__CUDACC__)
 // ---- mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) ------------------------------

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) em_col_small_kernel(EmParams P, int N, in
                 float rec[CF];
 #pragma unroll
                 for (int k = 0; k < CF; ++k) rec[k] = pts[t * CF + k];
-                Op::pair(P, row, rec, acc);
+                Op::template pair<float>(P, row, rec, acc);
             }
         }
     }

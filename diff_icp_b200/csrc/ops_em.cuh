@@ -48,15 +48,30 @@ static constexpr float kLn2 = 0.6931471805599453f;
 template <int D, bool LITE>
 struct EmRow {
     using Params = EmParams;
-    static constexpr bool PACKED = false;
+    // packed-fp32 form (pair_kernel_p): two components per call, one 64-bit register carries the same field of both; the
+    // running maximum of a row is ONE scalar shared by the two halves (kept duplicated in the A_M register)
+    static constexpr bool PACKED = true;
     static constexpr int THREADS = 128, MINB = 1, R = 2, TILE = 128;
     static constexpr int COLN = LITE ? (D + 1) : (2 * D + 3);
-    static constexpr int COLF4 = (COLN + 3) / 4;
+    static constexpr int NF = (COLN + 1) / 2 * 2;              // floats per column record (even)
+    static constexpr int COLF4 = (NF + 3) / 4;
+    static constexpr bool PAD_NULL = true;                     // a padded component contributes exactly 0
     // accumulators: m, S, then (full) Y(D), M2, L, T, DS
     static constexpr int A_M = 0, A_S = 1, A_Y = 2, A_M2 = 2 + D, A_L = 3 + D, A_T = 4 + D, A_DS = 5 + D;
     static constexpr int NACC = LITE ? 2 : (6 + D);
     static constexpr int NSCAL = LITE ? 0 : 4;   // P, Q, SQ, DS
     struct Row { float x[D]; float raw[D]; };   // raw = x - origin (unscaled)
+
+    static DICP_HD void init_packed(F2* a) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] = f2(0.f, 0.f);
+        a[A_M] = f2(-3.0e38f, -3.0e38f);
+    }
+    static DICP_HD void unpack_acc(const F2* a, float* out) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) out[k] = f2_sum(a[k]);
+        out[A_M] = vlane0(a[A_M]);
+    }
 
     static DICP_HD void pack_col(const Params& P, int j, int N, float* c) {
 #pragma unroll
@@ -110,24 +125,35 @@ struct EmRow {
 #pragma unroll
         for (int k = 1; k < NACC; ++k) a[k] += bb[k];
     }
-    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* a) {
-        float r2 = 0.f;
+    // V = float: one component; V = F2: two components (device kernel).  e = 2^(t2 - m) with m the row's running maximum
+    // (raised, with a rescale of the sums, whenever a t2 exceeds it by more than kRescaleSlack).
+    template <class V>
+    static DICP_HD void pair(const Params& P, const Row& r, const V* c, V* a) {
+        V r2;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            const float z = r.x[k] - c[k];
-            r2 = fmaf(z, z, r2);
+            const V z = vsub(vbc<V>(r.x[k]), c[k]);
+            r2 = k == 0 ? vmul(z, z) : vfma(z, z, r2);
         }
-        const float t2 = c[D] - r2;
-        if (t2 > a[A_M] + kRescaleSlack) rescale(a, t2);
-        const float e = ex2f_fast(t2 - a[A_M]);
-        a[A_S] += e;
+        const V t2 = vsub(c[D], r2);
+        float m = vlane0(a[A_M]);
+        const float tmax = vhmax(t2);
+        if (tmax > m + kRescaleSlack) {
+            const V sc = vbc<V>(ex2f_fast(m - tmax));          // 0 when m is the initial -3e38
+#pragma unroll
+            for (int k = 1; k < NACC; ++k) a[k] = vmul(a[k], sc);
+            a[A_M] = vbc<V>(tmax);
+            m = tmax;
+        }
+        const V e = vex2n(vsub(vbc<V>(m), t2));
+        a[A_S] = vadd(a[A_S], e);
         if (!LITE) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) a[A_Y + k] = fmaf(e, c[D + 1 + k], a[A_Y + k]);
-            a[A_M2] = fmaf(e, c[2 * D + 1], a[A_M2]);
-            a[A_L] = fmaf(e, c[2 * D + 2], a[A_L]);
-            a[A_T] = fmaf(e, t2, a[A_T]);
-            a[A_DS] = fmaf(e, r2, a[A_DS]);
+            for (int k = 0; k < D; ++k) a[A_Y + k] = vfma(e, c[D + 1 + k], a[A_Y + k]);
+            a[A_M2] = vfma(e, c[2 * D + 1], a[A_M2]);
+            a[A_L] = vfma(e, c[2 * D + 2], a[A_L]);
+            a[A_T] = vfma(e, t2, a[A_T]);
+            a[A_DS] = vfma(e, r2, a[A_DS]);
         }
     }
     static DICP_HD void finish(const Params& P, int i, const Row& r, const float* a, float* scal) {
@@ -162,12 +188,25 @@ struct EmRow {
 template <int D>
 struct EmCol {
     using Params = EmParams;
-    static constexpr bool PACKED = false;
+    static constexpr bool PACKED = true;                       // two points per call (see EmRow)
     static constexpr int THREADS = 128, MINB = 1, R = 1, TILE = 128;
-    static constexpr int COLF4 = (D + 1 + 3) / 4;
+    static constexpr int NF = (D + 1 + 1) / 2 * 2;             // x' (D), T2, padded to an even count
+    static constexpr int COLF4 = (NF + 3) / 4;
+    static constexpr bool PAD_NULL = true;                     // a padded point contributes exactly 0
     static constexpr int A_M = 0, A_S = 1, A_B = 2, A_A = 2 + D;
     static constexpr int NACC = 3 + D, NSCAL = 0;
     struct Row { float mu[D]; float wl2; };
+
+    static DICP_HD void init_packed(F2* a) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) a[k] = f2(0.f, 0.f);
+        a[A_M] = f2(-3.0e38f, -3.0e38f);
+    }
+    static DICP_HD void unpack_acc(const F2* a, float* out) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) out[k] = f2_sum(a[k]);
+        out[A_M] = vlane0(a[A_M]);
+    }
 
     static DICP_HD void pack_col(const Params& P, int j, int N, float* c) {
 #pragma unroll
@@ -208,21 +247,30 @@ struct EmCol {
 #pragma unroll
         for (int k = 1; k < NACC; ++k) a[k] += bb[k];
     }
-    static DICP_HD void pair(const Params& P, const Row& r, const float* c, float* a) {
-        float z[D];
-        float r2 = 0.f;
+    template <class V>
+    static DICP_HD void pair(const Params& P, const Row& r, const V* c, V* a) {
+        V z[D];
+        V r2;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            z[k] = c[k] - r.mu[k];                       // x'_n - mu'_c
-            r2 = fmaf(z[k], z[k], r2);
+            z[k] = vsub(c[k], vbc<V>(r.mu[k]));          // x'_n - mu'_c
+            r2 = k == 0 ? vmul(z[k], z[k]) : vfma(z[k], z[k], r2);
         }
-        const float l2 = (r.wl2 - c[D]) - r2;            // log2 gamma_nc  (<= 0 up to rounding)
-        if (l2 > a[A_M] + kRescaleSlack) rescale(a, l2);
-        const float e = ex2f_fast(l2 - a[A_M]);
-        a[A_S] += e;
+        const V l2 = vsub(vsub(vbc<V>(r.wl2), c[D]), r2);   // log2 gamma_nc  (<= 0 up to rounding)
+        float m = vlane0(a[A_M]);
+        const float lmax = vhmax(l2);
+        if (lmax > m + kRescaleSlack) {
+            const V sc = vbc<V>(ex2f_fast(m - lmax));
 #pragma unroll
-        for (int k = 0; k < D; ++k) a[A_B + k] = fmaf(e, z[k], a[A_B + k]);
-        a[A_A] = fmaf(e, r2, a[A_A]);
+            for (int k = 1; k < NACC; ++k) a[k] = vmul(a[k], sc);
+            a[A_M] = vbc<V>(lmax);
+            m = lmax;
+        }
+        const V e = vex2n(vsub(vbc<V>(m), l2));
+        a[A_S] = vadd(a[A_S], e);
+#pragma unroll
+        for (int k = 0; k < D; ++k) a[A_B + k] = vfma(e, z[k], a[A_B + k]);
+        a[A_A] = vfma(e, r2, a[A_A]);
     }
     static DICP_HD void finish(const Params& P, int i, const Row&, const float* a, float*) {
         float* o = P.o_stats + (size_t)i * (D + 3);

@@ -66,6 +66,14 @@ struct RhsParams {
     }                                                                                                         \
     static DICP_HD void combine(float* a, const float* b) {                                                   \
         for (int k = 0; k < NACC; ++k) a[k] += b[k];                                                          \
+    }                                                                                                         \
+    /* packed accumulators of pair_kernel_p: plain sums, one partial sum per half */                          \
+    static constexpr bool PAD_NULL = false;                                                                   \
+    static DICP_HD void init_packed(F2* a) {                                                                  \
+        for (int k = 0; k < NACC; ++k) a[k] = f2(0.f, 0.f);                                                   \
+    }                                                                                                         \
+    static DICP_HD void unpack_acc(const F2* a, float* out) {                                                 \
+        for (int k = 0; k < NACC; ++k) out[k] = f2_sum(a[k]);                                                 \
     }
 
 // column record (q', p): used by RhsQQ, RhsXQ, AdjXQx*

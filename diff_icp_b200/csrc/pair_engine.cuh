@@ -216,6 +216,7 @@ pair_kernel_p(typename Op::Params prm, const float4* __restrict__ colpack, float
         Op::load_row(prm, i < M ? i : M - 1, row[r]);
 #pragma unroll
         for (int k = 0; k < NACC; ++k) acc[r][k] = f2(0.f, 0.f);
+        Op::init_packed(acc[r]);
     }
 
     for (int t = 0; t < nt; ++t) {
@@ -224,7 +225,8 @@ pair_kernel_p(typename Op::Params prm, const float4* __restrict__ colpack, float
         const float4* sp = stage[s];
         const int left = N - (t0 + t) * TILE;
         const int ncol = left < TILE ? left : TILE;
-        const int npair = ncol >> 1;
+        // PAD_NULL Ops: the padded partner of an odd last column is a record that contributes exactly nothing
+        const int npair = Op::PAD_NULL ? (ncol + 1) >> 1 : ncol >> 1;
 _Pragma(DICP_STR(unroll DICP_COL_UNROLL))
         for (int P = 0; P < npair; ++P) {
             F2 c[NF];
@@ -237,7 +239,7 @@ _Pragma(DICP_STR(unroll DICP_COL_UNROLL))
 #pragma unroll
             for (int r = 0; r < R; ++r) Op::template pair<F2>(prm, row[r], c, acc[r]);
         }
-        if (ncol & 1) {                       // odd trailing column of the whole problem: one-column form
+        if (!Op::PAD_NULL && (ncol & 1)) {    // odd trailing column of the whole problem: one-column form
             float c[NF];
 #pragma unroll
             for (int k = 0; k < PF4; ++k) {
@@ -264,9 +266,7 @@ _Pragma(DICP_STR(unroll DICP_COL_UNROLL))
 
     float accf[R][NACC];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) accf[r][k] = f2_sum(acc[r][k]);
+    for (int r = 0; r < R; ++r) Op::unpack_acc(acc[r], accf[r]);
 
     if (nsplit == 1) {
         float scal[NSCAL > 0 ? NSCAL : 1];
