@@ -420,7 +420,7 @@ def kernel_roofline(args, LM, q, p, dev, ops):
         "achieved": 2 * fp_rate_adj / 1e12, "peak": 2 * peaks["ffma"] / 1e12, "unit": "TFLOP/s", "frac": frac_adj,
         "traffic": NCU_DRAM_BYTES.get(args.variant),
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of the adjoint kernel, ncu --set full "
-                        "(profiles/r01c_ncu_full_sym_adjoint_20k.csv); algorithmic bytes = 2 x 20000 x 48 B = 1.92 MB",
+                        "(profiles/r01c_ncu_full_bench_kernels.csv); algorithmic bytes = 2 x 20000 x 48 B = 1.92 MB",
         "note": "achieved = algorithmic FP32 instructions per ordered pair x M^2 pairs / event time, x2 flop; the adjoint "
                 "evaluates every UNORDERED pair once (symmetric engine), its per-ordered-pair count is half the unordered "
                 "one; peak = FFMA issue rate measured live by dicp_pipe_probe (x2 flop), of measured; frac = binding-pipe "
@@ -497,7 +497,7 @@ def em_roofline(dev, timeit, peaks):
 
 # DRAM bytes per launch of the adjoint kernel at 20k x 20k (one ncu --set full capture per variant, profiles/):
 # dram__bytes_read.sum + dram__bytes_write.sum; the row / column partials of the symmetric engine (~40 MB) stay in L2
-NCU_DRAM_BYTES = {"classic": None, "hybrid": None, "logdet": 1953792}
+NCU_DRAM_BYTES = {"classic": None, "hybrid": None, "logdet": 1990144}
 
 # algorithmic FP32 instruction counts per ORDERED pair, D = 3 (hand count of the formulas in csrc/ops_rhs.cuh).
 # The adjoint (q,q) pass runs on the symmetric engine: an unordered pair costs the shared part once plus both sides'
