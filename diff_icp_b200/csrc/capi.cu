@@ -209,19 +209,17 @@ static void dispatch_small_rhs(int D, int withlogdet, float eta, const SmallStep
     }
     launch_counter() += 1;
 }
-// ring form of the adjoint stage (small_adj_ring_kernel): eta = 0, data points present, at most kRingMaxQ support points
-static bool small_ring_applicable(float eta, long long maxM, long long maxNx) {
-    return sym_mode() != 0 && eta == 0.f && maxNx > 0 && maxM <= kRingMaxQ;
+// ring form of the adjoint stage (small_adj_ring_kernel): data points present, at most kRingMaxQ support points
+static bool small_ring_applicable(float, long long maxM, long long maxNx) {
+    return sym_mode() != 0 && maxNx > 0 && maxM <= kRingMaxQ;
 }
-static void dispatch_small_ring(int D, int withlogdet, const SmallStep& S, long long maxNx, unsigned frames, cudaStream_t st) {
+static void dispatch_small_ring(int D, int withlogdet, float eta, const SmallStep& S, long long maxNx, unsigned frames,
+                                cudaStream_t st) {
     const dim3 grid((unsigned)((maxNx + kRingRows - 1) / kRingRows) + 1u, frames);
-    if (D == 2) {
-        if (withlogdet) small_adj_ring_kernel<2, true><<<grid, kSmallThreads, 0, st>>>(S);
-        else small_adj_ring_kernel<2, false><<<grid, kSmallThreads, 0, st>>>(S);
-    } else {
-        if (withlogdet) small_adj_ring_kernel<3, true><<<grid, kSmallThreads, 0, st>>>(S);
-        else small_adj_ring_kernel<3, false><<<grid, kSmallThreads, 0, st>>>(S);
-    }
+#define DICP_LAUNCH(DD, W, E) small_adj_ring_kernel<DD, W, E><<<grid, kSmallThreads, 0, st>>>(S)
+    if (D == 2) { if (eta != 0.f) DICP_LAUNCH(2, true, true); else if (withlogdet) DICP_LAUNCH(2, true, false); else DICP_LAUNCH(2, false, false); }
+    else { if (eta != 0.f) DICP_LAUNCH(3, true, true); else if (withlogdet) DICP_LAUNCH(3, true, false); else DICP_LAUNCH(3, false, false); }
+#undef DICP_LAUNCH
     launch_counter() += 1;
 }
 static void dispatch_small_adj(int D, int withlogdet, float eta, const SmallStep& S, int nsplit, int xpass, dim3 grid,
@@ -393,7 +391,7 @@ int dicp_small_adj_step(int D, int withlogdet, float sigma, float eta, int64_t M
     const int xpass = small_xpass(1, Nx, device_info().sms);
     const unsigned grid = (unsigned)((Nx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass)) + nQB * (unsigned)nsplit;
     cudaStream_t st = (cudaStream_t)stream;
-    if (small_ring_applicable(eta, M, Nx)) dispatch_small_ring(D, withlogdet, S, Nx, 1u, st);
+    if (small_ring_applicable(eta, M, Nx)) dispatch_small_ring(D, withlogdet, eta, S, Nx, 1u, st);
     else dispatch_small_adj(D, withlogdet, eta, S, nsplit, xpass, dim3(grid), M, st);
     return last_error(DICP_OK);
 }
@@ -449,7 +447,7 @@ int dicp_batch_adj_step(int D, int withlogdet, float sigma, float eta, int K, co
     const dim3 grid((unsigned)((maxNx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass)) + nQB * (unsigned)nsplit,
                     (unsigned)K);
     cudaStream_t st = (cudaStream_t)stream;
-    if (small_ring_applicable(eta, maxM, maxNx)) dispatch_small_ring(D, withlogdet, S, maxNx, (unsigned)K, st);
+    if (small_ring_applicable(eta, maxM, maxNx)) dispatch_small_ring(D, withlogdet, eta, S, maxNx, (unsigned)K, st);
     else dispatch_small_adj(D, withlogdet, eta, S, nsplit, xpass, grid, maxM, st);
     return last_error(DICP_OK);
 }

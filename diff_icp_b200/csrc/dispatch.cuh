@@ -115,6 +115,7 @@ int rhs_adjoint_d(Exec& ex, int withlogdet, RhsParams prm, int M, int Nx) {
     if (prm.eta != 0.f) {                           // logdet model (withlogdet is implied)
         rc = ex.use_sym(M) ? ex.template run_sym<AdjQQEta<D>>(prm, M, nullptr) : ex.template run<AdjQQEta<D>>(prm, M, M, nullptr, 0);
         if (rc != DICP_OK || !hasx) return rc;
+        if (ex.use_rect(Nx, M)) return ex.template run_rect<AdjXQE<D>>(prm, Nx, M);      // both sides in one ring pass
         rc = ex.template run<AdjXQxEta<D>>(prm, Nx, M, nullptr, 0);
         if (rc != DICP_OK) return rc;
         prm.accumulate = 1;

@@ -874,6 +874,83 @@ struct AdjXQxEta {
     }
 };
 
+// logdet, (x,q) pass, BOTH sides from one evaluation of the pair (rectangular ring engine): rows = (x_k, wx_k), cols = (q_j, p_j).
+// psi is the same in AdjXQxEta and AdjXQqEta (zeta' = -z'), so with t = eta s wx_k + g s p_j + (2 g eta s alpha - alpha psi) z':
+//   row side    gx_k += K t
+//   column side gq_j -= K t ;  gp_j += K (wx_k + g alpha z')
+template <int D>
+struct AdjXQE {
+    using Params = RhsParams;
+    static constexpr bool PACKED = true;
+    static constexpr int NF = 2 * D, COLF4 = (NF + 3) / 4;
+    static constexpr int NACC = D;
+    static constexpr int C_GP = 0, C_GQ = D;
+    static constexpr int NACC_COL = 2 * D;
+    static constexpr int NSCAL = 0;
+    static constexpr int RECT_R = 4;
+    struct Row { float x[D], w[D], gc; };
+
+    static DICP_HD void pack_col(const Params& P, int j, int N, float* c) { pack_qp<D>(P, j, N, c, COLF4 * 4); }
+    static DICP_HD void load_row(const Params& P, int i, Row& r) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            r.x[k] = (P.x[(size_t)i * D + k] - P.origin[k]) * P.kappa;
+            r.w[k] = P.wx[(size_t)i * D + k];
+        }
+        r.gc = P.gc != nullptr ? P.gc[0] : 0.f;
+    }
+    template <class V, bool MASKED = false>
+    static DICP_HD void pair_sym(const Params& P, const Row& r, const V* c, V* acc, V* cacc, V km = V()) {
+        const float es = P.eta * P.s, al = P.alpha, g = r.gc;
+        V z[D];
+        V r2, wp, wz, pz;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            z[k] = vsub(vbc<V>(r.x[k]), c[k]);
+            if (k == 0) {
+                r2 = vmul(z[k], z[k]);
+                wp = vmul(vbc<V>(r.w[k]), c[D + k]);
+                wz = vmul(vbc<V>(r.w[k]), z[k]);
+                pz = vmul(c[D + k], z[k]);
+            } else {
+                r2 = vfma(z[k], z[k], r2);
+                wp = vfma(vbc<V>(r.w[k]), c[D + k], wp);
+                wz = vfma(vbc<V>(r.w[k]), z[k], wz);
+                pz = vfma(c[D + k], z[k], pz);
+            }
+        }
+        V K = vex2n(r2);
+        if (MASKED) K = vmul(K, km);
+        V psi = vfma(vbc<V>(P.eta * al), wz, wp);
+        psi = vfma(vbc<V>(g * al), pz, psi);
+        psi = vfma(vbc<V>(g * es * P.beta), r2, vadd(psi, vbc<V>(-g * es * (float)D)));
+        const V cz = vfma(vbc<V>(-al), psi, vbc<V>(2.f * g * es * al));
+        const V Kga = vmul(K, vbc<V>(g * al));
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            V t = vfma(vbc<V>(g * P.s), c[D + k], vbc<V>(es * r.w[k]));
+            t = vfma(cz, z[k], t);
+            const V Kt = vmul(K, t);
+            acc[k] = vadd(acc[k], Kt);
+            cacc[C_GQ + k] = vsub(cacc[C_GQ + k], Kt);
+            V gp = vfma(K, vbc<V>(r.w[k]), cacc[C_GP + k]);
+            cacc[C_GP + k] = vfma(Kga, z[k], gp);
+        }
+    }
+    static DICP_HD void finish(const Params& P, int i, const Row&, const float* acc, float*) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) P.gx[(size_t)i * D + k] = acc[k];
+    }
+    static DICP_HD void finish_col(const Params& P, int j, const float* cacc) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const size_t o = (size_t)j * D + k;
+            P.gp[o] += cacc[C_GP + k];
+            P.gq[o] += cacc[C_GQ + k];
+        }
+    }
+};
+
 // logdet, (x,q) pass w.r.t. (q,p): rows = (q_j, p_j), cols = (x_k, wx_k); zeta' = kappa (q_j - x_k)
 //   psi  = wx.p - eta alpha (wx.zeta') + g [-alpha (p.zeta') + eta s t0]
 //   gq_j = sum_k K { -eta s wx_k - g s p_j + (2 g eta s alpha - alpha psi) zeta' }

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_ADJ) small_adj_
     if (tid == 0) S.counters[1 + rb] = 0u;
 }
 
-// ---- adjoint stage, ring form (eta = 0, data points present, M <= 64) -------------------------------------------------------
+// ---- adjoint stage, ring form (data points present, M <= 64) -------------------------------------------------------
 // The x rows need sum_j over the support points (gx_k) and the support points need sum_k over the x rows (gq_j, gp_j) of terms
 // built from the SAME K, z', dot products: small_adj_step_kernel evaluates every (x_k, q_j) pair twice (x-row CTAs with
 // AdjXQx, q-row CTAs with AdjXQq over column splits of the data).  Here every pair is evaluated ONCE (Op AdjXQ, both sides):
@@ -505,10 +505,11 @@ static constexpr int kRingR = 4;                                   // x rows per
 static constexpr int kRingRows = kSmallThreads * kRingR;           // x rows per CTA
 static constexpr int kRingMaxQ = 64;                               // support points (one ring round)
 
-template <int D, bool WLD>
+template <int D, bool WLD, bool ETA>
 __global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep S) {
-    using OpX = AdjXQ<D, WLD>;
-    using OpQQ = AdjQQ<D, false, 1>;                               // x present: no divergence term in the (q,q) pass
+    using OpX = typename std::conditional<ETA, AdjXQE<D>, AdjXQ<D, WLD>>::type;
+    // x present: no divergence term in the (q,q) pass (AdjQQEta reads gc = 0 itself when x is given)
+    using OpQQ = typename std::conditional<ETA, AdjQQEta<D, 1>, AdjQQ<D, false, 1>>::type;
     constexpr int NF = OpX::NF, REC = 2 * NF, STRIDE = (REC % 8 == 4) ? REC : REC + 4, NC = OpX::NACC_COL;
     constexpr int NAQ = OpQQ::NACC;
     __shared__ __align__(16) float cols[32 * STRIDE > kRingMaxQ * 4 * D ? 32 * STRIDE : kRingMaxQ * 4 * D];

@@ -96,7 +96,7 @@ def test_small_and_huge_sizes_use_the_general_engine():
     assert torch.equal(r0[0], r1[0]) and torch.equal(r0[1], r1[1])          # below 4096 points: same engine, same bits
 
 
-def adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, mode):
+def adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, mode, eta=0.0):
     from diff_icp_b200 import ops
     lib = ops.load()
     prev = lib.dicp_sym_mode(mode)
@@ -104,7 +104,7 @@ def adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, mode):
         M, Nx = q.shape[0], x.shape[0]
         gq, gp, gx = torch.zeros_like(q), torch.zeros_like(q), torch.zeros_like(x)
         ws = ops.alloc_workspace(max(M, Nx), max(M, Nx), q.device)
-        ops.rhs_adjoint(D, withlogdet, sigma, 0.0, q, p, x, a, u, wx, gc, gq, gp, gx, ws)
+        ops.rhs_adjoint(D, withlogdet, sigma, eta, q, p, x, a, u, wx, gc, gq, gp, gx, ws)
         torch.cuda.synchronize()
         return gq, gp, gx
     finally:
@@ -112,7 +112,7 @@ def adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, mode):
 
 
 @pytest.mark.parametrize("D", [2, 3])
-@pytest.mark.parametrize("withlogdet", [False, True])
+@pytest.mark.parametrize("withlogdet", [False, True, "logdet"])
 @pytest.mark.parametrize("M,Nx", [(256, 2048), (257, 2049), (1584, 50000), (5000, 7001), (300, 100000)])
 def test_fused_xq_adjoint_matches_two_pass_path(D, withlogdet, M, Nx):
     """(x,q) adjoint from ONE ring pass (rect_pair_kernel, Op AdjXQ) vs the two passes AdjXQx + AdjXQq of the general engine."""
@@ -124,24 +124,28 @@ def test_fused_xq_adjoint_matches_two_pass_path(D, withlogdet, M, Nx):
     wx = torch.randn(Nx, D, generator=g).to(dev)
     gc = torch.tensor([-0.4], device=dev)
     sigma = 0.25
-    ref = adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, 0)
-    got = adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, 1)
+    eta = 0.03 if withlogdet == "logdet" else 0.0          # logdet model: the fused op is AdjXQE
+    withlogdet = bool(withlogdet)
+    ref = adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, 0, eta)
+    got = adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, 1, eta)
     for r, s in zip(ref, got):
         scale = float(r.abs().max())
         assert torch.isfinite(s).all()
         assert float((r - s).abs().max()) <= 3e-5 * scale, (float((r - s).abs().max()), scale)
-    again = adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, 1)
+    again = adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, 1, eta)
     assert all(torch.equal(a_, b_) for a_, b_ in zip(again, got))
 
 
 @pytest.mark.parametrize("D", [2, 3])
-@pytest.mark.parametrize("withlogdet", [False, True])
+@pytest.mark.parametrize("withlogdet", [False, True, "logdet"])
 @pytest.mark.parametrize("M,Nx", [(25, 10000), (7, 300), (33, 5111), (64, 2048), (1, 129)])
 def test_small_support_ring_adjoint_matches_two_sided_kernel(D, withlogdet, M, Nx):
     """One-launch adjoint stage for small supports: ring form (every (x,q) pair once) vs the x-row / q-row form."""
     from diff_icp_b200 import ops
     dev = torch.device("cuda:0")
     lib = ops.load()
+    eta = 0.03 if withlogdet == "logdet" else 0.0
+    withlogdet = bool(withlogdet)
     g = torch.Generator().manual_seed(M * 7 + Nx + D)
     S = 2 * M * D + Nx * D + 1
     state = torch.rand(S, generator=g).to(dev)
@@ -156,7 +160,7 @@ def test_small_support_ring_adjoint_matches_two_sided_kernel(D, withlogdet, M, N
             out, G = torch.zeros(S, device=dev), torch.zeros(S, device=dev)
             ws = ops.alloc_small_workspace(M, Nx, dev)
             for _ in range(2):                                   # twice: the ticket counters must reset themselves
-                ops.small_adj_step(D, withlogdet, 0.3, 0.0, M, Nx, state, lam, base, None, add, 0.1, 0.0, out, G, ws)
+                ops.small_adj_step(D, withlogdet, 0.3, eta, M, Nx, state, lam, base, None, add, 0.1, 0.0, out, G, ws)
             torch.cuda.synchronize()
             outs.append((out, G))
         finally:
