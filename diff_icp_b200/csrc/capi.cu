@@ -65,7 +65,12 @@ struct DeviceExec {
         return run_pair<Op>(prm, M, N, scal_out, accumulate, ws, wsb, st);
     }
     // (q,q) adjoint passes through the symmetric engine (sym_engine.cuh): every unordered pair once
-    bool use_sym(int M) const { return sym_mode() != 0 && sym_applicable(M); }
+    bool use_sym(int M) const {
+        if (sym_mode() == 0) return false;
+        if (sym_applicable(M)) return true;
+        // beyond 65536 points: super-blocks (run_pair_sym_blocked), if the workspace holds one tile's partials
+        return M > kSymMaxBlocks * kSymRows && ws != nullptr && wsb >= sym_blocked_workspace_bytes(device_info().sms);
+    }
     bool use_sym_forward(int M) const { return sym_mode() == 2 && sym_applicable(M); }
     // (x,q) adjoint: both sides from ONE ring pass (rect_pair_kernel) when the sets are large enough and the workspace fits
     bool use_rect(int Nx, int M) const {
@@ -77,6 +82,9 @@ struct DeviceExec {
     int run_rect(const typename Op::Params& prm, int Nx, int M) { return run_pair_rect<Op>(prm, Nx, M, ws, wsb, st); }
     template <class Op>
     int run_sym(const typename Op::Params& prm, int M, float* scal_out) {
+        if constexpr (Op::NSCAL == 0) {
+            if (!sym_applicable(M)) return run_pair_sym_blocked<Op>(prm, M, ws, wsb, st);
+        }
         return run_pair_sym<Op>(prm, M, scal_out, ws, wsb, st);
     }
     void scal_fix(float* scal, float eta, int withdiv) {
@@ -256,6 +264,10 @@ unsigned long long dicp_launch_count(void) { return launch_counter(); }
 
 size_t dicp_pair_workspace_bytes(int64_t rows, int64_t cols) {
     size_t b = pair_workspace_bound(rows, cols);
+    if (rows == cols && rows > (int64_t)kSymMaxBlocks * kSymRows) {      // blocked symmetric adjoint: one super-block tile
+        const size_t s = sym_blocked_workspace_bytes(device_info().sms);
+        if (s > b) b = s;
+    }
     if (rows == cols && sym_applicable(rows)) {          // symmetric (q,q) adjoint: packed columns + row / column partials
         const size_t col = align_up((size_t)(rows + 256) * kMaxColF4 * 16, 256);
         const size_t s = col + sym_workspace_bound(rows, device_info().sms) + 1024;

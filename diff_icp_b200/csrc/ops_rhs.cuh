@@ -53,6 +53,8 @@ struct RhsParams {
     float *vq, *dp, *vx;           // forward outputs
     float *gq, *gp, *gx;           // adjoint outputs
     int accumulate;                // adjoint outputs: 0 overwrite, 1 add to existing
+    int col0;                      // (q,q) ops: index offset of the COLUMN points relative to the row points (blocked symmetric
+                                   // evaluation of very large sets: rows from one super-block, columns from another); else 0
 };
 
 #define DICP_RHS_COMMON(NF_)                                                                                   \
@@ -95,7 +97,7 @@ DICP_HD void pack_qpau(const RhsParams& P, int j, int N, float* c, int nfloat) {
     if (j < N) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            const size_t o = (size_t)j * D + k;
+            const size_t o = ((size_t)j + (size_t)P.col0) * D + k;
             c[k] = (P.q[o] - P.origin[k]) * P.kappa;
             c[D + k] = P.p[o];
             c[2 * D + k] = P.a[o];
@@ -439,6 +441,16 @@ struct AdjQQ {
                 P.gp[o] = acc[A_GP + k];
                 P.gq[o] = acc[A_GQ + k];
             }
+        }
+    }
+    // column side of a rectangular pass between two super-blocks (sym_engine.cuh): ADDED to the outputs of column point j
+    static constexpr int RECT_R = 2;
+    static DICP_HD void finish_col(const Params& P, int j, const float* cacc) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const size_t o = ((size_t)j + (size_t)P.col0) * D + k;
+            P.gp[o] += cacc[A_GP + k];
+            P.gq[o] += cacc[A_GQ + k];
         }
     }
 };
@@ -810,6 +822,16 @@ struct AdjQQEta {
                 P.gp[o] = acc[A_GP + k];
                 P.gq[o] = acc[A_GQ + k];
             }
+        }
+    }
+    // column side of a rectangular pass between two super-blocks (sym_engine.cuh): ADDED to the outputs of column point j
+    static constexpr int RECT_R = 2;
+    static DICP_HD void finish_col(const Params& P, int j, const float* cacc) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const size_t o = ((size_t)j + (size_t)P.col0) * D + k;
+            P.gp[o] += cacc[A_GP + k];
+            P.gq[o] += cacc[A_GQ + k];
         }
     }
 };

@@ -528,6 +528,52 @@ inline int run_pair_rect(const typename Op::Params& prm, int Mrows, int Ncols, v
     return e == cudaSuccess ? DICP_OK : (int)e;
 }
 
+// Point sets beyond kSymMaxBlocks * 256 points: super-blocks of kSymSuper points.  The pairs inside a super-block go through
+// the symmetric kernel (rows = columns = the super-block), the pairs between super-blocks A < B through the rectangular ring
+// (rows from A, columns from B, Op::pair_sym: both sides), every launch ADDING to the outputs (zeroed first) in a fixed order.
+static constexpr int kSymSuper = 32768;
+
+// workspace of one super-block tile (symmetric or rectangular), for any adjoint Op (NF <= 12, NACC <= 6)
+inline size_t sym_blocked_workspace_bytes(int sms) {
+    const SymPlan sp = sym_make_plan(kSymSuper, sms);
+    const size_t mpad = (size_t)sp.ngroups_total * kSymGroup, npadcol = (mpad + 127) / 128 * 128;
+    const size_t symb = align_up(npadcol * 12 * 4, 256) + align_up(sym_rowpart_floats(sp, 6) * 4, 256) +
+                        align_up(sym_colpart_floats(sp, 6) * 4, 256) + align_up((size_t)((kSymSuper + 31) / 32) * 4, 256);
+    const RectPlan rp = rect_make_plan(kSymSuper, kSymSuper, 2, sms);
+    const size_t rectb = rect_workspace_bytes(rp, 12, 6, 6);
+    return (symb > rectb ? symb : rectb) + 4096;
+}
+
+template <class Op>
+inline int run_pair_sym_blocked(const typename Op::Params& prm0, int M, void* ws, size_t ws_bytes, cudaStream_t st) {
+    static_assert(Op::NSCAL == 0, "blocked symmetric evaluation: adjoint Ops (no row scalars)");
+    constexpr int D = Op::NF / 4;                                   // (q', p, a, u) records
+    typename Op::Params prm = prm0;
+    if (!prm.accumulate) {
+        cudaMemsetAsync(prm.gq, 0, (size_t)M * D * sizeof(float), st);
+        cudaMemsetAsync(prm.gp, 0, (size_t)M * D * sizeof(float), st);
+    }
+    prm.accumulate = 1;
+    const int nsb = (M + kSymSuper - 1) / kSymSuper;
+    for (int A = 0; A < nsb; ++A) {
+        const int a0 = A * kSymSuper, na = (M - a0 < kSymSuper) ? M - a0 : kSymSuper;
+        typename Op::Params pa = prm;                               // row (and, for the diagonal tile, column) view of block A
+        pa.q += (size_t)a0 * D; pa.p += (size_t)a0 * D; pa.a += (size_t)a0 * D; pa.u += (size_t)a0 * D;
+        pa.gq += (size_t)a0 * D; pa.gp += (size_t)a0 * D;
+        pa.col0 = 0;
+        int rc = sym_applicable(na) ? run_pair_sym<Op>(pa, na, nullptr, ws, ws_bytes, st)
+                                    : run_pair<Op>(pa, na, na, nullptr, 0, ws, ws_bytes, st);      // short last block
+        if (rc != DICP_OK) return rc;
+        for (int B = A + 1; B < nsb; ++B) {
+            const int b0 = B * kSymSuper, nb = (M - b0 < kSymSuper) ? M - b0 : kSymSuper;
+            pa.col0 = b0 - a0;
+            rc = run_pair_rect<Op>(pa, na, nb, ws, ws_bytes, st);
+            if (rc != DICP_OK) return rc;
+        }
+    }
+    return DICP_OK;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace dicp

@@ -169,3 +169,26 @@ def test_small_support_ring_adjoint_matches_two_sided_kernel(D, withlogdet, M, N
         scale = float(a.abs().max())
         assert torch.isfinite(b).all()
         assert float((a - b).abs().max()) <= 3e-5 * scale, (float((a - b).abs().max()), scale)
+
+
+@pytest.mark.parametrize("model", ["classic", "hybrid", "logdet"])
+@pytest.mark.parametrize("M", [66000, 70001])
+def test_blocked_symmetric_adjoint_beyond_65536_points(model, M):
+    """Above 65 536 points the (q,q) adjoint runs super-block by super-block (symmetric kernel inside a block, rectangular
+    ring between blocks, outputs accumulated in a fixed order); 66 000 leaves a short last block for the general engine."""
+    D = 3
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M)
+    q = torch.rand(M, D, generator=g).to(dev)
+    p, a, u = (torch.randn(M, D, generator=g).to(dev) for _ in range(3))
+    gc = torch.tensor([0.3], device=dev)
+    eta = 0.02 if model == "logdet" else 0.0
+    wld = model != "classic"
+    ref = adjoint(D, wld, 0.1, eta, q, p, a, u, gc, 0)
+    got = adjoint(D, wld, 0.1, eta, q, p, a, u, gc, 1)
+    for r, s in zip(ref, got):
+        scale = float(r.abs().max())
+        assert torch.isfinite(s).all()
+        assert float((r - s).abs().max()) <= 3e-5 * scale, (float((r - s).abs().max()), scale)
+    again = adjoint(D, wld, 0.1, eta, q, p, a, u, gc, 1)
+    assert torch.equal(again[0], got[0]) and torch.equal(again[1], got[1])
