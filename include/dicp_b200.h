@@ -50,7 +50,7 @@ int dicp_version(void);
 int dicp_sm_count(void);
 
 /* The (q,q) passes of dicp_rhs_adjoint run on the symmetric engine (every unordered pair evaluated once) for
- * 4096 <= M <= 65536.  mode 0 / 1 switches it off / on (process-wide; default 1, or the DICP_SYM environment variable);
+ * M >= 4096 (beyond 65536 points in super-blocks of 32768).  mode 0 / 1 switches it off / on (process-wide; default 1, or the DICP_SYM environment variable);
  * mode 2 also routes the (q,q) pass of dicp_rhs_forward through it (measured slower on B200, kept for experiments);
  * mode < 0 only queries.  Returns the previous mode.  Results of the two engines agree to fp32 rounding. */
 int dicp_sym_mode(int mode);
