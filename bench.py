@@ -403,7 +403,7 @@ def kernel_roofline(args, LM, q, p, dev, ops):
 
     # algorithmic FP32 instructions / MUFU per pair of the adjoint and forward kernels (DESIGN.md §6, D = 3)
     alg = dict(ALG_WORK[args.variant])
-    symmetric = bool(ops.load().dicp_sym_mode(-1)) and 4096 <= M <= 65536
+    symmetric = bool(ops.load().dicp_sym_mode(-1)) and M >= 4096
     if not symmetric:
         alg["adj_fp32"] = alg["adj_fp32_ordered"]
     pairs = float(M) * M
