@@ -506,7 +506,7 @@ static constexpr int kRingRows = kSmallThreads * kRingR;           // x rows per
 static constexpr int kRingMaxQ = 64;                               // support points (one ring round)
 
 template <int D, bool WLD, bool ETA>
-__global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep S) {
+__global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep S, int xpass) {
     using OpX = typename std::conditional<ETA, AdjXQE<D>, AdjXQ<D, WLD>>::type;
     // x present: no divergence term in the (q,q) pass (AdjQQEta reads gc = 0 itself when x is given)
     using OpQQ = typename std::conditional<ETA, AdjQQEta<D, 1>, AdjQQ<D, false, 1>>::type;
@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep
     __shared__ float xch[kSmallThreads * (2 * NC > NAQ ? 2 * NC : NAQ)];
     if (!small_select_frame(S)) return;
     const int tid = threadIdx.x, lane = tid & 31, M = S.M, Nx = S.Nx;
-    const int nXB = (Nx + kRingRows - 1) / kRingRows;
+    // an x CTA takes `xpass` consecutive blocks of kRingRows rows (host: chosen so that all CTAs of all frames are resident at once)
+    const int nXB = (Nx + kRingRows * xpass - 1) / (kRingRows * xpass);
     const unsigned nblk = (unsigned)nXB + 1u;
     if (blockIdx.x >= nblk) return;
     const size_t MD = (size_t)M * D, Ssz = 2 * MD + (size_t)Nx * D + 1;
@@ -539,23 +540,25 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep
             for (int k = 0; k < NF; ++k) dst[2 * k] = c[k];
         }
         __syncthreads();
+        F2 cacc[NC];                                  // column sums: kept over the passes (W steps bring every pair home)
+#pragma unroll
+        for (int k = 0; k < NC; ++k) cacc[k] = f2(0.f, 0.f);
+        const int lr = lane & (W - 1);
+      for (int ps = 0; ps < xpass; ++ps) {
         typename OpX::Row row[kRingR];
         float rmask[kRingR];
         int ri[kRingR];
 #pragma unroll
         for (int r = 0; r < kRingR; ++r) {
-            ri[r] = blockIdx.x * kRingRows + (tid >> 5) * (32 * kRingR) + r * 32 + lane;
+            ri[r] = (blockIdx.x * xpass + ps) * kRingRows + (tid >> 5) * (32 * kRingR) + r * 32 + lane;
             rmask[r] = ri[r] < Nx ? 1.f : 0.f;
             OpX::load_row(P, ri[r] < Nx ? ri[r] : Nx - 1, row[r]);
         }
-        F2 acc[kRingR][OpX::NACC], cacc[NC];
+        F2 acc[kRingR][OpX::NACC];
 #pragma unroll
         for (int r = 0; r < kRingR; ++r)
 #pragma unroll
             for (int k = 0; k < OpX::NACC; ++k) acc[r][k] = f2(0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) cacc[k] = f2(0.f, 0.f);
-        const int lr = lane & (W - 1);
         for (int s = 0; s < W; ++s) {
             const int pr = (lr + s) & (W - 1);
             const float4* rec = reinterpret_cast<const float4*>(cols + pr * STRIDE);
@@ -590,6 +593,7 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep
                 for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)ri[r] * D + k);
             }
         }
+      }
         // columns: lane lr of every ring holds pair lr; add the CTA's rings in ring order
         const int ring = tid / W, nring = kSmallThreads / W;
 #pragma unroll
@@ -698,7 +702,7 @@ inline size_t small_workspace_bytes(long long M, long long Nx) {
     const long long nXB = (Nx + kSmallThreads - 1) / kSmallThreads, nQB = (M + kSmallThreads - 1) / kSmallThreads;
     const size_t fwd = (size_t)(nXB + nQB) * 4 * 4;
     size_t adj = (size_t)small_adj_nsplit((int)Nx) * 16 * (size_t)M * 4;
-    const size_t ringb = (size_t)((Nx + kSmallThreads * 4 - 1) / (kSmallThreads * 4)) * 8 * 64 * 4;      // ring form: x CTAs x 8 x 64
+    const size_t ringb = (size_t)((Nx + kSmallThreads * 4 - 1) / (kSmallThreads * 4)) * 8 * 64 * 4;      // ring form: x CTAs (xpass = 1) x 8 x 64
     if (ringb > adj) adj = ringb;
     return kSmallCounters * 4 + (fwd > adj ? fwd : adj) + 256;
 }
