@@ -159,3 +159,52 @@ def test_empty_and_tiny_inputs():
     sh = LM.Shoot(q, p)                                         # a single support point: K = 1, dp = 0, straight line
     assert torch.allclose(sh[-1][0], q + p, atol=1e-6) and torch.allclose(sh[-1][1], p, atol=1e-7)
     assert LM.v(torch.rand(0, 2, device=dev()), q, p).shape == (0, 2)
+
+
+def test_groupwise_iteration_at_atlas_size_lockstep():
+    """configs[2] size: 64 frames x 10k points, 2-D, C = 50, hybrid, grid support -- the lock-step registration of all
+    frames.  Size-independent properties: the free energy never increases over the alternation, two identical runs agree
+    bit for bit, every frame's stored shoot is the shoot of its stored momenta, and the uncovered-point counts of the
+    batched coverage kernel equal GaussKernel.check_coverage on a frame."""
+    import math
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from groupwise_iteration import spiral_frames
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from diff_icp_b200.core.PSR import DiffPSR
+
+    def run():
+        frames = spiral_frames(64, 10000)
+        torch.manual_seed(1234)
+        G = GaussianMixtureUnif(torch.zeros(50, 2), spec=spec())
+        LM = LDDMMModel(sigma=0.2, D=2, lambd=500.0, version="hybrid", scheme="Euler", nt=10, spec=spec())
+        LM.use_cuda_graph = True
+        P = DiffPSR([f.to(dev()) for f in frames], G, LM, dataspec=spec(), compspec=spec())
+        P.printstuff = False
+        P.set_support_scheme("grid", rho=math.sqrt(2))
+        P.reinitialize_GMM()
+        fes = [P.FE]
+        for _ in range(2):
+            P.GMM_opt(max_iterations=10, tol=1e-3)
+            fes.append(P.FE)
+            P.Reg_opt(tol=1e-3, nmax=1)
+            fes.append(P.FE)
+        return P, fes
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Pa, fa = run()
+        Pb, fb = run()
+    assert Pa._batched_plan() is not None                       # the lock-step path was the one that ran
+    assert all(b <= a + 1e-6 * abs(a) for a, b in zip(fa, fa[1:])), fa
+    assert fa == fb
+    for k in (0, 31, 63):
+        assert torch.equal(Pa.a0[k], Pb.a0[k])
+        sh = Pa.LMi.Shoot(Pa.q0[k], Pa.a0[k], Pa.allx0[k])
+        assert torch.allclose(sh[-1][3], Pa.x1[k, 0], atol=2e-6)
+        mine = sum(int(Pa.LMi.Kernel.check_coverage(st[-1], st[0], 2.0).sum()) for st in Pa.shoot[k])
+        ref = sum(int(Pa.LMi.Kernel.check_coverage(st[-1], st[0], 2.0).sum()) for st in sh)
+        assert abs(mine - ref) <= 2
