@@ -149,6 +149,46 @@ DICP_D void sweep_range(const RhsParams& P, const typename Op::Row& row, const f
     }
 }
 
+// R rows at once against all n staged columns: one broadcast LDS.128 set per column pair serves the R rows, and the R
+// independent accumulator chains give the scheduler something to overlap
+template <class Op, int R>
+DICP_D void sweep_cols_multi(const RhsParams& P, const typename Op::Row (&row)[R], const float* smem, int n,
+                             F2 (&acc)[R][Op::NACC]) {
+    constexpr int NF = Op::NF, PF4 = NF / 2;
+    const float4* sp = reinterpret_cast<const float4*>(smem);
+    const int npair = n >> 1;
+#pragma unroll 2
+    for (int Pp = 0; Pp < npair; ++Pp) {
+        F2 c[NF];
+#pragma unroll
+        for (int k = 0; k < PF4; ++k) {
+            const float4 v = sp[Pp * PF4 + k];
+            c[2 * k] = f2(v.x, v.y);
+            c[2 * k + 1] = f2(v.z, v.w);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) Op::template pair<F2>(P, row[r], c, acc[r]);
+    }
+    if (n & 1) {
+        float c[NF];
+#pragma unroll
+        for (int k = 0; k < PF4; ++k) {
+            const float4 v = sp[npair * PF4 + k];
+            c[2 * k] = v.x;
+            c[2 * k + 1] = v.z;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float tmp[Op::NACC];
+#pragma unroll
+            for (int k = 0; k < Op::NACC; ++k) tmp[k] = 0.f;
+            Op::template pair<float>(P, row[r], c, tmp);
+#pragma unroll
+            for (int k = 0; k < Op::NACC; ++k) acc[r][k] = vadd(acc[r][k], f2(tmp[k], 0.f));
+        }
+    }
+}
+
 // all n staged columns
 template <class Op>
 DICP_D void sweep_cols(const RhsParams& P, const typename Op::Row& row, const float* smem, int n, F2* acc) {
@@ -206,16 +246,39 @@ __global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_FWD) small_rhs_
 
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     if ((int)blockIdx.x < nXB) {
-        typename OpXQ::Row row, nextrow;
-        {
-            const int i0 = (int)blockIdx.x * xpass * kSmallThreads + tid;
-            if (i0 < Nx) OpXQ::load_row(P, i0, nextrow);
+        // the CTA's xpass blocks of 128 rows, four blocks at a time (4 rows per thread swept together), then one by one
+        int ps = 0;
+        for (; ps + 4 <= xpass; ps += 4) {
+            typename OpXQ::Row row[4];
+            int ri[4];
+            F2 acc[4][OpXQ::NACC];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                ri[r] = ((int)blockIdx.x * xpass + ps + r) * kSmallThreads + tid;
+                OpXQ::load_row(P, ri[r] < Nx ? ri[r] : Nx - 1, row[r]);
+#pragma unroll
+                for (int k = 0; k < OpXQ::NACC; ++k) acc[r][k] = f2(0.f, 0.f);
+            }
+            sweep_cols_multi<OpXQ, 4>(P, row, cols, M, acc);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (ri[r] < Nx) {
+                    float a[OpXQ::NACC];
+#pragma unroll
+                    for (int k = 0; k < OpXQ::NACC; ++k) a[k] = f2_sum(acc[r][k]);
+                    float dc = 0.f;                 // finish ASSIGNS the row's dcost contribution
+                    OpXQ::finish(P, ri[r], row[r], a, &dc);
+                    rs[0] += dc;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)ri[r] * D + k);
+                }
+            }
         }
-        for (int ps = 0; ps < xpass; ++ps) {
+        for (; ps < xpass; ++ps) {
             const int i = ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid;
-            row = nextrow;
-            if (ps + 1 < xpass && i + kSmallThreads < Nx) OpXQ::load_row(P, i + kSmallThreads, nextrow);   // prefetch
             if (i < Nx) {
+                typename OpXQ::Row row;
+                OpXQ::load_row(P, i, row);
                 F2 acc[OpXQ::NACC];
 #pragma unroll
                 for (int k = 0; k < OpXQ::NACC; ++k) acc[k] = f2(0.f, 0.f);
@@ -223,7 +286,7 @@ __global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_FWD) small_rhs_
                 float a[OpXQ::NACC];
 #pragma unroll
                 for (int k = 0; k < OpXQ::NACC; ++k) a[k] = f2_sum(acc[k]);
-                float dc = 0.f;                     // finish ASSIGNS the row's dcost contribution
+                float dc = 0.f;
                 OpXQ::finish(P, i, row, a, &dc);
                 rs[0] += dc;
 #pragma unroll
