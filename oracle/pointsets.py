@@ -5,8 +5,9 @@ CPU restatements (dense torch / numpy, dtype-agnostic) of
   intrinsic_scale       /root/reference/diffICP/tools/point_sets.py:13-26   (KeOps Kmin(2): second smallest |x_i-x_j|^2)
   point_set_distance    /root/reference/diffICP/tools/point_sets.py:46-95
   decimate              /root/reference/diffICP/tools/point_sets.py:102-133 (greedy covering; index lists)
+  data_distance         /root/reference/diffICP/core/PSR_standard.py:37-58    (RKHS distance of point clouds as measures)
 
-Pinning: `decimate` and `point_set_distance` are pinned against the reference's OWN functions, executed in the build
+Pinning: `decimate`, `point_set_distance` and `data_distance` are pinned against the reference's OWN functions, executed in the build
 container from their source text by tests/golden/make_golden.py (the module itself cannot be imported: its line 8
 hard-imports pykeops) -> tests/golden/pointsets.npz.  `intrinsic_scale` is one KeOps reduction that can be run nowhere:
 parity unpinned for that function alone; it is restated from its definition (second smallest squared distance, the
@@ -68,3 +69,13 @@ def point_set_distance(X, Y, sigma_X=None, sigma_Y=None, w_X=None, w_Y=None) -> 
     k = lambda s, a, b, w: GaussOracle(s, D).KRedScal(a, b, w).flatten()
     return float(c(sXX) * (k(sXX, X, X, w_X) * w_X).sum() + c(sYY) * (k(sYY, Y, Y, w_Y) * w_Y).sum()
                  - 2 * c(sXY) * (k(sXY, X, Y, w_Y) * w_X).sum())
+
+
+def data_distance(sigma: float, x, y, w=None) -> float:
+    """core/PSR_standard.py:37-58 with a Gaussian kernel of width sigma."""
+    K = GaussOracle(sigma, x.shape[1])
+    Nx, Ny = x.shape[0], y.shape[0]
+    if w is None:
+        return float(K.KBase(x, x).sum() / Nx ** 2 + K.KBase(y, y).sum() / Ny ** 2 - 2 * K.KBase(y, x).sum() / (Nx * Ny))
+    return float(K.KBase(x, x).sum() / Nx ** 2 + (K.KRedScal(y, y, w).flatten() * w).sum()
+                 - 2 * (K.KBase(y, x).flatten() * w).sum() / Nx)

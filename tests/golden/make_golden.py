@@ -343,6 +343,15 @@ def gen_pointsets(rk):
         out[f"psd_{tag}_ref32"] = np.array(float(ref_psd(X, Y, **kw)))
         out[f"psd_{tag}_gold"] = np.array(float(ref_psd(X.double(), Y.double(), **kw)))
     out["psd_X"], out["psd_Y"] = X.numpy(), Y.numpy()
+    # data_distance of the comparator algorithm (core/PSR_standard.py:37-58), with and without template weights
+    ref_dd = reference_function("diffICP/core/PSR_standard.py", "data_distance", {"GenKernel": rk.GenKernel})
+    wts = torch.rand(Y.shape[0], generator=g)
+    wts = wts / wts.sum()
+    out["dd_w"], out["dd_sigma"] = wts.numpy(), np.array(0.15)
+    for prec, dt in (("ref32", torch.float32), ("gold", torch.float64)):
+        Kd = rk.GaussKernel(0.15, 3, computversion="torch")
+        out[f"dd_plain_{prec}"] = np.array(float(ref_dd(Kd, X.to(dt), Y.to(dt))))
+        out[f"dd_weighted_{prec}"] = np.array(float(ref_dd(Kd, X.to(dt), Y.to(dt), wts.to(dt))))
     out["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(OUT, "pointsets.npz"), **out)
     print("pointsets.npz", len(out))

@@ -69,6 +69,29 @@ def test_point_set_distance_matches_reference(golden):
         assert abs(v - gold) <= max(1e-5 * abs(gold), 2 * abs(ref32 - gold)) + 1e-7, (tag, v, gold, ref32)
 
 
+def test_data_distance_matches_reference(golden):
+    """RKHS distance of the comparator algorithm (core/PSR_standard.py:37-58) vs the reference's own function; the value is
+    a difference of three O(1) sums that cancel to ~6e-3, hence the tolerance relative to the reference's fp32 error."""
+    from diff_icp_b200.core.PSR_standard import data_distance
+    from diff_icp_b200.tools.kernel import GaussKernel
+    g = golden("pointsets")
+    X, Y, w = cu(g["psd_X"]), cu(g["psd_Y"]), cu(g["dd_w"])
+    K = GaussKernel(float(g["dd_sigma"]), 3, spec={"device": X.device, "dtype": torch.float32})
+    for tag, args in (("plain", ()), ("weighted", (w,))):
+        gold, ref32 = float(g[f"dd_{tag}_gold"]), float(g[f"dd_{tag}_ref32"])
+        v = float(data_distance(K, X, Y, *args))
+        assert abs(v - gold) <= max(2e-5 * abs(gold), 2 * abs(ref32 - gold)) + 2e-7, (tag, v, gold, ref32)
+    # differentiable through the kernel-sum VJPs: d/dx against a finite difference along a random direction
+    Xg = X.clone().requires_grad_(True)
+    L = data_distance(K, Xg, Y)
+    (gx,) = torch.autograd.grad(L, [Xg])
+    d = torch.randn_like(X)
+    eps = 1e-2
+    fd = (float(data_distance(K, X + eps * d, Y)) - float(data_distance(K, X - eps * d, Y))) / (2 * eps)
+    an = float((gx * d).sum())
+    assert abs(fd - an) <= 5e-2 * abs(an) + 1e-6, (fd, an)
+
+
 def test_cpu_tensors_are_refused():
     from diff_icp_b200.tools.point_sets import decimate, intrinsic_scale
     with pytest.raises(ValueError):
