@@ -313,8 +313,7 @@ int dicp_em_rowpass(int D, int lite, float sigma_old, const float* X, int64_t N,
                     const float* wl2, int64_t C, const float* mu_new, const float* lpi_new, float* T2, float* Y,
                     float* rowP, float* rowQ, float* sq, float* scal4, void* workspace, size_t workspace_bytes,
                     void* stream) {
-    // measured on B200: the one-launch form wins for the T-only pass up to 64 components, for the full pass up to 16
-    if (C >= 1 && C <= (lite ? kEmColMaxC : 16) && (D == 2 || D == 3) && sigma_old > 0.f && N >= 1 && N <= INT32_MAX && X &&
+    if (C >= 1 && C <= kEmColMaxC && (D == 2 || D == 3) && sigma_old > 0.f && N >= 1 && N <= INT32_MAX && X &&
         mu_old && wl2 && T2 && (lite || (mu_new && lpi_new && Y && scal4)) && workspace &&
         workspace_bytes >= em_row_small_workspace(N)) {
         // few components: one launch, components resident in shared memory (em_col_small.cuh)
@@ -323,16 +322,22 @@ int dicp_em_rowpass(int D, int lite, float sigma_old, const float* X, int64_t N,
         prm.kappa = gauss_const(sigma_old).kappa;
         prm.o_T2 = T2; prm.o_Y = Y; prm.o_rowP = rowP; prm.o_rowQ = rowQ; prm.o_sq = sq;
         cudaStream_t st = (cudaStream_t)stream;
-        unsigned* counter = (unsigned*)workspace;
         float* blockscal = (float*)((char*)workspace + 256);
-        const unsigned blocks = (unsigned)((N + kEmRowRows - 1) / kEmRowRows);
-        if (!lite) cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+        const long long groups = (N + kEmRowRows - 1) / kEmRowRows;
+        long long passes = groups / ((long long)device_info().sms * 8);          // about 8 CTAs per SM, at most 16 row groups each
+        if (passes < 1) passes = 1;
+        if (passes > 16) passes = 16;
+        const unsigned blocks = (unsigned)((groups + passes - 1) / passes);
         if (D == 2) {
-            if (lite) em_row_small_kernel<2, true><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, blockscal, counter, scal4);
-            else em_row_small_kernel<2, false><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, blockscal, counter, scal4);
+            if (lite) em_row_small_kernel<2, true><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, (int)passes, blockscal);
+            else em_row_small_kernel<2, false><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, (int)passes, blockscal);
         } else {
-            if (lite) em_row_small_kernel<3, true><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, blockscal, counter, scal4);
-            else em_row_small_kernel<3, false><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, blockscal, counter, scal4);
+            if (lite) em_row_small_kernel<3, true><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, (int)passes, blockscal);
+            else em_row_small_kernel<3, false><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, (int)passes, blockscal);
+        }
+        if (!lite) {
+            scalar_reduce_kernel<<<1, 256, 0, st>>>(blockscal, (int)blocks, 4, scal4, 0);
+            launch_counter() += 1;
         }
         launch_counter() += 1;
         return last_error(DICP_OK);

@@ -139,13 +139,13 @@ __global__ void __launch_bounds__(128) em_col_small_kernel(EmParams P, int N, in
 // Through the general engine a row pass is pack + pair kernel (TMA pipeline, one 128-column tile of which <= 64 columns are
 // real) + scalar reduction.  With the components resident in shared memory a thread simply sweeps them for its 4 rows (packed
 // fp32, EmRow::pair<F2>): no pipeline, coalesced row loads / stores, and the four free-energy sums of the full pass are block
-// partials added in block order by the last CTA to finish.  HBM-bound for C <~ 9 (12D + 8 bytes per point and EM step).
+// partials added in block order by scalar_reduce_kernel.  HBM-bound for C <~ 9 (12D + 8 bytes per point and EM step).
 static constexpr int kEmRowR = 4;
 static constexpr int kEmRowRows = 128 * kEmRowR;
 
 template <int D, bool LITE>
-__global__ void __launch_bounds__(128) em_row_small_kernel(EmParams P, int N, int C, float* __restrict__ blockscal,
-                                                           unsigned* __restrict__ counter, float* __restrict__ scal_out) {
+__global__ void __launch_bounds__(128) em_row_small_kernel(EmParams P, int N, int C, int passes,
+                                                           float* __restrict__ blockscal) {
     using Op = EmRow<D, LITE>;
     constexpr int NF = Op::NF, NACC = Op::NACC, NSCAL = Op::NSCAL, PF4 = NF / 2, REC = 2 * NF;
     static_assert(NF % 2 == 0, "packed records");
@@ -160,58 +160,55 @@ __global__ void __launch_bounds__(128) em_row_small_kernel(EmParams P, int N, in
 #pragma unroll
         for (int k = 0; k < NF; ++k) dst[2 * k] = c[k];
     }
-    typename Op::Row row[kEmRowR];
-    F2 acc[kEmRowR][NACC];
-    const int base = blockIdx.x * kEmRowRows + tid;
-#pragma unroll
-    for (int r = 0; r < kEmRowR; ++r) {
-        const int i = base + r * 128;
-        Op::load_row(P, i < N ? i : N - 1, row[r]);
-        Op::init_packed(acc[r]);
-    }
     __syncthreads();
     const float4* sp = reinterpret_cast<const float4*>(cols);
     const int npair = Cpad >> 1;
-    for (int Pp = 0; Pp < npair; ++Pp) {
-        F2 c[NF];
-#pragma unroll
-        for (int k = 0; k < PF4; ++k) {
-            const float4 v = sp[Pp * PF4 + k];
-            c[2 * k] = f2(v.x, v.y);
-            c[2 * k + 1] = f2(v.z, v.w);
-        }
-#pragma unroll
-        for (int r = 0; r < kEmRowR; ++r) Op::template pair<F2>(P, row[r], c, acc[r]);
-    }
     float scal[NSCAL > 0 ? NSCAL : 1];
 #pragma unroll
     for (int k = 0; k < NSCAL; ++k) scal[k] = 0.f;
+    // `passes` groups of kEmRowRows rows per CTA: the staging of the components is paid once per CTA
+    for (int ps = 0; ps < passes; ++ps) {
+        typename Op::Row row[kEmRowR];
+        F2 acc[kEmRowR][NACC];
+        const int base = (blockIdx.x * passes + ps) * kEmRowRows + tid;
+        if (base - tid >= N) break;
 #pragma unroll
-    for (int r = 0; r < kEmRowR; ++r) {
-        const int i = base + r * 128;
-        if (i < N) {
-            float a[NACC], rs[NSCAL > 0 ? NSCAL : 1];
-            Op::unpack_acc(acc[r], a);
-            Op::finish(P, i, row[r], a, rs);
+        for (int r = 0; r < kEmRowR; ++r) {
+            const int i = base + r * 128;
+            Op::load_row(P, i < N ? i : N - 1, row[r]);
+            Op::init_packed(acc[r]);
+        }
+        for (int Pp = 0; Pp < npair; ++Pp) {
+            F2 c[NF];
 #pragma unroll
-            for (int k = 0; k < NSCAL; ++k) scal[k] += rs[k];
+            for (int k = 0; k < PF4; ++k) {
+                const float4 v = sp[Pp * PF4 + k];
+                c[2 * k] = f2(v.x, v.y);
+                c[2 * k + 1] = f2(v.z, v.w);
+            }
+#pragma unroll
+            for (int r = 0; r < kEmRowR; ++r) Op::template pair<F2>(P, row[r], c, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kEmRowR; ++r) {
+            const int i = base + r * 128;
+            if (i < N) {
+                float a[NACC], rs[NSCAL > 0 ? NSCAL : 1];
+                Op::unpack_acc(acc[r], a);
+                Op::finish(P, i, row[r], a, rs);
+#pragma unroll
+                for (int k = 0; k < NSCAL; ++k) scal[k] += rs[k];
+            }
         }
     }
     if constexpr (NSCAL > 0) {
+        // block partials; summed in block order by scalar_reduce_kernel (a single ticket counter would serialise the atomics
+        // of thousands of CTAs: measured ~10 ns each)
 #pragma unroll
         for (int k = 0; k < NSCAL; ++k) {
             const float v = block_sum(scal[k], red);
             if (tid == 0) blockscal[(size_t)blockIdx.x * NSCAL + k] = v;
         }
-        if (!last_cta(counter, gridDim.x)) return;
-        for (int k = 0; k < NSCAL; ++k) {
-            float v = 0.f;
-            for (int b = tid; b < (int)gridDim.x; b += 128) v += __ldcg(&blockscal[(size_t)b * NSCAL + k]);
-            v = block_sum(v, red);
-            if (tid == 0) scal_out[k] = v;
-            __syncthreads();
-        }
-        if (tid == 0) *counter = 0u;
     }
 }
 inline size_t em_row_small_workspace(long long N) { return 256 + (size_t)((N + kEmRowRows - 1) / kEmRowRows) * 4 * 4; }
