@@ -64,8 +64,8 @@ template <int D>
 __global__ void __launch_bounds__(128) em_col_small_kernel(EmParams P, int N, int C, float* __restrict__ part,
                                                            unsigned* __restrict__ counter) {
     using Op = EmCol<D>;
-    constexpr int NACC = Op::NACC, CF = D + 1;                // staged record: x' (D), T2
-    __shared__ __align__(16) float pts[kEmColChunk * CF];
+    constexpr int NACC = Op::NACC, NF = Op::NF, REC = 2 * NF;       // staged pair records: (x' (D), T2 [, pad]) of two points
+    __shared__ __align__(16) float pts[(kEmColChunk / 2) * REC];
     __shared__ float xch[128 * NACC];
     const int tid = threadIdx.x;
     const int G = 128 / C;
@@ -77,28 +77,39 @@ __global__ void __launch_bounds__(128) em_col_small_kernel(EmParams P, int N, in
 
     typename Op::Row row;
     if (work) Op::load_row(P, c, row);
-    float acc[NACC];
-    Op::init(acc);
+    F2 accp[NACC];
+    Op::init_packed(accp);
     for (int j0 = n0; j0 < n1; j0 += kEmColChunk) {
         const int n = (n1 - j0 < kEmColChunk) ? n1 - j0 : kEmColChunk;
+        const int npad = (n + 1) & ~1;                              // an odd count gets a null partner (contributes exactly 0)
         __syncthreads();
-        for (int t = tid; t < n; t += 128) {
+        for (int t = tid; t < npad; t += 128) {
             float rec[Op::COLF4 * 4];
-            Op::pack_col(P, j0 + t, N, rec);
+            Op::pack_col(P, t < n ? j0 + t : N, N, rec);            // index N => the Op's null record
+            float* dst = pts + (t >> 1) * REC + (t & 1);
 #pragma unroll
-            for (int k = 0; k < CF; ++k) pts[t * CF + k] = rec[k];
+            for (int k = 0; k < NF; ++k) dst[2 * k] = rec[k];
         }
         __syncthreads();
         if (work) {
-            const int a = (int)(((long long)n * g) / G), b = (int)(((long long)n * (g + 1)) / G);
+            // packed fp32: two points per call (EmCol::pair<F2>), shares of whole pairs per group
+            const int npair = npad >> 1;
+            const int a = (int)(((long long)npair * g) / G), b = (int)(((long long)npair * (g + 1)) / G);
+            const float4* sp = reinterpret_cast<const float4*>(pts);
             for (int t = a; t < b; ++t) {
-                float rec[CF];
+                F2 cc[NF];
 #pragma unroll
-                for (int k = 0; k < CF; ++k) rec[k] = pts[t * CF + k];
-                Op::template pair<float>(P, row, rec, acc);
+                for (int k = 0; k < NF / 2; ++k) {
+                    const float4 v = sp[t * (NF / 2) + k];
+                    cc[2 * k] = f2(v.x, v.y);
+                    cc[2 * k + 1] = f2(v.z, v.w);
+                }
+                Op::template pair<F2>(P, row, cc, accp);
             }
         }
     }
+    float acc[NACC];
+    Op::unpack_acc(accp, acc);
     // groups -> one partial per component, in group order
     if (work && g > 0) {
 #pragma unroll
