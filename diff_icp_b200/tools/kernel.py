@@ -139,31 +139,71 @@ class GaussKernel(GenKernel):
         return self.min_sqdist(X, Y) > (Rthreshold * self.sigma) ** 2
 
     # ---- linear solves with K(x,x): setup-time, NOT on the hot path ---------------------
-    DENSE_SOLVE_MAX = 4000          # above this the reference's dense O(M^3) CPU lstsq is replaced by matrix-free CG
+    DENSE_SOLVE_MAX = 4000          # above this the reference's dense O(M^3) CPU lstsq is replaced by the matrix-free solve
+    PINV_MAX_RANK = 8192            # largest retained subspace of the matrix-free truncated pseudo-inverse
+
+    def _Kmatmat(self, x, V):
+        """K(x,x) @ V for V (M, r): the KRed kernel as mat-vec, D columns per sweep."""
+        M, D = x.shape
+        r = V.shape[1]
+        out = torch.empty(M, r, dtype=V.dtype, device=V.device)
+        for j in range(0, r, D):
+            w = min(D, r - j)
+            blk = V[:, j:j + D]
+            if w < D:
+                blk = torch.cat((blk, torch.zeros(M, D - w, dtype=V.dtype, device=V.device)), 1)
+            out[:, j:j + w] = ops.ksum(ops.K_RED, self.sigma, x, x, b=blk.contiguous())[ops.K_RED][:, :w]
+        return out
+
+    def top_eigenpairs(self, x, rcond, r0=96, power=2, seed=0):
+        """Eigenpairs (lam (r,) descending, U (M,r)) of the symmetric PSD matrix K(x,x) that span every eigenvalue above
+        rcond * lam_max: randomised subspace iteration with the tiled kernel sum as mat-vec (no M x M matrix), the rank
+        doubled until the smallest Ritz value sits two decades under the cut-off.  A Gaussian kernel matrix has a
+        super-exponentially decaying spectrum (a few hundred eigenvalues above 1e-3 * lam_max for sigma = 0.2 in the unit
+        cube, whatever M), which is what makes this cheap: O(M^2 r / D) pair evaluations instead of the O(M^3) dense SVD."""
+        M = x.shape[0]
+        gen = torch.Generator(device=x.device).manual_seed(seed)
+        r = min(M, r0)
+        Q = torch.empty(M, 0, dtype=x.dtype, device=x.device)
+        while True:
+            Om = torch.randn(M, r - Q.shape[1], generator=gen, dtype=x.dtype, device=x.device)
+            Q = torch.linalg.qr(torch.cat((Q, self._Kmatmat(x, Om)), 1)).Q      # previous subspace kept, new directions added
+            for _ in range(power):
+                Q = torch.linalg.qr(self._Kmatmat(x, Q)).Q
+            B = Q.double().t() @ self._Kmatmat(x, Q).double()                    # Rayleigh-Ritz in fp64 (r x r)
+            lam, W = torch.linalg.eigh(0.5 * (B + B.t()))
+            lam, W = lam.flip(0), W.flip(1)
+            if r >= M or r >= self.PINV_MAX_RANK or float(lam[-1]) < 1e-2 * rcond * float(lam[0]):
+                return lam, (Q.double() @ W)
+            r = min(M, 2 * r)
 
     def KpinvSolve(self, x, v, rcond=None):
         """Least-squares b with sum_j K(x_i-x_j) b_j ~ v_i (reference: tools/kernel.py:227-232, numpy lstsq on the
-        dense M x M matrix, rcond = relative singular-value cut-off).
+        dense M x M matrix; rcond = singular values below rcond * s_max are dropped, i.e. a truncated pseudo-inverse).
         * v == 0  =>  b = 0 exactly (minimum-norm solution): the case that runs before every optimisation
           (DiffPSR.initialize_a0 / update_a0 with eta = 0 and zero initial speeds).
-        * M <= DENSE_SOLVE_MAX: dense numpy lstsq, like the reference.
-        * larger M (where the reference is infeasible): matrix-free conjugate gradient on
-          (K + alpha I) b = v with alpha = rcond * lambda_max(K) (power iteration), i.e. Tikhonov damping at the scale
-          where the pseudo-inverse truncates; the KRed kernel is the mat-vec."""
+        * M <= DENSE_SOLVE_MAX: dense numpy lstsq, the reference's own call.
+        * larger M (where the reference's O(M^3) CPU solve is infeasible): the SAME truncated
+          pseudo-inverse, matrix-free: K is symmetric PSD, so its singular triplets are its eigenpairs;
+          b = sum_{lam_k > rcond lam_1} u_k (u_k . v) / lam_k with the eigenpairs from `top_eigenpairs`.
+          rcond = None (machine-precision cut-off: the retained rank is ~M) goes to conjugate gradients instead
+          (`KridgeSolve_keops` with a ridge at eps * M * lam_max); its fitted speeds K b agree with the reference's,
+          the momenta themselves are not determined at that cut-off (the reference's own fp32 and fp64 runs differ
+          by orders of magnitude there, tests/golden/v2p.npz)."""
         if not bool(v.any()):
             return torch.zeros_like(v)
         if x.shape[0] <= self.DENSE_SOLVE_MAX:
             K_xx = self.K_torch(x, x)
             sol = np.linalg.lstsq(K_xx.detach().cpu().numpy(), v.detach().cpu().numpy(), rcond=rcond)[0]
             return torch.from_numpy(sol).to(**getspec(x, v))
-        u = torch.ones_like(v)
-        lam = 1.0
-        for _ in range(8):
-            Ku = ops.ksum(ops.K_RED, self.sigma, x, x, b=u)[ops.K_RED]
-            lam = float(Ku.norm() / u.norm())
-            u = Ku / Ku.norm()
-        rc = 1e-6 if rcond is None else rcond
-        return self.KridgeSolve_keops(x, v, alpha=rc * lam)
+        if rcond is None:
+            lam, _ = self.top_eigenpairs(x, 0.5, r0=8)
+            alpha = float(torch.finfo(x.dtype).eps) * x.shape[0] * float(lam[0])
+            return self.KridgeSolve_keops(x, v, alpha=alpha)
+        lam, U = self.top_eigenpairs(x, rcond)
+        keep = lam > rcond * lam[0]
+        U, lam = U[:, keep], lam[keep]
+        return (U @ ((U.t() @ v.double()) / lam[:, None])).to(**getspec(x, v)).contiguous()
 
     def KridgeSolve_torch(self, x, v, alpha=1e-4):
         K_xx = self.K_torch(x, x)

@@ -162,6 +162,11 @@ def install_all(monkeypatch):
     monkeypatch.setattr(ops, "alloc_workspace", lambda r, c, dev: torch.empty(16, dtype=torch.uint8))
     monkeypatch.setattr(_lib, "require_cuda", lambda *t: torch.device("cpu"))
     monkeypatch.setattr(em_ops, "log_resp", None, raising=False)
+    # greedy decimation: the oracle's dense restatement stands in for the CUDA kernel (index lists are bit-exact, see
+    # tests/test_gpu_pointsets.py)
+    from oracle import pointsets as ops_oracle
+    from diff_icp_b200.core import PSR as psr_mod
+    monkeypatch.setattr(psr_mod, "decimate", ops_oracle.decimate)
 
 
 def quad_loss(x, y, inv, g, loss, ws):

@@ -29,36 +29,11 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 
 def load_reference():
-    class _Anything(types.ModuleType):
-        def __getattr__(self, name):
-            if name.startswith("__"):
-                raise AttributeError(name)
-            return _Anything(self.__name__ + "." + name)
-
-        def __call__(self, *a, **k):
-            return _Anything("call")
-
-    for name in ["matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors",
-                 "matplotlib.ticker", "mpl_toolkits", "mpl_toolkits.mplot3d"]:
-        sys.modules.setdefault(name, _Anything(name))
-    sys.path.insert(0, REF_ROOT)
-    warnings.filterwarnings("ignore")
-    import diffICP.tools  # noqa: F401
-    ps = types.ModuleType("diffICP.tools.point_sets")
-
-    def intrinsic_scale(x):
-        d2 = ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)
-        return float(d2.topk(2, dim=1, largest=False).values[:, 1].mean().sqrt())
-
-    def decimate(x, R):
-        raise NotImplementedError
-
-    ps.intrinsic_scale, ps.decimate = intrinsic_scale, decimate
-    sys.modules["diffICP.tools.point_sets"] = ps
-    import diffICP.tools.kernel as rk
-    import diffICP.core.LDDMM as rl
-    import diffICP.core.GMM as rg
-    return rk, rl, rg
+    """The shared loader (oracle/ref_loader.py): stubs for matplotlib, a pykeops-free point_sets module, torch twin."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle.ref_loader import load_reference as _load
+    ref = _load(REF_ROOT)
+    return ref.kernel, ref.LDDMM, ref.GMM
 
 
 def spec_of(dt):
@@ -300,6 +275,298 @@ def gen_psr():
     print("psr.npz", len(out))
 
 
+def gen_v2p(rl):
+    """LDDMMModel.v2p (core/LDDMM.py:235-253) -> KpinvSolve (tools/kernel.py:227-232, numpy lstsq with a relative
+    singular-value cut-off) and KridgeSolve_torch (:234-237): eta = 0 and eta != 0, zero and non-zero target speeds,
+    rcond = 1e-3 / 1e-1 / None, plus the author's own round trip v -> p -> v (core/LDDMM.py:809-813)."""
+    out, names = {}, []
+    for D, M, sig, lam, seed in ((2, 300, 0.25, 7.0, 501), (3, 280, 0.3, 20.0, 502), (2, 10, 2.0, 100.0, 503)):
+        g = torch.Generator().manual_seed(seed)
+        q = torch.rand(M, D, generator=g) if M > 10 else torch.randn(M, D, generator=g)
+        b = 0.3 * torch.randn(M, D, generator=g)
+        for version in ("classic", "logdet"):
+            tag = f"{D}d_M{M}_{version}"
+            names.append(tag)
+            out[f"{tag}_meta"] = np.array([D, M, sig, lam], dtype=np.float64)
+            out[f"{tag}_in_q"], out[f"{tag}_in_b"] = q.numpy(), b.numpy()
+            for prec, dt in [("ref32", torch.float32), ("gold", torch.float64)]:
+                LM = rl.LDDMMModel(sigma=sig, D=D, lambd=lam, spec=spec_of(dt), version=version, computversion="torch")
+                Q, B = q.to(dt), b.to(dt)
+                v = LM.v(Q, Q, B)
+                out[f"{tag}_{prec}_v"] = v.numpy()
+                for rc_tag, rc in (("rc3", 1e-3), ("rc1", 1e-1), ("rcNone", None)):
+                    p = LM.v2p(Q, v, rcond=rc)
+                    out[f"{tag}_{prec}_p_{rc_tag}"] = p.numpy()
+                    out[f"{tag}_{prec}_vback_{rc_tag}"] = LM.v(Q, Q, p).numpy()
+                    p0 = LM.v2p(Q, torch.zeros_like(Q), rcond=rc)          # what DiffPSR.initialize_a0 asks for
+                    out[f"{tag}_{prec}_pzero_{rc_tag}"] = p0.numpy()
+                    out[f"{tag}_{prec}_vzero_{rc_tag}"] = LM.v(Q, Q, p0).numpy()
+                # ridge solve (the reference's own dense torch form; its 'ridge_pytorch' dispatch name is broken, LDDMM.py:251)
+                rhs = v + LM.eta * LM.Kernel.GradKRed(Q, Q)
+                for a_tag, alpha in (("a2", 1e-2), ("a4", 1e-4)):
+                    K_xx = LM.Kernel.K_torch(Q, Q)
+                    pr = torch.linalg.solve(K_xx + alpha * torch.eye(M, dtype=dt), rhs)   # tools/kernel.py:234-237
+                    out[f"{tag}_{prec}_pridge_{a_tag}"] = pr.numpy()
+                # singular values of K(q,q): tells the tests how far the cut-offs sit from the nearest singular value
+                if prec == "gold":
+                    out[f"{tag}_gold_svals"] = torch.linalg.svdvals(LM.Kernel.K_torch(Q, Q)).numpy()
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "v2p.npz"), **out)
+    print("v2p.npz", len(out))
+
+
+class _fp64_defaults:
+    """Run reference code that hard-wires `defspec` (api/ICP_two_set.py builds its models without a spec argument) in
+    fp64: every module holds a reference to the SAME dict object, so its dtype entry is switched in place."""
+
+    def __enter__(self):
+        import diffICP.tools.spec as rs
+        import diffICP.core.PSR as rp
+        self.rs, self.rp = rs, rp
+        self.old = rs.defspec["dtype"]
+        rs.defspec["dtype"] = torch.float64
+        # read_point_sets type-checks bare tensors against torch.FloatTensor only (tools/in_out.py:21): wrap a bare fp64
+        # tensor the way it would wrap an fp32 one
+        self.old_read = rp.read_point_sets
+        rp.read_point_sets = lambda x: self.old_read([[x]] if isinstance(x, torch.Tensor) else x)
+
+    def __exit__(self, *a):
+        self.rs.defspec["dtype"] = self.old
+        self.rp.read_point_sets = self.old_read
+
+
+FE_TRACE = []
+
+
+def _patch_coverage():
+    from diffICP.tools.kernel import GaussKernel
+    import diffICP.core.PSR as rp
+    if not hasattr(rp.MultiPSR, "_orig_update_FE"):      # harness-side recording of every free-energy update
+        rp.MultiPSR._orig_update_FE = rp.MultiPSR.update_FE
+
+        def update_FE(self, message=None):
+            rp.MultiPSR._orig_update_FE(self, message=message)
+            FE_TRACE.append(float(self.FE))
+        rp.MultiPSR.update_FE = update_FE
+    # the torch branch of check_coverage is broken in the reference (tools/kernel.py:328); one-line fix of SURVEY App. C
+    GaussKernel.check_coverage = lambda self, X, Y, R: ((X[:, None, :] - Y[None, :, :]) ** 2).sum(-1).min(dim=1).values > (R * self.sigma) ** 2
+
+
+def gen_two_set():
+    """api.ICP_two_set of the unmodified reference (api/ICP_two_set.py:73-288): 3-D clouds, dense support, API-default
+    full logdet model, sigma optimised; 3 outer iterations.  Two cases: no outliers / optimised
+    outlier weight is NOT run (device-less zeros in log_ratio_to_proba make it CPU-only in the reference anyway, fine here)."""
+    import contextlib
+    import diffICP.api.ICP_two_set as rt
+    _patch_coverage()
+    out = {}
+    g = torch.Generator().manual_seed(611)
+    NA, NB = 400, 300
+    xA = torch.rand(NA, 3, generator=g)
+    cen = torch.rand(4, 3, generator=g)
+    amp = 0.05 * torch.randn(4, 3, generator=g)
+    xall = torch.cat((xA, torch.rand(NB, 3, generator=g)))
+    warp = torch.exp(-((xall[:, None, :] - cen[None]) ** 2).sum(-1) / (2 * 0.3 ** 2)) @ amp
+    xB = (xall + warp)[torch.randperm(NA + NB, generator=g)[:NB]] + 0.01 * torch.randn(NB, 3, generator=g)
+    out["in_xA"], out["in_xB"] = xA.numpy(), xB.contiguous().numpy()
+    for case, gmm_par, num_opt in (
+            ("dense", {"sigma": 0.1, "optimize_sigma": True, "outlier_weight": None}, {"support_LDDMM": {"scheme": "dense"}}),
+            ("decim", {"sigma": 0.1, "optimize_sigma": True, "outlier_weight": None}, {"support_LDDMM": {"scheme": "decim", "rho": 1.0}}),
+    ):
+        for prec, dt in [("ref32", torch.float32), ("gold", torch.float64)]:
+            ctx = _fp64_defaults() if dt == torch.float64 else contextlib.nullcontext()
+            with ctx:
+                FE_TRACE.clear()
+                PSR, evol = rt.ICP_two_set(xA.to(dt), xB.to(dt), dict(gmm_par),
+                                           {"type": "diffeomorphic", "lambda_LDDMM": 500.0, "sigma_LDDMM": 0.2},
+                                           numerical_options=dict(num_opt, computversion="torch"),
+                                           optim_options={"max_iterations": 3, "convergence_tolerance": 1e-3},
+                                           plotstuff=False, printstuff=False)
+            assert PSR.LMi.gradcomponent and PSR.LMi.eta == 1 / 500.0
+            out[f"{case}_{prec}_FE"] = np.array(float(PSR.FE))
+            out[f"{case}_{prec}_sigma"] = np.array(float(PSR.GMMi[0].sigma))
+            out[f"{case}_{prec}_x1"] = PSR.x1[0, 0].numpy()
+            out[f"{case}_{prec}_y"] = PSR.y[0, 0].numpy()
+            out[f"{case}_{prec}_q0"] = PSR.q0[0].numpy()
+            out[f"{case}_{prec}_a0_init"] = evol["a0"][0][0].numpy()       # what initialize_a0 / update_a0 (v2p) produced
+            out[f"{case}_{prec}_a0"] = PSR.a0[0].numpy()
+            out[f"{case}_{prec}_regloss"] = np.array(float(PSR.regloss[0]))
+            out[f"{case}_{prec}_quadloss"] = np.array(float(np.asarray(PSR.quadloss, dtype=np.float64).sum()))
+            out[f"{case}_{prec}_sigma_evol"] = np.array([float(G.sigma) for G in evol["GMMi"]])
+            out[f"{case}_{prec}_FE_trace"] = np.array(FE_TRACE)           # after every GMM_opt / Reg_opt (and set-up) update
+            for it in range(len(evol["a0"])):
+                out[f"{case}_{prec}_a0_it{it}"] = evol["a0"][it][0].numpy()
+    np.savez_compressed(os.path.join(OUT, "two_set.npz"), **out)
+    print("two_set.npz", len(out))
+
+
+def structure_sets(K, Ns, seed):
+    """K frames x 3 structures in 3-D: the three curves of examples/diffICP_full.py:44-56 lifted to 3-D (z = a slow wave
+    along the curve), sigma 0.025 / 0.04 / 0.2, each frame smoothly warped; ragged sizes.  No reference RNG involved."""
+    g = torch.Generator().manual_seed(seed)
+    C = 20
+    t = torch.linspace(0, 2 * np.pi, C + 1)[:-1]
+    mus = [torch.stack((0.5 + 0.4 * (t / 7) * t.cos(), 0.5 + 0.3 * t.sin(), 0.3 + 0.1 * t.cos()), 1),
+           torch.stack((1 + 0.4 * t.cos(), 0.5 + 0.4 * t.sin(), 0.5 + 0.2 * t.sin()), 1),
+           torch.stack((0.8 + 0.1 * (t - np.pi), -0.06 * (t - np.pi), 0.4 + 0.05 * (t - np.pi)), 1)]
+    sigs = (0.025, 0.04, 0.2)
+    frames = []
+    for k in range(K):
+        cen = torch.rand(3, 3, generator=g) * torch.tensor([1.5, 1.0, 0.8])
+        amp = 0.05 * torch.randn(3, 3, generator=g)
+        fr = []
+        for s in range(3):
+            n = Ns + 7 * k + 3 * s
+            x = mus[s][torch.randint(0, C, (n,), generator=g)] + sigs[s] * torch.randn(n, 3, generator=g)
+            w = torch.exp(-((x[:, None, :] - cen[None]) ** 2).sum(-1) / (2 * 0.3 ** 2))
+            fr.append((x + w @ amp).contiguous())
+        frames.append(fr)
+    return frames, mus, sigs
+
+
+def gen_atlas_s3():
+    """api.ICP_atlas with S = 3 structures (core/PSR.py:242-271 per-structure GMM loop, :498-516 per-structure sigma in
+    the data loss), 3 frames, 3-D, decimated support (the reference's grid is 2-D only), hybrid model, Euler."""
+    import diffICP.core.GMM as rg
+    import diffICP.api.ICP_atlas as ra
+    _patch_coverage()
+    out = {}
+    frames, mus, sigs = structure_sets(3, 90, 712)
+    g = torch.Generator().manual_seed(9)
+    Cs = (6, 5, 4)
+    mu_init = []
+    for s in range(3):
+        alls = torch.cat([fr[s] for fr in frames])
+        mu_init.append(alls[torch.randperm(len(alls), generator=g)[:Cs[s]]].clone())
+        out[f"in_mu{s}"] = mu_init[s].numpy()
+        out[f"in_sigma{s}"] = np.array(2.0 * sigs[s] + 0.05)
+        for k in range(3):
+            out[f"in_x{k}_{s}"] = frames[k][s].numpy()
+    for prec, dt in [("ref32", torch.float32), ("gold", torch.float64)]:
+        sp = spec_of(dt)
+        GM = [rg.GaussianMixtureUnif(mu_init[s].to(dt), sigma=2.0 * sigs[s] + 0.05, spec=sp, computversion="torch") for s in range(3)]
+        FE_TRACE.clear()
+        PSR, evol = ra.ICP_atlas([[x.to(dt) for x in fr] for fr in frames],
+                                 GMM_parameters={"init_components": GM, "optimize_weights": True},
+                                 registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.3},
+                                 numerical_options={"computversion": "torch", "compspec": sp, "dataspec": sp,
+                                                    "support_LDDMM": {"scheme": "decim", "rho": 1.0}},
+                                 optim_options={"max_iterations": 3, "max_repeat_GMM": 10, "convergence_tolerance": 1e-3},
+                                 printstuff=False)
+        out[f"{prec}_FE"] = np.array(float(PSR.FE))
+        out[f"{prec}_Cfe"] = np.array([float(c) for c in PSR.Cfe])
+        out[f"{prec}_FE_trace"] = np.array(FE_TRACE)
+        for it in range(len(evol["a0"])):
+            for k in range(3):
+                out[f"{prec}_a0_it{it}_{k}"] = evol["a0"][it][k].numpy()
+        out[f"{prec}_quadloss"] = np.asarray(PSR.quadloss, dtype=np.float64)
+        out[f"{prec}_regloss"] = np.array([float(r) for r in PSR.regloss])
+        for s in range(3):
+            out[f"{prec}_sigma{s}"] = np.array(float(PSR.GMMi[s].sigma))
+            out[f"{prec}_mu{s}"] = PSR.GMMi[s].mu.numpy()
+            out[f"{prec}_w{s}"] = PSR.GMMi[s].w.numpy()
+            for k in range(3):
+                out[f"{prec}_x1_{k}_{s}"] = PSR.x1[k, s].numpy()
+        for k in range(3):
+            out[f"{prec}_q0_{k}"] = PSR.q0[k].numpy()
+    np.savez_compressed(os.path.join(OUT, "atlas_s3.npz"), **out)
+    print("atlas_s3.npz", len(out))
+
+
+class _keops_ordering:
+    """Run the reference's own outer loops with the KeOps ORDERING of the M step (core/GMM.py:432-458, 462-496: sigma'
+    from distances to the NEW mu, Gaussian normalisation from the NEW sigma).  pykeops is absent, so EM_step_keops cannot
+    execute; the class attribute EM_step_torch -- the function every GMM object binds here (core/GMM.py:126-144) -- is
+    swapped for the oracle's restatement of that ordering (oracle/gmm.py, variant="keops"), acting on the reference
+    object's own state.  Everything else (EM_optimization, PSR loops, L-BFGS, LDDMM) stays the reference's code.
+    What this pins: the product's DEFAULT path (computversion="keops") through the reference's loops."""
+
+    def __enter__(self):
+        import diffICP.core.GMM as rg
+        sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+        from oracle.gmm import GMMOracle
+        self.rg, self.old = rg, rg.GaussianMixtureUnif.EM_step_torch
+
+        def em_step(gmm, X, skip_M=False):
+            O = GMMOracle(gmm.mu, gmm.sigma, w=gmm.w, outliers=gmm.outliers, to_optimize=gmm.to_optimize,
+                          ensure_continuum=gmm.ensure_continuum)
+            Y, Cfe, FE = O.em_step(X.detach(), skip_M=skip_M, variant="keops")
+            gmm.mu, gmm.w, gmm.sigma = O.mu, O.w, O.sigma
+            if gmm.outliers is not None:
+                gmm.outliers.update(O.outliers)
+            return Y, Cfe, FE
+        rg.GaussianMixtureUnif.EM_step_torch = em_step
+
+    def __exit__(self, *a):
+        self.rg.GaussianMixtureUnif.EM_step_torch = self.old
+
+
+def gen_keops_ordering():
+    """The end-to-end fixtures again (two-set dense, 2-D atlas of gen_psr, S = 3 atlas) under the KeOps M-step ordering."""
+    import contextlib
+    import diffICP.core.GMM as rg
+    import diffICP.api.ICP_atlas as ra
+    import diffICP.api.ICP_two_set as rt
+    _patch_coverage()
+    out = {}
+    two = np.load(os.path.join(OUT, "two_set.npz"))
+    s3 = np.load(os.path.join(OUT, "atlas_s3.npz"))
+    psr = np.load(os.path.join(OUT, "psr.npz"))
+    with _keops_ordering():
+        for prec, dt in [("ref32", torch.float32), ("gold", torch.float64)]:
+            sp = spec_of(dt)
+            # ---- two-set, dense support, API-default logdet model --------------------------------------------------
+            ctx = _fp64_defaults() if dt == torch.float64 else contextlib.nullcontext()
+            with ctx:
+                FE_TRACE.clear()
+                PSR, evol = rt.ICP_two_set(torch.from_numpy(two["in_xA"]).to(dt), torch.from_numpy(two["in_xB"]).to(dt),
+                                           {"sigma": 0.1, "optimize_sigma": True, "outlier_weight": None},
+                                           {"type": "diffeomorphic", "lambda_LDDMM": 500.0, "sigma_LDDMM": 0.2},
+                                           numerical_options={"support_LDDMM": {"scheme": "dense"}, "computversion": "torch"},
+                                           optim_options={"max_iterations": 3, "convergence_tolerance": 1e-3},
+                                           plotstuff=False, printstuff=False)
+            out[f"two_{prec}_FE_trace"] = np.array(FE_TRACE)
+            out[f"two_{prec}_sigma"] = np.array(float(PSR.GMMi[0].sigma))
+            out[f"two_{prec}_x1"] = PSR.x1[0, 0].numpy()
+            out[f"two_{prec}_a0"] = PSR.a0[0].numpy()
+            # ---- 2-D atlas of gen_psr (3 frames, C = 6, hybrid, Euler, grid) ------------------------------------------
+            sets = [torch.from_numpy(psr[f"atlas_in_x{k}"]) for k in range(3)]
+            G = rg.GaussianMixtureUnif(torch.from_numpy(psr["atlas_in_mu"]).to(dt), sigma=0.25 * float(torch.cat(sets).std()),
+                                       spec=sp, computversion="torch")
+            FE_TRACE.clear()
+            PSR, evol = ra.ICP_atlas([[x.to(dt)] for x in sets],
+                                     GMM_parameters={"init_components": [G], "optimize_weights": True},
+                                     registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.2},
+                                     numerical_options={"computversion": "torch", "compspec": sp, "dataspec": sp,
+                                                        "support_LDDMM": {"scheme": "grid", "rho": 1.0}},
+                                     optim_options={"max_iterations": 3, "max_repeat_GMM": 10, "convergence_tolerance": 1e-3},
+                                     printstuff=False)
+            out[f"atlas_{prec}_FE_trace"] = np.array(FE_TRACE)
+            out[f"atlas_{prec}_sigma"] = np.array(float(PSR.GMMi[0].sigma))
+            out[f"atlas_{prec}_mu"], out[f"atlas_{prec}_w"] = PSR.GMMi[0].mu.numpy(), PSR.GMMi[0].w.numpy()
+            for k in range(3):
+                out[f"atlas_{prec}_x1_{k}"] = PSR.x1[k, 0].numpy()
+            # ---- S = 3 atlas (3-D, decimated support) ----------------------------------------------------------------------
+            frames = [[torch.from_numpy(s3[f"in_x{k}_{s}"]).to(dt) for s in range(3)] for k in range(3)]
+            GM = [rg.GaussianMixtureUnif(torch.from_numpy(s3[f"in_mu{s}"]).to(dt), sigma=float(s3[f"in_sigma{s}"]), spec=sp,
+                                         computversion="torch") for s in range(3)]
+            FE_TRACE.clear()
+            PSR, evol = ra.ICP_atlas(frames, GMM_parameters={"init_components": GM, "optimize_weights": True},
+                                     registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.3},
+                                     numerical_options={"computversion": "torch", "compspec": sp, "dataspec": sp,
+                                                        "support_LDDMM": {"scheme": "decim", "rho": 1.0}},
+                                     optim_options={"max_iterations": 3, "max_repeat_GMM": 10, "convergence_tolerance": 1e-3},
+                                     printstuff=False)
+            out[f"s3_{prec}_FE_trace"] = np.array(FE_TRACE)
+            for s in range(3):
+                out[f"s3_{prec}_sigma{s}"] = np.array(float(PSR.GMMi[s].sigma))
+                out[f"s3_{prec}_mu{s}"] = PSR.GMMi[s].mu.numpy()
+                for k in range(3):
+                    out[f"s3_{prec}_x1_{k}_{s}"] = PSR.x1[k, s].numpy()
+    np.savez_compressed(os.path.join(OUT, "keops_order.npz"), **out)
+    print("keops_order.npz", len(out))
+
+
 def reference_function(relpath, name, namespace):
     """Compile ONE function of a reference module from its source text (for modules that cannot be imported here because
     they import pykeops at the top) and return it; nothing of the source is written anywhere."""
@@ -360,11 +627,18 @@ def gen_pointsets(rk):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     rk, rl, rg = load_reference()
-    if len(sys.argv) > 1 and sys.argv[1] == "pointsets":
-        gen_pointsets(rk)
+    if len(sys.argv) > 1:          # regenerate selected fixtures only
+        for what in sys.argv[1:]:
+            {"pointsets": lambda: gen_pointsets(rk), "v2p": lambda: gen_v2p(rl), "two_set": gen_two_set,
+             "atlas_s3": gen_atlas_s3, "kernels": lambda: gen_kernels(rk), "lddmm": lambda: gen_lddmm(rl),
+             "gmm": lambda: gen_gmm(rg), "psr": gen_psr, "keops_order": gen_keops_ordering}[what]()
         sys.exit(0)
     gen_kernels(rk)
     gen_lddmm(rl)
     gen_gmm(rg)
     gen_psr()
     gen_pointsets(rk)
+    gen_v2p(rl)
+    gen_two_set()
+    gen_atlas_s3()
+    gen_keops_ordering()
