@@ -18,7 +18,7 @@ evaluation or in one adjoint evaluation: pairs/step = M*C + 2 * nt * M^2 (implem
 visits each such pair 2-7 times per evaluation with separate reductions, this build once).
 
     python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
-    python bench.py --impl reference ...                      CPU arm: the oracle port of the reference's algorithm
+    python bench.py --impl reference ...                      CPU arm: the unmodified reference package (baseline/_ref)
 
 Prints ONE JSON line (rank 0).
 """
@@ -107,44 +107,89 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle port of its torch twin) on a bounded row sample of the same workload
-def cpu_sample_seconds(variant, m_rows, xA, p0, threads):
-    """One right-hand-side evaluation + its reverse-mode gradient for `m_rows` rows against all M columns, done the
-    way the reference does it: separate dense reductions (tools/kernel.py:186-203) + torch autograd."""
-    from oracle.kernels import GaussOracle
-    torch.set_num_threads(threads)
-    K = GaussOracle(SIGMA_LDDMM, DIM, chunk=256)
-    idx = torch.arange(0, xA.shape[0], max(1, xA.shape[0] // m_rows))[:m_rows]
-    q = xA.clone().requires_grad_(True)
+# CPU arm: the REFERENCE ITSELF (unmodified package from baseline/_ref or /root/reference through oracle/ref_loader.py, torch
+# twin because pykeops is absent) on a bounded sample of the same workload; the oracle port only if the package is missing
+CPU_SAMPLE_M = 768           # the step at M = N = 768 instead of 20 000: ~2-5 s of CPU work per step on 8-16 cores
+
+
+def load_reference_or_none():
+    try:
+        from oracle import ref_loader
+        if ref_loader.find_root() is None:
+            return None
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):          # the package prints on import
+            return ref_loader.load_reference()
+    except Exception as e:          # noqa: BLE001 -- reported in the JSON line
+        print(f"[bench] reference package could not be loaded: {e!r}", file=sys.stderr)
+        return None
+
+
+def reference_closure(ref, version, scheme, nt, sigma, lam, q, p0, x, y, inv2s2):
+    """One L-BFGS closure evaluation exactly as the reference runs it (tools/optim.py:34-47 calling the `lossfunc` of
+    core/LDDMM.py:363-371): Shoot + trajloss + quadratic data loss (core/PSR.py:498-516), then L.backward() through its
+    own integrator loop and torch-twin reductions."""
+    LM = ref.LDDMM.LDDMMModel(sigma=sigma, D=q.shape[1], lambd=lam, spec={"device": "cpu", "dtype": torch.float32},
+                              version=version, computversion="torch", scheme=scheme, nt=nt)
     p = p0.clone().requires_grad_(True)
-    t0 = time.perf_counter()
-    qs, ps = q[idx], p[idx]
-    eta = 1.0 / LAMBDA_LDDMM if variant == "logdet" else 0.0
-    vq = K.KRed(qs, q, p)
-    Gq = K.GenDKRed(qs, q, p, ps)
-    L = (vq ** 2).sum() + (Gq ** 2).sum()
-    if variant in ("hybrid", "logdet"):
-        L = L + (ps * K.GradKRed(qs, q)).sum()
-    if variant == "logdet":
-        vq2 = K.GradKRed(qs, q)
-        Gq2 = K.HessKRed(qs, q, p, ps)
-        Gq3 = K.GradLapKRed(qs, q)
-        L = L + eta * (vq2 ** 2).sum() + eta * (Gq2 ** 2).sum() + eta ** 2 * (Gq3 ** 2).sum() + eta * K.LapKRed(qs, q).sum()
+    shoot = LM.Shoot(q, p, x)
+    moved = shoot[-1][0] if x is None else shoot[-1][3]
+    L = LM.trajloss(shoot) + ((moved - y) ** 2).sum() * inv2s2
     L.backward()
-    dt_rhs = time.perf_counter() - t0
-    # E step of the same rows against all M centroids (dense (m,M) block, core/GMM.py:263-317)
+    return float(L), p.grad
+
+
+def cpu_step_reference(ref, variant, xA, y, p0, m, threads):
+    """The bench step (one EM step + one closure evaluation) of the reference at M = N = m: every m-th point of the same
+    clouds.  Returns (seconds, pairs)."""
+    torch.set_num_threads(threads)
+    idx = torch.arange(0, xA.shape[0], max(1, xA.shape[0] // m))[:m]
+    q, ys, ps = xA[idx].contiguous(), y[idx].contiguous(), p0[idx].contiguous()
     t0 = time.perf_counter()
-    with torch.no_grad():
-        d2 = ((xA[idx][:, None, :] - xA[None, :, :]) ** 2).sum(-1)
-        t = -d2 / (2 * SIGMA_GMM ** 2)
-        T = t.logsumexp(1)
-        gam = (t - T[:, None]).exp()
-        Y = gam @ xA
-        _ = (gam * d2).sum() + (gam * (t - T[:, None])).sum() + (Y ** 2).sum()
-    dt_em = time.perf_counter() - t0
-    # same workload mix as the GPU arm: a step has ONE E step per nt (RHS + adjoint) evaluations, so the sampled E step
-    # enters with weight 1/nt in both the time and the pair count
-    return dt_rhs + dt_em / NT, len(idx) * xA.shape[0] * (2.0 + 1.0 / NT)
+    G = ref.GMM.GaussianMixtureUnif(ys, sigma=SIGMA_GMM, spec={"device": "cpu", "dtype": torch.float32}, computversion="torch")
+    G.to_optimize = {"mu": False, "sigma": True, "w": False, "eta0": False}
+    Y, Cfe, FE = G.EM_step(q)                                    # core/GMM.py:236-325 (dense (m,m) block)
+    reference_closure(ref, variant, "Euler", NT, SIGMA_LDDMM, LAMBDA_LDDMM, q, ps, None, Y, 1.0 / (2 * SIGMA_GMM ** 2))
+    return time.perf_counter() - t0, pairs_per_step(len(idx))
+
+
+def cpu_step_port(variant, xA, y, p0, m, threads):
+    """Same step through the oracle port (only when the reference package is not available on this machine)."""
+    from oracle.gmm import GMMOracle
+    from oracle.lddmm import LDDMMOracle
+    torch.set_num_threads(threads)
+    idx = torch.arange(0, xA.shape[0], max(1, xA.shape[0] // m))[:m]
+    q, ys, ps = xA[idx].contiguous(), y[idx].contiguous(), p0[idx].contiguous()
+    t0 = time.perf_counter()
+    O = GMMOracle(ys, SIGMA_GMM, to_optimize={"mu": False, "sigma": True, "w": False, "eta0": False})
+    Y, _, _ = O.em_step(q, variant="torch")
+    OR = LDDMMOracle(sigma=SIGMA_LDDMM, D=DIM, lambd=LAMBDA_LDDMM, version=variant, scheme="Euler", nt=NT)
+    p = ps.clone().requires_grad_(True)
+    L, _ = OR.loss(q, p, None, Y, 1.0 / (2 * SIGMA_GMM ** 2))
+    L.backward()
+    return time.perf_counter() - t0, pairs_per_step(len(idx))
+
+
+def cpu_arm(variant, xA, y, p0, threads, steps=None, warmup=1, budget_s=None):
+    """Runs the CPU arm: `steps` timed steps (or as many as fit in budget_s seconds, at least 2).  Returns the
+    cpu_baseline dict and (total seconds, steps done)."""
+    ref = load_reference_or_none()
+    step = (lambda: cpu_step_reference(ref, variant, xA, y, p0, CPU_SAMPLE_M, threads)) if ref is not None else \
+        (lambda: cpu_step_port(variant, xA, y, p0, CPU_SAMPLE_M, threads))
+    for _ in range(warmup):
+        step()
+    tot_t, tot_pairs, n = 0.0, 0.0, 0
+    t_start = time.perf_counter()
+    while (steps is not None and n < steps) or (steps is None and (n < 2 or time.perf_counter() - t_start < budget_s)):
+        dt, npairs = step()
+        tot_t, tot_pairs, n = tot_t + dt, tot_pairs + npairs, n + 1
+    kind = "reference" if ref is not None else "port"
+    what = ("the unmodified reference package (diffICP.core.GMM.EM_step + LDDMMModel.Shoot / trajloss + backward(), torch twin: "
+            "pykeops absent)" if ref is not None else "the oracle port of the reference's algorithm (reference package not found)")
+    sample = (f"the bench step (1 EM step + 1 closure evaluation: shoot Euler nt={NT}, {variant} model, loss, autograd backward) at "
+              f"M=N={CPU_SAMPLE_M} (every {M_POINTS // CPU_SAMPLE_M}-th point of the same 20k clouds; dense 20k x 20k does not fit the "
+              f"reference's dense torch path: 4.8 GB per (M,N,D) temporary, tools/kernel.py:104), {n} steps, {what}")
+    return {"value": tot_pairs / tot_t, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}, tot_t, n
 
 
 def run_reference(args, rank, world):
@@ -152,25 +197,14 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     xA, y, p0 = make_workload(1234)
-    m_rows = 256
-    cpu_sample_seconds(args.variant, 64, xA, p0, threads)            # warm-up of the thread pool
-    for _ in range(max(0, args.warmup - 1)):
-        cpu_sample_seconds(args.variant, m_rows, xA, p0, threads)
-    tot_t, tot_pairs = 0.0, 0.0
-    for _ in range(args.steps):
-        dt, npairs = cpu_sample_seconds(args.variant, m_rows, xA, p0, threads)
-        tot_t += dt
-        tot_pairs += npairs
-    value = tot_pairs / tot_t
-    sample = (f"{m_rows} of {M_POINTS} rows x {M_POINTS} columns per step: one RHS evaluation + autograd backward, plus "
-              f"1/{NT} of one dense E step (the mix of a full step)")
+    cpu, tot_t, n = cpu_arm(args.variant, xA, y, p0, threads, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / n, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.variant),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -178,7 +212,9 @@ def run_reference(args, rank, world):
 def workload_config(variant):
     return {"workload": "two_set_3d_20k_dense: LBFGS closure evaluation (shoot + loss + adjoint), "
                         f"M=N={M_POINTS}, D={DIM}, Euler nt={NT}, sigma_LDDMM={SIGMA_LDDMM}, lambda={LAMBDA_LDDMM}",
-            "model_variant": variant, "pairs_per_step": pairs_per_step(M_POINTS), "gmm": f"C={M_POINTS} centroids frozen, sigma optimised",
+            "model_variant": variant, "pairs_per_step": pairs_per_step(M_POINTS),
+            "pairs_note": "ordered (i,j) pairs of the algorithm; the adjoint evaluates each UNORDERED pair once (symmetric engine), so the "
+                          f"physical pair evaluations per step are M*C + nt*M^2 + nt*M^2/2 = {float(M_POINTS) ** 2 * (1 + 1.5 * NT):.3g}", "gmm": f"C={M_POINTS} centroids frozen, sigma optimised",
             "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)"}
 
 
@@ -298,6 +334,25 @@ def run_b200(args, rank, world, local_rank):
                                                                    ("frames", "scaling", "gmm_opt_ms", "reg_opt_ms",
                                                                     "iteration_ms_steady", "FE", "sigma")}
 
+    # ---- the configuration BASELINE.json names for 8 GPUs (configs[3], "diffICP_full": 3 structures, 3-D, 50k points per
+    # frame, frames sharded k mod N), at a FIXED total of C4_FRAMES frames whatever N: strong scaling of compute-bound work
+    if groupwise is not None and not args.no_c4:
+        from groupwise_c4 import run_c4
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):
+            c4 = run_c4(rank, world, dev, GMM.comm, n_frames=C4_FRAMES, n_points=50000, iters=2)
+        if c4 is not None:
+            fe_rel = abs(c4["FE"] - C4_FE_1GPU) / abs(C4_FE_1GPU) if C4_FE_1GPU else None
+            groupwise["c4_shaped"] = {
+                "config": f"configs[3]-shaped: {C4_FRAMES} frames x 3 structures x 50k points, 3-D, {c4['support_points']} support points, "
+                          f"{c4['model']}; the SAME {C4_FRAMES} frames at every N (frames k mod N) = strong scaling",
+                "n_gpus": world, "frames": C4_FRAMES, "iteration_ms": c4["iteration_ms_steady"],
+                "gmm_opt_ms": c4["gmm_opt_ms"][-1], "reg_opt_ms": c4["reg_opt_ms"][-1],
+                "first_iteration_ms": c4["gmm_opt_ms"][0] + c4["reg_opt_ms"][0],
+                "FE": c4["FE"], "FE_1gpu_reference": C4_FE_1GPU, "FE_rel_diff_vs_1gpu": fe_rel,
+                "FE_matches_1gpu_to_1e-5": None if fe_rel is None else bool(fe_rel < 1e-5),
+                "sigma": c4["sigma"], "timing": "host wall clock around synchronised GMM_opt + Reg_opt, max over ranks, 2nd iteration"}
+
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e_total, wall_e2e * 1e3], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -318,20 +373,11 @@ def run_b200(args, rank, world, local_rank):
     threads = os.cpu_count() or 1
     cpu = None
     if not args.no_cpu_baseline:
-        cpu_sample_seconds(args.variant, 64, xA, p0, threads)
-        tt, pp_ = 0.0, 0.0
-        t_start = time.perf_counter()
-        while time.perf_counter() - t_start < 10.0:
-            dt, npairs = cpu_sample_seconds(args.variant, 256, xA, p0, threads)
-            tt += dt
-            pp_ += npairs
-        cpu = {"value": pp_ / tt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"256 of {M} rows x {M} columns per evaluation (RHS + autograd backward + 1/{NT} E step), repeated for 10 s"}
+        cpu, _, _ = cpu_arm(args.variant, xA, y, p0, threads, steps=None, warmup=1, budget_s=12.0)
 
     if groupwise is not None and cpu is not None:
         # CPU reference for the groupwise iteration: ONE closure evaluation of one frame (the reference's algorithm: separate
         # reductions + autograd through the Euler loop), scaled by the measured ~23.5 closures per frame
-        from oracle.lddmm import LDDMMOracle
         from groupwise_iteration import spiral_frames
         torch.set_num_threads(threads)
         fr = spiral_frames(1, groupwise["points_per_frame"])[0]
@@ -339,16 +385,24 @@ def run_b200(args, rank, world, local_rank):
         side = int(round(nq ** 0.5))
         gx = torch.linspace(float(fr[:, 0].min()), float(fr[:, 0].max()), side)
         gy = torch.linspace(float(fr[:, 1].min()), float(fr[:, 1].max()), max(1, nq // side))
-        qg = torch.stack(torch.meshgrid(gx, gy, indexing="ij"), -1).reshape(-1, 2)
-        OR = LDDMMOracle(sigma=0.2, D=2, lambd=500.0, version="hybrid", scheme="Euler", nt=10)
-        pc = (1e-3 * torch.randn(qg.shape)).requires_grad_(True)
+        qg = torch.stack(torch.meshgrid(gx, gy, indexing="ij"), -1).reshape(-1, 2).contiguous()
+        pc = 1e-3 * torch.randn(qg.shape)
+        ref = load_reference_or_none()
         t0 = time.perf_counter()
-        Lc, _ = OR.loss(qg, pc, fr, fr + 0.01, 50.0)
-        Lc.backward()
+        if ref is not None:
+            reference_closure(ref, "hybrid", "Euler", 10, 0.2, 500.0, qg, pc, fr, fr + 0.01, 50.0)
+            how = "the reference package itself (torch twin)"
+        else:
+            from oracle.lddmm import LDDMMOracle
+            OR = LDDMMOracle(sigma=0.2, D=2, lambd=500.0, version="hybrid", scheme="Euler", nt=10)
+            pc.requires_grad_(True)
+            Lc, _ = OR.loss(qg, pc, fr, fr + 0.01, 50.0)
+            Lc.backward()
+            how = "oracle port"
         tc = time.perf_counter() - t0
         groupwise["cpu_reference_estimate_ms"] = 1e3 * tc * 23.5 * groupwise["frames"]
-        groupwise["cpu_reference_note"] = (f"oracle port, {threads} threads: one closure evaluation of one frame took "
-                                           f"{1e3 * tc:.0f} ms; x 23.5 closures/frame x {groupwise['frames']} frames (EM excluded)")
+        groupwise["cpu_reference_note"] = (f"{how}, {threads} threads: one closure evaluation of one frame took "
+                                           f"{1e3 * tc:.0f} ms; x 23.5 closures/frame (SURVEY.md 3.3) x {groupwise['frames']} frames (EM excluded)")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -413,7 +467,16 @@ def kernel_roofline(args, LM, q, p, dev, ops):
     fp_rate_fwd = alg["fwd_fp32"] * pairs / t_fwd
     frac_fwd = max(fp_rate_fwd / peaks["ffma"], pairs / t_fwd / peaks["mufu_ex2"])
     em = em_roofline(dev, timeit, peaks)
+    sm_mhz = 1965.0
+    try:
+        sm_mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+    except Exception:
+        pass
+    lanes_clock = sms * 128 * sm_mhz * 1e6                     # FP32 lane-operations / s at the maximum SM clock
     return {
+        "frac_lanes_clock": fp_rate_adj / lanes_clock,
+        "lanes_clock_note": f"hardware-theoretical denominator: {sms} SMs x 128 FP32 lanes x {sm_mhz:.0f} MHz (MEASURED_PEAKS.json "
+                            "sm_max_mhz) = %.3g lane-ops/s; `frac` uses the live FFMA probe instead" % lanes_clock,
         "bound": "fp32_pipe",
         "kernel": ("sym_pair_kernel<AdjQQ*> (dicp_rhs_adjoint, symmetric engine)" if symmetric
                    else "pair_kernel_p<AdjQQ*> (dicp_rhs_adjoint)"),
@@ -425,8 +488,11 @@ def kernel_roofline(args, LM, q, p, dev, ops):
                 "evaluates every UNORDERED pair once (symmetric engine), its per-ordered-pair count is half the unordered "
                 "one; peak = FFMA issue rate measured live by dicp_pipe_probe (x2 flop), of measured; frac = binding-pipe "
                 "utilisation",
-        "adjoint": {"s_per_launch": t_adj, "pairs_per_s": pairs / t_adj, "fp32_per_pair": alg["adj_fp32"], "frac": frac_adj},
-        "forward": {"s_per_launch": t_fwd, "pairs_per_s": pairs / t_fwd, "fp32_per_pair": alg["fwd_fp32"], "frac": frac_fwd},
+        "adjoint": {"s_per_launch": t_adj, "pairs_per_s": pairs / t_adj, "fp32_per_pair": alg["adj_fp32"], "frac": frac_adj,
+                    "frac_lanes_clock": fp_rate_adj / lanes_clock,
+                    "physical_pair_evaluations_per_s": (0.5 if symmetric else 1.0) * pairs / t_adj},
+        "forward": {"s_per_launch": t_fwd, "pairs_per_s": pairs / t_fwd, "fp32_per_pair": alg["fwd_fp32"], "frac": frac_fwd,
+                    "frac_lanes_clock": fp_rate_fwd / lanes_clock},
         "measured_peaks": {"ffma_per_s": peaks["ffma"], "mufu_ex2_per_s": peaks["mufu_ex2"], "sms": sms},
         "em_step": em,
     }
@@ -497,6 +563,11 @@ def em_roofline(dev, timeit, peaks):
 
 # DRAM bytes per launch of the adjoint kernel at 20k x 20k (one ncu --set full capture per variant, profiles/):
 # dram__bytes_read.sum + dram__bytes_write.sum; the row / column partials of the symmetric engine (~40 MB) stay in L2
+# configs[3]-shaped strong-scaling entry: total frames (divisible by 8) and the free energy the 1-GPU run reaches after its
+# 2 iterations (deterministic kernels, seeded synthetic frames): every N must reproduce it to 1e-5
+C4_FRAMES = 64
+C4_FE_1GPU = None
+
 NCU_DRAM_BYTES = {"classic": None, "hybrid": None, "logdet": 1990144}
 
 # algorithmic FP32 instruction counts per ORDERED pair, D = 3 (hand count of the formulas in csrc/ops_rhs.cuh).
@@ -520,6 +591,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-groupwise", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the configs[3]-shaped strong-scaling entry (~25 s on one GPU)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -33,9 +33,9 @@ SIGNATURES = {
     "dicp_launch_count": (ctypes.c_ulonglong, []),
     "dicp_pair_workspace_bytes": (_sz, [_i64, _i64]),
     "dicp_ksum": (_int, [_int, _u, _f, _vp, _i64, _vp, _i64, _vp, _vp, _vp] + [_vp] * 11 + [_vp, _sz, _vp]),
-    "dicp_rhs_forward": (_int, [_int, _int, _f, _f, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dicp_rhs_forward": (_int, [_int, _int, _f, _f, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _int]),
     "dicp_rhs_adjoint": (_int, [_int, _int, _f, _f, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                _vp, _sz, _vp]),
+                                _vp, _sz, _vp, _int]),
     "dicp_em_rowpass": (_int, [_int, _int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dicp_em_colstats": (_int, [_int, _f, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "dicp_em_mstep": (_int, [_int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),

@@ -84,8 +84,19 @@ class GaussianMixtureUnif(Module):
         return self
 
     def set_vol0(self, X: torch.Tensor):
+        """Reference volume of the outlier distribution = bounding box of the data points (reference: core/GMM.py:163-172).
+        With `comm` (multi-GPU): the bounding box of the points of ALL ranks, so that every rank uses the same volume as the
+        single-process run (a rank without points contributes nothing)."""
         if self.outliers is not None:
-            self.outliers["vol0"] = (X.max(dim=0)[0] - X.min(dim=0)[0]).prod().item()
+            if self.comm is None:
+                self.outliers["vol0"] = (X.max(dim=0)[0] - X.min(dim=0)[0]).prod().item()
+            else:
+                if X.shape[0] > 0:
+                    both = torch.cat((-X.min(dim=0)[0], X.max(dim=0)[0])).to(**self.spec)
+                else:
+                    both = torch.full((2 * self.D,), -float("inf"), **self.spec)
+                both = self.comm.max(both)
+                self.outliers["vol0"] = (both[self.D:] + both[:self.D]).prod().item()
         return self
 
     def __str__(self):

@@ -131,6 +131,12 @@ class LDDMMModel:
         """d/dt (q, p, cost[, x])   (reference: core/LDDMM.py:176-227). Fused evaluation, forward only:
         gradients of the shooting path are produced by ``Shoot``'s adjoint."""
         spec = getspec(q, p, cost, x)
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (q, p, cost, x)):
+            # the reference's ODE is differentiable by autograd (core/LDDMM.py:176-227); here the fused evaluation is forward
+            # only and gradients of a shooting path come from Shoot's hand-written adjoint -- refuse to return silently
+            # non-differentiable outputs (INTEGRATION.md, deviations)
+            raise RuntimeError("LDDMMModel.ODE is forward-only in diff_icp_b200: differentiate through LDDMMModel.Shoot "
+                               "(discrete adjoint), or call ODE under torch.no_grad() / on detached tensors")
         if self.withlogdet and self.gradcomponent and self.try_trajcost_optim and x is None:
             vq = self.v(q, q, p)
             Gq = self.Kernel.GenDKRed(q, q, p, p) - self.eta * self.Kernel.HessKRed(q, q, p, p) \

@@ -67,6 +67,8 @@ class MultiPSR:
             raise ValueError("Spec (dtype+device) error : GMM 'spec' and multiPSR 'compspec' attributes should be the same")
         for gmm in self.GMMi:
             gmm.comm = comm
+        if comm is not None:
+            self._broadcast_GMMs()
 
         # full EM free energy  F = sum_{k,s} quadloss[k,s] + sum_k regloss[k] + sum_s Cfe[s]   (core/PSR.py:114-121)
         self.Cfe = [None] * self.S
@@ -75,6 +77,27 @@ class MultiPSR:
         self.FE = None
         self.update_GMM_targets()
         self.shoot = [None] * self.K
+
+    def _broadcast_GMMs(self):
+        """Multi-GPU: the merged column statistics are centred on mu_old (mu' = mu_old + B/S0), which is only valid if every
+        rank holds bit-identical GMM parameters.  Initial models built from a rank's own frame (init_components = ("set", k)
+        or {"set", "C"}) or from random centroids differ per rank: rank 0's parameters are made everyone's."""
+        for gmm in self.GMMi:
+            cc = torch.tensor([float(gmm.C), -float(gmm.C)], dtype=torch.float64, device=gmm.mu.device)
+            cc = self.comm.max(cc)
+            if cc[0] != -cc[1]:
+                raise ValueError("multi-GPU mode: every rank must build its initial GMM with the same number of components "
+                                 f"(this rank: {gmm.C}, over ranks: {int(-cc[1])}..{int(cc[0])}); pass an explicit model list")
+            head = torch.tensor([float(gmm.sigma), float(gmm.outliers["eta0"]) if gmm.outliers is not None else 0.0,
+                                 float(gmm.outliers["vol0"]) if gmm.outliers is not None and gmm.outliers["vol0"] is not None
+                                 else float("nan")], dtype=torch.float64, device=gmm.mu.device)
+            head = self.comm.broadcast(head)
+            gmm.mu = self.comm.broadcast(gmm.mu.contiguous())
+            gmm.w = self.comm.broadcast(gmm.w.contiguous())
+            gmm.sigma = float(head[0])
+            if gmm.outliers is not None:
+                gmm.outliers["eta0"] = float(head[1])
+                gmm.outliers["vol0"] = None if bool(torch.isnan(head[2])) else float(head[2])
 
     def __setstate__(self, state):
         self.__dict__.update(state)

@@ -1,4 +1,5 @@
 // extern "C" entry points of libdicp_b200.so (see include/dicp_b200.h).
+#include <atomic>
 #include "../../include/dicp_b200.h"
 #include "dispatch.cuh"
 #include <type_traits>
@@ -47,19 +48,22 @@ __global__ void quad_loss_kernel(const float* __restrict__ x, const float* __res
 }
 
 // symmetric engine switch: default on; DICP_SYM=0 in the environment or dicp_sym_mode(0) disable it (A/B measurements, tests)
-inline int& sym_mode_ref() {
-    static int mode = [] {
+// (process-wide DEFAULT only: dicp_rhs_forward / dicp_rhs_adjoint take the engine as a per-call argument)
+inline std::atomic<int>& sym_mode_ref() {
+    static std::atomic<int> mode([] {
         const char* e = getenv("DICP_SYM");
         return e ? atoi(e) : 1;
-    }();
+    }());
     return mode;
 }
-inline int sym_mode() { return sym_mode_ref(); }
+inline int sym_mode() { return sym_mode_ref().load(std::memory_order_relaxed); }
 
 struct DeviceExec {
     void* ws;
     size_t wsb;
     cudaStream_t st;
+    int engine = -1;          // DICP_ENGINE_*: -1 = the process-wide default
+    int sym_mode() const { return engine >= 0 ? engine : ::sym_mode(); }
     template <class Op>
     int run(const typename Op::Params& prm, int M, int N, float* scal_out, int accumulate) {
         return run_pair<Op>(prm, M, N, scal_out, accumulate, ws, wsb, st);
@@ -264,8 +268,8 @@ int dicp_version(void) { return 100; }
 int dicp_sm_count(void) { return device_info().sms; }
 
 int dicp_sym_mode(int mode) {
-    const int prev = sym_mode_ref();
-    if (mode >= 0) sym_mode_ref() = mode;
+    const int prev = sym_mode_ref().load();
+    if (mode >= 0) sym_mode_ref().store(mode);
     return prev;
 }
 
@@ -297,15 +301,17 @@ int dicp_ksum(int D, unsigned mask, float sigma, const float* x, int64_t M, cons
 
 int dicp_rhs_forward(int D, int withlogdet, float sigma, float eta, const float* q, const float* p, int64_t M,
                      const float* x, int64_t Nx, float* vq, float* dp, float* vx, float* scal,
-                     void* workspace, size_t workspace_bytes, void* stream) {
-    DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream};
+                     void* workspace, size_t workspace_bytes, void* stream, int engine) {
+    if (engine < DICP_ENGINE_DEFAULT || engine > DICP_ENGINE_SYMMETRIC_ALL) return DICP_EBADARG;
+    DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream, engine};
     return last_error(rhs_forward_entry(ex, D, withlogdet, sigma, eta, q, p, M, x, Nx, vq, dp, vx, scal));
 }
 
 int dicp_rhs_adjoint(int D, int withlogdet, float sigma, float eta, const float* q, const float* p, int64_t M,
                      const float* x, int64_t Nx, const float* a, const float* u, const float* wx, const float* gc,
-                     float* gq, float* gp, float* gx, void* workspace, size_t workspace_bytes, void* stream) {
-    DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream};
+                     float* gq, float* gp, float* gx, void* workspace, size_t workspace_bytes, void* stream, int engine) {
+    if (engine < DICP_ENGINE_DEFAULT || engine > DICP_ENGINE_SYMMETRIC_ALL) return DICP_EBADARG;
+    DeviceExec ex{workspace, workspace_bytes, (cudaStream_t)stream, engine};
     return last_error(rhs_adjoint_entry(ex, D, withlogdet, sigma, eta, q, p, M, x, Nx, a, u, wx, gc, gq, gp, gx));
 }
 

@@ -24,6 +24,7 @@
 // order (deterministic, no float atomics).  Row-scalars (dcost, Hamiltonian pieces, ...) are block-reduced
 // with a fixed tree and summed over blocks by `scalar_reduce_kernel`, also deterministic.
 #pragma once
+#include <atomic>
 #include <vector>
 #include "common.cuh"
 
@@ -382,8 +383,8 @@ __global__ void scalar_reduce_kernel(const float* __restrict__ blockscal, int nb
 
 // ---- host side --------------------------------------------------------------------------------
 // number of kernel launches issued by this library (a claim the bench reports as gpu_launches)
-inline unsigned long long& launch_counter() {
-    static unsigned long long n = 0;
+inline std::atomic<unsigned long long>& launch_counter() {          // atomic: frames may be registered from several host threads
+    static std::atomic<unsigned long long> n{0};
     return n;
 }
 struct DeviceInfo {

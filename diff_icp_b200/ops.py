@@ -53,21 +53,25 @@ def ksum(mask: int, sigma: float, x, y, b=None, c=None, d=None, ws=None):
     return outs
 
 
-def rhs_forward(D, withlogdet, sigma, eta, q, p, x, vq, dp, vx, scal, ws):
+ENGINE_DEFAULT, ENGINE_GENERAL, ENGINE_SYMMETRIC, ENGINE_SYMMETRIC_ALL = -1, 0, 1, 2      # include/dicp_b200.h
+
+
+def rhs_forward(D, withlogdet, sigma, eta, q, p, x, vq, dp, vx, scal, ws, engine=ENGINE_DEFAULT):
     """Fused ODE right-hand side; all arguments are preallocated contiguous fp32 CUDA tensors (x, vx may be None)."""
     M = q.shape[0]
     Nx = 0 if x is None else x.shape[0]
     rc = load().dicp_rhs_forward(D, int(bool(withlogdet)), float(sigma), float(eta), ptr(q), ptr(p), M,
-                                 ptr(x), Nx, ptr(vq), ptr(dp), ptr(vx), ptr(scal), ptr(ws), ws.numel(), stream_ptr())
+                                 ptr(x), Nx, ptr(vq), ptr(dp), ptr(vx), ptr(scal), ptr(ws), ws.numel(), stream_ptr(),
+                                 int(engine))
     check(rc, "dicp_rhs_forward")
 
 
-def rhs_adjoint(D, withlogdet, sigma, eta, q, p, x, a, u, wx, gc, gq, gp, gx, ws):
+def rhs_adjoint(D, withlogdet, sigma, eta, q, p, x, a, u, wx, gc, gq, gp, gx, ws, engine=ENGINE_DEFAULT):
     M = q.shape[0]
     Nx = 0 if x is None else x.shape[0]
     rc = load().dicp_rhs_adjoint(D, int(bool(withlogdet)), float(sigma), float(eta), ptr(q), ptr(p), M,
                                  ptr(x), Nx, ptr(a), ptr(u), ptr(wx), ptr(gc), ptr(gq), ptr(gp), ptr(gx),
-                                 ptr(ws), ws.numel(), stream_ptr())
+                                 ptr(ws), ws.numel(), stream_ptr(), int(engine))
     check(rc, "dicp_rhs_adjoint")
 
 

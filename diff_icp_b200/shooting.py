@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import torch
 
+import os
 import threading
 
 from . import ops
@@ -132,10 +133,48 @@ def adjoint_sweep(spec, traj, mid, gtraj, lam, mu, G1, G2, ws, sws=None, lam2=No
             ops.axpy(lam, lam, 1.0, gtraj[t], n=S)
 
 
-class ShootPlan:
-    """Buffers (and, optionally, captured CUDA graphs) for one ShootSpec. Cached per spec."""
+class _PlanCache:
+    """LRU cache of plans bounded by the BYTES of device memory they hold (a plan of a dense 1M-point frame keeps ~1 GB of
+    trajectory / adjoint buffers; a count-bound cache could exhaust the GPU with ragged large frames)."""
 
-    _cache = {}
+    def __init__(self, max_bytes):
+        from collections import OrderedDict
+        self.max_bytes = int(max_bytes)
+        self.items = OrderedDict()
+        self.bytes = 0
+
+    def get(self, key):
+        plan = self.items.get(key)
+        if plan is not None:
+            self.items.move_to_end(key)
+        return plan
+
+    def __len__(self):
+        return len(self.items)
+
+    def __setitem__(self, key, plan):
+        self.items[key] = plan
+        self.bytes += plan.nbytes
+        while self.bytes > self.max_bytes and len(self.items) > 1:
+            _, old = self.items.popitem(last=False)
+            self.bytes -= old.nbytes
+
+    def clear(self):
+        self.items.clear()
+        self.bytes = 0
+
+
+def _tensor_bytes(obj):
+    return sum(t.numel() * t.element_size() for t in vars(obj).values() if isinstance(t, torch.Tensor) and t.is_cuda)
+
+
+PLAN_CACHE_BYTES = int(float(os.environ.get("DICP_PLAN_CACHE_GB", "8")) * (1 << 30))
+
+
+class ShootPlan:
+    """Buffers (and, optionally, captured CUDA graphs) for one ShootSpec. Cached per spec (LRU, bounded by bytes)."""
+
+    _cache = _PlanCache(PLAN_CACHE_BYTES)
 
     def __init__(self, spec: ShootSpec, use_graph: bool):
         self.spec = spec
@@ -165,6 +204,7 @@ class ShootPlan:
         self.use_graph = use_graph
         self.fwd_graph = None
         self.bwd_graph = None
+        self.nbytes = _tensor_bytes(self)
 
     _lock = threading.Lock()
 
@@ -176,8 +216,6 @@ class ShootPlan:
             with cls._lock:
                 plan = cls._cache.get(key)
                 if plan is None:
-                    if len(cls._cache) > 1024:
-                        cls._cache.clear()
                     plan = cls(spec, use_graph)
                     cls._cache[key] = plan
         return plan
@@ -254,7 +292,7 @@ class ClosurePlan:
     [dcost(0), A, B, C, cost(1), data loss, -, - | d loss / d p0 (M*D)] so that the host reads loss and gradient with one
     device-to-host copy (the reference synchronises once per closure too, tools/optim.py:39)."""
 
-    _cache = {}
+    _cache = _PlanCache(PLAN_CACHE_BYTES)
     NS = 8
 
     def __init__(self, spec: ShootSpec, use_graph: bool, lam_reg: float):
@@ -270,6 +308,7 @@ class ClosurePlan:
             else torch.zeros(self.NS + spec.M * spec.D, dtype=torch.float32)
         self.plan.gtraj[spec.nt][spec.S - 1] = 1.0            # d loss / d cost(1) = 1
         self.graph = None
+        self.nbytes = self.plan.nbytes + _tensor_bytes(self)
 
     @classmethod
     def get(cls, spec, use_graph, lam_reg):
@@ -279,8 +318,6 @@ class ClosurePlan:
             with ShootPlan._lock:
                 cp = cls._cache.get(key)
                 if cp is None:
-                    if len(cls._cache) > 1024:
-                        cls._cache.clear()
                     cp = cls(spec, use_graph, lam_reg)
                     cls._cache[key] = cp
         return cp

@@ -49,15 +49,27 @@ int dicp_version(void);
 /* number of SMs of the current device (148 on B200) */
 int dicp_sm_count(void);
 
-/* The (q,q) passes of dicp_rhs_adjoint run on the symmetric engine (every unordered pair evaluated once) for
- * M >= 4096 (beyond 65536 points in super-blocks of 32768).  mode 0 / 1 switches it off / on (process-wide; default 1, or the DICP_SYM environment variable);
- * mode 2 also routes the (q,q) pass of dicp_rhs_forward through it (measured slower on B200, kept for experiments);
- * mode < 0 only queries.  Returns the previous mode.  Results of the two engines agree to fp32 rounding. */
+/* Engine selection.  The (q,q) passes of dicp_rhs_adjoint run on the symmetric engine (every unordered pair evaluated
+ * once) for M >= 4096 (beyond 65536 points in super-blocks of 32768), the (x,q) adjoint on its rectangular form.  The
+ * engine is a PER-CALL argument of dicp_rhs_forward / dicp_rhs_adjoint (re-entrant: nothing process-global is consulted
+ * when it is >= 0):
+ *   DICP_ENGINE_DEFAULT        the process-wide default below
+ *   DICP_ENGINE_GENERAL        every ordered pair through the general tiled engine
+ *   DICP_ENGINE_SYMMETRIC      symmetric / rectangular ring engines for the adjoint passes (the default's default)
+ *   DICP_ENGINE_SYMMETRIC_ALL  also the (q,q) pass of dicp_rhs_forward (measured slower on B200, kept for experiments)
+ * Results of the engines agree to fp32 rounding.
+ * dicp_sym_mode(mode) sets the process-wide DEFAULT (atomic; initial value 1 or the DICP_SYM environment variable) used by
+ * calls that pass DICP_ENGINE_DEFAULT and by the small-support stage kernels; mode < 0 only queries.  Returns the previous
+ * default. */
+#define DICP_ENGINE_DEFAULT (-1)
+#define DICP_ENGINE_GENERAL 0
+#define DICP_ENGINE_SYMMETRIC 1
+#define DICP_ENGINE_SYMMETRIC_ALL 2
 int dicp_sym_mode(int mode);
 
 /* number of kernel launches this library has issued so far in this process (launches recorded into a CUDA graph
  * are counted once, at capture) */
-unsigned long long dicp_launch_count(void);
+unsigned long long dicp_launch_count(void);          /* atomic counter: safe with several host threads */
 
 /* Upper bound of the workspace needed by any pair kernel with `rows` rows and `cols` columns. */
 size_t dicp_pair_workspace_bytes(int64_t rows, int64_t cols);
@@ -83,7 +95,7 @@ int dicp_ksum(int D, unsigned mask, float sigma,
 int dicp_rhs_forward(int D, int withlogdet, float sigma, float eta,
                      const float* q, const float* p, int64_t M, const float* x, int64_t Nx,
                      float* vq, float* dp, float* vx, float* scal,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     void* workspace, size_t workspace_bytes, void* stream, int engine);
 
 /* Adjoint (vector-Jacobian product) of dicp_rhs_forward: given cotangents a (of vq), u (of dp), wx (of vx)
  * and the device scalar gc (of dcost; null => 0), writes gq, gp (M,D) and gx (Nx,D). */
@@ -91,7 +103,7 @@ int dicp_rhs_adjoint(int D, int withlogdet, float sigma, float eta,
                      const float* q, const float* p, int64_t M, const float* x, int64_t Nx,
                      const float* a, const float* u, const float* wx, const float* gc,
                      float* gq, float* gp, float* gx,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     void* workspace, size_t workspace_bytes, void* stream, int engine);
 
 /* ---- GMM EM step (GaussianMixtureUnif.EM_step, core/GMM.py:236-325 torch twin, :402-529 KeOps formulation) ----
  * Row pass over points x components.  Responsibilities come from the OLD parameters

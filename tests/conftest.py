@@ -15,6 +15,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests need a CUDA device and the built library: skip them (instead of failing on 'no NVIDIA driver') when
+    plain `pytest tests` runs on a CPU box."""
+    try:
+        import torch
+        have = torch.cuda.is_available() and os.path.exists(os.path.join(ROOT, "diff_icp_b200", "libdicp_b200.so"))
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device and diff_icp_b200/libdicp_b200.so")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden():
     def load(name):

@@ -117,7 +117,7 @@ def _inplace(fn, outs):
             o.copy_(torch.from_numpy(a))
 
 
-def rhs_forward(D, withlogdet, sigma, eta, q, p, x, vq, dp, vx, scal, ws):
+def rhs_forward(D, withlogdet, sigma, eta, q, p, x, vq, dp, vx, scal, ws, engine=-1):
     M, Nx = q.shape[0], (0 if x is None else x.shape[0])
     qa, pa, xa = _np(q), _np(p), _np(x)
 
@@ -128,7 +128,7 @@ def rhs_forward(D, withlogdet, sigma, eta, q, p, x, vq, dp, vx, scal, ws):
     _inplace(run, [vq, dp, vx, scal[:4]])
 
 
-def rhs_adjoint(D, withlogdet, sigma, eta, q, p, x, a, u, wx, gc, gq, gp, gx, ws):
+def rhs_adjoint(D, withlogdet, sigma, eta, q, p, x, a, u, wx, gc, gq, gp, gx, ws, engine=-1):
     M, Nx = q.shape[0], (0 if x is None else x.shape[0])
     qa, pa, xa, aa, ua, wa, ga = _np(q), _np(p), _np(x), _np(a), _np(u), _np(wx), _np(gc)
 

@@ -59,6 +59,41 @@ def _worker_em(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_vol0(rank, world, port, out):
+    """Outlier reference volume left to be set automatically: must be the bounding box of ALL ranks' points."""
+    _setup(rank, world, port)
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    from diff_icp_b200.dist import StatsComm, shard_frames
+    frames, cent = _frames()
+    mine = shard_frames(len(frames), rank, world)
+    X = torch.cat([frames[k] for k in mine])
+    G = GaussianMixtureUnif(cent + 0.05, sigma=0.1, use_outliers=True, spec=CPU)
+    G.comm = StatsComm()
+    Y, Cfe, FE = G.EM_step(X)
+    torch.save({"vol0": G.outliers["vol0"], "eta0": G.outliers["eta0"], "FE": float(FE)}, os.path.join(out, f"vol{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def _worker_init_from_set(rank, world, port, out):
+    """init_components = {"set": 0, "C": 4}: every rank fits its initial GMM to ITS OWN first frame from random centroids;
+    the constructor must make rank 0's model everyone's."""
+    _setup(rank, world, port)
+    from diff_icp_b200.api.ICP_atlas import ICP_atlas
+    from diff_icp_b200.dist import StatsComm, shard_frames
+    frames, cent = _frames(K=4, N=60)
+    comm = StatsComm()
+    mine = shard_frames(len(frames), rank, world)
+    torch.manual_seed(100 + rank)                # different random draws per rank on purpose
+    PSR, evol = ICP_atlas([frames[k] for k in mine], GMM_parameters={"init_components": {"set": 0, "C": 4}},
+                          registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.3},
+                          numerical_options={"compspec": CPU, "dataspec": CPU, "comm": comm,
+                                             "support_LDDMM": {"scheme": "grid", "rho": 1.0}},
+                          optim_options={"max_iterations": 1, "max_repeat_GMM": 2}, printstuff=False)
+    torch.save({"mu0": evol["GMMi"][0].mu, "sigma0": evol["GMMi"][0].sigma, "mu": PSR.GMMi[0].mu, "FE": PSR.FE},
+               os.path.join(out, f"init{rank}.pt"))
+    dist.destroy_process_group()
+
+
 def _worker_psr(rank, world, port, out):
     _setup(rank, world, port)
     from diff_icp_b200.api.ICP_atlas import ICP_atlas
@@ -126,6 +161,28 @@ def test_em_statistics_allreduce_equals_single_process(monkeypatch):
     offs = np.concatenate(([0], np.cumsum(sizes)))
     Yg = torch.cat([Y[offs[k]:offs[k + 1]] for k in r0["mine"]])
     assert torch.allclose(Yg, r0["Y"], atol=2e-6)
+
+
+def test_outlier_volume_is_the_global_bounding_box(monkeypatch):
+    out = _spawn(_worker_vol0)
+    r0, r1 = (torch.load(os.path.join(out, f"vol{r}.pt"), weights_only=False) for r in (0, 1))
+    assert r0 == r1
+    import emu_backend
+    emu_backend.install_all(monkeypatch)
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    frames, cent = _frames()
+    G = GaussianMixtureUnif(cent + 0.05, sigma=0.1, use_outliers=True, spec=CPU)
+    Y, Cfe, FE = G.EM_step(torch.cat(frames))
+    assert abs(G.outliers["vol0"] - r0["vol0"]) < 1e-6 * G.outliers["vol0"]
+    assert abs(G.outliers["eta0"] - r0["eta0"]) < 1e-5
+    assert abs(float(FE) - r0["FE"]) < 2e-5 * abs(float(FE))
+
+
+def test_initial_model_built_per_rank_is_broadcast():
+    out = _spawn(_worker_init_from_set)
+    r0, r1 = (torch.load(os.path.join(out, f"init{r}.pt"), weights_only=False) for r in (0, 1))
+    assert torch.equal(r0["mu0"], r1["mu0"]) and r0["sigma0"] == r1["sigma0"]
+    assert torch.equal(r0["mu"], r1["mu"]) and r0["FE"] == r1["FE"]
 
 
 def test_sharded_atlas_equals_single_process(monkeypatch):

@@ -8,33 +8,24 @@ pytestmark = pytest.mark.gpu
 
 
 def adjoint(D, withlogdet, sigma, eta, q, p, a, u, gc, mode):
+    """mode = the per-call engine argument of the C ABI (DICP_ENGINE_GENERAL / _SYMMETRIC / _SYMMETRIC_ALL)."""
     from diff_icp_b200 import ops
-    lib = ops.load()
-    prev = lib.dicp_sym_mode(mode)
-    try:
-        M = q.shape[0]
-        gq, gp = torch.zeros_like(q), torch.zeros_like(q)
-        ws = ops.alloc_workspace(M, M, q.device)
-        ops.rhs_adjoint(D, withlogdet, sigma, eta, q, p, None, a, u, None, gc, gq, gp, None, ws)
-        torch.cuda.synchronize()
-        return gq, gp
-    finally:
-        lib.dicp_sym_mode(prev)
+    M = q.shape[0]
+    gq, gp = torch.zeros_like(q), torch.zeros_like(q)
+    ws = ops.alloc_workspace(M, M, q.device)
+    ops.rhs_adjoint(D, withlogdet, sigma, eta, q, p, None, a, u, None, gc, gq, gp, None, ws, engine=mode)
+    torch.cuda.synchronize()
+    return gq, gp
 
 
 def forward(D, withlogdet, sigma, eta, q, p, mode):
     from diff_icp_b200 import ops
-    lib = ops.load()
-    prev = lib.dicp_sym_mode(mode)
-    try:
-        M = q.shape[0]
-        vq, dp, scal = torch.zeros_like(q), torch.zeros_like(q), torch.zeros(4, device=q.device)
-        ws = ops.alloc_workspace(M, M, q.device)
-        ops.rhs_forward(D, withlogdet, sigma, eta, q, p, None, vq, dp, None, scal, ws)
-        torch.cuda.synchronize()
-        return vq, dp, scal
-    finally:
-        lib.dicp_sym_mode(prev)
+    M = q.shape[0]
+    vq, dp, scal = torch.zeros_like(q), torch.zeros_like(q), torch.zeros(4, device=q.device)
+    ws = ops.alloc_workspace(M, M, q.device)
+    ops.rhs_forward(D, withlogdet, sigma, eta, q, p, None, vq, dp, None, scal, ws, engine=mode)
+    torch.cuda.synchronize()
+    return vq, dp, scal
 
 
 @pytest.mark.parametrize("D", [2, 3])
@@ -98,17 +89,12 @@ def test_small_and_huge_sizes_use_the_general_engine():
 
 def adjoint_x(D, withlogdet, sigma, q, p, x, a, u, wx, gc, mode, eta=0.0):
     from diff_icp_b200 import ops
-    lib = ops.load()
-    prev = lib.dicp_sym_mode(mode)
-    try:
-        M, Nx = q.shape[0], x.shape[0]
-        gq, gp, gx = torch.zeros_like(q), torch.zeros_like(q), torch.zeros_like(x)
-        ws = ops.alloc_workspace(max(M, Nx), max(M, Nx), q.device)
-        ops.rhs_adjoint(D, withlogdet, sigma, eta, q, p, x, a, u, wx, gc, gq, gp, gx, ws)
-        torch.cuda.synchronize()
-        return gq, gp, gx
-    finally:
-        lib.dicp_sym_mode(prev)
+    M, Nx = q.shape[0], x.shape[0]
+    gq, gp, gx = torch.zeros_like(q), torch.zeros_like(q), torch.zeros_like(x)
+    ws = ops.alloc_workspace(max(M, Nx), max(M, Nx), q.device)
+    ops.rhs_adjoint(D, withlogdet, sigma, eta, q, p, x, a, u, wx, gc, gq, gp, gx, ws, engine=mode)
+    torch.cuda.synchronize()
+    return gq, gp, gx
 
 
 @pytest.mark.parametrize("D", [2, 3])
