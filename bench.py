@@ -109,7 +109,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arm: the REFERENCE ITSELF (unmodified package from baseline/_ref or /root/reference through oracle/ref_loader.py, torch
 # twin because pykeops is absent) on a bounded sample of the same workload; the oracle port only if the package is missing
-CPU_SAMPLE_M = 768           # the step at M = N = 768 instead of 20 000: ~2-5 s of CPU work per step on 8-16 cores
+CPU_SAMPLE_M = 1536          # the step at M = N = 1536 instead of 20 000: ~1 s of CPU work per step on the box's 16 cores
 
 
 def load_reference_or_none():
@@ -566,7 +566,7 @@ def em_roofline(dev, timeit, peaks):
 # configs[3]-shaped strong-scaling entry: total frames (divisible by 8) and the free energy the 1-GPU run reaches after its
 # 2 iterations (deterministic kernels, seeded synthetic frames): every N must reproduce it to 1e-5
 C4_FRAMES = 64
-C4_FE_1GPU = None
+C4_FE_1GPU = -6932362.935058594         # measured: 1 x B200, profiles/r02_bench_1gpu.json
 
 NCU_DRAM_BYTES = {"classic": None, "hybrid": None, "logdet": 1990144}
 
