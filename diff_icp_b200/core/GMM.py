@@ -120,6 +120,7 @@ class GaussianMixtureUnif(Module):
         state = dict(self.__dict__)
         state.pop("EM_step", None)            # bound method: rebuilt on load
         state.pop("_lpi_cache", None)
+        state.pop("_m_ref", None)
         state["comm"] = None
         return state
 
@@ -147,7 +148,18 @@ class GaussianMixtureUnif(Module):
     def _lgn(self, sigma):
         return self.D * (math.log(sigma) + 0.5 * math.log(2 * math.pi))
 
-    def EM_step_b200(self, X, skip_M=False):
+    # ---- multi-GPU: the exponent every rank rescales its column statistics to (one SUM all-reduce, no MAX round) ----
+    def _agreed_exponent(self):
+        """(C,) log2 column masses of the previous merged statistics -- identical bits on every rank because they are
+        computed from all-reduced numbers -- or None when there is none yet (first step, changed model size)."""
+        m = getattr(self, "_m_ref", None)
+        return m if (m is not None and m.shape[0] == self.C and m.device == self.mu.device) else None
+
+    def _remember_exponent(self, merged):
+        # round(): rescaling by an integer power of two is exact
+        self._m_ref = torch.round(merged[:, 0] + torch.log2(torch.clamp(merged[:, 1], min=1e-30)))
+
+    def EM_step_b200(self, X, skip_M=False, _safe_merge=False):
         """One (E step, M step) alternation; returns (Y, Cfe, FE) like the reference (core/GMM.py:236-325, :501-529).
         Y (N,D): quadratic targets sum_c gamma_nc mu_c;  Cfe: free-energy offset;  FE = Cfe + sum_n (1-gamma0_n)|x_n-y_n|^2/(2 sigma^2)."""
         X = X.detach().contiguous()
@@ -175,11 +187,18 @@ class GaussianMixtureUnif(Module):
         # ---- M step for mu / w (and the column form of sigma) from log-domain column statistics, ONE launch --
         ms = None
         mu_new, w_new, lpi_new = mu_old, w_old, lpi_old
+        merge_check = None
         if do_mu or do_w:
             T2 = em_ops.rowpass(sigma_old, X, mu_old, wl2)
             stats = em_ops.colstats(sigma_old, X, T2, mu_old, wl2) if N_local > 0 else _empty_stats(C, D, X.device)
             if comm is not None:
-                stats = comm.merge_colstats(stats)
+                m_ref = None if _safe_merge else self._agreed_exponent()
+                if m_ref is None:
+                    stats = comm.merge_colstats(stats)                      # MAX round + SUM round
+                else:
+                    stats, _, flag = comm.merge_colstats_ref(stats, m_ref)  # ONE round, checked at the step's host read
+                    merge_check = torch.stack((flag, (stats[:, 1] < 1e-30).any().to(flag.dtype)))
+                self._remember_exponent(stats)
             sig_mode = 0 if not do_sig else (1 if (keops_sem and do_mu) else 2)
             mu_new, w_new, lpi_new, ms = em_ops.mstep(stats, mu_old, w_old, do_mu, do_w, sig_mode)
         nds2 = ms[0] if (ms is not None and do_sig) else None
@@ -187,8 +206,7 @@ class GaussianMixtureUnif(Module):
 
         # ---- full row pass: old responsibilities, new centroids / weights ------------------------------------
         T2, Y, scal, rowP, rowQ, sq = em_ops.rowpass(sigma_old, X, mu_old, wl2, mu_new, lpi_new, per_point=use_out)
-        parts = [scal, torch.tensor([float(N_local)]).to(scal.device, non_blocking=True) if comm is not None
-                 else scal.new_zeros(1)]
+        parts = [scal, scal.new_full((1,), float(N_local))]
         if nds2 is not None:
             parts.append(nds2.reshape(1))
         if use_out:
@@ -207,7 +225,14 @@ class GaussianMixtureUnif(Module):
         if comm is not None:
             head = comm.sum(vec[:5].clone())                    # P, Q, SQ, DS, N are plain sums over frames
             vec = torch.cat((head, vec[5:]))
+        if merge_check is not None:
+            vec = torch.cat((vec, merge_check))
         vals = vec.tolist()                                     # the ONE host synchronisation of this EM step
+        if merge_check is not None:
+            if vals[-2] > 0 or vals[-1] > 0:                    # exponent drifted too far from the agreed one (every rank
+                self._m_ref = None                              # sees the same flags): redo the step with the MAX round
+                return self.EM_step_b200(X, skip_M=skip_M, _safe_merge=True)
+            vals = vals[:-2]
         P, Q, SQ, DS, N = vals[:5]
         if comm is None:
             N = float(N_local)
@@ -252,6 +277,8 @@ class GaussianMixtureUnif(Module):
         Returns (Y, Cfe, FE, number of steps)."""
         if X.shape[0] == 0 and self.comm is None:
             return torch.empty(X.shape, **self.spec), torch.tensor(0.0), torch.tensor(0.0), 0
+        if self._pipelined_applies():
+            return self._EM_optimization_pipelined(X, max_iterations, tol)
         Y = Cfe = FE = last_FE = None
         for i in range(max_iterations):
             Y, Cfe, FE = self.EM_step(X)
@@ -260,6 +287,107 @@ class GaussianMixtureUnif(Module):
             last_FE = FE
         print(f"GMM optimization - reached maximum number of iterations : {max_iterations}")
         return Y, Cfe, FE, i + 1
+
+    # ---- multi-GPU: ONE all-reduce per EM step ------------------------------------------------------------------------
+    pipelined_allreduce = True
+
+    def _pipelined_applies(self):
+        """The pipelined loop needs the next step's sigma right after the merged column statistics: the KeOps ordering with
+        mu optimised (sigma' from the column statistics, core/GMM.py:453-455), or a fixed sigma.  Other settings (torch
+        ordering with sigma from the row sums, outliers, frozen mu and w) keep the step-by-step loop."""
+        opt = self.to_optimize
+        return (self.comm is not None and self.pipelined_allreduce and self.outliers is None
+                and self.EM_step == self.EM_step_b200 and (opt["mu"] or opt["w"])
+                and (not opt["sigma"] or (self.computversion != "torch" and opt["mu"])))
+
+    def _EM_optimization_pipelined(self, X, max_iterations, tol):
+        """EM_optimization with the points sharded over ranks and ONE all-reduce per EM step.
+
+        Step i needs two global reductions: the column statistics (before its M step) and the four free-energy sums
+        [P, Q, SQ, DS] of its row pass (after it).  The sums of step i are only needed on the host -- for FE_i and the stop
+        test -- so they ride on the all-reduce of step i+1's column statistics: that step's first half (row LSE + column
+        statistics with the new parameters, ~50 us) is issued SPECULATIVELY; if FE_i then says "stop", its result is
+        dropped and the model stays at step i's parameters, exactly what the step-by-step loop returns.  The buffer is
+        [S0, B, A rescaled to the rank-agreed exponents | overflow flag | P, Q, SQ, DS, N]; a final all-reduce of the five
+        sums alone closes the loop when the step limit is reached.  Same arithmetic as EM_step_b200 on every rank."""
+        comm, D, C = self.comm, self.D, self.C
+        opt = self.to_optimize
+        do_mu, do_w, do_sig = opt["mu"], opt["w"], opt["sigma"]
+        X = X.detach().contiguous()
+        N_local = X.shape[0]
+        dev = self.mu.device
+        sig_mode = 1 if do_sig else 0
+
+        def first_half(sigma, mu, lpi):
+            wl2 = ((lpi - self._lgn(sigma)) * _LOG2E).contiguous()
+            if N_local == 0:
+                return wl2, _empty_stats(C, D, dev)
+            T2 = em_ops.rowpass(sigma, X, mu, wl2)
+            return wl2, em_ops.colstats(sigma, X, T2, mu, wl2)
+
+        def values(sums, sigma_new):
+            P, Q, SQ, DS, N = sums
+            inv2s2 = 1.0 / (2 * sigma_new * sigma_new)
+            Cfe_val = P * inv2s2 + Q + N * self._lgn(sigma_new)
+            return Cfe_val, Cfe_val + SQ * inv2s2, N
+
+        sigma = float(self.sigma)
+        mu, w = self.mu.contiguous(), self.w.contiguous()
+        lpi = w - torch.logsumexp(w, 0)
+        wl2, stats = first_half(sigma, mu, lpi)
+        pending = None            # (Y, local sums, sigma after that step) of the last completed step, FE not yet known
+        last_FE, done, N_glob = None, None, None
+        zeros5 = torch.zeros(5, dtype=torch.float32, device=dev)
+        i = 0
+        while True:
+            # ---- the ONE collective of step i: its column statistics + the previous step's sums ------------------------
+            extra = pending[1] if pending is not None else torch.cat((zeros5[:4], zeros5.new_full((1,), float(N_local))))
+            m_ref = self._agreed_exponent()
+            if m_ref is None:
+                merged = comm.merge_colstats(stats)
+                red, check = comm.sum(extra.clone()), None
+            else:
+                merged, red, flag = comm.merge_colstats_ref(stats, m_ref, extra)
+                check = torch.stack((flag, (merged[:, 1] < 1e-30).any().to(flag.dtype)))
+            mu_new, w_new, lpi_new, ms = em_ops.mstep(merged, mu, w, do_mu, do_w, sig_mode)
+            host = torch.cat((ms[:1], red, check if check is not None else zeros5[:2])).tolist()       # ONE host read
+            if check is not None and (host[-2] > 0 or host[-1] > 0):       # exponents drifted: repeat with the MAX round
+                self._m_ref = None
+                continue
+            self._remember_exponent(merged)
+            N_glob = host[5]
+            if pending is not None:                                     # FE of step i-1 is now known
+                Cfe_val, FE_val, _ = values(host[1:6], pending[2])
+                if last_FE is not None and tol is not None and abs(FE_val - last_FE) < tol * abs(last_FE):
+                    done = (pending[0], Cfe_val, FE_val, i)             # step i's speculative first half is dropped
+                    break
+                last_FE = FE_val
+            if i == max_iterations:
+                break
+            # ---- second half of step i: new parameters, row pass with the OLD responsibilities -------------------------
+            sigma_new = math.sqrt(max(host[0], 0.0) / (D * N_glob)) if do_sig else sigma
+            if do_sig and self.ensure_continuum:
+                sigma_new = max(sigma_new, intrinsic_scale(mu_new))
+            lpi_new = lpi_new.contiguous()
+            if N_local > 0:
+                _, Y, scal, _, _, _ = em_ops.rowpass(sigma, X, mu, wl2, mu_new, lpi_new)
+            else:
+                Y, scal = torch.empty(0, D, dtype=torch.float32, device=dev), zeros5[:4]
+            pending = (Y, torch.cat((scal, scal.new_full((1,), float(N_local)))), sigma_new)
+            sigma, mu, w, lpi = sigma_new, (mu_new if do_mu else mu), (w_new if do_w else w), lpi_new
+            self.sigma, self.mu, self.w = sigma, mu, w
+            self._lpi_cache = (self.w, self.w._version, lpi)
+            i += 1
+            if i < max_iterations:
+                wl2, stats = first_half(sigma, mu, lpi)                 # speculative first half of the next step
+            else:                                                       # step limit: only the sums remain to be reduced
+                red = comm.sum(pending[1].clone()).tolist()
+                Cfe_val, FE_val, _ = values(red, pending[2])
+                print(f"GMM optimization - reached maximum number of iterations : {max_iterations}")
+                done = (pending[0], Cfe_val, FE_val, i)
+                break
+        Y, Cfe_val, FE_val, steps = done
+        return Y, torch.tensor(Cfe_val, dtype=self.spec["dtype"]), torch.tensor(FE_val, dtype=self.spec["dtype"]), steps
 
     @staticmethod
     def get_GMM_model(X, C, fixed_sigma=None, optimize_w=False, use_outliers=False, max_iterations=100, tol=1e-5,

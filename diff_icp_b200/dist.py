@@ -45,6 +45,25 @@ class StatsComm:
         scaled = self.sum(scaled)
         return torch.cat((m_glob[:, None], scaled), dim=1)
 
+    def merge_colstats_ref(self, stats, m_ref, extra=None):
+        """ONE all-reduce (SUM) for the column statistics AND whatever plain sums ride along.
+        stats (C, D+3) = [m, S0, B, A] of the local points; m_ref (C,): an exponent every rank agrees on bit for bit (the log2
+        column mass of the previous EM step, see GaussianMixtureUnif); extra: 1-D tensor of per-rank partial sums.
+        Every rank rescales its sums to 2^m_ref -- no MAX round -- and appends a flag (1 if one of its exponents is so far
+        above m_ref that the rescaled sums could overflow).  Returns (merged stats with exponent m_ref, reduced extra,
+        flag sum); the caller falls back to `merge_colstats` when flag > 0 or a merged S0 vanished (all ranks see the same
+        numbers, so they take the same decision)."""
+        d = stats[:, 0] - m_ref
+        scaled = stats[:, 1:] * torch.exp2(torch.clamp(d, max=120.0))[:, None]
+        flag = (d > 100.0).any().to(stats.dtype).reshape(1)
+        parts = [scaled.reshape(-1), flag]
+        if extra is not None:
+            parts.append(extra.to(stats.dtype).reshape(-1))
+        buf = self.sum(torch.cat(parts))
+        n = scaled.numel()
+        merged = torch.cat((m_ref[:, None], buf[:n].view_as(scaled)), dim=1)
+        return merged, (buf[n + 1:] if extra is not None else None), buf[n]
+
     def logsumexp_pair(self, a, b):
         """Global logsumexp of two per-rank log-sums (outlier log-odds update, core/GMM.py:290)."""
         v = torch.stack((a, b))

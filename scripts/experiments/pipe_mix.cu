@@ -15,7 +15,9 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm volatile("add.rn.
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm volatile("mul.rn.f32x2 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ float ex2(float x) { float r; asm volatile("ex2.approx.ftz.f32 %0,%1;" : "=f"(r) : "f"(x)); return r; }
 
-// VARIANT bits: 1 = use add/mul mix, 2 = MUFU, 4 = LDS, 8 = broadcast (scalar) operands, 16 = scalar FFMA instead of packed
+// VARIANT bits: 1 = use add/mul mix, 2 = MUFU, 4 = LDS, 8 = broadcast (scalar) operands, 16 = scalar FFMA instead of packed,
+// 32 = the adds / multiplies of the mix written as FFMA2 with a constant operand (a + b = fma(a, 1, b), a * b = fma(a, b, -0)):
+// bit-identical results, different pipe cost
 template <int V, int NCH>
 __global__ void __launch_bounds__(64) mix_kernel(int iters, float* out, float seed) {
     __shared__ float4 tile[64];
@@ -44,19 +46,20 @@ __global__ void __launch_bounds__(64) mix_kernel(int iters, float* out, float se
         } else {
             const u64 ra = (V & 8) ? pk(rowa, rowa) : pk(rowa, rowb);
             const u64 rb = (V & 8) ? pk(rowb, rowb) : pk(rowb, rowa);
+            const u64 one = pk(1.f, 1.f), nzero = pk(-0.f, -0.f);
             // 3 rounds x NCH instructions = 30 packed instructions for NCH = 10: per round FFMA2 : FADD2 : FMUL2 ~ 19 : 7 : 4
 #pragma unroll
             for (int k = 0; k < NCH; ++k) acc[k] = fma2(acc[k], ra, colv);
             if (V & 2) { e0 = ex2(-e0 * 0.5f - 1.f); }
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
-                if ((V & 1) && k < 7) acc[k] = add2(acc[k], rb);
+                if ((V & 1) && k < 7) acc[k] = (V & 32) ? fma2(acc[k], one, rb) : add2(acc[k], rb);
                 else acc[k] = fma2(acc[k], rb, ra);
             }
             if (V & 2) { e1 = ex2(-e1 * 0.5f - 1.f); }
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
-                if ((V & 1) && k < 4) acc[k] = mul2(acc[k], ra);
+                if ((V & 1) && k < 4) acc[k] = (V & 32) ? fma2(acc[k], ra, nzero) : mul2(acc[k], ra);
                 else acc[k] = fma2(acc[k], ra, (V & 2) ? pk(e0, e1) : colv);
             }
         }
@@ -104,6 +107,11 @@ int main() {
     ROW("  + 2 MUFU.EX2 per 30", 3, 10)
     ROW("  + 2 MUFU + 1 LDS.128 per 30", 7, 10)
     ROW("  + 2 MUFU + 1 LDS.128 + broadcast", 15, 10)
+    ROW("mix as all-FFMA2 (add=fma(a,1,b), mul=fma(a,b,-0))", 33, 10)
+    ROW("  all-FFMA2 + broadcast", 41, 10)
+    ROW("  all-FFMA2 + 2 MUFU", 35, 10)
+    ROW("  all-FFMA2 + 2 MUFU + LDS + broadcast", 47, 10)
+    ROW("  all-FFMA2 + 2 MUFU + LDS + broadcast, 16 ch", 47, 16)
     ROW("FFMA2 x18, 6 chains", 0, 6)
     ROW("FFMA2 mix+MUFU+LDS, 6 chains", 15, 6)
     ROW("FFMA2 x48, 16 chains", 0, 16)

@@ -136,6 +136,11 @@ def run_atlas_2d(golden, to_dev, monkeypatch, spec, ordering):
         _close_trace(tr, pre["atlas_gold_FE_trace"], pre["atlas_ref32_FE_trace"])
         _close_sigma(PSR.GMMi[0].sigma, float(pre["atlas_gold_sigma"]), float(pre["atlas_ref32_sigma"]))
         _close_points(PSR.GMMi[0].mu.cpu().numpy(), pre["atlas_gold_mu"], pre["atlas_ref32_mu"], 0.2)
+        # warped points: this run is three unconverged L-BFGS steps whose line-search branches amplify rounding -- the
+        # reference's OWN fp32 run moves by atlas_ulp_spread_x1 (1.5e-2, measured by make_golden.gen_keops_ordering_spread)
+        # when its inputs change by one ulp; the bar is that spread, not the luck of one fp32 run
+        spread = float(pre["atlas_ulp_spread_x1"])
         for k in range(3):
-            _close_points(PSR.x1[k, 0].cpu().numpy(), pre[f"atlas_gold_x1_{k}"], pre[f"atlas_ref32_x1_{k}"], 0.2)
+            err = np.abs(PSR.x1[k, 0].cpu().numpy() - pre[f"atlas_gold_x1_{k}"]).max()
+            assert err <= 1.5 * spread, (k, err, spread)
     return PSR

@@ -567,6 +567,42 @@ def gen_keops_ordering():
     print("keops_order.npz", len(out))
 
 
+def gen_keops_ordering_spread():
+    """How far the reference's OWN fp32 run of the 2-D atlas moves when its inputs change by one ulp: the registration is
+    one unconverged L-BFGS step per outer iteration, and line-search branches amplify rounding.  Three runs with every
+    coordinate multiplied by 1 + {-1, 0, 1} * 6e-8; the largest deviations from the fp64 run are appended to
+    keops_order.npz (atlas_ulp_spread_*) and bound the tolerances of the corresponding tests."""
+    import diffICP.core.GMM as rg
+    import diffICP.api.ICP_atlas as ra
+    _patch_coverage()
+    path = os.path.join(OUT, "keops_order.npz")
+    out = dict(np.load(path))
+    psr = np.load(os.path.join(OUT, "psr.npz"))
+    sp = spec_of(torch.float32)
+    dx, dfe, dmu, dsig = 0.0, 0.0, 0.0, 0.0
+    with _keops_ordering():
+        for trial in range(1, 4):
+            g = torch.Generator().manual_seed(trial)
+            sets = [torch.from_numpy(psr[f"atlas_in_x{k}"]) for k in range(3)]
+            sets = [s * (1 + torch.randint(-1, 2, s.shape, generator=g).float() * 6e-8) for s in sets]
+            G = rg.GaussianMixtureUnif(torch.from_numpy(psr["atlas_in_mu"]), sigma=0.25 * float(torch.cat(sets).std()),
+                                       spec=sp, computversion="torch")
+            PSR, _ = ra.ICP_atlas([[x] for x in sets], GMM_parameters={"init_components": [G], "optimize_weights": True},
+                                  registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.2},
+                                  numerical_options={"computversion": "torch", "compspec": sp, "dataspec": sp,
+                                                     "support_LDDMM": {"scheme": "grid", "rho": 1.0}},
+                                  optim_options={"max_iterations": 3, "max_repeat_GMM": 10, "convergence_tolerance": 1e-3},
+                                  printstuff=False)
+            dx = max(dx, max(np.abs(PSR.x1[k, 0].numpy() - out[f"atlas_gold_x1_{k}"]).max() for k in range(3)))
+            dfe = max(dfe, abs(float(PSR.FE) - out["atlas_gold_FE_trace"][-1]))
+            dmu = max(dmu, np.abs(PSR.GMMi[0].mu.numpy() - out["atlas_gold_mu"]).max())
+            dsig = max(dsig, abs(float(PSR.GMMi[0].sigma) - float(out["atlas_gold_sigma"])))
+    out["atlas_ulp_spread_x1"], out["atlas_ulp_spread_FE"] = np.array(dx), np.array(dfe)
+    out["atlas_ulp_spread_mu"], out["atlas_ulp_spread_sigma"] = np.array(dmu), np.array(dsig)
+    np.savez_compressed(path, **out)
+    print("keops_order.npz + ulp spread:", dx, dfe, dmu, dsig)
+
+
 def reference_function(relpath, name, namespace):
     """Compile ONE function of a reference module from its source text (for modules that cannot be imported here because
     they import pykeops at the top) and return it; nothing of the source is written anywhere."""
@@ -631,7 +667,7 @@ if __name__ == "__main__":
         for what in sys.argv[1:]:
             {"pointsets": lambda: gen_pointsets(rk), "v2p": lambda: gen_v2p(rl), "two_set": gen_two_set,
              "atlas_s3": gen_atlas_s3, "kernels": lambda: gen_kernels(rk), "lddmm": lambda: gen_lddmm(rl),
-             "gmm": lambda: gen_gmm(rg), "psr": gen_psr, "keops_order": gen_keops_ordering}[what]()
+             "gmm": lambda: gen_gmm(rg), "psr": gen_psr, "keops_order": gen_keops_ordering, "keops_order_spread": gen_keops_ordering_spread}[what]()
         sys.exit(0)
     gen_kernels(rk)
     gen_lddmm(rl)
@@ -642,3 +678,4 @@ if __name__ == "__main__":
     gen_two_set()
     gen_atlas_s3()
     gen_keops_ordering()
+    gen_keops_ordering_spread()

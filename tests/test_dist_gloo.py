@@ -59,6 +59,39 @@ def _worker_em(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_em_opt(rank, world, port, out):
+    """EM_optimization over sharded points: the pipelined loop (ONE all-reduce per EM step, next step's first half issued
+    speculatively) and the step-by-step loop, with a stop tolerance that triggers and with the step limit reached."""
+    _setup(rank, world, port)
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    from diff_icp_b200.dist import StatsComm, shard_frames
+    import torch.distributed as tdist
+    frames, cent = _frames(K=5, N=150)
+    mine = shard_frames(len(frames), rank, world)
+    X = torch.cat([frames[k] for k in mine])
+    res = {}
+    for tag, pipelined, max_it, tol in (("pipe_tol", True, 40, 1e-4), ("seq_tol", False, 40, 1e-4),
+                                        ("pipe_max", True, 4, 1e-12), ("seq_max", False, 4, 1e-12)):
+        G = GaussianMixtureUnif(cent + 0.05, sigma=0.1, spec=CPU)
+        G.comm = StatsComm()
+        G.pipelined_allreduce = pipelined
+        calls = {"n": 0}
+        orig = tdist.all_reduce
+
+        def counting(*a, **k):
+            calls["n"] += 1
+            return orig(*a, **k)
+        tdist.all_reduce = counting
+        try:
+            Y, Cfe, FE, steps = G.EM_optimization(X, max_iterations=max_it, tol=tol)
+        finally:
+            tdist.all_reduce = orig
+        res[tag] = {"mu": G.mu, "w": G.w, "sigma": G.sigma, "FE": float(FE), "Cfe": float(Cfe), "steps": steps, "Y": Y,
+                    "allreduces": calls["n"]}
+    torch.save(res, os.path.join(out, f"emopt{rank}.pt"))
+    dist.destroy_process_group()
+
+
 def _worker_vol0(rank, world, port, out):
     """Outlier reference volume left to be set automatically: must be the bounding box of ALL ranks' points."""
     _setup(rank, world, port)
@@ -161,6 +194,34 @@ def test_em_statistics_allreduce_equals_single_process(monkeypatch):
     offs = np.concatenate(([0], np.cumsum(sizes)))
     Yg = torch.cat([Y[offs[k]:offs[k + 1]] for k in r0["mine"]])
     assert torch.allclose(Yg, r0["Y"], atol=2e-6)
+
+
+def test_pipelined_em_optimization_one_allreduce_per_step(monkeypatch):
+    out = _spawn(_worker_em_opt)
+    r0, r1 = (torch.load(os.path.join(out, f"emopt{r}.pt"), weights_only=False) for r in (0, 1))
+    for tag in r0:
+        assert torch.equal(r0[tag]["mu"], r1[tag]["mu"]) and r0[tag]["FE"] == r1[tag]["FE"] and r0[tag]["steps"] == r1[tag]["steps"]
+    for a, b in (("pipe_tol", "seq_tol"), ("pipe_max", "seq_max")):
+        p, q = r0[a], r0[b]
+        assert p["steps"] == q["steps"]
+        assert torch.allclose(p["mu"], q["mu"], atol=2e-6) and torch.allclose(p["w"], q["w"], atol=2e-5)
+        assert abs(p["sigma"] - q["sigma"]) < 1e-6 * q["sigma"]
+        assert abs(p["FE"] - q["FE"]) < 2e-5 * abs(q["FE"]) and abs(p["Cfe"] - q["Cfe"]) < 2e-5 * abs(q["Cfe"])
+        assert torch.allclose(p["Y"], q["Y"], atol=2e-6)
+        # one collective per EM step (+ the MAX round of the very first step, + the closing reduction of the sums)
+        assert p["allreduces"] <= p["steps"] + 3, (p["allreduces"], p["steps"])
+        assert q["allreduces"] >= 2 * q["steps"]
+    assert r0["pipe_tol"]["steps"] < 40 and r0["pipe_max"]["steps"] == 4
+    # and the same model as one process holding all points
+    import emu_backend
+    emu_backend.install_all(monkeypatch)
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    frames, cent = _frames(K=5, N=150)
+    G = GaussianMixtureUnif(cent + 0.05, sigma=0.1, spec=CPU)
+    Y, Cfe, FE, steps = G.EM_optimization(torch.cat(frames), max_iterations=40, tol=1e-4)
+    assert steps == r0["pipe_tol"]["steps"]
+    assert torch.allclose(G.mu, r0["pipe_tol"]["mu"], atol=5e-6)
+    assert abs(float(FE) - r0["pipe_tol"]["FE"]) < 5e-5 * abs(float(FE))
 
 
 def test_outlier_volume_is_the_global_bounding_box(monkeypatch):

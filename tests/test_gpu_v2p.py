@@ -54,7 +54,11 @@ def test_large_support_pinv_equals_dense_truncated_svd(D, M, sig):
         gold = U[:, keep] @ ((U[:, keep].t() @ rhs) / lam[keep, None])
         p = LM.v2p(q, v, rcond=rcond)
         assert relerr(p.cpu().numpy(), gold.cpu().numpy()) < 2e-4
-        assert relerr(LM.v(q, q, p).cpu().numpy(), (K @ gold - LM.eta * LM.Kernel.GradKRed(q, q).double()).cpu().numpy()) < 2e-5
+        # fitted speeds v(p) = K p - eta gradK: compared on the scale of the solve's right-hand side (for zero target
+        # speeds v(p) itself is only the small residual of the truncated solve)
+        vb = LM.v(q, q, p).double()
+        want = K @ gold - LM.eta * LM.Kernel.GradKRed(q, q).double()
+        assert float((vb - want).abs().max()) < 5e-5 * float(rhs.abs().max())
 
 
 def test_v2p_round_trip_of_the_author(golden):
