@@ -52,6 +52,9 @@ SIGNATURES = {
     "dicp_batch_quad_workspace_bytes": (_sz, [_int]),
     "dicp_batch_quad_loss": (_int, [_int, _int, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _sz, _vp]),
     "dicp_batch_closure_out": (_int, [_int, _int, _vp, _vp, _i64, _i64, _f, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "dicp_batch_closure_cluster_rows": (_int, [_int, _f, _int, _i64, _i64, _int]),
+    "dicp_batch_closure_cluster": (_int, [_int, _int, _f, _f, _int, _vp, _vp, _i64, _i64, _i64, _int, _vp, _i64, _vp, _i64, _vp,
+                                          _vp, _i64, _f, _vp, _i64, _int, _vp]),
     "dicp_batch_coverage": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _int, _f, _vp, _vp]),
     "dicp_lbfgs_create": (_vp, [_int, _vp, _i64, _int, _int, _int, ctypes.c_double, ctypes.c_double]),
     "dicp_lbfgs_destroy": (None, [_vp]),

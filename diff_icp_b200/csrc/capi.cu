@@ -6,6 +6,7 @@
 #include "small_step.cuh"
 #include "sym_engine.cuh"
 #include "batch_closure.cuh"
+#include "cluster_closure.cuh"
 #include "pointset.cuh"
 #include "em_col_small.cuh"
 
@@ -553,6 +554,56 @@ int dicp_batch_closure_out(int D, int K, const int* dims, const int* active, int
     BatchDims B{dims, active, fstride};
     const dim3 grid((unsigned)((maxM * D + 127) / 128), (unsigned)K);
     batch_closure_out_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(B, D, lam_reg, lam, F0, state_end, out, ostride, nscal);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
+// ---- whole closure of every frame in ONE launch (cluster_closure.cuh) ------------------------------------------------------
+int dicp_batch_closure_cluster_rows(int D, float eta, int scheme_euler, int64_t maxM, int64_t maxNx, int nt) {
+    if ((D != 2 && D != 3) || eta != 0.f || !scheme_euler || maxM < 1 || maxM > kCcMaxM || maxNx < 1 || nt < 1) return 0;
+    const long long per = (long long)kCcCluster * kCcThreads;
+    const long long rn = (maxNx + per - 1) / per;
+    if (rn > kCcMaxRows) return 0;
+    const int cap = (int)rn * kCcThreads;
+    if (cluster_closure_smem_floats((int)maxM, D, nt, cap) * 4 > 200 * 1024) return 0;
+    return cap;
+}
+
+int dicp_batch_closure_cluster(int D, int withlogdet, float sigma, float eta, int K, const int* dims, const int* active,
+                               int64_t maxM, int64_t maxNx, int64_t fstride, int nt, float* traj, int64_t tstride,
+                               const float* X, int64_t xstride, const float* y, const float* inv, int64_t ystride,
+                               float lam_reg, float* out, int64_t ostride, int nscal, void* stream) {
+    if (!batch_dims_ok(D, K, dims, fstride) || !traj || !X || !y || !inv || !out || nscal < 6 || !(sigma > 0.f) ||
+        ostride < nscal + maxM * D || xstride < maxM * D || ystride < maxNx)
+        return DICP_EBADARG;
+    const int cap = dicp_batch_closure_cluster_rows(D, eta, 1, maxM, maxNx, nt);
+    if (cap == 0) return DICP_EUNSUPPORTED;
+    const GaussConst gcst = gauss_const(sigma);
+    ClusterClosure C{};
+    C.dims = dims; C.active = active; C.traj = traj; C.fstride = fstride; C.tstride = tstride;
+    C.X = X; C.xstride = xstride; C.y = y; C.inv = inv; C.ystride = ystride;
+    C.out = out; C.ostride = ostride; C.ns = nscal; C.nt = nt; C.rows_cap = cap;
+    C.h = 1.f / (float)nt; C.kappa = gcst.kappa; C.s = gcst.s; C.alpha = gcst.alpha; C.beta = gcst.beta; C.lam_reg = lam_reg;
+    const size_t smem = cluster_closure_smem_floats((int)maxM, D, nt, cap) * 4;
+    void (*kern)(ClusterClosure) = nullptr;
+    if (D == 2) kern = withlogdet ? cluster_closure_kernel<2, true> : cluster_closure_kernel<2, false>;
+    else kern = withlogdet ? cluster_closure_kernel<3, true> : cluster_closure_kernel<3, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kCcCluster, (unsigned)K, 1);
+    cfg.blockDim = dim3(kCcThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCcCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, C);
+    if (e != cudaSuccess) return (int)e;
     launch_counter() += 1;
     return last_error(DICP_OK);
 }

@@ -172,6 +172,19 @@ def batch_closure_out(D, K, dims, active, maxM, fstride, lam_reg, lam, F0, state
     check(rc, "dicp_batch_closure_out")
 
 
+def batch_closure_cluster_rows(D, eta, scheme, maxM, maxNx, nt):
+    """Rows per CTA of the one-launch closure (csrc/cluster_closure.cuh) if it applies to these sizes, else 0."""
+    return int(load().dicp_batch_closure_cluster_rows(int(D), float(eta), int(scheme == "Euler"), int(maxM), int(maxNx), int(nt)))
+
+
+def batch_closure_cluster(D, withlogdet, sigma, eta, K, dims, active, maxM, maxNx, fstride, nt, traj, tstride, X, xstride,
+                          y, inv, ystride, lam_reg, out, ostride, nscal):
+    rc = load().dicp_batch_closure_cluster(D, int(bool(withlogdet)), float(sigma), float(eta), K, ptr(dims), ptr(active), maxM,
+                                           maxNx, fstride, nt, ptr(traj), tstride, ptr(X), xstride, ptr(y), ptr(inv), ystride,
+                                           float(lam_reg), ptr(out), ostride, nscal, stream_ptr())
+    check(rc, "dicp_batch_closure_cluster")
+
+
 def batch_coverage(D, K, dims, active, maxM, maxNx, fstride, traj, tstride, ntimes, radius, counts):
     rc = load().dicp_batch_coverage(D, K, ptr(dims), ptr(active), maxM, maxNx, fstride, ptr(traj), tstride, ntimes,
                                     float(radius), ptr(counts), stream_ptr())

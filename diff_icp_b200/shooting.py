@@ -465,6 +465,7 @@ class BatchedClosurePlan:
     Every frame's arithmetic is independent of which other frames are active, and deterministic."""
 
     NS = 8
+    one_launch_closure = True          # class-level switch (tests compare the two forms)
 
     def __init__(self, D, nt, scheme, withlogdet, sigma, eta, lam_reg, device, Ms, Nxs, use_graph=True):
         import numpy as np
@@ -518,6 +519,10 @@ class BatchedClosurePlan:
         self.use_graph = bool(use_graph) and device.type == "cuda"
         self.graph = None
         self.evaluations = 0
+        # the whole closure of every frame in ONE launch (one thread-block cluster per frame, csrc/cluster_closure.cuh) when
+        # the model / sizes allow it: eta = 0, data points present, Euler, small supports
+        self.one_launch = (BatchedClosurePlan.one_launch_closure and device.type == "cuda" and min(self.Nxs) > 0
+                           and ops.batch_closure_cluster_rows(D, eta, scheme, self.maxM, self.maxNx, nt) > 0)
 
     # ---- problem data -------------------------------------------------------------------------------------------------
     def set_geometry(self, q0_list, x0_list):
@@ -573,6 +578,13 @@ class BatchedClosurePlan:
 
     def _body(self):
         self.d_in.copy_(self.h_in, non_blocking=True)
+        if self.one_launch:
+            ops.batch_closure_cluster(self.D, self.withlogdet, self.sigma, self.eta, self.K, self.dims, self.d_active,
+                                      self.maxM, self.maxNx, self.fstride, self.nt, self.traj, self.K * self.fstride,
+                                      self.d_X, self.ostride, self.y, self.inv, self.maxNd, self.lam_reg, self.d_out,
+                                      self.ostride, self.NS)
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            return
         self._forward()
         lam = self._adjoint()
         ops.batch_closure_out(self.D, self.K, self.dims, self.d_active, self.maxM, self.fstride, self.lam_reg, lam,

@@ -198,6 +198,19 @@ int dicp_batch_quad_loss(int D, int K, const int* dims, const int* active, int64
 int dicp_batch_closure_out(int D, int K, const int* dims, const int* active, int64_t maxM, int64_t fstride,
                            float lam_reg, const float* lam, const float* F0, const float* state_end, float* out,
                            int64_t ostride, int nscal, void* stream);
+/* The WHOLE closure of every active frame -- Euler shoot from (q0, p0 = X[k]), lambda*H(q0,p0) + cost(1), quadratic data loss
+ * against (y, inv), adjoint sweep, d loss / d p0 -- in ONE launch: one thread-block cluster per frame, stages separated by
+ * cluster barriers instead of kernel launches (csrc/cluster_closure.cuh; replaces 1 + nt + 1 + nt + 1 launches of the
+ * dicp_batch_* stage kernels above; same values up to fp32 summation order).  eta = 0 models with data points, Euler.
+ * traj: (nt+1, K, fstride) states, time-major with stride tstride; traj[0] must hold q0 and x0 of every frame, the data points
+ * x(t) are written to traj[t] (support points and momenta of t > 0 are NOT written).  out as in dicp_batch_closure_out
+ * (scalars 1 = A, 4 = cost(1), 5 = data loss).  dicp_batch_closure_cluster_rows returns the rows handled per CTA (> 0) when
+ * this form applies to the given sizes, else 0; the launcher returns DICP_EUNSUPPORTED in that case. */
+int dicp_batch_closure_cluster_rows(int D, float eta, int scheme_euler, int64_t maxM, int64_t maxNx, int nt);
+int dicp_batch_closure_cluster(int D, int withlogdet, float sigma, float eta, int K, const int* dims, const int* active,
+                               int64_t maxM, int64_t maxNx, int64_t fstride, int nt, float* traj, int64_t tstride,
+                               const float* X, int64_t xstride, const float* y, const float* inv, int64_t ystride,
+                               float lam_reg, float* out, int64_t ostride, int nscal, void* stream);
 /* counts[k*ntimes + t] += #{data points of frame k farther than `radius` from every support point at stored time t}
  * (GaussKernel.check_coverage over a whole trajectory, tools/kernel.py:324-329 as used in core/PSR.py:559-566);
  * traj: time-major, time point t of frame k at traj + t*tstride + k*fstride.  counts must be zeroed by the caller. */

@@ -19,7 +19,7 @@ __device__ __forceinline__ float ex2(float x) { float r; asm volatile("ex2.appro
 // 32 = the adds / multiplies of the mix written as FFMA2 with a constant operand (a + b = fma(a, 1, b), a * b = fma(a, b, -0)):
 // bit-identical results, different pipe cost
 template <int V, int NCH>
-__global__ void __launch_bounds__(64) mix_kernel(int iters, float* out, float seed) {
+__global__ void __launch_bounds__(64) mix_kernel(int iters, float* out, float seed, float onev, float nzerov) {
     __shared__ float4 tile[64];
     if (threadIdx.x < 64) tile[threadIdx.x] = make_float4(seed, seed * 0.5f, 1.f - seed, 0.25f);
     __syncthreads();
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(64) mix_kernel(int iters, float* out, float se
         } else {
             const u64 ra = (V & 8) ? pk(rowa, rowa) : pk(rowa, rowb);
             const u64 rb = (V & 8) ? pk(rowb, rowb) : pk(rowb, rowa);
-            const u64 one = pk(1.f, 1.f), nzero = pk(-0.f, -0.f);
+            const u64 one = pk(onev, onev), nzero = pk(nzerov, nzerov);      // run-time values: ptxas cannot fold them back
             // 3 rounds x NCH instructions = 30 packed instructions for NCH = 10: per round FFMA2 : FADD2 : FMUL2 ~ 19 : 7 : 4
 #pragma unroll
             for (int k = 0; k < NCH; ++k) acc[k] = fma2(acc[k], ra, colv);
@@ -74,13 +74,13 @@ template <int V, int NCH>
 double run(int ctas_per_sm, int sms, float clock_ghz, float* out) {
     const int iters = 20000;
     dim3 grid(sms * ctas_per_sm), block(64);
-    mix_kernel<V, NCH><<<grid, block>>>(100, out, 0.37f);
+    mix_kernel<V, NCH><<<grid, block>>>(100, out, 0.37f, 1.f, -0.f);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0);
-        mix_kernel<V, NCH><<<grid, block>>>(iters, out, 0.37f);
+        mix_kernel<V, NCH><<<grid, block>>>(iters, out, 0.37f, 1.f, -0.f);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);

@@ -82,7 +82,8 @@ def run_c4(rank, world, dev, comm, n_frames=256, n_points=50000, C=20, iters=3, 
         tt = torch.tensor(times, device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         times = tt.tolist()
-    plan = getattr(P, "_bplan", None)
+    plans = getattr(P, "_bplan", None)
+    plan = plans[0] if plans else None
     return {"metric": "groupwise_psr_iteration_ms", "config": "diffICP_full-like (configs[3])", "n_gpus": world,
             "frames": n_frames, "structures": 3, "points_per_frame": n_points, "C_per_structure": C,
             "support_points": int(P.q0[0].shape[0]),

@@ -35,7 +35,7 @@ def spiral_frames(K, N, seed=1234):
 
 
 def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, iters=3, graph=True, workers=1,
-                  lockstep=True, weak=False):
+                  lockstep=True, weak=False, groups=None):
     """Returns the dict reported as `groupwise_psr_iteration` (rank 0) -- times are the max over ranks.
     weak=True: `n_frames` frames PER RANK (atlas of n_frames * world frames) instead of n_frames in total."""
     if weak:
@@ -55,6 +55,8 @@ def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, ite
     P.printstuff = False
     P.frame_workers = workers
     P.batched_lbfgs = bool(lockstep)
+    if groups is not None:
+        P.lockstep_groups = int(groups)
     P.set_support_scheme("grid", rho=math.sqrt(2))
     P.reinitialize_GMM()
     times = []
@@ -78,7 +80,7 @@ def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, ite
         times = tt.tolist()
     return {"metric": "groupwise_psr_iteration_ms", "n_gpus": world, "frames": n_frames, "points_per_frame": n_points,
             "C": C, "support_points": int(P.q0[0].shape[0]), "model": "hybrid, Euler nt=10, grid support rho=sqrt(2), 2-D",
-            "scaling": "weak (frames per rank fixed)" if weak else "strong (frames sharded over ranks)", "cuda_graph": bool(graph), "frame_workers": workers, "lockstep_lbfgs": bool(lockstep),
+            "scaling": "weak (frames per rank fixed)" if weak else "strong (frames sharded over ranks)", "cuda_graph": bool(graph), "frame_workers": workers, "lockstep_lbfgs": bool(lockstep), "lockstep_groups": len(getattr(P, "_bplan", None) or []),
             "FE": P.FE, "sigma": P.GMMi[0].sigma,
             "gmm_opt_ms": [1e3 * a for a, _ in times], "reg_opt_ms": [1e3 * b for _, b in times],
             "iteration_ms_steady": 1e3 * sum(times[-1])}
@@ -94,6 +96,7 @@ def main():
     ap.add_argument("--workers", type=int, default=1)
     ap.add_argument("--lockstep", type=int, default=1)
     ap.add_argument("--weak", type=int, default=0, help="1: --frames is the number of frames per rank")
+    ap.add_argument("--groups", type=int, default=None, help="frame groups of the lock-step registration (default: DiffPSR's)")
     args = ap.parse_args()
     rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     dev = torch.device("cuda", lr)
@@ -104,7 +107,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
         from diff_icp_b200.dist import StatsComm
         comm = StatsComm()
-    res = run_groupwise(rank, world, dev, comm, args.frames, args.points, args.C, args.iters, args.graph, args.workers, args.lockstep, bool(args.weak))
+    res = run_groupwise(rank, world, dev, comm, args.frames, args.points, args.C, args.iters, args.graph, args.workers, args.lockstep, bool(args.weak), args.groups)
     if rank == 0:
         print(json.dumps(res))
     if comm is not None:

@@ -54,7 +54,8 @@ def main():
         pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(args.top)
         print(f"==== {name}: {1e3 * dt:.2f} ms (under cProfile)")
         print(s.getvalue()[:9000])
-    plan = getattr(P, "_bplan", None)
+    plans = getattr(P, "_bplan", None)
+    plan = plans[0] if plans else None
     if plan is not None:
         print("closure evaluation rounds so far:", plan.evaluations)
 

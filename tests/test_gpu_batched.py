@@ -34,13 +34,20 @@ CASES = [
     # many frames x many data points: the x-row CTAs take several blocks of 128 rows each (xpass > 1 in small_step.cuh)
     (2, "hybrid", "Euler", 3, [25] * 40, [13000 + 10 * k for k in range(40)]),
     (3, "logdet", "Ralston", 2, [30] * 36, [14000] * 36),
+    # sizes at the limits of the one-launch closure (one thread-block cluster per frame): 64 support points, 16384 data points
+    (3, "classic", "Euler", 5, [12, 64, 33], [700, 3000, 16384]),
+    (3, "hybrid", "Euler", 4, [64, 1, 2], [16384, 5, 2049]),
 ]
 
 
+@pytest.mark.parametrize("one_launch", [True, False])
 @pytest.mark.parametrize("D,version,scheme,nt,Ms,Nxs", CASES)
-def test_batched_closure_equals_per_frame_closure(D, version, scheme, nt, Ms, Nxs):
+def test_batched_closure_equals_per_frame_closure(D, version, scheme, nt, Ms, Nxs, one_launch, monkeypatch):
+    """one_launch=True: the whole closure of a frame in ONE kernel (csrc/cluster_closure.cuh) where it applies (eta = 0, data
+    points, Euler, <= 64 support points, <= 16384 data points); False: the stage kernels, one launch per integrator stage."""
     from diff_icp_b200 import shooting
     from diff_icp_b200.core.LDDMM import LDDMMModel
+    monkeypatch.setattr(shooting.BatchedClosurePlan, "one_launch_closure", one_launch)
     sig, lam = 0.25, 50.0
     LM = LDDMMModel(sigma=sig, D=D, lambd=lam, version=version, scheme=scheme, nt=nt, spec=spec())
     K = len(Ms)
@@ -54,6 +61,10 @@ def test_batched_closure_equals_per_frame_closure(D, version, scheme, nt, Ms, Nx
 
     for use_graph in (False, True):
         plan = shooting.BatchedClosurePlan(D, nt, scheme, LM.withlogdet, sig, LM.eta, lam, dev(), Ms, Nxs, use_graph=use_graph)
+        eligible = version != "logdet" and scheme == "Euler" and min(Nxs) > 0 and max(Ms) <= 64 and max(Nxs) <= 16384
+        assert plan.one_launch == (one_launch and eligible)
+        if not one_launch and not eligible and use_graph:
+            return                                   # identical to the one_launch=True run of this case
         plan.set_geometry(q0, x0)
         plan.set_targets(torch.cat(y), torch.cat(inv))
         for rep in range(2):                         # second pass: graph replay, and a different active set
@@ -77,6 +88,8 @@ def test_batched_closure_equals_per_frame_closure(D, version, scheme, nt, Ms, Nx
                 if K > 8 and k % 9 != 0:             # many-frame cases: check every 9th frame
                     continue
                 tol = 1.0 if max(Ms) <= 512 else 100.0       # same kernels / different engines (summation orders differ)
+                if plan.one_launch:
+                    tol = 10.0                               # other summation order (per-thread sums over all stages), fixed origin
                 assert abs(plan.losses[k] - L) <= tol * 2e-6 * abs(L), (k, plan.losses[k], L)
                 gr = gr.reshape(-1).numpy()
                 assert np.abs(go - gr).max() <= tol * 1e-6 * np.abs(gr).max(), (k, np.abs(go - gr).max(), np.abs(gr).max())
@@ -186,3 +199,30 @@ def test_lockstep_is_deterministic():
     assert Pa.FE == Pb.FE
     for k in range(Pa.K):
         assert torch.equal(Pa.a0[k], Pb.a0[k])
+
+
+@pytest.mark.parametrize("one_launch", [False, True])
+def test_frame_groups_agree_with_a_single_batch(one_launch, monkeypatch):
+    """lockstep_groups: the frames registered as 1, 2 or 3 groups (own plan / stream / host thread each).  With the stage
+    kernels the groups give the same BITS here (the kernels' column-split counts coincide for these batch sizes); with the
+    one-launch closure the rows-per-CTA split follows the group's largest frame, so the groups agree to rounding."""
+    from diff_icp_b200 import shooting
+    monkeypatch.setattr(shooting.BatchedClosurePlan, "one_launch_closure", one_launch)
+    outs = []
+    for groups in (1, 2, 3):
+        P = make_psr(True)
+        P.lockstep_groups, P.lockstep_group_min_frames = groups, 2
+        assert len(P._batched_plan()) == groups
+        for _ in range(2):
+            P.GMM_opt(max_iterations=5, tol=1e-3)
+            P.Reg_opt(nmax=2, tol=1e-3)
+        outs.append((P.FE, [a.clone() for a in P.a0], [P.x1[k, 0].clone() for k in range(P.K)], [float(r) for r in P.regloss]))
+    for o in outs[1:]:
+        if not one_launch:
+            assert o[0] == outs[0][0] and o[3] == outs[0][3]
+            assert all(torch.equal(a, b) for a, b in zip(o[1], outs[0][1]))
+            assert all(torch.equal(a, b) for a, b in zip(o[2], outs[0][2]))
+        else:
+            assert abs(o[0] - outs[0][0]) <= 1e-5 * abs(outs[0][0])
+            for a, b in zip(o[2], outs[0][2]):
+                assert (a - b).abs().max().item() <= 2e-3 * 0.2          # points: well inside one kernel width
