@@ -443,8 +443,21 @@ def kernel_roofline(args, LM, q, p, dev, ops):
         ts.sort()
         return ts[len(ts) // 2]
 
-    t_adj = timeit(lambda: shooting._vjp(sp, state, lam, G, ws))
-    t_fwd = timeit(lambda: shooting._rhs(sp, state, F, ws))
+    def graph_time(fn, reps=10):
+        """Device time per call as the call runs inside the step: `reps` calls captured in one CUDA graph (the closure of the
+        timed step is such a graph), events around the replay -- no host launch latency between the call's launches."""
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        return timeit(g.replay, n=10) / reps
+
+    t_adj_eager = timeit(lambda: shooting._vjp(sp, state, lam, G, ws))
+    t_fwd_eager = timeit(lambda: shooting._rhs(sp, state, F, ws))
+    t_adj = graph_time(lambda: shooting._vjp(sp, state, lam, G, ws))
+    t_fwd = graph_time(lambda: shooting._rhs(sp, state, F, ws))
 
     sms = ops.load().dicp_sm_count()
     peaks = {}
@@ -488,10 +501,14 @@ def kernel_roofline(args, LM, q, p, dev, ops):
                 "evaluates every UNORDERED pair once (symmetric engine), its per-ordered-pair count is half the unordered "
                 "one; peak = FFMA issue rate measured live by dicp_pipe_probe (x2 flop), of measured; frac = binding-pipe "
                 "utilisation",
-        "adjoint": {"s_per_launch": t_adj, "pairs_per_s": pairs / t_adj, "fp32_per_pair": alg["adj_fp32"], "frac": frac_adj,
+        "timing_note": "s_per_launch = device time of one dicp_rhs_adjoint / dicp_rhs_forward call (pack + pair kernel + merge "
+                       "launches) as it runs inside the step's CUDA graph: 10 calls per captured graph, CUDA events around "
+                       "the replay, median of 10; s_per_launch_eager = the same call launched from the host one by one "
+                       "(includes host launch latency between its launches)",
+        "adjoint": {"s_per_launch_eager": t_adj_eager, "s_per_launch": t_adj, "pairs_per_s": pairs / t_adj, "fp32_per_pair": alg["adj_fp32"], "frac": frac_adj,
                     "frac_lanes_clock": fp_rate_adj / lanes_clock,
                     "physical_pair_evaluations_per_s": (0.5 if symmetric else 1.0) * pairs / t_adj},
-        "forward": {"s_per_launch": t_fwd, "pairs_per_s": pairs / t_fwd, "fp32_per_pair": alg["fwd_fp32"], "frac": frac_fwd,
+        "forward": {"s_per_launch_eager": t_fwd_eager, "s_per_launch": t_fwd, "pairs_per_s": pairs / t_fwd, "fp32_per_pair": alg["fwd_fp32"], "frac": frac_fwd,
                     "frac_lanes_clock": fp_rate_fwd / lanes_clock},
         "measured_peaks": {"ffma_per_s": peaks["ffma"], "mufu_ex2_per_s": peaks["mufu_ex2"], "sms": sms},
         "em_step": em,
@@ -526,8 +543,10 @@ def em_roofline(dev, timeit, peaks):
 
     out = {"hbm_peak_gbs": hbm, "hbm_peak_source": src,
            "note": "device time per call = pack + pair kernel (+ split merge / scalar reduction), 10 calls per CUDA-graph "
-                   "replay; algorithmic bytes per point: 12D+8 per EM step (SURVEY.md 8d): pass 1 reads 4D and writes 4, "
-                   "the column pass reads 4D+4, pass 2 reads 4D+4 and writes 4D"}
+                   "replay; algorithmic bytes per point: 12D+8 per EM step in three sweeps (SURVEY.md 8d): pass 1 reads 4D and "
+                   "writes 4, the column pass reads 4D+4, pass 2 reads 4D+4 and writes 4D; with <= 64 components the first two "
+                   "are ONE sweep that reads 4D (first_sweep_fused), i.e. 12D+4 per EM step; em_step_s = the sweeps an EM "
+                   "step actually runs"}
     for tag, (N, C, D, sig) in {"atlas": (640000, 50, 2, 0.05), "two_set": (20000, 20000, 3, 0.1),
                                 "few_components": (4000000, 8, 3, 0.2)}.items():
         g = torch.Generator().manual_seed(7)
@@ -544,11 +563,15 @@ def em_roofline(dev, timeit, peaks):
             "row_lite": (lambda: em_ops.rowpass(sig, X, mu, wl2), 8, 4 * D + 4),
             "col_stats": (lambda: em_ops.colstats(sig, X, T2, mu, wl2), 14, 4 * D + 4),
             "row_full": (lambda: em_ops.rowpass(sig, X, mu, wl2, mu, lpi), 17, 4 * D + 4 + 4 * D),
+            # row LSE + column statistics from ONE read of X (C <= 64: one launch; more components: the two sweeps above)
+            "first_sweep_fused": (lambda: em_ops.lse_colstats(sig, X, mu, wl2), 22, 4 * D),
         }
         total = 0.0
+        fused = C <= em_ops.SMALL_C
         for name, (fn, fp, nbytes) in passes.items():
             t = graph_time(fn)
-            total += t
+            if name == "row_full" or (name == "first_sweep_fused") == fused:
+                total += t          # what an EM step runs: fused first sweep + full row pass, or the three sweeps
             pairs = float(N) * C
             res[name] = {"s_per_call": t, "pairs_per_s": pairs / t, "fp32_per_pair": fp,
                          "frac_fp32": fp * pairs / t / peaks["ffma"], "frac_sfu": pairs / t / peaks["mufu_ex2"],

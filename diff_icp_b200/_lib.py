@@ -38,6 +38,7 @@ SIGNATURES = {
                                 _vp, _sz, _vp, _int]),
     "dicp_em_rowpass": (_int, [_int, _int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dicp_em_colstats": (_int, [_int, _f, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "dicp_em_lse_colstats": (_int, [_int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dicp_em_mstep": (_int, [_int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "dicp_log_resp": (_int, [_int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "dicp_small_max_support": (_int, []),

@@ -189,8 +189,7 @@ class GaussianMixtureUnif(Module):
         mu_new, w_new, lpi_new = mu_old, w_old, lpi_old
         merge_check = None
         if do_mu or do_w:
-            T2 = em_ops.rowpass(sigma_old, X, mu_old, wl2)
-            stats = em_ops.colstats(sigma_old, X, T2, mu_old, wl2) if N_local > 0 else _empty_stats(C, D, X.device)
+            stats = em_ops.lse_colstats(sigma_old, X, mu_old, wl2) if N_local > 0 else _empty_stats(C, D, X.device)
             if comm is not None:
                 m_ref = None if _safe_merge else self._agreed_exponent()
                 if m_ref is None:
@@ -322,8 +321,7 @@ class GaussianMixtureUnif(Module):
             wl2 = ((lpi - self._lgn(sigma)) * _LOG2E).contiguous()
             if N_local == 0:
                 return wl2, _empty_stats(C, D, dev)
-            T2 = em_ops.rowpass(sigma, X, mu, wl2)
-            return wl2, em_ops.colstats(sigma, X, T2, mu, wl2)
+            return wl2, em_ops.lse_colstats(sigma, X, mu, wl2)
 
         def values(sums, sigma_new):
             P, Q, SQ, DS, N = sums

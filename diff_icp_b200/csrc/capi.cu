@@ -378,6 +378,35 @@ int dicp_em_colstats(int D, float sigma_old, const float* X, int64_t N, const fl
     return last_error(em_colstats_entry(ex, D, sigma_old, X, N, T2, mu_old, wl2, C, stats));
 }
 
+int dicp_em_lse_colstats(int D, float sigma_old, const float* X, int64_t N, const float* mu_old, const float* wl2, int64_t C,
+                         float* T2_scratch, float* stats, void* workspace, size_t workspace_bytes, void* stream) {
+    if (C >= 1 && C <= kEmColMaxC && (D == 2 || D == 3) && sigma_old > 0.f && N >= 1 && N <= INT32_MAX && X && mu_old &&
+        wl2 && stats && workspace && workspace_bytes >= em_col_small_workspace(N, (int)C, device_info().sms)) {
+        // few components: row log-sum-exp and column statistics from ONE read of X (em_lse_col_small_kernel)
+        EmParams prm{};
+        prm.X = X; prm.mu_old = mu_old; prm.wl2 = wl2; prm.origin = mu_old;
+        prm.kappa = gauss_const(sigma_old).kappa;
+        prm.o_stats = stats;
+        cudaStream_t st = (cudaStream_t)stream;
+        unsigned* counter = (unsigned*)workspace;
+        const size_t cbytes = em_col_small_counter_bytes(N, device_info().sms);
+        float* part = (float*)((char*)workspace + cbytes);
+        cudaMemsetAsync(counter, 0, cbytes, st);
+        int blocks = 1, passes = 1;
+        em_lse_col_small_grid(N, device_info().sms, &blocks, &passes);
+        if (D == 2) em_lse_col_small_kernel<2><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, passes, part, counter);
+        else em_lse_col_small_kernel<3><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, passes, part, counter);
+        launch_counter() += 1;
+        return last_error(DICP_OK);
+    }
+    // many components: the two sweeps of the general engine, T2 through the caller's scratch array
+    if (!T2_scratch) return DICP_EBADARG;
+    const int rc = dicp_em_rowpass(D, 1, sigma_old, X, N, mu_old, wl2, C, nullptr, nullptr, T2_scratch, nullptr, nullptr,
+                                   nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
+    if (rc != DICP_OK) return rc;
+    return dicp_em_colstats(D, sigma_old, X, N, T2_scratch, mu_old, wl2, C, stats, workspace, workspace_bytes, stream);
+}
+
 int dicp_em_mstep(int D, const float* stats, const float* mu_old, const float* w_old, int64_t C, int do_mu, int do_w,
                   int sig_mode, float* mu_new, float* w_new, float* lpi_new, float* out_scal, void* stream) {
     if ((D != 2 && D != 3) || C < 1 || C > INT32_MAX || sig_mode < 0 || sig_mode > 2 || !mu_old || !w_old || !mu_new ||

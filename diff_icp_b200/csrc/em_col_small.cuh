@@ -19,6 +19,8 @@ static constexpr int kEmColMaxC = 64;
 static constexpr int kEmColChunk = 512;      // points staged per step
 
 static constexpr int kEmColGroup = 16;     // CTAs per level-1 merge group
+static constexpr int kEmRowR = 4;          // points per thread in the row passes
+static constexpr int kEmRowRows = 128 * kEmRowR;
 
 // acc <- merge (in a fixed order) of the partials s in [s0, s1) of component c: thread group g takes s0+g, s0+g+G, ...
 // (loads of a batch of 8 issued before they are combined), then the groups are merged in group order through `xch`.
@@ -58,6 +60,38 @@ DICP_D void em_col_merge(const float* part, int s0, int s1, int g, int G, int c,
             Op::combine(acc, b);
         }
     }
+}
+
+// Tail shared by the column-statistics kernels: two-level merge of the CTAs' partials (a single serial merge of hundreds of
+// partials by one CTA is a chain of dependent L2 round trips): the last CTA of every group of kEmColGroup consecutive CTAs
+// merges that group's partials into a level-2 partial, and the last of those mergers merges the level-2 partials and writes
+// the statistics.  `acc` holds the CTA's own partial in the threads with g == 0 on entry.
+template <int D>
+DICP_D void em_col_publish_and_merge(const EmParams& P, int C, int g, int G, int c, bool work, float* xch, float* acc,
+                                     const typename EmCol<D>::Row& row, float* __restrict__ part,
+                                     unsigned* __restrict__ counter) {
+    using Op = EmCol<D>;
+    constexpr int NACC = Op::NACC;
+    const int tid = threadIdx.x, nsplit = gridDim.x;
+    if (work && g == 0) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) part[((size_t)blockIdx.x * NACC + k) * C + c] = acc[k];
+    }
+    const int ngroups = (nsplit + kEmColGroup - 1) / kEmColGroup;
+    const int grp = blockIdx.x / kEmColGroup;
+    const int s0 = grp * kEmColGroup, s1 = (s0 + kEmColGroup < nsplit) ? s0 + kEmColGroup : nsplit;
+    if (!last_cta(&counter[1 + grp], (unsigned)(s1 - s0))) return;
+    float* part2 = part + (size_t)nsplit * NACC * C;
+    em_col_merge<D>(part, s0, s1, g, G, c, C, work, xch, acc);
+    if (work && g == 0) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) part2[((size_t)grp * NACC + k) * C + c] = acc[k];
+    }
+    if (tid == 0) counter[1 + grp] = 0u;
+    if (!last_cta(&counter[0], (unsigned)ngroups)) return;
+    em_col_merge<D>(part2, 0, ngroups, g, G, c, C, work, xch, acc);
+    if (work && g == 0) Op::finish(P, c, row, acc, nullptr);
+    if (tid == 0) counter[0] = 0u;
 }
 
 template <int D>
@@ -123,27 +157,139 @@ __global__ void __launch_bounds__(128) em_col_small_kernel(EmParams P, int N, in
             for (int k = 0; k < NACC; ++k) b[k] = xch[(g2 * NACC + k) * C + c];
             Op::combine(acc, b);
         }
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) part[((size_t)blockIdx.x * NACC + k) * C + c] = acc[k];
     }
-    // Two-level merge of the CTAs' partials (a single serial merge of hundreds of partials by one CTA is a chain of
-    // dependent L2 round trips): the last CTA of every group of kEmColGroup consecutive CTAs merges that group's partials
-    // into a level-2 partial, and the last of those mergers merges the level-2 partials and writes the statistics.
-    const int ngroups = (nsplit + kEmColGroup - 1) / kEmColGroup;
-    const int grp = blockIdx.x / kEmColGroup;
-    const int s0 = grp * kEmColGroup, s1 = (s0 + kEmColGroup < nsplit) ? s0 + kEmColGroup : nsplit;
-    if (!last_cta(&counter[1 + grp], (unsigned)(s1 - s0))) return;
-    float* part2 = part + (size_t)nsplit * NACC * C;
-    em_col_merge<D>(part, s0, s1, g, G, c, C, work, xch, acc);
+    em_col_publish_and_merge<D>(P, C, g, G, c, work, xch, acc, row, part, counter);
+}
+
+// ---- first sweep of the EM step in ONE pass over the points (C <= 64) ----------------------------------------------------------
+// Row log-sum-exp AND the column statistics from a single read of X: a CTA takes groups of 512 points; per group
+//   phase A  every thread owns 4 points and sweeps the components (resident in shared memory, EmRow<D,true>::pair<F2>):
+//            T2_n = log2 sum_c 2^t2_nc stays in registers;
+//   staging  the thread writes its points' packed records (x'_n, T2_n) to shared memory -- what em_col_small_kernel packs
+//            from global memory, here without the round trip of T2 through HBM;
+//   phase B  the threads regroup as G = 128 / C groups of C lanes, lane c of group g sweeps the group's share of the staged
+//            points for component c (EmCol::pair<F2>, online-max rescaling), accumulators live in registers across groups.
+// Then the CTA partial and the two-level ticket merge exactly as in em_col_small_kernel.  Algorithmic HBM traffic of this
+// sweep: 4 D bytes per point (X once); 8 + 14 FP32 operations and 2 MUFU.EX2 per (point, component).
+template <int D>
+__global__ void __launch_bounds__(128) em_lse_col_small_kernel(EmParams P, int N, int C, int passes,
+                                                               float* __restrict__ part, unsigned* __restrict__ counter) {
+    using OpR = EmRow<D, true>;
+    using OpC = EmCol<D>;
+    constexpr int NFR = OpR::NF, RECR = 2 * NFR, PF4R = NFR / 2;
+    constexpr int NFC = OpC::NF, RECC = 2 * NFC, NACC = OpC::NACC;
+    constexpr int R = kEmRowR, ROWS = kEmRowRows;
+    static_assert(ROWS == kEmColChunk, "one staged chunk per row group");
+    __shared__ __align__(16) float cols[(kEmColMaxC / 2) * RECR];
+    __shared__ __align__(16) float pts[(ROWS / 2) * RECC];
+    __shared__ float xch[128 * NACC];
+    const int tid = threadIdx.x;
+    const int Cpad = (C + 1) & ~1;
+    for (int j = tid; j < Cpad; j += 128) {
+        float rec[OpR::COLF4 * 4];
+        OpR::pack_col(P, j, C, rec);
+        float* dst = cols + (j >> 1) * RECR + (j & 1);
+#pragma unroll
+        for (int k = 0; k < NFR; ++k) dst[2 * k] = rec[k];
+    }
+    const int G = 128 / C;
+    const int g = tid / C, c = tid - g * C;
+    const bool work = g < G;
+    typename OpC::Row rowc;
+    if (work) OpC::load_row(P, c, rowc);
+    F2 accp[NACC];
+    OpC::init_packed(accp);
+    const float4* spc = reinterpret_cast<const float4*>(cols);
+    const float4* spp = reinterpret_cast<const float4*>(pts);
+    const int ncp = Cpad >> 1;
+    __syncthreads();
+    for (int ps = 0; ps < passes; ++ps) {
+        const long long base = ((long long)blockIdx.x * passes + ps) * ROWS;
+        if (base >= N) break;
+        const int n = (N - base < ROWS) ? (int)(N - base) : ROWS;
+        const int npad = (n + 1) & ~1;
+        // phase A: row log-sum-exp of this thread's 4 points
+        typename OpR::Row row[R];
+        F2 acc[R][OpR::NACC];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int t = tid + r * 128;
+            OpR::load_row(P, (int)(base + (t < n ? t : n - 1)), row[r]);
+            OpR::init_packed(acc[r]);
+        }
+        for (int Pp = 0; Pp < ncp; ++Pp) {
+            F2 cc[NFR];
+#pragma unroll
+            for (int k = 0; k < PF4R; ++k) {
+                const float4 v = spc[Pp * PF4R + k];
+                cc[2 * k] = f2(v.x, v.y);
+                cc[2 * k + 1] = f2(v.z, v.w);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) OpR::template pair<F2>(P, row[r], cc, acc[r]);
+        }
+        __syncthreads();                       // the previous group's phase B is done with `pts`
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int t = tid + r * 128;
+            if (t < npad) {
+                float a[OpR::NACC];
+                OpR::unpack_acc(acc[r], a);
+                float* dst = pts + (t >> 1) * RECC + (t & 1);
+                if (t < n) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) dst[2 * k] = row[r].x[k];
+                    dst[2 * D] = a[OpR::A_M] + lg2f_fast(a[OpR::A_S]);
+                } else {                       // null partner of an odd last point (EmCol::pack_col's padding record)
+#pragma unroll
+                    for (int k = 0; k < D; ++k) dst[2 * k] = DICP_FAR;
+                    dst[2 * D] = 1.0e30f;
+                }
+#pragma unroll
+                for (int k = D + 1; k < NFC; ++k) dst[2 * k] = 0.f;
+            }
+        }
+        __syncthreads();
+        // phase B: column statistics of the staged points
+        if (work) {
+            const int npair = npad >> 1;
+            const int a = (int)(((long long)npair * g) / G), b = (int)(((long long)npair * (g + 1)) / G);
+            for (int t = a; t < b; ++t) {
+                F2 cc[NFC];
+#pragma unroll
+                for (int k = 0; k < NFC / 2; ++k) {
+                    const float4 v = spp[t * (NFC / 2) + k];
+                    cc[2 * k] = f2(v.x, v.y);
+                    cc[2 * k + 1] = f2(v.z, v.w);
+                }
+                OpC::template pair<F2>(P, rowc, cc, accp);
+            }
+        }
+    }
+    float acc[NACC];
+    OpC::unpack_acc(accp, acc);
+    if (work && g > 0) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) xch[(g * NACC + k) * C + c] = acc[k];
+    }
+    __syncthreads();
     if (work && g == 0) {
+        for (int g2 = 1; g2 < G; ++g2) {
+            float b[NACC];
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) part2[((size_t)grp * NACC + k) * C + c] = acc[k];
+            for (int k = 0; k < NACC; ++k) b[k] = xch[(g2 * NACC + k) * C + c];
+            OpC::combine(acc, b);
+        }
     }
-    if (tid == 0) counter[1 + grp] = 0u;
-    if (!last_cta(&counter[0], (unsigned)ngroups)) return;
-    em_col_merge<D>(part2, 0, ngroups, g, G, c, C, work, xch, acc);
-    if (work && g == 0) Op::finish(P, c, row, acc, nullptr);
-    if (tid == 0) counter[0] = 0u;
+    em_col_publish_and_merge<D>(P, C, g, G, c, work, xch, acc, rowc, part, counter);
+}
+// CTAs of the fused sweep: about 4 per SM, whole 512-point groups each
+inline void em_lse_col_small_grid(long long N, int sms, int* blocks, int* passes) {
+    const long long groups = (N + kEmRowRows - 1) / kEmRowRows;
+    long long ps = (groups + (long long)sms * 4 - 1) / ((long long)sms * 4);
+    if (ps < 1) ps = 1;
+    *passes = (int)ps;
+    *blocks = (int)((groups + ps - 1) / ps);
 }
 
 // ---- row passes of the EM step for FEW components (C <= 64): one launch ------------------------------------------------------
@@ -151,8 +297,6 @@ __global__ void __launch_bounds__(128) em_col_small_kernel(EmParams P, int N, in
 // real) + scalar reduction.  With the components resident in shared memory a thread simply sweeps them for its 4 rows (packed
 // fp32, EmRow::pair<F2>): no pipeline, coalesced row loads / stores, and the four free-energy sums of the full pass are block
 // partials added in block order by scalar_reduce_kernel.  HBM-bound for C <~ 9 (12D + 8 bytes per point and EM step).
-static constexpr int kEmRowR = 4;
-static constexpr int kEmRowRows = 128 * kEmRowR;
 
 template <int D, bool LITE>
 __global__ void __launch_bounds__(128) em_row_small_kernel(EmParams P, int N, int C, int passes,

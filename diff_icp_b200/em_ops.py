@@ -1,4 +1,5 @@
-"""Functional wrappers over the EM entry points of the C ABI (dicp_em_rowpass / dicp_em_colstats / dicp_log_resp).
+"""Functional wrappers over the EM entry points of the C ABI (dicp_em_rowpass / dicp_em_colstats / dicp_em_lse_colstats /
+dicp_em_mstep / dicp_log_resp).
 
 Inputs and outputs are contiguous fp32 CUDA tensors; everything is enqueued on the current stream without host
 synchronisation.  No CPU path.
@@ -47,6 +48,24 @@ def colstats(sigma_old, X, T2, mu_old, wl2):
     rc = load().dicp_em_colstats(D, float(sigma_old), ptr(X), N, ptr(T2), ptr(mu_old), ptr(wl2), C, ptr(stats),
                                  ptr(ws), ws.numel(), stream_ptr())
     check(rc, "dicp_em_colstats")
+    return stats
+
+
+SMALL_C = 64        # up to this many components the first sweep is one launch / one read of X (csrc/em_col_small.cuh)
+
+
+def lse_colstats(sigma_old, X, mu_old, wl2):
+    """First sweep of the EM step: column statistics (C, D+3) = [m (log2), S0, B (D), A] of every component, with the row
+    log-sum-exp computed on the way (rowpass(lite) + colstats as ONE call; one launch and one read of X when C <= SMALL_C)."""
+    dev = require_cuda(X, mu_old, wl2)
+    N, D = X.shape
+    C = mu_old.shape[0]
+    stats = torch.empty(C, D + 3, dtype=torch.float32, device=dev)
+    T2 = torch.empty(N, dtype=torch.float32, device=dev) if C > SMALL_C else None
+    ws = workspace(max(N, C), max(N, C), dev)
+    rc = load().dicp_em_lse_colstats(D, float(sigma_old), ptr(X), N, ptr(mu_old), ptr(wl2), C, ptr(T2), ptr(stats),
+                                     ptr(ws), ws.numel(), stream_ptr())
+    check(rc, "dicp_em_lse_colstats")
     return stats
 
 

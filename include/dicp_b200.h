@@ -132,6 +132,13 @@ int dicp_em_rowpass(int D, int lite, float sigma_old, const float* X, int64_t N,
 int dicp_em_colstats(int D, float sigma_old, const float* X, int64_t N, const float* T2, const float* mu_old,
                      const float* wl2, int64_t C, float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* First sweep of the EM step -- row log-sum-exp AND column statistics -- as one call: same statistics as dicp_em_rowpass(lite)
+ * followed by dicp_em_colstats (the six KeOps reductions of core/GMM.py:410-415, :443-455 collapse into this sweep and the
+ * full row pass).  With C <= 64 components it is ONE launch and ONE read of X (the row LSE never leaves the chip; T2_scratch
+ * may be null); with more components it runs the two sweeps of the general engine and T2_scratch (N floats) is required. */
+int dicp_em_lse_colstats(int D, float sigma_old, const float* X, int64_t N, const float* mu_old, const float* wl2, int64_t C,
+                         float* T2_scratch, float* stats, void* workspace, size_t workspace_bytes, void* stream);
+
 /* M step on the column statistics, one launch (core/GMM.py:286-297 / :442-456):
  *   mu_new = do_mu ? mu_old + B/S0 : mu_old;   w_new = do_w ? (m + log2 S0) ln 2 : w_old;   lpi_new = w_new - LSE(w_new);
  *   out_scal = { N D sigma'^2 (sig_mode 1: sum_c 2^m_c (A_c - |B_c|^2/S0_c), 2: sum_c 2^m_c A_c, 0: 0), LSE(w_new) }.

@@ -62,6 +62,10 @@ def colstats(sigma_old, X, T2, mu_old, wl2):
     return torch.from_numpy(stats)
 
 
+def lse_colstats(sigma_old, X, mu_old, wl2):
+    return colstats(sigma_old, X, rowpass(sigma_old, X, mu_old, wl2), mu_old, wl2)
+
+
 def mstep(stats, mu_old, w_old, do_mu, do_w, sig_mode):
     """CPU stand-in of dicp_em_mstep: the same formulas with torch ops (csrc/em_col_small.cuh, em_mstep_kernel)."""
     D = mu_old.shape[1]
@@ -82,6 +86,7 @@ def install(monkeypatch):
     from diff_icp_b200 import em_ops
     monkeypatch.setattr(em_ops, "rowpass", rowpass)
     monkeypatch.setattr(em_ops, "colstats", colstats)
+    monkeypatch.setattr(em_ops, "lse_colstats", lse_colstats)
     monkeypatch.setattr(em_ops, "mstep", mstep)
 
 

@@ -214,3 +214,48 @@ def test_concurrent_frame_registration_is_bit_identical():
         assert o[0] == outs[0][0]
         assert all(torch.equal(a, b) for a, b in zip(o[1], outs[0][1]))
         assert all(torch.equal(a, b) for a, b in zip(o[2], outs[0][2]))
+
+
+@pytest.mark.parametrize("D,N,C", [(2, 1, 1), (2, 511, 7), (3, 512, 8), (2, 513, 50), (3, 70001, 33), (2, 200000, 64),
+                                   (3, 3000, 65), (2, 40000, 50)])
+def test_fused_first_sweep_equals_row_lse_then_column_statistics(D, N, C):
+    """dicp_em_lse_colstats (row log-sum-exp + column statistics from ONE read of X when C <= 64, csrc/em_col_small.cuh)
+    against the two separate sweeps and against a float64 evaluation of the same sums (core/GMM.py:410-415, :443-455).
+    The reference exponents m_c of the two forms may differ (other merge orders), the statistics they stand for may not:
+    log2 mass m + log2 S0, first moment B / S0, second moment A / S0.  One component sits far from every point (mass
+    ~2^-400: representable only in the log domain)."""
+    from diff_icp_b200 import em_ops
+    g = torch.Generator().manual_seed(N + C)
+    sig = 0.07
+    X = torch.rand(N, D, generator=g)
+    mu = torch.rand(C, D, generator=g)
+    if C > 2:
+        mu[C // 2] = 1.0 + 1.7           # dead component
+    w = torch.randn(C, generator=g)
+    lgn = D * (np.log(sig) + 0.5 * np.log(2 * np.pi))
+    wl2 = ((w - torch.logsumexp(w, 0) - lgn) * 1.4426950408889634).contiguous()
+    Xd, mud, wd = X.to(dev()), mu.to(dev()), wl2.to(dev())
+    fused = em_ops.lse_colstats(sig, Xd, mud, wd).cpu().double()
+    two = em_ops.colstats(sig, Xd, em_ops.rowpass(sig, Xd, mud, wd), mud, wd).cpu().double()
+    # float64 evaluation
+    X64, mu64 = X.double(), mu.double()
+    t = wl2.double()[None, :] * np.log(2.0) - ((X64[:, None, :] - mu64[None]) ** 2).sum(-1) / (2 * sig * sig)
+    lg = t - torch.logsumexp(t, 1, keepdim=True)                     # ln gamma_nc
+    lmass = torch.logsumexp(lg, 0) / np.log(2.0)
+    gam = torch.exp(lg - lg.max(0, keepdim=True).values)             # column-normalised, like the kernels
+    S = gam.sum(0)
+    d = X64[:, None, :] - mu64[None]
+    B = (gam[:, :, None] * d).sum(0) / S[:, None]
+    A = (gam * (d ** 2).sum(-1)).sum(0) / S
+
+    def norm(st):
+        return st[:, 0] + torch.log2(st[:, 1]), st[:, 2:2 + D] / st[:, 1:2], st[:, 2 + D] / st[:, 1]
+    for st in (fused, two):
+        assert torch.isfinite(st).all()
+        lm, b, a = norm(st)
+        assert (lm - lmass).abs().max() <= 2e-4 * max(1.0, lmass.abs().max().item())
+        assert (b - B).abs().max() <= 2e-5
+        assert (a - A).abs().max() <= 2e-5 * max(1.0, A.abs().max().item())
+    lf, bf, af = norm(fused)
+    lt, bt, at = norm(two)
+    assert (lf - lt).abs().max() <= 1e-4 and (bf - bt).abs().max() <= 1e-5 and (af - at).abs().max() <= 1e-5
