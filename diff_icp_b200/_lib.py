@@ -39,6 +39,8 @@ SIGNATURES = {
     "dicp_em_rowpass": (_int, [_int, _int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dicp_em_colstats": (_int, [_int, _f, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "dicp_em_lse_colstats": (_int, [_int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "dicp_em_reduce_pack": (_int, [_int, _vp, _vp, _i64, _vp, _int, _vp, _vp]),
+    "dicp_em_mstep_merged": (_int, [_int, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dicp_em_mstep": (_int, [_int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "dicp_log_resp": (_int, [_int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "dicp_small_max_support": (_int, []),
@@ -53,7 +55,7 @@ SIGNATURES = {
     "dicp_batch_quad_workspace_bytes": (_sz, [_int]),
     "dicp_batch_quad_loss": (_int, [_int, _int, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _sz, _vp]),
     "dicp_batch_closure_out": (_int, [_int, _int, _vp, _vp, _i64, _i64, _f, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
-    "dicp_batch_closure_cluster_rows": (_int, [_int, _f, _int, _i64, _i64, _int]),
+    "dicp_batch_closure_cluster_rows": (_int, [_int, _f, _int, _i64, _i64, _int, _int]),
     "dicp_batch_closure_cluster": (_int, [_int, _int, _f, _f, _int, _vp, _vp, _i64, _i64, _i64, _int, _vp, _i64, _vp, _i64, _vp,
                                           _vp, _i64, _f, _vp, _i64, _int, _vp]),
     "dicp_batch_coverage": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _int, _f, _vp, _vp]),

@@ -343,16 +343,19 @@ class GaussianMixtureUnif(Module):
             m_ref = self._agreed_exponent()
             if m_ref is None:
                 merged = comm.merge_colstats(stats)
-                red, check = comm.sum(extra.clone()), None
+                red = comm.sum(extra.clone())
+                mu_new, w_new, lpi_new, ms = em_ops.mstep(merged, mu, w, do_mu, do_w, sig_mode)
+                host = torch.cat((ms[:1], red, zeros5[:2])).tolist()
+                self._remember_exponent(merged)
             else:
-                merged, red, flag = comm.merge_colstats_ref(stats, m_ref, extra)
-                check = torch.stack((flag, (merged[:, 1] < 1e-30).any().to(flag.dtype)))
-            mu_new, w_new, lpi_new, ms = em_ops.mstep(merged, mu, w, do_mu, do_w, sig_mode)
-            host = torch.cat((ms[:1], red, check if check is not None else zeros5[:2])).tolist()       # ONE host read
-            if check is not None and (host[-2] > 0 or host[-1] > 0):       # exponents drifted: repeat with the MAX round
-                self._m_ref = None
-                continue
-            self._remember_exponent(merged)
+                # pack (one launch) -> all-reduce -> M step on the reduced buffer (one launch) -> ONE host read
+                buf = comm.sum(em_ops.reduce_pack(stats, m_ref, extra))
+                mu_new, w_new, lpi_new, m_next, hostv = em_ops.mstep_merged(buf, m_ref, mu, w, do_mu, do_w, sig_mode, 5)
+                host = hostv.tolist()
+                if host[-2] > 0 or host[-1] > 0:                        # exponents drifted: repeat with the MAX round
+                    self._m_ref = None
+                    continue
+                self._m_ref = m_next
             N_glob = host[5]
             if pending is not None:                                     # FE of step i-1 is now known
                 Cfe_val, FE_val, _ = values(host[1:6], pending[2])

@@ -3,6 +3,8 @@
 #include "../../include/dicp_b200.h"
 #include "dispatch.cuh"
 #include <type_traits>
+#include <cstdlib>
+#include <cstring>
 #include "small_step.cuh"
 #include "sym_engine.cuh"
 #include "batch_closure.cuh"
@@ -419,6 +421,32 @@ int dicp_em_mstep(int D, const float* stats, const float* mu_old, const float* w
     return last_error(DICP_OK);
 }
 
+int dicp_em_reduce_pack(int D, const float* stats, const float* m_ref, int64_t C, const float* extra, int n_extra, float* buf,
+                        void* stream) {
+    if ((D != 2 && D != 3) || C < 1 || C > INT32_MAX || !stats || !m_ref || !buf || n_extra < 0 || (n_extra > 0 && !extra))
+        return DICP_EBADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (D == 2) em_reduce_pack_kernel<2><<<1, 256, 0, st>>>(stats, m_ref, (int)C, extra, n_extra, buf);
+    else em_reduce_pack_kernel<3><<<1, 256, 0, st>>>(stats, m_ref, (int)C, extra, n_extra, buf);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
+int dicp_em_mstep_merged(int D, const float* buf, const float* m_ref, const float* mu_old, const float* w_old, int64_t C,
+                         int do_mu, int do_w, int sig_mode, int n_extra, float* mu_new, float* w_new, float* lpi_new,
+                         float* m_next, float* host, void* stream) {
+    if ((D != 2 && D != 3) || C < 1 || C > INT32_MAX || sig_mode < 0 || sig_mode > 2 || n_extra < 0 || !buf || !m_ref ||
+        !mu_old || !w_old || !mu_new || !w_new || !lpi_new || !m_next || !host)
+        return DICP_EBADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (D == 2) em_mstep_merged_kernel<2><<<1, 256, 0, st>>>(buf, m_ref, mu_old, w_old, (int)C, do_mu, do_w, sig_mode, n_extra,
+                                                            mu_new, w_new, lpi_new, m_next, host);
+    else em_mstep_merged_kernel<3><<<1, 256, 0, st>>>(buf, m_ref, mu_old, w_old, (int)C, do_mu, do_w, sig_mode, n_extra,
+                                                     mu_new, w_new, lpi_new, m_next, host);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
 int dicp_log_resp(int D, float sigma, const float* X, int64_t N, const float* mu, const float* w, int64_t C,
                   float* lgam, long long* argmax, void* stream) {
     if ((D != 2 && D != 3) || !(sigma > 0.f) || N < 0 || C < 1 || N > INT32_MAX || C > INT32_MAX) return DICP_EBADARG;
@@ -588,14 +616,10 @@ int dicp_batch_closure_out(int D, int K, const int* dims, const int* active, int
 }
 
 // ---- whole closure of every frame in ONE launch (cluster_closure.cuh) ------------------------------------------------------
-int dicp_batch_closure_cluster_rows(int D, float eta, int scheme_euler, int64_t maxM, int64_t maxNx, int nt) {
-    if ((D != 2 && D != 3) || eta != 0.f || !scheme_euler || maxM < 1 || maxM > kCcMaxM || maxNx < 1 || nt < 1) return 0;
-    const long long per = (long long)kCcCluster * kCcThreads;
-    const long long rn = (maxNx + per - 1) / per;
-    if (rn > kCcMaxRows) return 0;
-    const int cap = (int)rn * kCcThreads;
-    if (cluster_closure_smem_floats((int)maxM, D, nt, cap) * 4 > 200 * 1024) return 0;
-    return cap;
+
+int dicp_batch_closure_cluster_rows(int D, float eta, int scheme_euler, int64_t maxM, int64_t maxNx, int nt, int K) {
+    if ((D != 2 && D != 3) || eta != 0.f || !scheme_euler || maxM < 1 || maxNx < 1 || nt < 1 || K < 1) return 0;
+    return cc_pick_shape(D, maxM, maxNx, nt, K).cap;
 }
 
 int dicp_batch_closure_cluster(int D, int withlogdet, float sigma, float eta, int K, const int* dims, const int* active,
@@ -605,34 +629,24 @@ int dicp_batch_closure_cluster(int D, int withlogdet, float sigma, float eta, in
     if (!batch_dims_ok(D, K, dims, fstride) || !traj || !X || !y || !inv || !out || nscal < 6 || !(sigma > 0.f) ||
         ostride < nscal + maxM * D || xstride < maxM * D || ystride < maxNx)
         return DICP_EBADARG;
-    const int cap = dicp_batch_closure_cluster_rows(D, eta, 1, maxM, maxNx, nt);
-    if (cap == 0) return DICP_EUNSUPPORTED;
+    if (dicp_batch_closure_cluster_rows(D, eta, 1, maxM, maxNx, nt, K) == 0) return DICP_EUNSUPPORTED;
+    const CcShape sh = cc_pick_shape(D, maxM, maxNx, nt, K);
     const GaussConst gcst = gauss_const(sigma);
     ClusterClosure C{};
     C.dims = dims; C.active = active; C.traj = traj; C.fstride = fstride; C.tstride = tstride;
     C.X = X; C.xstride = xstride; C.y = y; C.inv = inv; C.ystride = ystride;
-    C.out = out; C.ostride = ostride; C.ns = nscal; C.nt = nt; C.rows_cap = cap;
+    C.out = out; C.ostride = ostride; C.ns = nscal; C.nt = nt; C.rows_cap = sh.cap;
     C.h = 1.f / (float)nt; C.kappa = gcst.kappa; C.s = gcst.s; C.alpha = gcst.alpha; C.beta = gcst.beta; C.lam_reg = lam_reg;
-    const size_t smem = cluster_closure_smem_floats((int)maxM, D, nt, cap) * 4;
-    void (*kern)(ClusterClosure) = nullptr;
-    if (D == 2) kern = withlogdet ? cluster_closure_kernel<2, true> : cluster_closure_kernel<2, false>;
-    else kern = withlogdet ? cluster_closure_kernel<3, true> : cluster_closure_kernel<3, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(kCcCluster, (unsigned)K, 1);
-    cfg.blockDim = dim3(kCcThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCcCluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, C);
-    if (e != cudaSuccess) return (int)e;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (sh.T == 128) {
+        if (D == 2) rc = withlogdet ? cc_launch<2, true, 128>(C, sh, K, st) : cc_launch<2, false, 128>(C, sh, K, st);
+        else rc = withlogdet ? cc_launch<3, true, 128>(C, sh, K, st) : cc_launch<3, false, 128>(C, sh, K, st);
+    } else {
+        if (D == 2) rc = withlogdet ? cc_launch<2, true, 64>(C, sh, K, st) : cc_launch<2, false, 64>(C, sh, K, st);
+        else rc = withlogdet ? cc_launch<3, true, 64>(C, sh, K, st) : cc_launch<3, false, 64>(C, sh, K, st);
+    }
+    if (rc != DICP_OK) return rc;
     launch_counter() += 1;
     return last_error(DICP_OK);
 }

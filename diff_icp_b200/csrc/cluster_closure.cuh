@@ -18,25 +18,23 @@
 // The per-pair arithmetic is the SAME Op code as everywhere else (ops_rhs.cuh: RhsXQ, RhsQQ, AdjXQx, AdjXQq, AdjQQ), fed from
 // shared-memory copies of the state instead of global memory.
 //
-// Scope: eta = 0 (classic / hybrid model), data points present, Euler scheme, M <= kCcMaxM support points,
-// Nx <= kCcCluster * kCcThreads * kCcMaxRows data points per frame.  Everything else keeps the stage kernels.
+// Scope: eta = 0 (classic / hybrid model), data points present, Euler scheme, M <= T / 2 support points (T = 64 or 128 threads
+// per CTA), Nx <= cluster size * kCcMaxRowsPerCta data points per frame.  Everything else keeps the stage kernels.
 #pragma once
 #include "small_step.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
+#include <cstring>
 
 namespace dicp {
 namespace cg = cooperative_groups;
 
-#ifndef DICP_CC_THREADS
-#define DICP_CC_THREADS 128                    // threads per CTA (swept on B200)
-#endif
-#ifndef DICP_CC_MINB
-#define DICP_CC_MINB 4                         // resident CTAs per SM asked of the compiler (register cap 65536 / (T * MINB))
-#endif
-static constexpr int kCcThreads = DICP_CC_THREADS;
-static constexpr int kCcCluster = 8;           // portable cluster size
-static constexpr int kCcMaxRows = 2048 / kCcThreads;   // rows per thread at most: up to 8 * 2048 = 16384 data points per frame
-static constexpr int kCcMaxM = kCcThreads / 2; // support points (one q row per thread, >= 2 column groups in the reduction)
+// Launch shapes: T threads per CTA (template), `cluster` CTAs per frame (run time; 16 is the non-portable size, opt-in).  More,
+// smaller CTAs per frame even out the load over the SMs (64 frames: 8 x 128 threads = 512 CTAs on 148 SMs leave every SM
+// with 3 or 4 of them, 16 x 64 threads = 1024 CTAs with 6 or 7) and use more SMs when a rank holds few frames.
+static constexpr int kCcRegCap = 128;          // registers per thread asked of the compiler (65536 / (T * resident CTAs))
+static constexpr int kCcMaxRowsPerCta = 2048;  // data points per CTA at most
+DICP_HD int cc_max_support(int T) { return T / 2; }   // one q row per thread, >= 2 column groups in the reduction
 
 struct ClusterClosure {
     const int* dims;          // (K,2): M_k, Nx_k
@@ -52,12 +50,12 @@ struct ClusterClosure {
     long long ostride;
     int ns;
     int nt;
-    int rows_cap;             // rows per CTA (multiple of kCcThreads)
+    int rows_cap;             // rows per CTA (multiple of the CTA size)
     float h, kappa, s, alpha, beta, lam_reg;
 };
 
 DICP_HD size_t cc_al4(size_t n) { return (n + 3) & ~(size_t)3; }      // segments start on 16-byte boundaries (float4 reads)
-DICP_HD size_t cluster_closure_smem_floats(int M, int D, int nt, int rows_cap) {
+DICP_HD size_t cluster_closure_smem_floats(int M, int D, int nt, int rows_cap, int T) {
     const size_t Mp = (size_t)(M + 1) / 2 * 2, cap = (size_t)rows_cap, MD = (size_t)M * D;
     return cc_al4((size_t)(nt + 1) * 2 * MD)   // support trajectory (q_t | p_t)
            + 3 * cc_al4(2 * MD)                 // cotangents (a | u), F (vq | dp), G (gq | gp)
@@ -66,18 +64,73 @@ DICP_HD size_t cluster_closure_smem_floats(int M, int D, int nt, int rows_cap) {
            + cc_al4(cap * 2 * D)                // packed data-point columns (x', wx)
            + 2 * cc_al4(cap * D)                // x, lambda_x of the CTA's rows
            + cc_al4(2 * (size_t)(2 * D + 1) * M)    // published partial sums, double buffered
-           + cc_al4((size_t)kCcThreads * (2 * D + 1))   // group reduction scratch
+           + cc_al4((size_t)T * (2 * D + 1))            // group reduction scratch
            + 64;                                // origin, gc, block scalars
 }
 
-template <int D, bool WLD>
-__global__ void __launch_bounds__(kCcThreads, DICP_CC_MINB) cluster_closure_kernel(ClusterClosure C) {
+// R rows of one thread (j, j + T, ...) of the forward (x,q) pass swept together: x <- x + h v(x), trajectory write, dcost sum
+template <class OpXQ, int D, bool WLD, int T, int R>
+DICP_D void cc_fwd_rows(const RhsParams& P, const ClusterClosure& C, const float* cols, float* sx, const float* misc, int M,
+                        int j, int t, long long xoff, float h, float& dcsum) {
+    typename OpXQ::Row row[R];
+    F2 acc[R][OpXQ::NACC];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) row[r].x[c] = (sx[(size_t)(j + r * T) * D + c] - misc[c]) * C.kappa;
+#pragma unroll
+        for (int a = 0; a < OpXQ::NACC; ++a) acc[r][a] = f2(0.f, 0.f);
+    }
+    sweep_cols_multi<OpXQ, R>(P, row, cols, M, acc);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const size_t o = (size_t)(j + r * T) * D;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const float xn = fmaf(h, f2_sum(acc[r][OpXQ::A_V + c]), sx[o + c]);
+            sx[o + c] = xn;
+            C.traj[(long long)(t + 1) * C.tstride + xoff + (long long)o + c] = xn;
+        }
+        if (WLD) dcsum = fmaf(C.alpha, f2_sum(acc[r][OpXQ::A_DS]), dcsum);
+    }
+}
+
+// R rows of one thread of the adjoint (x,q) pass w.r.t. x: lambda_x <- lambda_x + h gx
+template <class OpX, int D, bool WLD, int T, int R>
+DICP_D void cc_adj_rows(const RhsParams& P, const ClusterClosure& C, const float* cols, const float* sx, float* slx,
+                        const float* misc, int M, int j, float h) {
+    typename OpX::Row row[R];
+    F2 acc[R][OpX::NACC];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            row[q].x[c] = (sx[(size_t)(j + q * T) * D + c] - misc[c]) * C.kappa;
+            row[q].w[c] = slx[(size_t)(j + q * T) * D + c];
+        }
+        row[q].gc = WLD ? 1.f : 0.f;
+#pragma unroll
+        for (int a = 0; a < OpX::NACC; ++a) acc[q][a] = f2(0.f, 0.f);
+    }
+    sweep_cols_multi<OpX, R>(P, row, cols, M, acc);
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const size_t o = (size_t)(j + q * T) * D + c;
+            slx[o] = fmaf(h, f2_sum(acc[q][c]), slx[o]);
+        }
+    }
+}
+
+template <int D, bool WLD, int T>
+__global__ void __launch_bounds__(T, 65536 / (T * kCcRegCap)) cluster_closure_kernel(ClusterClosure C) {
     using OpXQ = RhsXQ<D, WLD, false, 1>;        // forward, rows x
     using OpQQf = RhsQQ<D, false, false, 1>;     // forward, rows q (x present: the divergence cost comes from the x rows)
     using OpX = AdjXQx<D, WLD, 1>;               // adjoint, rows x, cols (q,p)
     using OpQx = AdjXQq<D, WLD, 1>;              // adjoint, rows q, cols (x, wx)
     using OpQQa = AdjQQ<D, false, 1>;            // adjoint, rows q, cols (q,p,a,u)
-    constexpr int NAX = OpQx::NACC, T = kCcThreads;
+    constexpr int NAX = OpQx::NACC;
     extern __shared__ __align__(16) float sm[];
     __shared__ float red[32];
 
@@ -136,47 +189,12 @@ __global__ void __launch_bounds__(kCcThreads, DICP_CC_MINB) cluster_closure_kern
         P.p = P.q + MD;
         stage_cols<OpXQ>(P, 0, M, M, cols);
         __syncthreads();
-        // x rows of this CTA, four at a time
-        int j = tid;
-        for (; j + 3 * T < n_cta; j += 4 * T) {
-            typename OpXQ::Row row[4];
-            F2 acc[4][OpXQ::NACC];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) row[r].x[c] = (sx[(size_t)(j + r * T) * D + c] - misc[c]) * C.kappa;
-#pragma unroll
-                for (int a = 0; a < OpXQ::NACC; ++a) acc[r][a] = f2(0.f, 0.f);
-            }
-            sweep_cols_multi<OpXQ, 4>(P, row, cols, M, acc);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const size_t o = (size_t)(j + r * T) * D;
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    const float xn = fmaf(h, f2_sum(acc[r][OpXQ::A_V + c]), sx[o + c]);
-                    sx[o + c] = xn;
-                    C.traj[(long long)(t + 1) * C.tstride + xoff + (long long)o + c] = xn;
-                }
-                if (WLD) dcsum = fmaf(C.alpha, f2_sum(acc[r][OpXQ::A_DS]), dcsum);
-            }
-        }
-        for (; j < n_cta; j += T) {
-            typename OpXQ::Row row;
-            F2 acc[OpXQ::NACC];
-#pragma unroll
-            for (int c = 0; c < D; ++c) row.x[c] = (sx[(size_t)j * D + c] - misc[c]) * C.kappa;
-#pragma unroll
-            for (int a = 0; a < OpXQ::NACC; ++a) acc[a] = f2(0.f, 0.f);
-            sweep_cols<OpXQ>(P, row, cols, M, acc);
-            const size_t o = (size_t)j * D;
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                const float xn = fmaf(h, f2_sum(acc[OpXQ::A_V + c]), sx[o + c]);
-                sx[o + c] = xn;
-                C.traj[(long long)(t + 1) * C.tstride + xoff + (long long)o + c] = xn;
-            }
-            if (WLD) dcsum = fmaf(C.alpha, f2_sum(acc[OpXQ::A_DS]), dcsum);
+        // x rows of this CTA: 4, then 2, then 1 rows of a thread swept together (independent chains hide the pair latency)
+        {
+            int j = tid;
+            for (; j + 3 * T < n_cta; j += 4 * T) cc_fwd_rows<OpXQ, D, WLD, T, 4>(P, C, cols, sx, misc, M, j, t, xoff, h, dcsum);
+            if (j + T < n_cta) { cc_fwd_rows<OpXQ, D, WLD, T, 2>(P, C, cols, sx, misc, M, j, t, xoff, h, dcsum); j += 2 * T; }
+            if (j < n_cta) cc_fwd_rows<OpXQ, D, WLD, T, 1>(P, C, cols, sx, misc, M, j, t, xoff, h, dcsum);
         }
         // q rows (every CTA, redundantly): vq, dp, A_i; then the Euler update into the next slot of the support trajectory
         if (tid < M) {
@@ -261,48 +279,11 @@ __global__ void __launch_bounds__(kCcThreads, DICP_CC_MINB) cluster_closure_kern
         }
         cluster.barrier_arrive();                                  // release: my partials are published
         // (2) x rows: gx from the OLD cotangents, lambda_x <- lambda_x + h gx (overlaps the other ranks' arrival)
-        int j = tid;
-        for (; j + 3 * T < n_cta; j += 4 * T) {
-            typename OpX::Row row[4];
-            F2 acc[4][OpX::NACC];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    row[q].x[c] = (sx[(size_t)(j + q * T) * D + c] - misc[c]) * C.kappa;
-                    row[q].w[c] = slx[(size_t)(j + q * T) * D + c];
-                }
-                row[q].gc = WLD ? 1.f : 0.f;
-#pragma unroll
-                for (int a = 0; a < OpX::NACC; ++a) acc[q][a] = f2(0.f, 0.f);
-            }
-            sweep_cols_multi<OpX, 4>(P, row, cols, M, acc);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    const size_t o = (size_t)(j + q * T) * D + c;
-                    slx[o] = fmaf(h, f2_sum(acc[q][c]), slx[o]);
-                }
-            }
-        }
-        for (; j < n_cta; j += T) {
-            typename OpX::Row row;
-            F2 acc[OpX::NACC];
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                row.x[c] = (sx[(size_t)j * D + c] - misc[c]) * C.kappa;
-                row.w[c] = slx[(size_t)j * D + c];
-            }
-            row.gc = WLD ? 1.f : 0.f;
-#pragma unroll
-            for (int a = 0; a < OpX::NACC; ++a) acc[a] = f2(0.f, 0.f);
-            sweep_cols<OpX>(P, row, cols, M, acc);
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                const size_t o = (size_t)j * D + c;
-                slx[o] = fmaf(h, f2_sum(acc[c]), slx[o]);
-            }
+        {
+            int j = tid;
+            for (; j + 3 * T < n_cta; j += 4 * T) cc_adj_rows<OpX, D, WLD, T, 4>(P, C, cols, sx, slx, misc, M, j, h);
+            if (j + T < n_cta) { cc_adj_rows<OpX, D, WLD, T, 2>(P, C, cols, sx, slx, misc, M, j, h); j += 2 * T; }
+            if (j < n_cta) cc_adj_rows<OpX, D, WLD, T, 1>(P, C, cols, sx, slx, misc, M, j, h);
         }
         __syncthreads();                                           // every thread is done with `cols` (2D records)
         // (3) (q,q) interaction columns (q', p, a, u)
@@ -369,6 +350,67 @@ __global__ void __launch_bounds__(kCcThreads, DICP_CC_MINB) cluster_closure_kern
         }
     }
     cluster.sync();                                                // nobody leaves while rank 0 still reads its shared memory
+}
+
+// ---- host side: launch shape and launch ------------------------------------------------------------------------------------------
+struct CcShape { int T = 0, cluster = 0, cap = 0; size_t smem = 0; };
+
+// Launch shape for K frames of at most maxM support / maxNx data points: 128 threads per CTA when the support allows 64
+// (MEASURED on B200, 64 frames x 10k points, 25 support points, 2-D: 0.43 ms with 8 x 128 threads per frame, 0.47 with 8 x 64,
+// 0.49 with 16 x 128 (two waves), 0.55 with 16 x 64 -- the per-CTA fixed work of a stage, redundant support integration, staging,
+// barriers, outweighs the better SM balance of many small CTAs); 16 CTAs per frame (the non-portable cluster size) when 8 per
+// frame would leave SMs without a CTA (8 frames: 0.172 vs 0.184 ms) or when a frame has more than 8 x 2048 data points.
+// DICP_CC_SHAPE="T,cluster" forces a shape (experiments, tests).
+inline CcShape cc_pick_shape(int D, int64_t maxM, int64_t maxNx, int nt, int K) {
+    int forcedT = 0, forcedC = 0;
+    if (const char* e = getenv("DICP_CC_SHAPE")) {
+        forcedT = atoi(e);
+        const char* c = strchr(e, ',');
+        forcedC = c ? atoi(c + 1) : 0;
+    }
+    const int sms = device_info().sms;
+    auto shape = [&](int T, int cl) {
+        CcShape sh;
+        if ((T != 64 && T != 128) || cl < 1 || cl > 16 || maxM > cc_max_support(T)) return sh;
+        const long long per = (long long)cl * T;
+        const long long cap = (maxNx + per - 1) / per * T;
+        if (cap > kCcMaxRowsPerCta) return sh;
+        const size_t smem = cluster_closure_smem_floats((int)maxM, D, nt, (int)cap, T) * 4;
+        if (smem > 200 * 1024) return sh;
+        sh.T = T; sh.cluster = cl; sh.cap = (int)cap; sh.smem = smem;
+        return sh;
+    };
+    if (forcedT) return shape(forcedT, forcedC);
+    const int T = maxM <= cc_max_support(64) && maxNx <= 8 * 64 ? 64 : 128;      // tiny frames: one row per thread at most
+    CcShape sh = shape(T, (long long)K * 8 < sms ? 16 : 8);
+    if (sh.T == 0) sh = shape(T, 16);
+    if (sh.T == 0) sh = shape(128, 16);
+    return sh;
+}
+
+template <int D, bool WLD, int T>
+int cc_launch(const ClusterClosure& C, const CcShape& sh, int K, cudaStream_t st) {
+    auto kern = cluster_closure_kernel<D, WLD, T>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
+    if (e != cudaSuccess) return (int)e;
+    if (sh.cluster > 8) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return (int)e;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)sh.cluster, (unsigned)K, 1);
+    cfg.blockDim = dim3(T, 1, 1);
+    cfg.dynamicSmemBytes = sh.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)sh.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, C);
+    return e == cudaSuccess ? DICP_OK : (int)e;
 }
 
 }  // namespace dicp

@@ -19,6 +19,10 @@ static constexpr int kEmColMaxC = 64;
 static constexpr int kEmColChunk = 512;      // points staged per step
 
 static constexpr int kEmColGroup = 16;     // CTAs per level-1 merge group
+#ifndef DICP_EM_CTAS_PER_SM
+#define DICP_EM_CTAS_PER_SM 8
+#endif
+static constexpr int kEmColCtasPerSm = DICP_EM_CTAS_PER_SM;   // CTAs per SM of the column-statistics kernels (latency-bound: more resident warps)
 static constexpr int kEmRowR = 4;          // points per thread in the row passes
 static constexpr int kEmRowRows = 128 * kEmRowR;
 
@@ -283,10 +287,11 @@ __global__ void __launch_bounds__(128) em_lse_col_small_kernel(EmParams P, int N
     }
     em_col_publish_and_merge<D>(P, C, g, G, c, work, xch, acc, rowc, part, counter);
 }
-// CTAs of the fused sweep: about 4 per SM, whole 512-point groups each
+// CTAs of the fused sweep: up to kEmColCtasPerSm per SM, whole 512-point groups each
 inline void em_lse_col_small_grid(long long N, int sms, int* blocks, int* passes) {
     const long long groups = (N + kEmRowRows - 1) / kEmRowRows;
-    long long ps = (groups + (long long)sms * 4 - 1) / ((long long)sms * 4);
+    const long long cap = (long long)sms * kEmColCtasPerSm;
+    long long ps = (groups + cap - 1) / cap;
     if (ps < 1) ps = 1;
     *passes = (int)ps;
     *blocks = (int)((groups + ps - 1) / ps);
@@ -423,10 +428,105 @@ __global__ void __launch_bounds__(256) em_mstep_kernel(const float* __restrict__
     if (tid == 0) { out_scal[0] = nd; out_scal[1] = lse; }
 }
 
-// number of point ranges (CTAs): about 4 per SM, at least one chunk of points each
+// ---- multi-GPU EM step: the buffer of the ONE all-reduce, and the M step on the reduced buffer ---------------------------------
+// (core/GMM.py's _EM_optimization_pipelined; the frames of an atlas are sharded over ranks)
+// pack:  buf = [ S0, B, A of every component rescaled from the local exponent m_c to the rank-agreed one m_ref_c (C x (D+2)) |
+//                flag = 1 if some m_c - m_ref_c > 100 (the rescaled sums could overflow) | extra (n_extra plain partial sums) ]
+// One launch instead of ~10 element-wise ones; every rank's buf is then summed by NCCL.
+template <int D>
+__global__ void __launch_bounds__(256) em_reduce_pack_kernel(const float* __restrict__ stats, const float* __restrict__ m_ref,
+                                                             int C, const float* __restrict__ extra, int n_extra,
+                                                             float* __restrict__ buf) {
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    int over = 0;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const float* st = stats + (size_t)c * (D + 3);
+        const float d = st[0] - m_ref[c];
+        if (d > 100.f) over = 1;
+        const float sc = exp2f(fminf(d, 120.f));
+#pragma unroll
+        for (int k = 0; k < D + 2; ++k) buf[(size_t)c * (D + 2) + k] = st[1 + k] * sc;
+    }
+    if (over) any = 1;                       // benign race: every writer stores 1
+    __syncthreads();
+    float* tail = buf + (size_t)C * (D + 2);
+    if (threadIdx.x == 0) tail[0] = any ? 1.f : 0.f;
+    for (int k = threadIdx.x; k < n_extra; k += 256) tail[1 + k] = extra[k];
+}
+
+// M step on the all-reduced buffer (same formulas as em_mstep_kernel with m = m_ref), plus what the host loop needs next:
+//   m_next_c = round(m_ref_c + log2 max(S0_c, 1e-30))        the exponent every rank agrees on for the next step
+//   host     = [ N D sigma'^2 | the n_extra reduced sums | flag sum | 1 if some merged S0_c < 1e-30 ]   (ONE small D2H read)
+template <int D>
+__global__ void __launch_bounds__(256) em_mstep_merged_kernel(const float* __restrict__ buf, const float* __restrict__ m_ref,
+                                                              const float* __restrict__ mu_old, const float* __restrict__ w_old,
+                                                              int C, int do_mu, int do_w, int sig_mode, int n_extra,
+                                                              float* __restrict__ mu_new, float* __restrict__ w_new,
+                                                              float* __restrict__ lpi_new, float* __restrict__ m_next,
+                                                              float* __restrict__ host) {
+    __shared__ float red[32];
+    __shared__ float bc;
+    __shared__ int vanished;
+    const int tid = threadIdx.x;
+    if (tid == 0) vanished = 0;
+    __syncthreads();
+    float wmax = -INFINITY, nd = 0.f;
+    int van = 0;
+    for (int c = tid; c < C; c += 256) {
+        const float* st = buf + (size_t)c * (D + 2);
+        const float m = m_ref[c], S0 = st[0], A = st[1 + D];
+        if (S0 < 1e-30f) van = 1;
+        float b2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float B = st[1 + k];
+            b2 = fmaf(B, B, b2);
+            mu_new[(size_t)c * D + k] = do_mu ? mu_old[(size_t)c * D + k] + B / S0 : mu_old[(size_t)c * D + k];
+        }
+        const float w = do_w ? (m + log2f(S0)) * kLn2 : w_old[c];
+        w_new[c] = w;
+        wmax = fmaxf(wmax, w);
+        if (sig_mode == 1) nd += exp2f(m) * (A - b2 / S0);
+        else if (sig_mode == 2) nd += exp2f(m) * A;
+        m_next[c] = rintf(m + log2f(fmaxf(S0, 1e-30f)));
+    }
+    if (van) vanished = 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if ((tid & 31) == 0) red[tid >> 5] = wmax;
+    __syncthreads();
+    if (tid == 0) {
+        float v = red[0];
+        for (int k = 1; k < 8; ++k) v = fmaxf(v, red[k]);
+        bc = v;
+    }
+    __syncthreads();
+    wmax = bc;
+    __syncthreads();
+    float se = 0.f;
+    for (int c = tid; c < C; c += 256) se += expf(w_new[c] - wmax);
+    se = block_sum(se, red);
+    if (tid == 0) bc = wmax + logf(se);
+    __syncthreads();
+    const float lse = bc;
+    for (int c = tid; c < C; c += 256) lpi_new[c] = w_new[c] - lse;
+    __syncthreads();
+    nd = block_sum(nd, red);
+    const float* tail = buf + (size_t)C * (D + 2);
+    if (tid == 0) {
+        host[0] = nd;
+        host[1 + n_extra] = tail[0];
+        host[2 + n_extra] = vanished ? 1.f : 0.f;
+    }
+    for (int k = tid; k < n_extra; k += 256) host[1 + k] = tail[1 + k];
+}
+
+// number of point ranges (CTAs): up to kEmColCtasPerSm per SM, at least one chunk of points each
 inline int em_col_small_splits(long long N, int sms) {
     long long s = (N + kEmColChunk - 1) / kEmColChunk;
-    const long long cap = (long long)sms * 4;
+    const long long cap = (long long)sms * kEmColCtasPerSm;
     if (s > cap) s = cap;
     return s < 1 ? 1 : (int)s;
 }

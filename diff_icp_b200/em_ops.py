@@ -82,6 +82,32 @@ def mstep(stats, mu_old, w_old, do_mu, do_w, sig_mode):
     return mu_new, w_new, lpi_new, scal
 
 
+def reduce_pack(stats, m_ref, extra):
+    """The buffer of the EM step's one all-reduce: [S0, B, A rescaled to the exponents m_ref | overflow flag | extra]."""
+    dev = require_cuda(stats, m_ref, extra)
+    C, D = stats.shape[0], stats.shape[1] - 3
+    n_extra = 0 if extra is None else extra.numel()
+    buf = torch.empty(C * (D + 2) + 1 + n_extra, dtype=torch.float32, device=dev)
+    rc = load().dicp_em_reduce_pack(D, ptr(stats), ptr(m_ref), C, ptr(extra), n_extra, ptr(buf), stream_ptr())
+    check(rc, "dicp_em_reduce_pack")
+    return buf
+
+
+def mstep_merged(buf, m_ref, mu_old, w_old, do_mu, do_w, sig_mode, n_extra):
+    """M step on the all-reduced buffer of `reduce_pack`.  Returns (mu_new, w_new, lpi_new, m_next (C,), host (3 + n_extra,) =
+    [N D sigma'^2, reduced extras..., flag sum, vanished-mass flag])."""
+    dev = require_cuda(buf, m_ref, mu_old, w_old)
+    C, D = mu_old.shape
+    f32 = dict(dtype=torch.float32, device=dev)
+    mu_new, w_new, lpi_new, m_next = torch.empty(C, D, **f32), torch.empty(C, **f32), torch.empty(C, **f32), torch.empty(C, **f32)
+    host = torch.empty(3 + n_extra, **f32)
+    rc = load().dicp_em_mstep_merged(D, ptr(buf), ptr(m_ref), ptr(mu_old), ptr(w_old), C, int(bool(do_mu)), int(bool(do_w)),
+                                     int(sig_mode), int(n_extra), ptr(mu_new), ptr(w_new), ptr(lpi_new), ptr(m_next), ptr(host),
+                                     stream_ptr())
+    check(rc, "dicp_em_mstep_merged")
+    return mu_new, w_new, lpi_new, m_next, host
+
+
 def log_resp(sigma, X, mu, w, want_lgam=True, want_argmax=False):
     dev = require_cuda(X, mu, w)
     N, D = X.shape

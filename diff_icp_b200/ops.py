@@ -172,9 +172,10 @@ def batch_closure_out(D, K, dims, active, maxM, fstride, lam_reg, lam, F0, state
     check(rc, "dicp_batch_closure_out")
 
 
-def batch_closure_cluster_rows(D, eta, scheme, maxM, maxNx, nt):
+def batch_closure_cluster_rows(D, eta, scheme, maxM, maxNx, nt, K):
     """Rows per CTA of the one-launch closure (csrc/cluster_closure.cuh) if it applies to these sizes, else 0."""
-    return int(load().dicp_batch_closure_cluster_rows(int(D), float(eta), int(scheme == "Euler"), int(maxM), int(maxNx), int(nt)))
+    return int(load().dicp_batch_closure_cluster_rows(int(D), float(eta), int(scheme == "Euler"), int(maxM), int(maxNx), int(nt),
+                                                      int(K)))
 
 
 def batch_closure_cluster(D, withlogdet, sigma, eta, K, dims, active, maxM, maxNx, fstride, nt, traj, tstride, X, xstride,

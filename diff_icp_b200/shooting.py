@@ -522,7 +522,7 @@ class BatchedClosurePlan:
         # the whole closure of every frame in ONE launch (one thread-block cluster per frame, csrc/cluster_closure.cuh) when
         # the model / sizes allow it: eta = 0, data points present, Euler, small supports
         self.one_launch = (BatchedClosurePlan.one_launch_closure and device.type == "cuda" and min(self.Nxs) > 0
-                           and ops.batch_closure_cluster_rows(D, eta, scheme, self.maxM, self.maxNx, nt) > 0)
+                           and ops.batch_closure_cluster_rows(D, eta, scheme, self.maxM, self.maxNx, nt, K) > 0)
 
     # ---- problem data -------------------------------------------------------------------------------------------------
     def set_geometry(self, q0_list, x0_list):

@@ -132,6 +132,19 @@ int dicp_em_rowpass(int D, int lite, float sigma_old, const float* X, int64_t N,
 int dicp_em_colstats(int D, float sigma_old, const float* X, int64_t N, const float* T2, const float* mu_old,
                      const float* wl2, int64_t C, float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Multi-GPU EM step (frames sharded over ranks): the buffer of the step's ONE all-reduce and the M step on it.
+ * dicp_em_reduce_pack: buf = [ S0, B (D), A of every component, rescaled from the local exponent stats[c][0] to the exponent
+ *   m_ref[c] every rank agrees on (C x (D+2)) | flag (1 if some local exponent exceeds m_ref by more than 100) | extra[0..n_extra) ]
+ *   -- (C (D+2) + 1 + n_extra) floats, summed over ranks by the caller (NCCL).
+ * dicp_em_mstep_merged: dicp_em_mstep on the reduced buf with m = m_ref, plus m_next[c] = round(m_ref[c] + log2 max(S0_c, 1e-30))
+ *   and host = [ N D sigma'^2 | the n_extra reduced sums | flag sum | 1 if some merged S0_c < 1e-30 ] (2 + 1 + n_extra floats,
+ *   the one device-to-host read of the step).  Replaces the partial sums of core/GMM.py:286-297 / :442-456 across frames. */
+int dicp_em_reduce_pack(int D, const float* stats, const float* m_ref, int64_t C, const float* extra, int n_extra, float* buf,
+                        void* stream);
+int dicp_em_mstep_merged(int D, const float* buf, const float* m_ref, const float* mu_old, const float* w_old, int64_t C,
+                         int do_mu, int do_w, int sig_mode, int n_extra, float* mu_new, float* w_new, float* lpi_new,
+                         float* m_next, float* host, void* stream);
+
 /* First sweep of the EM step -- row log-sum-exp AND column statistics -- as one call: same statistics as dicp_em_rowpass(lite)
  * followed by dicp_em_colstats (the six KeOps reductions of core/GMM.py:410-415, :443-455 collapse into this sweep and the
  * full row pass).  With C <= 64 components it is ONE launch and ONE read of X (the row LSE never leaves the chip; T2_scratch
@@ -211,9 +224,11 @@ int dicp_batch_closure_out(int D, int K, const int* dims, const int* active, int
  * dicp_batch_* stage kernels above; same values up to fp32 summation order).  eta = 0 models with data points, Euler.
  * traj: (nt+1, K, fstride) states, time-major with stride tstride; traj[0] must hold q0 and x0 of every frame, the data points
  * x(t) are written to traj[t] (support points and momenta of t > 0 are NOT written).  out as in dicp_batch_closure_out
- * (scalars 1 = A, 4 = cost(1), 5 = data loss).  dicp_batch_closure_cluster_rows returns the rows handled per CTA (> 0) when
- * this form applies to the given sizes, else 0; the launcher returns DICP_EUNSUPPORTED in that case. */
-int dicp_batch_closure_cluster_rows(int D, float eta, int scheme_euler, int64_t maxM, int64_t maxNx, int nt);
+ * (scalars 1 = A, 4 = cost(1), 5 = data loss).  The launch shape (64 or 128 threads per CTA, 8 or 16 CTAs per frame) is chosen
+ * from the sizes and the frame count K.  dicp_batch_closure_cluster_rows returns the rows handled per CTA (> 0) when this form
+ * applies to the given sizes (<= 64 support points, <= 16 x 2048 data points per frame), else 0; the launcher returns
+ * DICP_EUNSUPPORTED in that case. */
+int dicp_batch_closure_cluster_rows(int D, float eta, int scheme_euler, int64_t maxM, int64_t maxNx, int nt, int K);
 int dicp_batch_closure_cluster(int D, int withlogdet, float sigma, float eta, int K, const int* dims, const int* active,
                                int64_t maxM, int64_t maxNx, int64_t fstride, int nt, float* traj, int64_t tstride,
                                const float* X, int64_t xstride, const float* y, const float* inv, int64_t ystride,

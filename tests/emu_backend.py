@@ -82,12 +82,35 @@ def mstep(stats, mu_old, w_old, do_mu, do_w, sig_mode):
     return mu_new, w_new, w_new - lse, torch.stack((nd, lse)).float()
 
 
+def reduce_pack(stats, m_ref, extra):
+    """CPU stand-in of dicp_em_reduce_pack (csrc/em_col_small.cuh, em_reduce_pack_kernel)."""
+    d = stats[:, 0] - m_ref
+    scaled = stats[:, 1:] * torch.exp2(torch.clamp(d, max=120.0))[:, None]
+    flag = (d > 100.0).any().to(stats.dtype).reshape(1)
+    parts = [scaled.reshape(-1), flag] + ([extra.to(stats.dtype).reshape(-1)] if extra is not None else [])
+    return torch.cat(parts)
+
+
+def mstep_merged(buf, m_ref, mu_old, w_old, do_mu, do_w, sig_mode, n_extra):
+    """CPU stand-in of dicp_em_mstep_merged."""
+    C, D = mu_old.shape
+    n = C * (D + 2)
+    sums = buf[:n].view(C, D + 2)
+    merged = torch.cat((m_ref[:, None], sums), dim=1)
+    mu_new, w_new, lpi_new, ms = mstep(merged, mu_old, w_old, do_mu, do_w, sig_mode)
+    m_next = torch.round(m_ref + torch.log2(torch.clamp(sums[:, 0], min=1e-30)))
+    host = torch.cat((ms[:1], buf[n + 1:n + 1 + n_extra], buf[n:n + 1], (sums[:, 0] < 1e-30).any().to(buf.dtype).reshape(1)))
+    return mu_new, w_new, lpi_new, m_next, host
+
+
 def install(monkeypatch):
     from diff_icp_b200 import em_ops
     monkeypatch.setattr(em_ops, "rowpass", rowpass)
     monkeypatch.setattr(em_ops, "colstats", colstats)
     monkeypatch.setattr(em_ops, "lse_colstats", lse_colstats)
     monkeypatch.setattr(em_ops, "mstep", mstep)
+    monkeypatch.setattr(em_ops, "reduce_pack", reduce_pack)
+    monkeypatch.setattr(em_ops, "mstep_merged", mstep_merged)
 
 
 # ---- kernel sums / LDDMM right-hand side on the CPU emulation -------------------------------------------------------

@@ -37,16 +37,24 @@ CASES = [
     # sizes at the limits of the one-launch closure (one thread-block cluster per frame): 64 support points, 16384 data points
     (3, "classic", "Euler", 5, [12, 64, 33], [700, 3000, 16384]),
     (3, "hybrid", "Euler", 4, [64, 1, 2], [16384, 5, 2049]),
+    (2, "hybrid", "Euler", 3, [40, 9], [32768, 12345]),
 ]
 
 
-@pytest.mark.parametrize("one_launch", [True, False])
+# one_launch: False = stage kernels; True = launch shape chosen by the library; "T,cluster" = that shape forced (DICP_CC_SHAPE)
+@pytest.mark.parametrize("one_launch", [True, False, "64,8", "64,16", "128,8", "128,16"])
 @pytest.mark.parametrize("D,version,scheme,nt,Ms,Nxs", CASES)
 def test_batched_closure_equals_per_frame_closure(D, version, scheme, nt, Ms, Nxs, one_launch, monkeypatch):
     """one_launch=True: the whole closure of a frame in ONE kernel (csrc/cluster_closure.cuh) where it applies (eta = 0, data
-    points, Euler, <= 64 support points, <= 16384 data points); False: the stage kernels, one launch per integrator stage."""
+    points, Euler, <= 64 support points, <= 32768 data points); False: the stage kernels, one launch per integrator stage."""
     from diff_icp_b200 import shooting
     from diff_icp_b200.core.LDDMM import LDDMMModel
+    if isinstance(one_launch, str):
+        T, cl = (int(v) for v in one_launch.split(","))
+        if not (version != "logdet" and scheme == "Euler" and min(Nxs) > 0 and max(Ms) <= T // 2 and max(Nxs) <= cl * 2048):
+            pytest.skip("shape does not apply to these sizes")
+        monkeypatch.setenv("DICP_CC_SHAPE", one_launch)
+        one_launch = True
     monkeypatch.setattr(shooting.BatchedClosurePlan, "one_launch_closure", one_launch)
     sig, lam = 0.25, 50.0
     LM = LDDMMModel(sigma=sig, D=D, lambd=lam, version=version, scheme=scheme, nt=nt, spec=spec())
@@ -61,7 +69,7 @@ def test_batched_closure_equals_per_frame_closure(D, version, scheme, nt, Ms, Nx
 
     for use_graph in (False, True):
         plan = shooting.BatchedClosurePlan(D, nt, scheme, LM.withlogdet, sig, LM.eta, lam, dev(), Ms, Nxs, use_graph=use_graph)
-        eligible = version != "logdet" and scheme == "Euler" and min(Nxs) > 0 and max(Ms) <= 64 and max(Nxs) <= 16384
+        eligible = version != "logdet" and scheme == "Euler" and min(Nxs) > 0 and max(Ms) <= 64 and max(Nxs) <= 32768
         assert plan.one_launch == (one_launch and eligible)
         if not one_launch and not eligible and use_graph:
             return                                   # identical to the one_launch=True run of this case

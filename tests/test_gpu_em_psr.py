@@ -259,3 +259,40 @@ def test_fused_first_sweep_equals_row_lse_then_column_statistics(D, N, C):
     lf, bf, af = norm(fused)
     lt, bt, at = norm(two)
     assert (lf - lt).abs().max() <= 1e-4 and (bf - bt).abs().max() <= 1e-5 and (af - at).abs().max() <= 1e-5
+
+
+@pytest.mark.parametrize("D,C", [(2, 50), (3, 7), (2, 700)])
+def test_allreduce_buffer_and_merged_mstep(D, C):
+    """dicp_em_reduce_pack / dicp_em_mstep_merged (the two launches around the multi-GPU EM step's one all-reduce) against
+    the element-wise formulas they replace (dist.StatsComm.merge_colstats_ref + dicp_em_mstep, core/GMM.py:286-297)."""
+    from diff_icp_b200 import em_ops
+    g = torch.Generator().manual_seed(C)
+    stats = torch.rand(C, D + 3, generator=g)
+    stats[:, 0] = torch.randint(-40, 5, (C,), generator=g).float() + torch.rand(C, generator=g)
+    stats[:, 2:2 + D] -= 0.5
+    m_ref = torch.round(stats[:, 0] + torch.randint(-3, 4, (C,), generator=g).float())
+    extra = torch.rand(5, generator=g)
+    mu, w = torch.rand(C, D, generator=g), torch.randn(C, generator=g)
+    sd, md, ed, mud, wd = (t.to(dev()) for t in (stats, m_ref, extra, mu, w))
+    for overflow in (False, True):
+        if overflow:
+            sd = sd.clone()
+            sd[C // 2, 0] = md[C // 2] + 101.0
+        buf = em_ops.reduce_pack(sd, md, ed)
+        d = sd[:, 0] - md
+        scaled = sd[:, 1:] * torch.exp2(torch.clamp(d, max=120.0))[:, None]
+        assert buf.numel() == C * (D + 2) + 6
+        assert torch.allclose(buf[:C * (D + 2)].view(C, D + 2), scaled, rtol=1e-6, atol=0)
+        assert float(buf[C * (D + 2)]) == (1.0 if overflow else 0.0)
+        assert torch.equal(buf[C * (D + 2) + 1:], ed)
+    buf = em_ops.reduce_pack(stats.to(dev()), md, ed) * 2.0             # "two ranks with the same statistics"
+    for sig_mode in (0, 1, 2):
+        mu_new, w_new, lpi_new, m_next, host = em_ops.mstep_merged(buf, md, mud, wd, True, True, sig_mode, 5)
+        merged = torch.cat((md[:, None], buf[:C * (D + 2)].view(C, D + 2)), dim=1).contiguous()
+        mu_r, w_r, lpi_r, ms = em_ops.mstep(merged, mud, wd, True, True, sig_mode)
+        assert torch.equal(mu_new, mu_r) and torch.equal(w_new, w_r) and torch.equal(lpi_new, lpi_r)
+        assert torch.equal(m_next, torch.round(md + torch.log2(torch.clamp(merged[:, 1], min=1e-30))))
+        h = host.tolist()
+        assert h[0] == float(ms[0]) and h[1:6] == (2.0 * ed).tolist() and h[6] == 0.0 and h[7] == 0.0
+    buf[3 * (D + 2)] = 0.0                                               # a vanished column mass is reported
+    assert em_ops.mstep_merged(buf, md, mud, wd, True, True, 0, 5)[4].tolist()[7] == 1.0
