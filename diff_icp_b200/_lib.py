@@ -39,6 +39,13 @@ SIGNATURES = {
     "dicp_em_rowpass": (_int, [_int, _int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dicp_em_colstats": (_int, [_int, _f, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "dicp_em_lse_colstats": (_int, [_int, _f, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "dicp_em_state_workspace_bytes": (_sz, [_i64, _i64]),
+    "dicp_em_state_step": (_int, [_int, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int,
+                                  _int, _int, _vp, _sz, _vp]),
+    "dicp_em_loop_create": (_vp, [_int, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int,
+                                  _int, _int, _vp, _sz, _vp]),
+    "dicp_em_loop_launch": (_int, [_vp, _vp]),
+    "dicp_em_loop_destroy": (None, [_vp]),
     "dicp_em_reduce_pack": (_int, [_int, _vp, _vp, _i64, _vp, _int, _vp, _vp]),
     "dicp_em_mstep_merged": (_int, [_int, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dicp_em_mstep": (_int, [_int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),

@@ -120,6 +120,7 @@ class GaussianMixtureUnif(Module):
         state = dict(self.__dict__)
         state.pop("EM_step", None)            # bound method: rebuilt on load
         state.pop("_lpi_cache", None)
+        state.pop("_em_loop", None)          # device buffers + captured CUDA graph of the EM loop
         state.pop("_m_ref", None)
         state["comm"] = None
         return state
@@ -278,6 +279,8 @@ class GaussianMixtureUnif(Module):
             return torch.empty(X.shape, **self.spec), torch.tensor(0.0), torch.tensor(0.0), 0
         if self._pipelined_applies():
             return self._EM_optimization_pipelined(X, max_iterations, tol)
+        if self._graph_loop_applies(X, max_iterations):
+            return self._EM_optimization_graph(X, max_iterations, tol)
         Y = Cfe = FE = last_FE = None
         for i in range(max_iterations):
             Y, Cfe, FE = self.EM_step(X)
@@ -286,6 +289,46 @@ class GaussianMixtureUnif(Module):
             last_FE = FE
         print(f"GMM optimization - reached maximum number of iterations : {max_iterations}")
         return Y, Cfe, FE, i + 1
+
+    # ---- one GPU, few components: the whole loop as one CUDA graph replay (em_loop.py) ----------------------------------------
+    graph_em_loop = True
+
+    def _graph_loop_applies(self, X, max_iterations):
+        opt = self.to_optimize
+        return (self.graph_em_loop and self.comm is None and self.outliers is None and X.is_cuda and X.shape[0] > 0
+                and self.EM_step == self.EM_step_b200 and self.C <= em_ops.SMALL_C and (opt["mu"] or opt["w"])
+                and not (opt["sigma"] and self.ensure_continuum) and 1 <= max_iterations <= 1000
+                and X.dtype == torch.float32 and self.mu.is_cuda)
+
+    def _EM_optimization_graph(self, X, max_iterations, tol):
+        from ..em_loop import EMLoopGraph
+        opt = self.to_optimize
+        keops_sem = self.computversion != "torch"
+        sig_mode = 0 if not opt["sigma"] else (1 if (keops_sem and opt["mu"]) else 2)
+        X = X.detach().contiguous()
+        key = (X.shape[0], self.C, self.D, str(X.device), bool(opt["mu"]), bool(opt["w"]), sig_mode, keops_sem)
+        loop = getattr(self, "_em_loop", None)
+        if loop is None or loop[0] != key:
+            loop = (key, EMLoopGraph(X.shape[0], self.C, self.D, X.device, opt["mu"], opt["w"], sig_mode, keops_sem))
+            self._em_loop = loop
+        w_old = self.w.contiguous()
+        cache = getattr(self, "_lpi_cache", None)
+        if cache is not None and cache[0] is self.w and cache[1] == self.w._version:
+            lpi_old = cache[2]
+        else:
+            lpi_old = w_old - torch.logsumexp(w_old, 0)
+        Y, mu, w, lpi, sigma, Cfe_val, FE_val, steps, stopped = loop[1].run(X, self.mu.contiguous(), w_old, lpi_old,
+                                                                            float(self.sigma), tol, int(max_iterations))
+        if opt["sigma"]:
+            self.sigma = sigma
+        if opt["mu"]:
+            self.mu = mu
+        if opt["w"]:
+            self.w = w
+        self._lpi_cache = (self.w, self.w._version, lpi)
+        if not stopped:
+            print(f"GMM optimization - reached maximum number of iterations : {max_iterations}")
+        return (Y, torch.tensor(Cfe_val, dtype=self.spec["dtype"]), torch.tensor(FE_val, dtype=self.spec["dtype"]), steps)
 
     # ---- multi-GPU: ONE all-reduce per EM step ------------------------------------------------------------------------
     pipelined_allreduce = True

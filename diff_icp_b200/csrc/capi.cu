@@ -3,6 +3,7 @@
 #include "../../include/dicp_b200.h"
 #include "dispatch.cuh"
 #include <type_traits>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include "small_step.cuh"
@@ -419,6 +420,126 @@ int dicp_em_mstep(int D, const float* stats, const float* mu_old, const float* w
     else em_mstep_kernel<3><<<1, 256, 0, st>>>(stats, mu_old, w_old, (int)C, do_mu, do_w, sig_mode, mu_new, w_new, lpi_new, out_scal);
     launch_counter() += 1;
     return last_error(DICP_OK);
+}
+
+size_t dicp_em_state_workspace_bytes(int64_t N, int64_t C) {
+    if (N < 1 || C < 1 || C > kEmColMaxC) return 0;
+    const size_t a = (em_col_small_workspace(N, (int)C, device_info().sms) + 255) / 256 * 256;
+    return a + em_row_small_workspace(N);
+}
+
+static int em_state_step_launch(int D, const float* X, int64_t N, int64_t C, float* mu, float* w, float* lpi, float* wl2,
+                                float* mu_new, float* w_new, float* lpi_new, float* stats, float* Y, float* T2, float* scal4,
+                                double* state, int do_mu, int do_w, int sig_mode, int keops_sem, void* workspace,
+                                size_t workspace_bytes, cudaStream_t st, int use_cond, cudaGraphConditionalHandle cond) {
+    if ((D != 2 && D != 3) || N < 1 || N > INT32_MAX || C < 1 || C > kEmColMaxC || sig_mode < 0 || sig_mode > 2 || !X || !mu ||
+        !w || !lpi || !wl2 || !mu_new || !w_new || !lpi_new || !stats || !Y || !T2 || !scal4 || !state || !workspace)
+        return DICP_EBADARG;
+    if (workspace_bytes < dicp_em_state_workspace_bytes(N, C)) return DICP_EWORKSPACE;
+    const int sms = device_info().sms;
+    // (1) row log-sum-exp + column statistics, old parameters
+    EmParams prm{};
+    prm.X = X; prm.mu_old = mu; prm.wl2 = wl2; prm.origin = mu; prm.o_stats = stats; prm.state = state;
+    unsigned* counter = (unsigned*)workspace;
+    const size_t cbytes = em_col_small_counter_bytes(N, sms);
+    float* part = (float*)((char*)workspace + cbytes);
+    cudaMemsetAsync(counter, 0, cbytes, st);
+    int blocks = 1, passes = 1;
+    em_lse_col_small_grid(N, sms, &blocks, &passes);
+    if (D == 2) em_lse_col_small_kernel<2><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, passes, part, counter);
+    else em_lse_col_small_kernel<3><<<blocks, 128, 0, st>>>(prm, (int)N, (int)C, passes, part, counter);
+    // (2) M step; sigma' into the state
+    if (D == 2) em_mstep_state_kernel<2><<<1, 256, 0, st>>>(stats, mu, w, (int)C, do_mu, do_w, sig_mode, mu_new, w_new, lpi_new, state);
+    else em_mstep_state_kernel<3><<<1, 256, 0, st>>>(stats, mu, w, (int)C, do_mu, do_w, sig_mode, mu_new, w_new, lpi_new, state);
+    // (3) full row pass: old responsibilities, new centroids / weights
+    EmParams row{};
+    row.X = X; row.mu_old = mu; row.wl2 = wl2; row.mu_new = mu_new; row.lpi_new = lpi_new; row.origin = mu;
+    row.o_T2 = T2; row.o_Y = Y; row.state = state;
+    float* blockscal = (float*)((char*)workspace + (em_col_small_workspace(N, (int)C, sms) + 255) / 256 * 256 + 256);
+    const long long groups = (N + kEmRowRows - 1) / kEmRowRows;
+    long long rp = groups / ((long long)sms * 8);
+    if (rp < 1) rp = 1;
+    if (rp > 16) rp = 16;
+    const unsigned rblocks = (unsigned)((groups + rp - 1) / rp);
+    if (D == 2) em_row_small_kernel<2, false><<<rblocks, 128, 0, st>>>(row, (int)N, (int)C, (int)rp, blockscal);
+    else em_row_small_kernel<3, false><<<rblocks, 128, 0, st>>>(row, (int)N, (int)C, (int)rp, blockscal);
+    scalar_reduce_kernel<<<1, 256, 0, st>>>(blockscal, (int)rblocks, 4, scal4, 0);
+    // (4) free energy, stop test, commit of the new parameters (and, inside a WHILE node, the loop condition)
+    if (D == 2) em_state_finalize_kernel<2><<<1, 256, 0, st>>>(scal4, (int)C, keops_sem, mu_new, w_new, lpi_new, mu, w, lpi, wl2, state, use_cond, cond);
+    else em_state_finalize_kernel<3><<<1, 256, 0, st>>>(scal4, (int)C, keops_sem, mu_new, w_new, lpi_new, mu, w, lpi, wl2, state, use_cond, cond);
+    return DICP_OK;
+}
+
+int dicp_em_state_step(int D, const float* X, int64_t N, int64_t C, float* mu, float* w, float* lpi, float* wl2, float* mu_new,
+                       float* w_new, float* lpi_new, float* stats, float* Y, float* T2, float* scal4, double* state, int do_mu,
+                       int do_w, int sig_mode, int keops_sem, void* workspace, size_t workspace_bytes, void* stream) {
+    const int rc = em_state_step_launch(D, X, N, C, mu, w, lpi, wl2, mu_new, w_new, lpi_new, stats, Y, T2, scal4, state, do_mu,
+                                        do_w, sig_mode, keops_sem, workspace, workspace_bytes, (cudaStream_t)stream, 0,
+                                        cudaGraphConditionalHandle{});
+    if (rc != DICP_OK) return rc;
+    launch_counter() += 5;
+    return last_error(DICP_OK);
+}
+
+// ---- the EM loop as ONE graph launch: a WHILE conditional node whose body is one step -------------------------------------
+struct EmLoopGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+};
+
+void* dicp_em_loop_create(int D, const float* X, int64_t N, int64_t C, float* mu, float* w, float* lpi, float* wl2, float* mu_new,
+                          float* w_new, float* lpi_new, float* stats, float* Y, float* T2, float* scal4, double* state, int do_mu,
+                          int do_w, int sig_mode, int keops_sem, void* workspace, size_t workspace_bytes, void* stream) {
+    EmLoopGraph* L = new EmLoopGraph();
+    cudaGraphConditionalHandle cond;
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    cudaGraphNode_t node;
+    (void)stream;
+    cudaStream_t st = nullptr;             // capture needs a stream of its own (the caller's may be the legacy default stream)
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { delete L; return nullptr; }
+    bool ok = cudaGraphCreate(&L->graph, 0) == cudaSuccess &&
+              cudaGraphConditionalHandleCreate(&cond, L->graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+    if (ok) {
+        np.conditional.handle = cond;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        ok = cudaGraphAddNode(&node, L->graph, nullptr, 0, &np) == cudaSuccess;
+    }
+    if (ok) ok = cudaStreamBeginCaptureToGraph(st, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                               cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        const int rc = em_state_step_launch(D, X, N, C, mu, w, lpi, wl2, mu_new, w_new, lpi_new, stats, Y, T2, scal4, state,
+                                            do_mu, do_w, sig_mode, keops_sem, workspace, workspace_bytes, st, 1, cond);
+        cudaGraph_t captured = nullptr;
+        ok = cudaStreamEndCapture(st, &captured) == cudaSuccess && rc == DICP_OK;
+    }
+    if (ok) ok = cudaGraphInstantiate(&L->exec, L->graph, 0) == cudaSuccess;
+    cudaStreamDestroy(st);
+    if (!ok) {
+        fprintf(stderr, "dicp_em_loop_create: %s\n", cudaGetErrorString(cudaPeekAtLastError()));
+        cudaGetLastError();
+        if (L->graph) cudaGraphDestroy(L->graph);
+        delete L;
+        return nullptr;
+    }
+    return L;
+}
+
+int dicp_em_loop_launch(void* loop, void* stream) {
+    EmLoopGraph* L = (EmLoopGraph*)loop;
+    if (!L || !L->exec) return DICP_EBADARG;
+    const cudaError_t e = cudaGraphLaunch(L->exec, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    launch_counter() += 1;
+    return DICP_OK;
+}
+
+void dicp_em_loop_destroy(void* loop) {
+    EmLoopGraph* L = (EmLoopGraph*)loop;
+    if (!L) return;
+    if (L->exec) cudaGraphExecDestroy(L->exec);
+    if (L->graph) cudaGraphDestroy(L->graph);
+    delete L;
 }
 
 int dicp_em_reduce_pack(int D, const float* stats, const float* m_ref, int64_t C, const float* extra, int n_extra, float* buf,

@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(128) em_lse_col_small_kernel(EmParams P, int N
     __shared__ __align__(16) float cols[(kEmColMaxC / 2) * RECR];
     __shared__ __align__(16) float pts[(ROWS / 2) * RECC];
     __shared__ float xch[128 * NACC];
+    DICP_EM_STATE_PROLOGUE(P)
     const int tid = threadIdx.x;
     const int Cpad = (C + 1) & ~1;
     for (int j = tid; j < Cpad; j += 128) {
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(128) em_row_small_kernel(EmParams P, int N, in
     static_assert(NF % 2 == 0, "packed records");
     __shared__ __align__(16) float cols[(kEmColMaxC / 2) * REC];
     __shared__ float red[32];
+    DICP_EM_STATE_PROLOGUE(P)
     const int tid = threadIdx.x;
     const int Cpad = (C + 1) & ~1;                                   // an odd count gets a null partner record
     for (int j = tid; j < Cpad; j += 128) {
@@ -426,6 +428,117 @@ __global__ void __launch_bounds__(256) em_mstep_kernel(const float* __restrict__
     __syncthreads();
     nd = block_sum(nd, red);
     if (tid == 0) { out_scal[0] = nd; out_scal[1] = lse; }
+}
+
+// ---- EM loop with its state on the device (one CUDA graph replay per GMM_opt, no host read between steps) --------------------
+// Host loop being replaced: GaussianMixtureUnif.EM_optimization (/root/reference/diffICP/core/GMM.py:330-357) around EM_step
+// (:402-496): per step the host reads sigma' and the free-energy sums, updates the model and tests |FE - FE_prev| < tol |FE_prev|.
+// Here sigma, kappa, the normalisation constant, FE_prev and the stop flag live in `state` (doubles, EmState); a step is
+//   em_lse_col_small_kernel -> em_mstep_state_kernel -> em_row_small_kernel<D,false> -> scalar_reduce_kernel -> em_state_finalize_kernel
+// and every kernel returns at once when the stop flag is set, so max_iterations steps can be enqueued back to back: the model
+// freezes at the step that met the criterion, exactly where the host loop returns.  As the body of a WHILE conditional node of
+// a CUDA graph (dicp_em_loop_create) the last kernel of a step decides on the device whether another step runs, so exactly the
+// steps the host loop would execute are executed, from ONE graph launch.  Scalars are computed in double like the
+// host code (Python floats), the stop test in fp32 like the reference's 0-d fp32 tensors.
+template <int D>
+__global__ void __launch_bounds__(256) em_mstep_state_kernel(const float* __restrict__ stats, const float* __restrict__ mu_old,
+                                                             const float* __restrict__ w_old, int C, int do_mu, int do_w,
+                                                             int sig_mode, float* __restrict__ mu_new, float* __restrict__ w_new,
+                                                             float* __restrict__ lpi_new, double* __restrict__ state) {
+    __shared__ float red[32];
+    __shared__ float bc;
+    if (state[ES_DONE] != 0.0) return;
+    const int tid = threadIdx.x;
+    float wmax = -INFINITY, nd = 0.f;
+    for (int c = tid; c < C; c += 256) {
+        const float* st = stats + (size_t)c * (D + 3);
+        const float m = st[0], S0 = st[1], A = st[2 + D];
+        float b2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float B = st[2 + k];
+            b2 = fmaf(B, B, b2);
+            mu_new[(size_t)c * D + k] = do_mu ? mu_old[(size_t)c * D + k] + B / S0 : mu_old[(size_t)c * D + k];
+        }
+        const float w = do_w ? (m + log2f(S0)) * kLn2 : w_old[c];
+        w_new[c] = w;
+        wmax = fmaxf(wmax, w);
+        if (sig_mode == 1) nd += exp2f(m) * (A - b2 / S0);
+        else if (sig_mode == 2) nd += exp2f(m) * A;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if ((tid & 31) == 0) red[tid >> 5] = wmax;
+    __syncthreads();
+    if (tid == 0) {
+        float v = red[0];
+        for (int k = 1; k < 8; ++k) v = fmaxf(v, red[k]);
+        bc = v;
+    }
+    __syncthreads();
+    wmax = bc;
+    __syncthreads();
+    float se = 0.f;
+    for (int c = tid; c < C; c += 256) se += expf(w_new[c] - wmax);
+    se = block_sum(se, red);
+    if (tid == 0) bc = wmax + logf(se);
+    __syncthreads();
+    const float lse = bc;
+    for (int c = tid; c < C; c += 256) lpi_new[c] = w_new[c] - lse;
+    __syncthreads();
+    nd = block_sum(nd, red);
+    if (tid == 0) {
+        // sigma' = sqrt(max(N D sigma'^2, 0) / (D N))  (core/GMM.py:296 / :455), or the old sigma when it is not optimised
+        double sg = state[ES_SIGMA];
+        if (sig_mode != 0) {
+            const double ndd = (double)nd;
+            sg = sqrt((ndd > 0.0 ? ndd : 0.0) / ((double)D * state[ES_N]));
+        }
+        state[ES_SIGMA_NEW] = sg;
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) em_state_finalize_kernel(const float* __restrict__ scal4, int C, int keops_sem,
+                                                                const float* __restrict__ mu_new, const float* __restrict__ w_new,
+                                                                const float* __restrict__ lpi_new, float* __restrict__ mu,
+                                                                float* __restrict__ w, float* __restrict__ lpi,
+                                                                float* __restrict__ wl2, double* __restrict__ state,
+                                                                int use_cond, cudaGraphConditionalHandle cond) {
+    if (state[ES_DONE] != 0.0) return;
+    const int tid = threadIdx.x;
+    const double sg = state[ES_SIGMA_NEW];
+    const double lgn_new = (double)D * (log(sg) + 0.5 * log(2.0 * 3.141592653589793));
+    const float lgnf = (float)lgn_new;
+    for (int i = tid; i < C * D; i += 256) mu[i] = mu_new[i];
+    for (int c = tid; c < C; c += 256) {
+        w[c] = w_new[c];
+        const float l = lpi_new[c];
+        lpi[c] = l;
+        wl2[c] = (l - lgnf) * 1.4426950408889634f;
+    }
+    __syncthreads();                               // every thread has read the old state
+    if (tid == 0) {
+        const double P = scal4[0], Q = scal4[1], SQ = scal4[2], N = state[ES_N];
+        const double lgn = keops_sem ? lgn_new : state[ES_LGN];             // core/GMM.py:485-488 vs :312-317
+        const double inv2s2 = 1.0 / (2.0 * sg * sg);
+        const double Cfe = P * inv2s2 + Q + N * lgn;
+        const double FE = Cfe + SQ * inv2s2;
+        const float FEf = (float)FE, lastf = (float)state[ES_LAST_FE], tolf = (float)state[ES_TOL];
+        const bool stop = state[ES_HAVE_LAST] != 0.0 && tolf >= 0.f && fabsf(FEf - lastf) < tolf * fabsf(lastf);
+        state[ES_SIGMA] = sg;
+        state[ES_KAPPA] = (double)(float)(sqrt(0.5 * 1.4426950408889634) / (double)(float)sg);   // gauss_const((float)sigma).kappa
+        state[ES_LGN] = lgn_new;
+        state[ES_CFE] = Cfe;
+        state[ES_FE] = FE;
+        state[ES_LAST_FE] = (double)FEf;
+        state[ES_HAVE_LAST] = 1.0;
+        const double steps = state[ES_STEPS] + 1.0;
+        state[ES_STEPS] = steps;
+        if (stop) state[ES_DONE] = 1.0;
+        // body of a WHILE node of a CUDA graph (dicp_em_loop_*): run another step?
+        if (use_cond) cudaGraphSetConditional(cond, (!stop && steps < state[ES_MAXIT]) ? 1u : 0u);
+    }
 }
 
 // ---- multi-GPU EM step: the buffer of the ONE all-reduce, and the M step on the reduced buffer ---------------------------------

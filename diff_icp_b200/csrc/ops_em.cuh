@@ -37,7 +37,19 @@ struct EmParams {
     float* o_rowQ;         // (N)   sum_c gamma (ln gamma - ln pi'_c)          (optional)
     float* o_sq;           // (N)   |x_n - Y_n|^2                              (optional)
     float* o_stats;        // (C, D+3) column statistics: m (log2), S0, B (D, unscaled), A (unscaled)
+    const double* state;   // device-resident EM loop (em_col_small.cuh, EmState): kappa is read from it and the kernel does
+                           // nothing once the loop's stop flag is set; null = kappa above, always run
 };
+
+// Device-resident state of an EM loop replayed as a CUDA graph (no host read between steps): doubles.
+enum EmState { ES_SIGMA = 0, ES_KAPPA, ES_LGN, ES_DONE, ES_HAVE_LAST, ES_LAST_FE, ES_STEPS, ES_CFE, ES_FE, ES_N, ES_TOL,
+               ES_SIGMA_NEW, ES_MAXIT, ES_COUNT = 16 };
+// kernel prologue: returns false when the loop has stopped; otherwise takes kappa from the state
+#define DICP_EM_STATE_PROLOGUE(P)                         \
+    if ((P).state != nullptr) {                           \
+        if ((P).state[ES_DONE] != 0.0) return;            \
+        (P).kappa = (float)(P).state[ES_KAPPA];           \
+    }
 
 static constexpr float kRescaleSlack = 8.0f;
 static constexpr float kLn2 = 0.6931471805599453f;

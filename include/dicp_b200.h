@@ -132,6 +132,30 @@ int dicp_em_rowpass(int D, int lite, float sigma_old, const float* X, int64_t N,
 int dicp_em_colstats(int D, float sigma_old, const float* X, int64_t N, const float* T2, const float* mu_old,
                      const float* wl2, int64_t C, float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One EM step with the loop state on the device, for CUDA-graph replay of a whole EM_optimization (core/GMM.py:330-357 around
+ * EM_step :402-496 / :236-325) without a host read between steps.  C <= 64 components, no outlier term.
+ *   state: 16 doubles -- [0] sigma, [1] kappa = sqrt(log2(e)/2)/sigma as rounded to fp32, [2] D(ln sigma + ln(2 pi)/2),
+ *          [3] stop flag, [4] 1 if [5] holds a previous free energy, [5] previous FE (as rounded to fp32), [6] steps executed,
+ *          [7] Cfe, [8] FE of the last executed step, [9] number of points N, [10] tol (< 0: never stop), [11] scratch,
+ *          [12] step limit (dicp_em_loop_* only).  The caller initialises [0,1,2,9,10,12] and zeroes the rest.
+ *   mu, w, lpi (= w - LSE(w)), wl2 (= (lpi - state[2]) log2(e)): the CURRENT parameters, updated in place by the step;
+ *   mu_new, w_new, lpi_new, stats (C, D+3), T2 (N), scal4: scratch;  Y (N,D): targets of the last executed step.
+ * The step does nothing once state[3] != 0 (set when |FE - FE_prev| < tol |FE_prev| in fp32, the reference's test), so
+ * max_iterations steps may be enqueued back to back; sig_mode / keops_sem as in dicp_em_mstep / the two EM orderings.
+ * dicp_em_loop_create builds a CUDA graph whose only node is a WHILE conditional node with one such step as its body: the last
+ * kernel of the step sets the loop condition on the device (another step iff not stopped and state[6] < state[12]), so
+ * dicp_em_loop_launch executes exactly the steps the reference's host loop would, from one graph launch; state[12] = the step
+ * limit (>= 1) is set by the caller before every launch.  All pointers are baked into the graph.  Returns null on failure. */
+size_t dicp_em_state_workspace_bytes(int64_t N, int64_t C);
+void* dicp_em_loop_create(int D, const float* X, int64_t N, int64_t C, float* mu, float* w, float* lpi, float* wl2, float* mu_new,
+                          float* w_new, float* lpi_new, float* stats, float* Y, float* T2, float* scal4, double* state, int do_mu,
+                          int do_w, int sig_mode, int keops_sem, void* workspace, size_t workspace_bytes, void* stream);
+int dicp_em_loop_launch(void* loop, void* stream);
+void dicp_em_loop_destroy(void* loop);
+int dicp_em_state_step(int D, const float* X, int64_t N, int64_t C, float* mu, float* w, float* lpi, float* wl2, float* mu_new,
+                       float* w_new, float* lpi_new, float* stats, float* Y, float* T2, float* scal4, double* state, int do_mu,
+                       int do_w, int sig_mode, int keops_sem, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Multi-GPU EM step (frames sharded over ranks): the buffer of the step's ONE all-reduce and the M step on it.
  * dicp_em_reduce_pack: buf = [ S0, B (D), A of every component, rescaled from the local exponent stats[c][0] to the exponent
  *   m_ref[c] every rank agrees on (C x (D+2)) | flag (1 if some local exponent exceeds m_ref by more than 100) | extra[0..n_extra) ]

@@ -296,3 +296,42 @@ def test_allreduce_buffer_and_merged_mstep(D, C):
         assert h[0] == float(ms[0]) and h[1:6] == (2.0 * ed).tolist() and h[6] == 0.0 and h[7] == 0.0
     buf[3 * (D + 2)] = 0.0                                               # a vanished column mass is reported
     assert em_ops.mstep_merged(buf, md, mud, wd, True, True, 0, 5)[4].tolist()[7] == 1.0
+
+
+@pytest.mark.parametrize("version,opt,tol,D", [
+    ("keops", dict(mu=True, sigma=True, w=False, eta0=True), 1e-3, 2),       # atlas settings
+    ("keops", dict(mu=True, sigma=True, w=True, eta0=True), 1e-2, 3),        # stops early
+    ("torch", dict(mu=True, sigma=True, w=True, eta0=True), 1e-5, 2),        # sigma from the old centroids' distances
+    ("keops", dict(mu=True, sigma=False, w=True, eta0=True), None, 3),       # fixed sigma, never stops
+    ("torch", dict(mu=False, sigma=True, w=True, eta0=True), 1e-4, 2),
+])
+def test_em_loop_as_one_cuda_graph_equals_the_step_by_step_loop(version, opt, tol, D):
+    """GaussianMixtureUnif.EM_optimization with the loop state on the device (em_loop.EMLoopGraph: max_iterations steps
+    enqueued as one CUDA graph, stop flag tested by the kernels) against the host loop around EM_step_b200 -- same kernels,
+    same arithmetic: identical bits for mu, w, sigma, targets, Cfe, FE and the step count.  Second and third calls replay
+    the captured graph from the model the first call left."""
+    from diff_icp_b200.core.GMM import GaussianMixtureUnif
+    g = torch.Generator().manual_seed(11)
+    C, N = 9, 20011
+    cen = torch.rand(C, D, generator=g)
+    X = (cen[torch.randint(0, C, (N,), generator=g)] + 0.04 * torch.randn(N, D, generator=g)).to(dev())
+    mu0 = X[torch.randint(0, N, (C,), generator=g)].clone()
+
+    def run(graph):
+        G = GaussianMixtureUnif(mu0.clone(), sigma=0.2, spec=spec(), computversion=version)
+        G.to_optimize = dict(opt)
+        G.graph_em_loop = graph
+        out = []
+        for it, nmax in enumerate((7, 5, 9)):
+            Xi = X + 0.001 * it
+            Y, Cfe, FE, steps = G.EM_optimization(Xi, max_iterations=nmax, tol=tol)
+            out.append((Y.clone(), float(Cfe), float(FE), steps, G.mu.clone(), G.w.clone(), float(G.sigma)))
+        assert (getattr(G, "_em_loop", None) is not None) == graph
+        return out
+    a, b = run(True), run(False)
+    for ra, rb in zip(a, b):
+        assert ra[3] == rb[3], (ra[3], rb[3])
+        assert ra[1] == rb[1] and ra[2] == rb[2] and ra[6] == rb[6], (ra[1:4], rb[1:4], ra[6], rb[6])
+        assert torch.equal(ra[0], rb[0]) and torch.equal(ra[4], rb[4]) and torch.equal(ra[5], rb[5])
+    if tol == 1e-2:
+        assert any(r[3] < n for r, n in zip(a, (7, 5, 9)))         # the early stop was exercised
