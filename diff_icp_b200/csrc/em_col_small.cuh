@@ -66,6 +66,38 @@ DICP_D void em_col_merge(const float* part, int s0, int s1, int g, int G, int c,
     }
 }
 
+// accp += EmCol pairs of component `row` with the staged point pairs [a, b): four pairs per block (EmCol::pair_cols: one branch
+// per block, four independent chains), then the rest one by one.  Same values as one call of pair() per staged pair.
+template <int D>
+DICP_D void em_col_sweep(const EmParams& P, const typename EmCol<D>::Row& row, const float4* sp, int a, int b, F2* accp) {
+    using Op = EmCol<D>;
+    constexpr int NF = Op::NF, U = 4;
+    int t = a;
+    for (; t + U <= b; t += U) {
+        F2 cc[U][NF];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int k = 0; k < NF / 2; ++k) {
+                const float4 v = sp[(t + u) * (NF / 2) + k];
+                cc[u][2 * k] = f2(v.x, v.y);
+                cc[u][2 * k + 1] = f2(v.z, v.w);
+            }
+        }
+        Op::template pair_cols<F2, U>(P, row, cc, accp);
+    }
+    for (; t < b; ++t) {
+        F2 cc[NF];
+#pragma unroll
+        for (int k = 0; k < NF / 2; ++k) {
+            const float4 v = sp[t * (NF / 2) + k];
+            cc[2 * k] = f2(v.x, v.y);
+            cc[2 * k + 1] = f2(v.z, v.w);
+        }
+        Op::template pair<F2>(P, row, cc, accp);
+    }
+}
+
 // Tail shared by the column-statistics kernels: two-level merge of the CTAs' partials (a single serial merge of hundreds of
 // partials by one CTA is a chain of dependent L2 round trips): the last CTA of every group of kEmColGroup consecutive CTAs
 // merges that group's partials into a level-2 partial, and the last of those mergers merges the level-2 partials and writes
@@ -134,16 +166,7 @@ __global__ void __launch_bounds__(128) em_col_small_kernel(EmParams P, int N, in
             const int npair = npad >> 1;
             const int a = (int)(((long long)npair * g) / G), b = (int)(((long long)npair * (g + 1)) / G);
             const float4* sp = reinterpret_cast<const float4*>(pts);
-            for (int t = a; t < b; ++t) {
-                F2 cc[NF];
-#pragma unroll
-                for (int k = 0; k < NF / 2; ++k) {
-                    const float4 v = sp[t * (NF / 2) + k];
-                    cc[2 * k] = f2(v.x, v.y);
-                    cc[2 * k + 1] = f2(v.z, v.w);
-                }
-                Op::template pair<F2>(P, row, cc, accp);
-            }
+            em_col_sweep<D>(P, row, sp, a, b, accp);
         }
     }
     float acc[NACC];
@@ -230,8 +253,7 @@ __global__ void __launch_bounds__(128) em_lse_col_small_kernel(EmParams P, int N
                 cc[2 * k] = f2(v.x, v.y);
                 cc[2 * k + 1] = f2(v.z, v.w);
             }
-#pragma unroll
-            for (int r = 0; r < R; ++r) OpR::template pair<F2>(P, row[r], cc, acc[r]);
+            OpR::template pair_rows<F2, R>(P, row, cc, acc);
         }
         __syncthreads();                       // the previous group's phase B is done with `pts`
 #pragma unroll
@@ -259,16 +281,7 @@ __global__ void __launch_bounds__(128) em_lse_col_small_kernel(EmParams P, int N
         if (work) {
             const int npair = npad >> 1;
             const int a = (int)(((long long)npair * g) / G), b = (int)(((long long)npair * (g + 1)) / G);
-            for (int t = a; t < b; ++t) {
-                F2 cc[NFC];
-#pragma unroll
-                for (int k = 0; k < NFC / 2; ++k) {
-                    const float4 v = spp[t * (NFC / 2) + k];
-                    cc[2 * k] = f2(v.x, v.y);
-                    cc[2 * k + 1] = f2(v.z, v.w);
-                }
-                OpC::template pair<F2>(P, rowc, cc, accp);
-            }
+            em_col_sweep<D>(P, rowc, spp, a, b, accp);
         }
     }
     float acc[NACC];
@@ -348,8 +361,7 @@ __global__ void __launch_bounds__(128) em_row_small_kernel(EmParams P, int N, in
                 c[2 * k] = f2(v.x, v.y);
                 c[2 * k + 1] = f2(v.z, v.w);
             }
-#pragma unroll
-            for (int r = 0; r < kEmRowR; ++r) Op::template pair<F2>(P, row[r], c, acc[r]);
+            Op::template pair_rows<F2, kEmRowR>(P, row, c, acc);
         }
 #pragma unroll
         for (int r = 0; r < kEmRowR; ++r) {

@@ -25,6 +25,7 @@
 // with a fixed tree and summed over blocks by `scalar_reduce_kernel`, also deterministic.
 #pragma once
 #include <atomic>
+#include <type_traits>
 #include <vector>
 #include "common.cuh"
 
@@ -163,6 +164,12 @@ _Pragma(DICP_STR(unroll DICP_COL_UNROLL))
 // ---- packed variant: two columns per lane-pair (FFMA2 / FADD2 / FMUL2) -----------------------------------------
 // Column records are stored per PAIR of columns, interleaved: pair P holds NF float2 = (c_{2P}[k], c_{2P+1}[k]), so one
 // 64-bit register carries the same field of two columns and a float4 LDS delivers two such fields.
+// Ops that offer pair_rows<V, R>() (all R rows of a thread against one packed column record in one call)
+template <class Op, class = void>
+struct has_fused_rows : std::false_type {};
+template <class Op>
+struct has_fused_rows<Op, std::enable_if_t<Op::FUSED_ROWS>> : std::true_type {};
+
 template <class Op>
 __global__ void pack_kernel_p(typename Op::Params prm, float* __restrict__ colpack, int N, int Npad) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -237,8 +244,12 @@ _Pragma(DICP_STR(unroll DICP_COL_UNROLL))
                 c[2 * k] = f2(v.x, v.y);
                 c[2 * k + 1] = f2(v.z, v.w);
             }
+            if constexpr (has_fused_rows<Op>::value) {
+                Op::template pair_rows<F2, R>(prm, row, c, acc);     // R rows, one rarely taken branch (EM row pass)
+            } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) Op::template pair<F2>(prm, row[r], c, acc[r]);
+                for (int r = 0; r < R; ++r) Op::template pair<F2>(prm, row[r], c, acc[r]);
+            }
         }
         if (!Op::PAD_NULL && (ncol & 1)) {    // odd trailing column of the whole problem: one-column form
             float c[NF];
