@@ -25,6 +25,22 @@ _int = ctypes.c_int
 _u = ctypes.c_uint
 _sz = ctypes.c_size_t
 
+_dbl = ctypes.c_double
+
+
+class LbfgsDev(ctypes.Structure):
+    """`dicp_lbfgs_dev` of include/dicp_b200.h (device-resident lock-step L-BFGS state)."""
+    _fields_ = [("K", _int), ("stride", ctypes.c_longlong), ("history", _int), ("max_iter", _int), ("max_eval", _int),
+                ("max_ls", _int), ("tol_grad", _dbl), ("tol_change", _dbl), ("lr", _dbl), ("c1", _dbl), ("c2", _dbl),
+                ("ints", _vp), ("dbl", _vp), ("vec", _vp), ("best_x", _vp), ("dirs", _vp), ("stps", _vp), ("ro", _vp),
+                ("al", _vp), ("counters", _vp)]
+
+
+_ldp = ctypes.POINTER(LbfgsDev)
+# arguments of dicp_batch_closure_cluster up to `nscal` (shared by the dicp_lbfgs_dev_round / _loop_create entry points)
+_CLOSURE_ARGS = [_int, _int, _f, _f, _int, _vp, _vp, _i64, _i64, _i64, _int, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _f, _vp, _i64,
+                 _int]
+
 # name -> (restype, argtypes); mirrors include/dicp_b200.h one to one
 SIGNATURES = {
     "dicp_version": (_int, []),
@@ -65,6 +81,11 @@ SIGNATURES = {
     "dicp_batch_closure_cluster_rows": (_int, [_int, _f, _int, _i64, _i64, _int, _int]),
     "dicp_batch_closure_cluster": (_int, [_int, _int, _f, _f, _int, _vp, _vp, _i64, _i64, _i64, _int, _vp, _i64, _vp, _i64, _vp,
                                           _vp, _i64, _f, _vp, _i64, _int, _vp]),
+    "dicp_lbfgs_dev_begin": (_int, [_ldp, _vp, _vp, _i64, _vp, _vp]),
+    "dicp_lbfgs_dev_round": (_int, [_ldp] + _CLOSURE_ARGS + [_vp]),
+    "dicp_lbfgs_dev_loop_create": (_vp, [_ldp] + _CLOSURE_ARGS + [_int]),
+    "dicp_lbfgs_dev_loop_launch": (_int, [_vp, _vp]),
+    "dicp_lbfgs_dev_loop_destroy": (None, [_vp]),
     "dicp_batch_coverage": (_int, [_int, _int, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _int, _f, _vp, _vp]),
     "dicp_lbfgs_create": (_vp, [_int, _vp, _i64, _int, _int, _int, ctypes.c_double, ctypes.c_double]),
     "dicp_lbfgs_destroy": (None, [_vp]),

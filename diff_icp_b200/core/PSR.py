@@ -326,14 +326,14 @@ class DiffPSR(MultiPSR):
     batched_lbfgs = True
 
     # Frame groups of the lock-step registration: the K frames can be split into `lockstep_groups` contiguous groups, each
-    # with its own BatchedClosurePlan, CUDA stream, L-BFGS state machines and host thread, so that one group's host work
-    # (L-BFGS updates, graph launch, wake-up after the stream synchronisation: ~0.2 ms per round) overlaps the other group's
-    # device work.  Per frame the algorithm is unchanged; values agree with the single batch up to the summation order of the
-    # kernels' row / column splits (chosen from the group's sizes) and are bit-identical when those coincide
-    # (tests/test_gpu_batched.py).  MEASURED on B200 (64 frames x 10k points, 25 support points, Reg_opt of one iteration):
-    # with the one-launch closure (compute-bound rounds of 0.44 ms) 16.2 / 14.7 / 14.9 / 16.2 ms with 1 / 2 / 3 / 4 groups;
-    # with the stage kernels (latency-bound rounds of ~23 dependent launches) a second group did not help (20.6 / 20.9 ms).
-    lockstep_groups = 2
+    # with its own BatchedClosurePlan, CUDA stream, L-BFGS state machines and host thread.  Per frame the algorithm is
+    # unchanged; values agree with the single batch up to the summation order of the kernels' row / column splits (chosen
+    # from the group's sizes) and are bit-identical when those coincide (tests/test_gpu_batched.py).  MEASURED on B200
+    # (64 frames x 10k points, 25 support points, Reg_opt of one iteration): with the L-BFGS state machines on the HOST and the
+    # one-launch closure, a second group hides the host work of a round behind the other group's kernel (16.2 / 14.7 / 14.9 /
+    # 16.2 ms with 1 / 2 / 3 / 4 groups); with the state machines on the DEVICE (the default where the one-launch closure
+    # applies) there is no host work per round left to hide: 12.8 / 12.7 / 16.0 ms with 1 / 2 / 4 groups.  Default 1.
+    lockstep_groups = 1
     lockstep_group_min_frames = 8          # below 2 x this many frames a second group is never formed
 
     def _frame_groups(self):

@@ -10,6 +10,7 @@
 #include "sym_engine.cuh"
 #include "batch_closure.cuh"
 #include "cluster_closure.cuh"
+#include "lbfgs_device.cuh"
 #include "pointset.cuh"
 #include "em_col_small.cuh"
 
@@ -771,6 +772,83 @@ int dicp_batch_closure_cluster(int D, int withlogdet, float sigma, float eta, in
     launch_counter() += 1;
     return last_error(DICP_OK);
 }
+
+// ---- lock-step L-BFGS on the device (lbfgs_device.cuh) ----------------------------------------------------------------------
+int dicp_lbfgs_dev_begin(const dicp_lbfgs_dev* L, const unsigned char* mask, float* X, int64_t xstride, int* active, void* stream) {
+    if (!L || L->K < 1 || !L->ints || !L->dbl || !L->vec || !L->counters || !X || !active || xstride < L->stride) return DICP_EBADARG;
+    lbfgs_dev_begin_kernel<<<(L->K + kLdWarps - 1) / kLdWarps, kLdWarps * 32, 0, (cudaStream_t)stream>>>(*L, mask, X, xstride, active);
+    launch_counter() += 1;
+    return last_error(DICP_OK);
+}
+
+static int lbfgs_dev_round_launch(const dicp_lbfgs_dev* L, int D, int withlogdet, float sigma, float eta, int K, const int* dims,
+                                  int* active, int64_t maxM, int64_t maxNx, int64_t fstride, int nt, float* traj, int64_t tstride,
+                                  float* X, int64_t xstride, const float* y, const float* inv, int64_t ystride, float lam_reg,
+                                  float* out, int64_t ostride, int nscal, cudaStream_t st, int max_rounds, int use_cond,
+                                  cudaGraphConditionalHandle cond) {
+    if (!L || L->K != K || !L->ints || !L->dbl || !L->vec || !L->best_x || !L->dirs || !L->stps || !L->ro || !L->al ||
+        !L->counters || L->history < 1 || L->stride < maxM * D || maxM * D > 32 * kLdNpl || !active)
+        return DICP_EBADARG;
+    const int rc = dicp_batch_closure_cluster(D, withlogdet, sigma, eta, K, dims, active, maxM, maxNx, fstride, nt, traj, tstride,
+                                              X, xstride, y, inv, ystride, lam_reg, out, ostride, nscal, st);
+    if (rc != DICP_OK) return rc;
+    lbfgs_dev_feed_kernel<<<(K + kLdWarps - 1) / kLdWarps, kLdWarps * 32, 0, st>>>(*L, out, ostride, nscal, (double)lam_reg,
+                                                                                 (double)eta, X, xstride, active, max_rounds,
+                                                                                 use_cond, cond);
+    launch_counter() += 1;
+    const cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? DICP_OK : (int)e;
+}
+
+int dicp_lbfgs_dev_round(const dicp_lbfgs_dev* L, int D, int withlogdet, float sigma, float eta, int K, const int* dims,
+                         int* active, int64_t maxM, int64_t maxNx, int64_t fstride, int nt, float* traj, int64_t tstride,
+                         float* X, int64_t xstride, const float* y, const float* inv, int64_t ystride, float lam_reg, float* out,
+                         int64_t ostride, int nscal, void* stream) {
+    return last_error(lbfgs_dev_round_launch(L, D, withlogdet, sigma, eta, K, dims, active, maxM, maxNx, fstride, nt, traj, tstride,
+                                             X, xstride, y, inv, ystride, lam_reg, out, ostride, nscal, (cudaStream_t)stream,
+                                             1 << 30, 0, cudaGraphConditionalHandle{}));
+}
+
+void* dicp_lbfgs_dev_loop_create(const dicp_lbfgs_dev* L, int D, int withlogdet, float sigma, float eta, int K, const int* dims,
+                                 int* active, int64_t maxM, int64_t maxNx, int64_t fstride, int nt, float* traj, int64_t tstride,
+                                 float* X, int64_t xstride, const float* y, const float* inv, int64_t ystride, float lam_reg,
+                                 float* out, int64_t ostride, int nscal, int max_rounds) {
+    EmLoopGraph* G = new EmLoopGraph();
+    cudaGraphConditionalHandle cond;
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    cudaGraphNode_t node;
+    cudaStream_t st = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { delete G; return nullptr; }
+    bool ok = cudaGraphCreate(&G->graph, 0) == cudaSuccess &&
+              cudaGraphConditionalHandleCreate(&cond, G->graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+    if (ok) {
+        np.conditional.handle = cond;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        ok = cudaGraphAddNode(&node, G->graph, nullptr, 0, &np) == cudaSuccess;
+    }
+    if (ok) ok = cudaStreamBeginCaptureToGraph(st, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                               cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        const int rc = lbfgs_dev_round_launch(L, D, withlogdet, sigma, eta, K, dims, active, maxM, maxNx, fstride, nt, traj, tstride,
+                                              X, xstride, y, inv, ystride, lam_reg, out, ostride, nscal, st, max_rounds, 1, cond);
+        cudaGraph_t captured = nullptr;
+        ok = cudaStreamEndCapture(st, &captured) == cudaSuccess && rc == DICP_OK;
+    }
+    if (ok) ok = cudaGraphInstantiate(&G->exec, G->graph, 0) == cudaSuccess;
+    cudaStreamDestroy(st);
+    if (!ok) {
+        fprintf(stderr, "dicp_lbfgs_dev_loop_create: %s\n", cudaGetErrorString(cudaPeekAtLastError()));
+        cudaGetLastError();
+        if (G->graph) cudaGraphDestroy(G->graph);
+        delete G;
+        return nullptr;
+    }
+    return G;
+}
+
+int dicp_lbfgs_dev_loop_launch(void* loop, void* stream) { return dicp_em_loop_launch(loop, stream); }
+void dicp_lbfgs_dev_loop_destroy(void* loop) { dicp_em_loop_destroy(loop); }
 
 int dicp_batch_coverage(int D, int K, const int* dims, const int* active, int64_t maxM, int64_t maxNx, int64_t fstride,
                         const float* traj, int64_t tstride, int ntimes, float radius, int* counts, void* stream) {

@@ -466,6 +466,7 @@ class BatchedClosurePlan:
 
     NS = 8
     one_launch_closure = True          # class-level switch (tests compare the two forms)
+    device_lbfgs_enabled = True        # with the one-launch closure: L-BFGS state machines on the device (tools/optim.py)
 
     def __init__(self, D, nt, scheme, withlogdet, sigma, eta, lam_reg, device, Ms, Nxs, use_graph=True):
         import numpy as np
@@ -524,6 +525,22 @@ class BatchedClosurePlan:
         self.one_launch = (BatchedClosurePlan.one_launch_closure and device.type == "cuda" and min(self.Nxs) > 0
                            and ops.batch_closure_cluster_rows(D, eta, scheme, self.maxM, self.maxNx, nt, K) > 0)
 
+    @property
+    def device_lbfgs(self):
+        return bool(self.one_launch and BatchedClosurePlan.device_lbfgs_enabled)
+
+    def device_optimizer(self, sizes):
+        """A DeviceLockstepLBFGS bound to this plan's buffers, with fresh state (its device buffers and its captured graph are
+        reused from call to call; the state arrays are re-initialised)."""
+        from .tools.optim import DeviceLockstepLBFGS
+        opt = getattr(self, "_dev_opt", None)
+        if opt is None or opt.sizes != [int(n) for n in sizes]:
+            opt = DeviceLockstepLBFGS(sizes, self)
+            self._dev_opt = opt
+        else:
+            opt.fresh()
+        return opt
+
     # ---- problem data -------------------------------------------------------------------------------------------------
     def set_geometry(self, q0_list, x0_list):
         """Support points and data points of every frame (constant over the outer iterations of DiffPSR)."""
@@ -575,6 +592,13 @@ class BatchedClosurePlan:
                                    self.ws, self.ws_frame)
             cur = nxt
         return cur
+
+    def cluster_args(self):
+        """Arguments of dicp_batch_closure_cluster up to `nscal` (also the closure part of dicp_lbfgs_dev_round / _loop_create)."""
+        return (self.D, int(self.withlogdet), float(self.sigma), float(self.eta), self.K, ops.ptr(self.dims), ops.ptr(self.d_active),
+                self.maxM, self.maxNx, self.fstride, self.nt, ops.ptr(self.traj), self.K * self.fstride, ops.ptr(self.d_X),
+                self.ostride, ops.ptr(self.y), ops.ptr(self.inv), self.maxNd, float(self.lam_reg), ops.ptr(self.d_out), self.ostride,
+                self.NS)
 
     def _body(self):
         self.d_in.copy_(self.h_in, non_blocking=True)

@@ -167,6 +167,170 @@ class LockstepLBFGS:
         return rounds
 
 
+class DeviceLockstepLBFGS:
+    """LockstepLBFGS with the optimiser state on the DEVICE (csrc/lbfgs_device.cuh): the per-frame state machines run in a
+    kernel right after the one-launch closure of `plan` (shooting.BatchedClosurePlan with plan.one_launch), one warp per frame,
+    and the rounds of one optimizer.step() of all frames are ONE CUDA graph launch (a WHILE conditional node whose condition
+    "some frame still waits for a closure value" is set on the device) -- no host round trip per round.  Same algorithm and
+    settings as LockstepLBFGS; iterates agree with it to fp64 rounding of the dot products (other summation order)."""
+
+    MAX_ROUNDS = 400                      # per optimizer.step(): max_eval = 100 closure values per frame leaves a wide margin
+
+    def __init__(self, sizes, plan, max_iter=20, max_eval=100, history_size=100, tolerance_grad=1e-7, tolerance_change=1e-9):
+        import numpy as np
+        from .. import _lib
+        self._np, self._libmod = np, _lib
+        self._lib = _lib.load()
+        self.plan = plan
+        self.K = K = len(sizes)
+        self.sizes = [int(n) for n in sizes]
+        self.stride = int(plan.pstride)
+        if max(self.sizes) > self.stride or K != plan.K:
+            raise ValueError("DeviceLockstepLBFGS: sizes do not match the closure plan")
+        dev = plan.device
+        self.history = int(history_size)
+        NI, ND, NV = 24, 24, 12
+        ints = np.zeros((K, NI), np.int32)
+        ints[:, 0] = self.sizes
+        ints[:, 1] = 1
+        dbl = np.zeros((K, ND), np.float64)
+        dbl[:, 1] = 1.0
+        dbl[:, 18] = np.nan
+        dbl[:, 19] = np.inf
+        self._ints0, self._dbl0 = torch.from_numpy(ints).to(dev), torch.from_numpy(dbl).to(dev)
+        self.ints = self._ints0.clone()
+        self.dbl = self._dbl0.clone()
+        self.vec = torch.zeros(K, NV, self.stride, dtype=torch.float64, device=dev)
+        self.best_x = torch.zeros(K, self.stride, dtype=torch.float32, device=dev)
+        self.dirs = torch.zeros(K, self.history, self.stride, dtype=torch.float64, device=dev)
+        self.stps = torch.zeros(K, self.history, self.stride, dtype=torch.float64, device=dev)
+        self.ro = torch.zeros(K, self.history, dtype=torch.float64, device=dev)
+        self.al = torch.zeros(K, self.history, dtype=torch.float64, device=dev)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.mask = torch.zeros(K, dtype=torch.uint8, device=dev)
+        self.h_counters = torch.zeros(4, dtype=torch.int32).pin_memory()
+        L = _lib.LbfgsDev()
+        L.K, L.stride, L.history = K, self.stride, self.history
+        L.max_iter, L.max_eval, L.max_ls = int(max_iter), int(max_eval), 25
+        L.tol_grad, L.tol_change, L.lr, L.c1, L.c2 = float(tolerance_grad), float(tolerance_change), 1.0, 1e-4, 0.9
+        L.ints, L.dbl, L.vec, L.best_x = self.ints.data_ptr(), self.dbl.data_ptr(), self.vec.data_ptr(), self.best_x.data_ptr()
+        L.dirs, L.stps, L.ro, L.al = self.dirs.data_ptr(), self.stps.data_ptr(), self.ro.data_ptr(), self.al.data_ptr()
+        L.counters = self.counters.data_ptr()
+        self.L = L
+        self.graph = None
+        self._cache, self._pin = None, None
+
+    def __del__(self):
+        g, self.graph = getattr(self, "graph", None), None
+        if g:
+            self._lib.dicp_lbfgs_dev_loop_destroy(g)
+
+    def fresh(self):
+        """Back to the state of a newly created optimiser (new LockstepLBFGS object in the host version)."""
+        self.ints.copy_(self._ints0)
+        self.dbl.copy_(self._dbl0)
+        self._cache = None
+
+    # ---- parameters / state ---------------------------------------------------------------------------------------------------
+    def set_x(self, k, x):
+        a = torch.from_numpy(self._np.ascontiguousarray(x, dtype=self._np.float32).reshape(-1).astype(self._np.float64))
+        assert a.numel() == self.sizes[k]
+        self.vec[k, 0, :self.sizes[k]] = a.to(self.vec.device)
+        self._cache = None
+
+    def set_all(self, xs):
+        X = self._np.zeros((self.K, self.stride), self._np.float64)
+        for k, x in enumerate(xs):
+            X[k, :self.sizes[k]] = self._np.asarray(x, dtype=self._np.float32).reshape(-1)
+        self.vec[:, 0, :] = torch.from_numpy(X).to(self.vec.device)
+        self._cache = None
+
+    def reset(self, k, line_search=True):
+        # dicp_lbfgs_reset: fresh optimiser memory, counters and step size; best / last closure values persist
+        idx = torch.tensor([1, 2, 6, 7, 17, 18], device=self.ints.device)
+        self.ints[k, idx] = torch.tensor([int(bool(line_search)), 0, 0, 0, 0, 0], dtype=torch.int32, device=self.ints.device)
+        self.dbl[k, :2] = torch.tensor([0.0, 1.0], dtype=torch.float64, device=self.dbl.device)
+        self._cache = None
+
+    def reset_all(self, line_search=True):
+        idx = torch.tensor([1, 2, 6, 7, 17, 18], device=self.ints.device)
+        self.ints[:, idx] = torch.tensor([int(bool(line_search)), 0, 0, 0, 0, 0], dtype=torch.int32, device=self.ints.device)
+        self.dbl[:, :2] = torch.tensor([0.0, 1.0], dtype=torch.float64, device=self.dbl.device)
+        self._cache = None
+
+    def _fetch(self):
+        """One read of everything the host driver looks at (state integers / scalars, current and best parameters): four
+        asynchronous copies into pinned buffers and ONE synchronisation; cached until the state changes."""
+        if self._cache is None:
+            if self._pin is None:
+                self._pin = (torch.zeros_like(self.ints, device="cpu").pin_memory(), torch.zeros_like(self.dbl, device="cpu").pin_memory(),
+                             torch.zeros(self.K, self.stride, dtype=torch.float32).pin_memory(),
+                             torch.zeros(self.K, self.stride, dtype=torch.float32).pin_memory())
+            hi, hd, hx, hb = self._pin
+            hi.copy_(self.ints, non_blocking=True)
+            hd.copy_(self.dbl, non_blocking=True)
+            hx.copy_(self.vec[:, 0, :].float(), non_blocking=True)
+            hb.copy_(self.best_x, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self._cache = (hi.numpy().copy(), hd.numpy().copy(), hx.numpy().copy(), hb.numpy().copy())
+        return self._cache
+
+    def get_all(self, best=False):
+        i, _, x, b = self._fetch()
+        if best:
+            if not (i[:, 16] != 0).all():
+                raise RuntimeError("DeviceLockstepLBFGS.get_all: no value")
+            return b
+        return x
+
+    def get_x(self, k, best=False):
+        return self.get_all(best)[k, :self.sizes[k]].copy()
+
+    def stats_all(self):
+        i, d, _, _ = self._fetch()
+        out = self._np.zeros((self.K, 4), self._np.float64)
+        out[:, 0], out[:, 1], out[:, 2], out[:, 3] = d[:, 18], d[:, 19], i[:, 6], i[:, 7]
+        return out
+
+    def stats(self, k):
+        s = self.stats_all()[k]
+        return {"last": s[0], "best": s[1], "func_evals": int(s[2]), "n_iter": int(s[3])}
+
+    # ---- one optimizer.step() of the selected frames ----------------------------------------------------------------------------
+    def step(self, mask, evaluate=None, X=None, active=None, losses=None, grads=None):
+        from ..shooting import ShootPlan
+        from .._lib import check, stream_ptr
+        np, plan, lib = self._np, self.plan, self._lib
+        self._cache = None
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        self.mask.copy_(torch.from_numpy(m), non_blocking=False)
+        st = stream_ptr()
+        check(lib.dicp_lbfgs_dev_begin(self.L, self.mask.data_ptr(), plan.d_X.data_ptr(), plan.ostride, plan.d_active.data_ptr(), st),
+              "dicp_lbfgs_dev_begin")
+        if self.graph is None:
+            # first step: the rounds one by one with a host read of the waiting count (this also loads the kernels); then the
+            # WHILE graph is built for all later steps
+            rounds = 0
+            while True:
+                check(lib.dicp_lbfgs_dev_round(self.L, *plan.cluster_args(), st), "dicp_lbfgs_dev_round")
+                rounds += 1
+                self.h_counters.copy_(self.counters)
+                if int(self.h_counters[3]) == 0 or rounds >= self.MAX_ROUNDS:
+                    break
+            with ShootPlan._lock:
+                self.graph = lib.dicp_lbfgs_dev_loop_create(self.L, *plan.cluster_args(), self.MAX_ROUNDS)
+            if not self.graph:
+                raise RuntimeError("dicp_lbfgs_dev_loop_create failed")
+        else:
+            check(lib.dicp_lbfgs_dev_loop_launch(self.graph, st), "dicp_lbfgs_dev_loop_launch")
+            self.h_counters.copy_(self.counters)               # synchronises
+            rounds = int(self.h_counters[2])
+        if int(self.h_counters[3]) != 0:
+            raise RuntimeError("DeviceLockstepLBFGS.step: frames still waiting after MAX_ROUNDS rounds")
+        plan.evaluations += rounds
+        return rounds
+
+
 def LBFGS_optimization_lockstep(p0, evaluator, nmax=10, tol=1e-3, errthresh=1e8):
     """`LBFGS_optimization` (tools/optim.py:10-110) for K independent problems advanced in lock step.
 
@@ -180,10 +344,15 @@ def LBFGS_optimization_lockstep(p0, evaluator, nmax=10, tol=1e-3, errthresh=1e8)
     K = len(p0)
     shapes = [np.shape(p) for p in p0]
     sizes = [int(np.prod(s)) for s in shapes]
-    opt = LockstepLBFGS(sizes, stride=evaluator.X.shape[1])
-    for k in range(K):
-        opt.set_x(k, np.asarray(p0[k], dtype=np.float32))
-        opt.reset(k, True)
+    if getattr(evaluator, "device_lbfgs", False):
+        # optimiser state on the device, rounds of a step as one CUDA graph launch (csrc/lbfgs_device.cuh)
+        opt = evaluator.device_optimizer(sizes)         # fresh state: line search on, empty memory
+        opt.set_all(p0)
+    else:
+        opt = LockstepLBFGS(sizes, stride=evaluator.X.shape[1])
+        for k in range(K):
+            opt.set_x(k, np.asarray(p0[k], dtype=np.float32))
+            opt.reset(k, True)
     steps = [0] * K
     go_on = [True] * K
     L = [math.inf] * K
@@ -197,6 +366,10 @@ def LBFGS_optimization_lockstep(p0, evaluator, nmax=10, tol=1e-3, errthresh=1e8)
         rounds += opt.step(mask, evaluator.evaluate, evaluator.X, evaluator.active, evaluator.losses, evaluator.grads)
         redo = []
         st_all, now_all = opt.stats_all(), opt.get_all()
+        # RMS change and RMS size of every frame's parameters in one go (rows are zero beyond the frame's size)
+        szs = np.asarray(sizes, dtype=np.float64)
+        delta_all = np.sqrt(((now_all.astype(np.float32) - before.astype(np.float32)) ** 2).sum(1, dtype=np.float32) / szs)
+        scale_all = np.sqrt((before.astype(np.float32) ** 2).sum(1, dtype=np.float32) / szs)
         for k in np.flatnonzero(mask):
             k = int(k)
             steps[k] += 1
@@ -223,9 +396,7 @@ def LBFGS_optimization_lockstep(p0, evaluator, nmax=10, tol=1e-3, errthresh=1e8)
                 change[k] = "None (divergent iteration step)"
                 opt.reset(k, False)
             else:
-                n = sizes[k]
-                delta = float(np.sqrt(np.mean((now_all[k, :n] - before[k, :n]) ** 2)))
-                scale = float(np.sqrt(np.mean(before[k, :n] ** 2)))
+                delta, scale = float(delta_all[k]), float(scale_all[k])
                 go_on[k] = delta > tol * scale
                 change[k] = delta
         if redo:                                   # loss at the perturbed points (tools/optim.py:73), outside the optimisers

@@ -257,6 +257,48 @@ int dicp_batch_closure_cluster(int D, int withlogdet, float sigma, float eta, in
                                int64_t maxM, int64_t maxNx, int64_t fstride, int nt, float* traj, int64_t tstride,
                                const float* X, int64_t xstride, const float* y, const float* inv, int64_t ystride,
                                float lam_reg, float* out, int64_t ostride, int nscal, void* stream);
+/* ---- Lock-step L-BFGS with the optimiser state on the device (csrc/lbfgs_device.cuh) -------------------------------------------
+ * The per-frame state machines of dicp_lbfgs_* (torch.optim.LBFGS with strong-Wolfe line search as tools/optim.py:26,56 uses
+ * it), one warp per frame, running in a kernel right after dicp_batch_closure_cluster: a lock-step round needs no host round
+ * trip.  The caller owns all memory (device pointers below) and initialises it: ints zero except [0] = n_k, [1] = line search
+ * on/off; dbl zero except [1] = 1 (H_diag), [18] = NaN (last closure value), [19] = +inf (best closure value); vec slot 0 = the
+ * parameters (fp64).  Host-readable slots: ints [6] closure evaluations, [7] L-BFGS iterations, [16] has-best flag;
+ * dbl [18], [19]; vec slot 0 (current parameters); best_x (fp32 parameters of the best closure value so far). */
+#define DICP_LBFGS_DEV_NI 24
+#define DICP_LBFGS_DEV_ND 24
+#define DICP_LBFGS_DEV_NV 12
+typedef struct dicp_lbfgs_dev {
+    int K;                       /* frames */
+    long long stride;            /* row stride of the per-frame vectors (>= max n_k) */
+    int history, max_iter, max_eval, max_ls;
+    double tol_grad, tol_change, lr, c1, c2;
+    int* ints;                   /* (K, DICP_LBFGS_DEV_NI) */
+    double* dbl;                 /* (K, DICP_LBFGS_DEV_ND) */
+    double* vec;                 /* (K, DICP_LBFGS_DEV_NV, stride) */
+    float* best_x;               /* (K, stride) */
+    double *dirs, *stps;         /* (K, history, stride) curvature pairs (ring buffers) */
+    double *ro, *al;             /* (K, history) */
+    unsigned* counters;          /* 4 words: ticket, waiting frames of the round, rounds since begin, waiting frames at the end */
+} dicp_lbfgs_dev;
+/* optimizer.step() begins for the frames with mask[k] != 0 (null = all): writes their trial points into X (K, xstride) and the
+ * flags active (K), the input buffers of dicp_batch_closure_cluster. */
+int dicp_lbfgs_dev_begin(const dicp_lbfgs_dev* L, const unsigned char* mask, float* X, int64_t xstride, int* active, void* stream);
+/* One lock-step round: dicp_batch_closure_cluster (same arguments) + the optimiser kernel, which consumes (loss, gradient) of
+ * every waiting frame from `out` and writes the next trial points / active flags.  counters[3] = frames still waiting. */
+int dicp_lbfgs_dev_round(const dicp_lbfgs_dev* L, int D, int withlogdet, float sigma, float eta, int K, const int* dims,
+                         int* active, int64_t maxM, int64_t maxNx, int64_t fstride, int nt, float* traj, int64_t tstride,
+                         float* X, int64_t xstride, const float* y, const float* inv, int64_t ystride, float lam_reg, float* out,
+                         int64_t ostride, int nscal, void* stream);
+/* The rounds of one optimizer.step() of ALL frames as ONE CUDA graph launch: a WHILE conditional node whose body is such a round
+ * and whose condition (some frame still waits and fewer than max_rounds rounds ran) the optimiser kernel sets on the device.
+ * All pointers are baked into the graph.  Returns null on failure. */
+void* dicp_lbfgs_dev_loop_create(const dicp_lbfgs_dev* L, int D, int withlogdet, float sigma, float eta, int K, const int* dims,
+                                 int* active, int64_t maxM, int64_t maxNx, int64_t fstride, int nt, float* traj, int64_t tstride,
+                                 float* X, int64_t xstride, const float* y, const float* inv, int64_t ystride, float lam_reg,
+                                 float* out, int64_t ostride, int nscal, int max_rounds);
+int dicp_lbfgs_dev_loop_launch(void* loop, void* stream);
+void dicp_lbfgs_dev_loop_destroy(void* loop);
+
 /* counts[k*ntimes + t] += #{data points of frame k farther than `radius` from every support point at stored time t}
  * (GaussKernel.check_coverage over a whole trajectory, tools/kernel.py:324-329 as used in core/PSR.py:559-566);
  * traj: time-major, time point t of frame k at traj + t*tstride + k*fstride.  counts must be zeroed by the caller. */

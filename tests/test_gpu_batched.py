@@ -234,3 +234,48 @@ def test_frame_groups_agree_with_a_single_batch(one_launch, monkeypatch):
             assert abs(o[0] - outs[0][0]) <= 1e-5 * abs(outs[0][0])
             for a, b in zip(o[2], outs[0][2]):
                 assert (a - b).abs().max().item() <= 2e-3 * 0.2          # points: well inside one kernel width
+
+
+@pytest.mark.parametrize("D,Ms,Nxs,nmax", [(2, [25] * 7, [3000 + 100 * k for k in range(7)], 1),
+                                           (3, [12, 40, 64, 27, 5], [900, 5000, 2500, 16000, 300], 3),
+                                           (2, [9], [700], 2)])
+def test_device_lbfgs_equals_host_lbfgs(D, Ms, Nxs, nmax, monkeypatch):
+    """tools.optim.DeviceLockstepLBFGS (csrc/lbfgs_device.cuh: the L-BFGS state machines of all frames in a kernel after the
+    one-launch closure, the rounds of a step as ONE CUDA graph launch with a WHILE node) against the host state machines
+    (csrc/lbfgs_batch.cu, tested against torch.optim.LBFGS in test_lockstep_lbfgs.py) on the same registration problems:
+    same step / evaluation / iteration counts and, up to the fp64 rounding of the dot products (other summation order)
+    amplified by the line search, the same momenta.  Run twice: the second run replays the captured graph."""
+    from diff_icp_b200 import shooting
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from diff_icp_b200.tools.optim import LBFGS_optimization_lockstep
+    sig, lam = 0.25, 50.0
+    LM = LDDMMModel(sigma=sig, D=D, lambd=lam, version="hybrid", scheme="Euler", nt=6, spec=spec())
+    K = len(Ms)
+    g = torch.Generator().manual_seed(21)
+    q0 = [torch.rand(m, D, generator=g).to(dev()) for m in Ms]
+    x0 = [torch.rand(n, D, generator=g).to(dev()) for n in Nxs]
+    y = [(x + 0.05 * torch.randn(x.shape, generator=g).to(dev()) + 0.03) for x in x0]
+    inv = [torch.full((n,), 30.0, device=dev()) for n in Nxs]
+    p0 = [np.zeros((m, D), np.float32) for m in Ms]
+    res = {}
+    for device_opt in (True, False):
+        monkeypatch.setattr(shooting.BatchedClosurePlan, "device_lbfgs_enabled", device_opt)
+        plan = shooting.BatchedClosurePlan(D, 6, "Euler", LM.withlogdet, sig, LM.eta, lam, dev(), Ms, Nxs, use_graph=True)
+        assert plan.one_launch and plan.device_lbfgs == device_opt
+        plan.set_geometry(q0, x0)
+        plan.set_targets(torch.cat(y), torch.cat(inv))
+        runs = []
+        for rep in range(2):
+            bp, bL, steps, change, rounds = LBFGS_optimization_lockstep(p0, plan, nmax=nmax, tol=1e-4)
+            runs.append((bp, bL, steps, rounds))
+        res[device_opt] = runs
+    for (bpd, bLd, sd, rd), (bph, bLh, sh, rh) in zip(res[True], res[False]):
+        assert sd == sh
+        assert abs(rd - rh) <= max(2, rh // 10)
+        for k in range(K):
+            assert abs(bLd[k] - bLh[k]) <= 2e-5 * abs(bLh[k]), (k, bLd[k], bLh[k])
+            scale = max(np.abs(bph[k]).max(), 1e-6)
+            assert np.abs(bpd[k] - bph[k]).max() <= 2e-2 * scale, (k, np.abs(bpd[k] - bph[k]).max(), scale)
+    # replay = first (eager) run: deterministic kernels, same state machine
+    (bp1, bL1, s1, r1), (bp2, bL2, s2, r2) = res[True]
+    assert s1 == s2 and r1 == r2 and bL1 == bL2 and all(np.array_equal(a, b) for a, b in zip(bp1, bp2))
