@@ -1,4 +1,5 @@
-"""Small invocations of every kernel family added late in round 1 (a quick smoke run; also usable under a memory checker):
+"""Small invocations of every kernel family added late in round 1 and in round 2 (a quick smoke run; also usable under a memory
+checker):
     python scripts/sanitize_smoke.py"""
 import os
 import sys
@@ -55,6 +56,28 @@ T2 = em_ops.rowpass(0.2, X, mu, wl2)
 st = em_ops.colstats(0.2, X, T2, mu, wl2)
 mu2, w2, lpi, ms = em_ops.mstep(st, mu, w, True, True, 1)
 em_ops.rowpass(0.2, X, mu, wl2, mu2, lpi.contiguous())
+# round 2: fused first sweep, all-reduce buffer + merged M step, EM loop on the device (eager first call, WHILE graph second)
+st2 = em_ops.lse_colstats(0.2, X, mu, wl2)
+buf = em_ops.reduce_pack(st2, torch.round(st2[:, 0]), torch.zeros(5, device=dev))
+em_ops.mstep_merged(buf, torch.round(st2[:, 0]), mu, w, True, True, 1, 5)
+from diff_icp_b200.core.GMM import GaussianMixtureUnif        # noqa: E402
+G = GaussianMixtureUnif(mu.clone(), sigma=0.2, spec={"device": dev, "dtype": torch.float32})
+for _ in range(2):
+    G.EM_optimization(X, max_iterations=4, tol=1e-6)
+# round 2: one-launch closure on thread-block clusters (both CTA sizes, 8 and 16 CTAs per frame) and the device L-BFGS
+from diff_icp_b200.tools.optim import LBFGS_optimization_lockstep      # noqa: E402
+for D, Ms, Nxs, shape in ((2, [25, 7, 33], [1000, 333, 1290], "128,8"), (3, [9, 30], [257, 2100], "64,16"),
+                          (2, [64, 5], [4000, 17], "128,16")):
+    os.environ["DICP_CC_SHAPE"] = shape
+    plan = shooting.BatchedClosurePlan(D, 3, "Euler", True, 0.3, 0.0, 10.0, dev, Ms, Nxs, use_graph=False)
+    assert plan.one_launch and plan.device_lbfgs
+    plan.set_geometry([uni(m, D) for m in Ms], [uni(n, D) for n in Nxs])
+    plan.set_targets(uni(sum(Nxs), D), torch.full((sum(Nxs),), 5.0, device=dev))
+    plan.active[:] = 1
+    plan.evaluate()
+    for _ in range(2):                       # eager rounds, then the WHILE graph
+        LBFGS_optimization_lockstep([np.zeros((m, D), np.float32) for m in Ms], plan, nmax=1, tol=1e-4)
+os.environ.pop("DICP_CC_SHAPE", None)
 # point-set helpers
 x = uni(700, 2)
 decimate(x, 0.08)
