@@ -299,11 +299,24 @@ class DiffPSR(MultiPSR):
         dataloss_func.targets, dataloss_func.inv2sig2 = y, inv       # lets LDDMMModel.Optimize fuse the whole closure
         return dataloss_func
 
-    # number of frames registered concurrently (one Python thread + one CUDA stream each). Frames are independent
-    # (core/PSR.py:528), and every frame's computation is deterministic, so results do not depend on this setting
-    # (asserted bit for bit in the tests).  Measured on B200 with 64 frames x 10k points it does NOT pay off: the
-    # per-frame L-BFGS is bound by host Python time, which threads serialise on the GIL -- hence the default of 1.
-    frame_workers = 1
+    # number of frames registered concurrently on the frame-by-frame path (one Python thread + one CUDA stream each). Frames
+    # are independent (core/PSR.py:528), and every frame's computation is deterministic, so results do not depend on this
+    # setting (asserted bit for bit in the tests).  None = automatic.  MEASURED on B200: with 64 frames x 10k points and 25
+    # support points it does not pay off (closures of microseconds: the per-frame L-BFGS is bound by host Python time, which
+    # threads serialise on the GIL; that regime is served by the lock-step path anyway); with configs[3]-shaped frames (50k
+    # points, 1210 support points, 3-D, Ralston: closures of ~3 ms of which ~45 % are latency-bound launches of a few
+    # microseconds) a second frame in flight fills those gaps: Reg_opt of 16 frames 1.37 -> 1.13 s with 2 workers, 0.99-1.18 s
+    # with 4.  Automatic = 3 workers when a frame's closure sweeps >= 2e7 (point, support point) pairs per stage, else 1.
+    frame_workers = None
+    frame_workers_big_pairs = 2.0e7
+
+    def _auto_frame_workers(self):
+        if self.frame_workers is not None:
+            return int(self.frame_workers)
+        if self.K < 2:
+            return 1
+        pairs = sorted(float(self.q0[k].shape[0]) * float(self.allx0[k].shape[0]) for k in range(self.K))
+        return 3 if pairs[len(pairs) // 2] >= self.frame_workers_big_pairs else 1
 
     def _register_frame(self, k, nmax, tol):
         """Optimise a0[k] and collect everything Reg_opt's bookkeeping needs (no shared state is written here)."""
@@ -450,7 +463,7 @@ class DiffPSR(MultiPSR):
         plan = self._batched_plan()
         if plan is not None:
             return self._register_all_lockstep(plan, nmax, tol)
-        W = min(int(self.frame_workers), K)
+        W = min(self._auto_frame_workers(), K)
         if W <= 1 or dev.type != "cuda":
             return [self._register_frame(k, nmax, tol) for k in range(K)]
         import threading

@@ -45,7 +45,8 @@ def full_frames_3d(frames, n_points, seed=1234):
     return out
 
 
-def run_c4(rank, world, dev, comm, n_frames=256, n_points=50000, C=20, iters=3, graph=True, lockstep=True, scheme="Ralston"):
+def run_c4(rank, world, dev, comm, n_frames=256, n_points=50000, C=20, iters=3, graph=True, lockstep=True, scheme="Ralston",
+           workers=None):
     from diff_icp_b200.core.GMM import GaussianMixtureUnif
     from diff_icp_b200.core.LDDMM import LDDMMModel
     from diff_icp_b200.core.PSR import DiffPSR
@@ -61,6 +62,8 @@ def run_c4(rank, world, dev, comm, n_frames=256, n_points=50000, C=20, iters=3, 
     P = DiffPSR([[x.to(dev) for x in fr] for fr in frames], G, LM, dataspec=spec, compspec=spec, comm=comm)
     P.printstuff = False
     P.batched_lbfgs = bool(lockstep)
+    if workers is not None:
+        P.frame_workers = int(workers)
     P.set_support_scheme("grid", rho=math.sqrt(2))
     P.reinitialize_GMM()
     times = []
@@ -103,6 +106,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--lockstep", type=int, default=1)
+    ap.add_argument("--workers", type=int, default=None, help="frames registered concurrently on the per-frame path (threads + streams)")
     ap.add_argument("--scheme", default="Ralston")
     args = ap.parse_args()
     rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -114,7 +118,8 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
         from diff_icp_b200.dist import StatsComm
         comm = StatsComm()
-    res = run_c4(rank, world, dev, comm, args.frames, args.points, 20, args.iters, args.graph, args.lockstep, args.scheme)
+    res = run_c4(rank, world, dev, comm, args.frames, args.points, 20, args.iters, args.graph, args.lockstep, args.scheme,
+                 args.workers)
     if rank == 0:
         print(json.dumps(res))
     if comm is not None:
