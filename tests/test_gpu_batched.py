@@ -279,3 +279,49 @@ def test_device_lbfgs_equals_host_lbfgs(D, Ms, Nxs, nmax, monkeypatch):
     # replay = first (eager) run: deterministic kernels, same state machine
     (bp1, bL1, s1, r1), (bp2, bL2, s2, r2) = res[True]
     assert s1 == s2 and r1 == r2 and bL1 == bL2 and all(np.array_equal(a, b) for a, b in zip(bp1, bp2))
+
+
+def test_device_lbfgs_fixed_step_mode_and_masks():
+    """The paths the end-to-end runs rarely take: optimisers restarted WITHOUT line search (the reference's fall-back after a
+    divergent step, tools/optim.py:77), a step of a SUBSET of the frames, set_x / get_x / stats of single frames -- device
+    state machines against the host ones on the same closure plan."""
+    from diff_icp_b200 import shooting
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from diff_icp_b200.tools.optim import DeviceLockstepLBFGS, LockstepLBFGS
+    D, Ms, Nxs, sig, lam = 2, [16, 25, 9, 30], [1500, 2600, 800, 4000], 0.25, 50.0
+    LM = LDDMMModel(sigma=sig, D=D, lambd=lam, version="classic", scheme="Euler", nt=5, spec=spec())
+    K = len(Ms)
+    g = torch.Generator().manual_seed(33)
+    q0 = [torch.rand(m, D, generator=g).to(dev()) for m in Ms]
+    x0 = [torch.rand(n, D, generator=g).to(dev()) for n in Nxs]
+    y = [(x + 0.04 * torch.randn(x.shape, generator=g).to(dev())) for x in x0]
+    inv = [torch.full((n,), 20.0, device=dev()) for n in Nxs]
+    plan = shooting.BatchedClosurePlan(D, 5, "Euler", LM.withlogdet, sig, LM.eta, lam, dev(), Ms, Nxs, use_graph=True)
+    assert plan.one_launch
+    plan.set_geometry(q0, x0)
+    plan.set_targets(torch.cat(y), torch.cat(inv))
+    sizes = [m * D for m in Ms]
+    p_start = [(1e-3 * torch.randn(n, generator=g)).numpy() for n in sizes]
+    host = LockstepLBFGS(sizes, stride=plan.X.shape[1], max_iter=6)
+    devo = DeviceLockstepLBFGS(sizes, plan, max_iter=6)
+    for k in range(K):
+        host.set_x(k, p_start[k])
+        devo.set_x(k, p_start[k])
+        host.reset(k, k % 2 == 0)                # frames 1 and 3: fixed-step mode
+        devo.reset(k, k % 2 == 0)
+    for mask in ([1, 1, 1, 1], [0, 1, 1, 0], [1, 0, 0, 1], [1, 1, 1, 1]):
+        m = np.array(mask, np.uint8)
+        host.step(m, plan.evaluate, plan.X, plan.active, plan.losses, plan.grads)
+        devo.step(m)
+        sh, sd = host.stats_all(), devo.stats_all()
+        assert np.array_equal(sh[:, 2:], sd[:, 2:]), (sh[:, 2:], sd[:, 2:])          # evaluation / iteration counts
+        assert np.allclose(sh[:, :2], sd[:, :2], rtol=3e-5, atol=0, equal_nan=True)
+        xh, xd = host.get_all(), devo.get_all()
+        for k in range(K):
+            n = sizes[k]
+            assert np.abs(xh[k, :n] - xd[k, :n]).max() <= 1e-2 * max(np.abs(xh[k, :n]).max(), 1e-6)
+            assert np.array_equal(devo.get_x(k), xd[k, :n])
+            assert devo.stats(k)["func_evals"] == int(sd[k, 2])
+    bh, bd = host.get_all(best=True), devo.get_all(best=True)
+    for k in range(K):
+        assert np.abs(bh[k, :sizes[k]] - bd[k, :sizes[k]]).max() <= 1e-2 * max(np.abs(bh[k, :sizes[k]]).max(), 1e-6)
