@@ -46,7 +46,7 @@ def full_frames_3d(frames, n_points, seed=1234):
 
 
 def run_c4(rank, world, dev, comm, n_frames=256, n_points=50000, C=20, iters=3, graph=True, lockstep=True, scheme="Ralston",
-           workers=None):
+           workers=None, rho=None):
     from diff_icp_b200.core.GMM import GaussianMixtureUnif
     from diff_icp_b200.core.LDDMM import LDDMMModel
     from diff_icp_b200.core.PSR import DiffPSR
@@ -64,7 +64,7 @@ def run_c4(rank, world, dev, comm, n_frames=256, n_points=50000, C=20, iters=3, 
     P.batched_lbfgs = bool(lockstep)
     if workers is not None:
         P.frame_workers = int(workers)
-    P.set_support_scheme("grid", rho=math.sqrt(2))
+    P.set_support_scheme("grid", rho=math.sqrt(2) if rho is None else float(rho))
     P.reinitialize_GMM()
     times = []
     for it in range(iters):
@@ -106,6 +106,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--lockstep", type=int, default=1)
+    ap.add_argument("--rho", type=float, default=None, help="grid spacing in units of sigma (default sqrt(2))")
     ap.add_argument("--workers", type=int, default=None, help="frames registered concurrently on the per-frame path (threads + streams)")
     ap.add_argument("--scheme", default="Ralston")
     args = ap.parse_args()
@@ -119,7 +120,7 @@ def main():
         from diff_icp_b200.dist import StatsComm
         comm = StatsComm()
     res = run_c4(rank, world, dev, comm, args.frames, args.points, 20, args.iters, args.graph, args.lockstep, args.scheme,
-                 args.workers)
+                 args.workers, args.rho)
     if rank == 0:
         print(json.dumps(res))
     if comm is not None:
