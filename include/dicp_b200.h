@@ -242,7 +242,9 @@ int dicp_batch_quad_loss(int D, int K, const int* dims, const int* active, int64
 int dicp_batch_closure_out(int D, int K, const int* dims, const int* active, int64_t maxM, int64_t fstride,
                            float lam_reg, const float* lam, const float* F0, const float* state_end, float* out,
                            int64_t ostride, int nscal, void* stream);
-/* The WHOLE closure of every active frame -- Euler shoot from (q0, p0 = X[k]), lambda*H(q0,p0) + cost(1), quadratic data loss
+/* The WHOLE closure of every active frame -- what one closure() call of tools/optim.py:32-50 computes for one frame of
+ * DiffPSR.Reg_opt (core/PSR.py:521-569 -> core/LDDMM.py:338-398: Shoot :286-299, trajloss :318-334, QuadLossFunctor
+ * core/PSR.py:498-516, backward()): Euler shoot from (q0, p0 = X[k]), lambda*H(q0,p0) + cost(1), quadratic data loss
  * against (y, inv), adjoint sweep, d loss / d p0 -- in ONE launch: one thread-block cluster per frame, stages separated by
  * cluster barriers instead of kernel launches (csrc/cluster_closure.cuh; replaces 1 + nt + 1 + nt + 1 launches of the
  * dicp_batch_* stage kernels above; same values up to fp32 summation order).  eta = 0 models with data points, Euler.
