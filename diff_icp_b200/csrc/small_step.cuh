@@ -356,6 +356,33 @@ __global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_FWD) small_rhs_
 // In a q-row CTA with Mr <= 64 rows the 128 threads form G = 128 / Mr groups; every group sweeps its own share of the
 // staged columns for all Mr rows and the group results are added in group order through shared memory, so that all lanes
 // work even when the support set is tiny (25 points: G = 5).
+// R rows (i0, i0 + 128, ...) of one thread of the adjoint x-row pass: gx and the fused cotangent update of those rows
+template <class OpX, int D, int R>
+DICP_D void small_adj_x_rows(const SmallStep& S, const RhsParams& P, const float* cols, int M, int Nx, size_t MD, int i0) {
+    typename OpX::Row row[R];
+    F2 acc[R][OpX::NACC];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r * kSmallThreads;
+        OpX::load_row(P, i < Nx ? i : Nx - 1, row[r]);
+#pragma unroll
+        for (int k = 0; k < OpX::NACC; ++k) acc[r][k] = f2(0.f, 0.f);
+    }
+    sweep_cols_multi<OpX, R>(P, row, cols, M, acc);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r * kSmallThreads;
+        if (i < Nx) {
+            float a[OpX::NACC];
+#pragma unroll
+            for (int k = 0; k < OpX::NACC; ++k) a[k] = f2_sum(acc[r][k]);
+            OpX::finish(P, i, row[r], a, nullptr);
+#pragma unroll
+            for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)i * D + k);
+        }
+    }
+}
+
 template <int D, bool WLD, bool ETA>
 __global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_ADJ) small_adj_step_kernel(SmallStep S, int nsplit, int xpass) {
     using OpX = typename std::conditional<ETA, AdjXQxEta<D, 1>, AdjXQx<D, WLD, 1>>::type;       // rows x, cols (q,p)
@@ -382,28 +409,12 @@ __global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_ADJ) small_adj_
         stage_cols<OpX>(P, 0, M, M, cols);
         __syncthreads();
         P.accumulate = 0;
-        typename OpX::Row row, nextrow;
-        {
-            const int i0 = (int)blockIdx.x * xpass * kSmallThreads + tid;
-            if (i0 < Nx) OpX::load_row(P, i0, nextrow);
-        }
-        for (int ps = 0; ps < xpass; ++ps) {
-            const int i = ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid;
-            row = nextrow;
-            if (ps + 1 < xpass && i + kSmallThreads < Nx) OpX::load_row(P, i + kSmallThreads, nextrow);      // prefetch
-            if (i < Nx) {
-                F2 acc[OpX::NACC];
-#pragma unroll
-                for (int k = 0; k < OpX::NACC; ++k) acc[k] = f2(0.f, 0.f);
-                sweep_cols<OpX>(P, row, cols, M, acc);
-                float a[OpX::NACC];
-#pragma unroll
-                for (int k = 0; k < OpX::NACC; ++k) a[k] = f2_sum(acc[k]);
-                OpX::finish(P, i, row, a, nullptr);
-#pragma unroll
-                for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)i * D + k);
-            }
-        }
+        // the CTA's xpass blocks of 128 rows: 4, then 2, then 1 rows of a thread swept together (one broadcast LDS per column
+        // pair serves the rows, independent accumulator chains), like the forward stage
+        int ps = 0;
+        for (; ps + 4 <= xpass; ps += 4) small_adj_x_rows<OpX, D, 4>(S, P, cols, M, Nx, MD, ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid);
+        if (ps + 2 <= xpass) { small_adj_x_rows<OpX, D, 2>(S, P, cols, M, Nx, MD, ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid); ps += 2; }
+        if (ps < xpass) small_adj_x_rows<OpX, D, 1>(S, P, cols, M, Nx, MD, ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid);
         if (blockIdx.x == 0 && tid == 0) {          // cost entry: the right-hand side does not depend on cost
             S.This[Ssz - 1] = 0.f;
             small_update(S, Ssz - 1);
