@@ -226,6 +226,37 @@ DICP_D bool last_cta(unsigned* counter, unsigned total) {
 // ---- forward stage -------------------------------------------------------------------------------------------------
 // CTAs [0, nXB): x rows, `xpass` consecutive blocks of 128 rows each (more rows per CTA amortise the staging of the support
 // set, the block reductions and the ticket when many frames / data points make the grid large); then the q-row CTAs.
+// R rows (i0, i0 + 128, ...) of one thread of the forward x-row pass: vx, the fused state update, and the rows' dcost sum
+template <class OpXQ, int D, int R>
+DICP_D float small_fwd_x_rows(const SmallStep& S, const RhsParams& P, const float* cols, int M, int Nx, size_t MD, int i0) {
+    typename OpXQ::Row row[R];
+    F2 acc[R][OpXQ::NACC];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r * kSmallThreads;
+        OpXQ::load_row(P, i < Nx ? i : Nx - 1, row[r]);
+#pragma unroll
+        for (int k = 0; k < OpXQ::NACC; ++k) acc[r][k] = f2(0.f, 0.f);
+    }
+    sweep_cols_multi<OpXQ, R>(P, row, cols, M, acc);
+    float dcs = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r * kSmallThreads;
+        if (i < Nx) {
+            float a[OpXQ::NACC];
+#pragma unroll
+            for (int k = 0; k < OpXQ::NACC; ++k) a[k] = f2_sum(acc[r][k]);
+            float dc = 0.f;                 // finish ASSIGNS the row's dcost contribution
+            OpXQ::finish(P, i, row[r], a, &dc);
+            dcs += dc;
+#pragma unroll
+            for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)i * D + k);
+        }
+    }
+    return dcs;
+}
+
 template <int D, bool WLD, bool ETA>
 __global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_FWD) small_rhs_step_kernel(SmallStep S, int xpass) {
     using OpQQx = RhsQQ<D, false, ETA, 1>;       // x present: the divergence cost comes from the (x,q) pass
@@ -246,53 +277,16 @@ __global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_FWD) small_rhs_
 
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     if ((int)blockIdx.x < nXB) {
-        // the CTA's xpass blocks of 128 rows, four blocks at a time (4 rows per thread swept together), then one by one
+        // the CTA's xpass blocks of 128 rows: 4, then 2, then 1 rows of a thread swept together
         int ps = 0;
-        for (; ps + 4 <= xpass; ps += 4) {
-            typename OpXQ::Row row[4];
-            int ri[4];
-            F2 acc[4][OpXQ::NACC];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                ri[r] = ((int)blockIdx.x * xpass + ps + r) * kSmallThreads + tid;
-                OpXQ::load_row(P, ri[r] < Nx ? ri[r] : Nx - 1, row[r]);
-#pragma unroll
-                for (int k = 0; k < OpXQ::NACC; ++k) acc[r][k] = f2(0.f, 0.f);
-            }
-            sweep_cols_multi<OpXQ, 4>(P, row, cols, M, acc);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (ri[r] < Nx) {
-                    float a[OpXQ::NACC];
-#pragma unroll
-                    for (int k = 0; k < OpXQ::NACC; ++k) a[k] = f2_sum(acc[r][k]);
-                    float dc = 0.f;                 // finish ASSIGNS the row's dcost contribution
-                    OpXQ::finish(P, ri[r], row[r], a, &dc);
-                    rs[0] += dc;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)ri[r] * D + k);
-                }
-            }
+        for (; ps + 4 <= xpass; ps += 4)
+            rs[0] += small_fwd_x_rows<OpXQ, D, 4>(S, P, cols, M, Nx, MD, ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid);
+        if (ps + 2 <= xpass) {
+            rs[0] += small_fwd_x_rows<OpXQ, D, 2>(S, P, cols, M, Nx, MD, ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid);
+            ps += 2;
         }
-        for (; ps < xpass; ++ps) {
-            const int i = ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid;
-            if (i < Nx) {
-                typename OpXQ::Row row;
-                OpXQ::load_row(P, i, row);
-                F2 acc[OpXQ::NACC];
-#pragma unroll
-                for (int k = 0; k < OpXQ::NACC; ++k) acc[k] = f2(0.f, 0.f);
-                sweep_cols<OpXQ>(P, row, cols, M, acc);
-                float a[OpXQ::NACC];
-#pragma unroll
-                for (int k = 0; k < OpXQ::NACC; ++k) a[k] = f2_sum(acc[k]);
-                float dc = 0.f;
-                OpXQ::finish(P, i, row, a, &dc);
-                rs[0] += dc;
-#pragma unroll
-                for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)i * D + k);
-            }
-        }
+        if (ps < xpass)
+            rs[0] += small_fwd_x_rows<OpXQ, D, 1>(S, P, cols, M, Nx, MD, ((int)blockIdx.x * xpass + ps) * kSmallThreads + tid);
     } else {
         const int i = ((int)blockIdx.x - nXB) * kSmallThreads + tid;
         if (i < M) {
@@ -754,10 +748,10 @@ inline int small_xpass(long long frames, long long maxNx, int sms) {
     }();
     if (forced) return forced;
     const long long ctas = frames * ((maxNx + kSmallThreads - 1) / kSmallThreads);
-    long long r = ctas / ((long long)sms * 8);
-    if (r < 1) r = 1;
-    if (r > 8) r = 8;
-    return (int)r;
+    const long long r = ctas / ((long long)sms * 8);
+    // a power of two: the kernels sweep 4 rows of a thread together (then 2, then 1), and a leftover single-row pass costs
+    // about as much as a four-row one (latency-bound), so 5 passes were 4 + 1 = two sweeps where 4 passes are one
+    return r >= 8 ? 8 : r >= 4 ? 4 : r >= 2 ? 2 : 1;
 }
 
 // dynamic shared memory of the two kernels: the staged column records (pair-interleaved, so an even number of columns)
