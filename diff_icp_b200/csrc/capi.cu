@@ -194,14 +194,27 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, float* out) {
 }
 
 // launch the instantiation selected by (D, withlogdet, eta != 0) with `smem` bytes of dynamic shared memory
-template <int DD, bool W, bool E>
-static void launch_small_rhs(const SmallStep& S, int xpass, dim3 grid, size_t smem, cudaStream_t st) {
+template <int DD, bool W, bool E, bool BIG>
+static void launch_small_rhs_v(const SmallStep& S, int xpass, dim3 grid, size_t smem, cudaStream_t st) {
     static const bool optin = [] {          // static + dynamic shared memory may exceed the 48 KB default: opt in once
-        return cudaFuncSetAttribute(small_rhs_step_kernel<DD, W, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        return cudaFuncSetAttribute(small_rhs_step_kernel<DD, W, E, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)small_fwd_smem_bytes(kSmallMaxQ, DD)) == cudaSuccess;
     }();
     (void)optin;
-    small_rhs_step_kernel<DD, W, E><<<grid, kSmallThreads, smem, st>>>(S, xpass);
+    small_rhs_step_kernel<DD, W, E, BIG><<<grid, kSmallThreads, smem, st>>>(S, xpass);
+}
+// supports beyond the ring form's 64 points: the instantiation with 128 registers per thread (small_step.cuh: kSmallMinbBig)
+static bool small_big(long long maxM) {
+    static const long long minM = [] {       // DICP_SMALL_BIG_MIN: tuning sweeps only
+        const char* e = getenv("DICP_SMALL_BIG_MIN");
+        return e ? atoll(e) : (long long)kRingMaxQ + 1;
+    }();
+    return maxM >= minM;
+}
+template <int DD, bool W, bool E>
+static void launch_small_rhs(const SmallStep& S, int xpass, dim3 grid, size_t smem, cudaStream_t st) {
+    if (small_big(S.M)) launch_small_rhs_v<DD, W, E, true>(S, xpass, grid, smem, st);
+    else launch_small_rhs_v<DD, W, E, false>(S, xpass, grid, smem, st);
 }
 template <int DD, bool W, bool E>
 static void launch_small_adj(const SmallStep& S, int nsplit, int xpass, dim3 grid, size_t smem, cudaStream_t st) {
@@ -247,6 +260,31 @@ static void dispatch_small_ring(int D, int withlogdet, float eta, const SmallSte
     else { if (eta != 0.f) DICP_LAUNCH(3, true, true); else if (withlogdet) DICP_LAUNCH(3, true, false); else DICP_LAUNCH(3, false, false); }
 #undef DICP_LAUNCH
     launch_counter() += 1;
+}
+// mid form of the adjoint stage (small_adj_mid_kernel + small_mid_finish_kernel): more than kRingMaxQ support points and
+// enough data points that the 512-row x CTAs of all frames fill the SMs at least once
+static bool small_mid_applicable(long long maxM, long long maxNx, long long frames) {
+    static const int forced = [] {           // DICP_SMALL_MID = 0 / 1: never / whenever it can run (tests, tuning sweeps)
+        const char* e = getenv("DICP_SMALL_MID");
+        return e ? atoi(e) : -1;
+    }();
+    if (sym_mode() == 0 || maxM <= kRingMaxQ || maxNx <= 0 || forced == 0) return false;
+    return forced == 1 || frames * ((maxNx + kRingRows - 1) / kRingRows) >= device_info().sms;
+}
+template <int DD, bool W, bool E>
+static void launch_small_mid(const SmallStep& S, long long maxM, long long maxNx, unsigned frames, cudaStream_t st) {
+    const dim3 grid((unsigned)((maxNx + kRingRows - 1) / kRingRows + (maxM + kSmallThreads - 1) / kSmallThreads), frames);
+    small_adj_mid_kernel<DD, W, E><<<grid, kSmallThreads, 0, st>>>(S);
+    const dim3 gfin((unsigned)((maxM + 31) / 32), frames);
+    small_mid_finish_kernel<DD, W, E><<<gfin, kSmallThreads, 0, st>>>(S);
+}
+static void dispatch_small_mid(int D, int withlogdet, float eta, const SmallStep& S, long long maxM, long long maxNx,
+                               unsigned frames, cudaStream_t st) {
+#define DICP_LAUNCH(DD, W, E) launch_small_mid<DD, W, E>(S, maxM, maxNx, frames, st)
+    if (D == 2) { if (eta != 0.f) DICP_LAUNCH(2, true, true); else if (withlogdet) DICP_LAUNCH(2, true, false); else DICP_LAUNCH(2, false, false); }
+    else { if (eta != 0.f) DICP_LAUNCH(3, true, true); else if (withlogdet) DICP_LAUNCH(3, true, false); else DICP_LAUNCH(3, false, false); }
+#undef DICP_LAUNCH
+    launch_counter() += 2;
 }
 static void dispatch_small_adj(int D, int withlogdet, float eta, const SmallStep& S, int nsplit, int xpass, dim3 grid,
                                long long maxM, cudaStream_t st) {
@@ -605,7 +643,7 @@ int dicp_small_rhs_step(int D, int withlogdet, float sigma, float eta, int64_t M
     if (rc != DICP_OK) return rc;
     if (!s_eval || !F || (out && !base) || (eta != 0.f && !withlogdet)) return DICP_EBADARG;
     S.s_eval = s_eval; S.base = base; S.other = other; S.out = out; S.This = F; S.c_this = c_this; S.c_other = c_other;
-    const int xpass = small_xpass(1, Nx, device_info().sms);
+    const int xpass = small_big(M) ? small_xpass_big(1, Nx, device_info().sms) : small_xpass(1, Nx, device_info().sms);
     const unsigned grid = (unsigned)((Nx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass) + (M + kSmallThreads - 1) / kSmallThreads);
     cudaStream_t st = (cudaStream_t)stream;
     dispatch_small_rhs(D, withlogdet, eta, S, xpass, dim3(grid), M, st);
@@ -628,6 +666,7 @@ int dicp_small_adj_step(int D, int withlogdet, float sigma, float eta, int64_t M
     const unsigned grid = (unsigned)((Nx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass)) + nQB * (unsigned)nsplit;
     cudaStream_t st = (cudaStream_t)stream;
     if (small_ring_applicable(eta, M, Nx)) dispatch_small_ring(D, withlogdet, eta, S, Nx, 1u, st);
+    else if (small_mid_applicable(M, Nx, 1)) dispatch_small_mid(D, withlogdet, eta, S, M, Nx, 1u, st);
     else dispatch_small_adj(D, withlogdet, eta, S, nsplit, xpass, dim3(grid), M, st);
     return last_error(DICP_OK);
 }
@@ -657,7 +696,7 @@ int dicp_batch_rhs_step(int D, int withlogdet, float sigma, float eta, int K, co
     if (rc != DICP_OK) return rc;
     if (!s_eval || !F || (out && !base) || (eta != 0.f && !withlogdet)) return DICP_EBADARG;
     S.s_eval = s_eval; S.base = base; S.other = other; S.out = out; S.This = F; S.c_this = c_this; S.c_other = c_other;
-    const int xpass = small_xpass(K, maxNx, device_info().sms);
+    const int xpass = small_big(maxM) ? small_xpass_big(K, maxNx, device_info().sms) : small_xpass(K, maxNx, device_info().sms);
     const dim3 grid((unsigned)((maxNx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass) +
                                (maxM + kSmallThreads - 1) / kSmallThreads), (unsigned)K);
     cudaStream_t st = (cudaStream_t)stream;
@@ -684,6 +723,7 @@ int dicp_batch_adj_step(int D, int withlogdet, float sigma, float eta, int K, co
                     (unsigned)K);
     cudaStream_t st = (cudaStream_t)stream;
     if (small_ring_applicable(eta, maxM, maxNx)) dispatch_small_ring(D, withlogdet, eta, S, maxNx, (unsigned)K, st);
+    else if (small_mid_applicable(maxM, maxNx, K)) dispatch_small_mid(D, withlogdet, eta, S, maxM, maxNx, (unsigned)K, st);
     else dispatch_small_adj(D, withlogdet, eta, S, nsplit, xpass, grid, maxM, st);
     return last_error(DICP_OK);
 }

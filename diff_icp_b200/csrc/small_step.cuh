@@ -16,11 +16,12 @@
 // State / cotangent layout: flat [ q (M,D) | p (M,D) | x (Nx,D) | cost ];  F layout: [ vq | dp | vx | dcost, A, B, C ].
 #pragma once
 #include "ops_rhs.cuh"
+#include "sym_engine.cuh"
 #include <cstdlib>
 
 namespace dicp {
 
-static constexpr int kSmallMaxQ = 1024;       // support points staged entirely in (dynamic) shared memory
+static constexpr int kSmallMaxQ = 2048;       // support points staged entirely in (dynamic) shared memory (forward stage: 48 KB in 3-D)
 static constexpr int kSmallThreads = 128;     // rows per CTA (one row per thread)
 #ifndef DICP_SMALL_MINB_FWD
 #define DICP_SMALL_MINB_FWD 12                // minimum resident CTAs per SM asked of the compiler (register cap); swept on B200
@@ -28,6 +29,10 @@ static constexpr int kSmallThreads = 128;     // rows per CTA (one row per threa
 #ifndef DICP_SMALL_MINB_ADJ
 #define DICP_SMALL_MINB_ADJ 8
 #endif
+// Mid-size supports (more than kRingMaxQ = 64 points): a thread sweeps hundreds of columns for 4 rows at a time, which needs
+// ~100 registers -- under the caps above the 4-row sweep spills (224-688 bytes of stack per thread) and the forward stage ran at
+// a quarter of the FP32 roof.  The BIG instantiation asks for 4 resident CTAs (128 registers), like the tiled engine.
+static constexpr int kSmallMinbBig = 4;
 static constexpr int kSmallChunk = 512;       // data-point columns per q-row CTA in the adjoint
 static constexpr int kSmallCounters = 64;     // uint32 counters at the head of the workspace
 
@@ -257,8 +262,8 @@ DICP_D float small_fwd_x_rows(const SmallStep& S, const RhsParams& P, const floa
     return dcs;
 }
 
-template <int D, bool WLD, bool ETA>
-__global__ void __launch_bounds__(kSmallThreads, DICP_SMALL_MINB_FWD) small_rhs_step_kernel(SmallStep S, int xpass) {
+template <int D, bool WLD, bool ETA, bool BIG = false>
+__global__ void __launch_bounds__(kSmallThreads, BIG ? kSmallMinbBig : DICP_SMALL_MINB_FWD) small_rhs_step_kernel(SmallStep S, int xpass) {
     using OpQQx = RhsQQ<D, false, ETA, 1>;       // x present: the divergence cost comes from the (x,q) pass
     using OpQQn = RhsQQ<D, WLD, ETA, 1>;         // x absent
     using OpXQ = RhsXQ<D, WLD, ETA, 1>;
@@ -738,6 +743,197 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep
     if (tid == 0) S.counters[0] = 0u;
 }
 
+// ---- adjoint stage, mid-size supports (kRingMaxQ < M <= kSmallMaxQ, data points present) ---------------------------------
+// The ring form above generalised to any number of column groups: an x CTA owns kRingRows = 512 data points (4 per lane) and
+// meets ALL support points, 64 at a time (one ring round of sym_ring_round per group of 32 column pairs: every (x_k, q_j) pair
+// is evaluated once, Op AdjXQ / AdjXQE, row AND column side).  The group's records are packed straight from the state vector
+// into a double-buffered shared-memory tile (the loads of group g + 1 are in flight during the ring round of group g; no pack
+// kernel, no packed copy in HBM).  Rows finish in the kernel (gx, cotangent update of the x entries); the column sums of the
+// CTA's four warps are added in warp order and go to the workspace [x CTA][k][column].  nQB further CTAs do the (q,q)
+// interaction (one support point per thread, the columns staged in chunks) and write gq, gp.  A second, tiny launch
+// (small_mid_finish_kernel) adds the x CTAs' column sums in CTA order, finishes the support points' gradients and applies their
+// cotangent update.  Two launches per adjoint stage; before, mid-size supports paid every (x,q) pair twice
+// (small_adj_step_kernel) or ~15 launches per stage (tiled engine).  Deterministic, no atomics.
+static constexpr int kMidQChunk = 256;                             // support columns per staged chunk of a (q,q) CTA
+
+template <int D, bool WLD, bool ETA>
+__global__ void __launch_bounds__(kSmallThreads, kSmallMinbBig) small_adj_mid_kernel(SmallStep S) {
+    using OpX = typename std::conditional<ETA, AdjXQE<D>, AdjXQ<D, WLD>>::type;
+    using OpQQ = typename std::conditional<ETA, AdjQQEta<D, 1>, AdjQQ<D, false, 1>>::type;      // x present: see the ring form
+    constexpr int NF = OpX::NF, REC = 2 * NF, STRIDE = SymStride<REC>::value, NC = OpX::NACC_COL, NAQ = OpQQ::NACC;
+    constexpr int R = kRingR, NW = kSmallThreads / 32, TILE = 32 * STRIDE;
+    constexpr int SM_X = 2 * TILE + NW * NC * kSymGroup, SM_Q = kMidQChunk * OpQQ::NF;
+    __shared__ __align__(16) float sm[SM_X > SM_Q ? SM_X : SM_Q];
+    if (!small_select_frame(S)) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, M = S.M, Nx = S.Nx;
+    const int nXB = (Nx + kRingRows - 1) / kRingRows;
+    if ((int)blockIdx.x >= nXB + (M + kSmallThreads - 1) / kSmallThreads) return;
+    const size_t MD = (size_t)M * D, Ssz = 2 * MD + (size_t)Nx * D + 1;
+    RhsParams P = small_params<D>(S);
+    P.a = S.lam; P.u = S.lam + MD; P.wx = S.lam + 2 * MD; P.gc = S.lam + (Ssz - 1);
+    P.gq = S.This; P.gp = S.This + MD; P.gx = S.This + 2 * MD;
+    P.accumulate = 0;
+
+    if ((int)blockIdx.x < nXB) {
+        const int ngroups = (M + kSymGroup - 1) / kSymGroup, mpad = ngroups * kSymGroup;
+        float* xch = sm + 2 * TILE;
+        float* part = S.ws + (size_t)blockIdx.x * NC * mpad;      // [k][column]
+        typename OpX::Row row[R];
+        float rmask[R];
+        int ri[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            ri[r] = (int)blockIdx.x * kRingRows + warp * (32 * R) + r * 32 + lane;
+            rmask[r] = ri[r] < Nx ? 1.f : 0.f;
+            OpX::load_row(P, ri[r] < Nx ? ri[r] : Nx - 1, row[r]);
+        }
+        F2 acc[R][OpX::NACC];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < OpX::NACC; ++k) acc[r][k] = f2(0.f, 0.f);
+        const bool rows_ragged = ((int)blockIdx.x + 1) * kRingRows > Nx;
+        // threads 0..63 pack one column each (zero record beyond M)
+        float creg[OpX::COLF4 * 4];
+        if (tid < kSymGroup) {
+            OpX::pack_col(P, tid, M, creg);
+            float* dst = sm + (tid >> 1) * STRIDE + (tid & 1);
+#pragma unroll
+            for (int k = 0; k < NF; ++k) dst[2 * k] = creg[k];
+        }
+        for (int g = 0; g < ngroups; ++g) {
+            __syncthreads();                         // tile g complete; the previous group's column sums have been read
+            const bool more = g + 1 < ngroups;
+            if (more && tid < kSymGroup) OpX::pack_col(P, (g + 1) * kSymGroup + tid, M, creg);       // in flight during the round
+            const float* tile = sm + (g & 1) * TILE;
+            const int g0 = g * kSymGroup;
+            F2 cacc[NC];
+#pragma unroll
+            for (int k = 0; k < NC; ++k) cacc[k] = f2(0.f, 0.f);
+            if (rows_ragged || g0 + kSymGroup > M) sym_ring_round<OpX, true, R>(P, row, tile, STRIDE, lane, rmask, g0, M, acc, cacc);
+            else sym_ring_round<OpX, false, R>(P, row, tile, STRIDE, lane, rmask, g0, M, acc, cacc);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                float a, b;
+                f2_unpack(cacc[k], a, b);
+                xch[((warp * NC + k) * 32 + lane) * 2] = a;
+                xch[((warp * NC + k) * 32 + lane) * 2 + 1] = b;
+            }
+            if (more && tid < kSymGroup) {
+                float* dst = sm + ((g + 1) & 1) * TILE + (tid >> 1) * STRIDE + (tid & 1);
+#pragma unroll
+                for (int k = 0; k < NF; ++k) dst[2 * k] = creg[k];
+            }
+            __syncthreads();
+            for (int t = tid; t < NC * kSymGroup; t += kSmallThreads) {
+                const int k = t / kSymGroup, cc = t - k * kSymGroup;
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) v += xch[((w * NC + k) * 32 + (cc >> 1)) * 2 + (cc & 1)];
+                part[(size_t)k * mpad + g0 + cc] = v;
+            }
+        }
+        // rows: gx and the cotangent update of the x entries
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (ri[r] < Nx) {
+                float a[OpX::NACC];
+#pragma unroll
+                for (int k = 0; k < OpX::NACC; ++k) a[k] = f2_sum(acc[r][k]);
+                OpX::finish(P, ri[r], row[r], a, nullptr);
+#pragma unroll
+                for (int k = 0; k < D; ++k) small_update(S, 2 * MD + (size_t)ri[r] * D + k);
+            }
+        }
+        if (blockIdx.x == 0 && tid == 0) {            // cost entry: the right-hand side does not depend on cost
+            S.This[Ssz - 1] = 0.f;
+            small_update(S, Ssz - 1);
+        }
+    } else {
+        // (q,q) interaction: one support point per thread, all M columns in chunks; gq, gp written (the finish kernel adds the
+        // (x,q) column sums and applies the update)
+        const int i = ((int)blockIdx.x - nXB) * kSmallThreads + tid;
+        const bool valid = i < M;
+        typename OpQQ::Row row;
+        OpQQ::load_row(P, valid ? i : M - 1, row);
+        F2 acc[NAQ];
+#pragma unroll
+        for (int k = 0; k < NAQ; ++k) acc[k] = f2(0.f, 0.f);
+        for (int j0 = 0; j0 < M; j0 += kMidQChunk) {
+            const int n = (M - j0 < kMidQChunk) ? M - j0 : kMidQChunk;
+            __syncthreads();
+            stage_cols<OpQQ>(P, j0, n, M, sm);
+            __syncthreads();
+            if (valid) sweep_cols<OpQQ>(P, row, sm, n, acc);
+        }
+        if (valid) {
+            float a[NAQ];
+#pragma unroll
+            for (int k = 0; k < NAQ; ++k) a[k] = f2_sum(acc[k]);
+            OpQQ::finish(P, i, row, a, nullptr);
+        }
+    }
+}
+
+// grid (ceil(maxM / 32), frames): 32 support points x 4 thread groups per CTA; group g adds the x CTAs g, g + 4, ... in that
+// order, the groups are added in group order
+template <int D, bool WLD, bool ETA>
+__global__ void __launch_bounds__(kSmallThreads) small_mid_finish_kernel(SmallStep S) {
+    using OpX = typename std::conditional<ETA, AdjXQE<D>, AdjXQ<D, WLD>>::type;
+    constexpr int NC = OpX::NACC_COL, FR = 32, G = kSmallThreads / FR;
+    __shared__ float xch[G * NC * FR];
+    if (!small_select_frame(S)) return;
+    const int tid = threadIdx.x, r = tid & (FR - 1), g = tid / FR, M = S.M, Nx = S.Nx;
+    if ((int)blockIdx.x * FR >= M) return;
+    const int j = (int)blockIdx.x * FR + r;
+    const int nXB = (Nx + kRingRows - 1) / kRingRows;
+    const int mpad = (M + kSymGroup - 1) / kSymGroup * kSymGroup;
+    const bool valid = j < M;
+    float cs[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) cs[k] = 0.f;
+    if (valid) {
+        const float* part = S.ws + j;
+        int b = g;
+        for (; b + 3 * G < nXB; b += 4 * G) {         // 4 x NC independent loads in flight, added in CTA order
+            float v[4][NC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < NC; ++k) v[u][k] = __ldcg(&part[((size_t)(b + u * G) * NC + k) * mpad]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < NC; ++k) cs[k] += v[u][k];
+        }
+        for (; b < nXB; b += G) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) cs[k] += __ldcg(&part[((size_t)b * NC + k) * mpad]);
+        }
+    }
+    if (g > 0) {
+#pragma unroll
+        for (int k = 0; k < NC; ++k) xch[(g * NC + k) * FR + r] = cs[k];
+    }
+    __syncthreads();
+    if (g == 0 && valid) {
+        for (int g2 = 1; g2 < G; ++g2) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) cs[k] += xch[(g2 * NC + k) * FR + r];
+        }
+        const size_t MD = (size_t)M * D, Ssz = 2 * MD + (size_t)Nx * D + 1;
+        RhsParams P = small_params<D>(S);
+        P.gc = S.lam + (Ssz - 1);
+        P.gq = S.This; P.gp = S.This + MD;
+        OpX::finish_col(P, j, cs);
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            small_update(S, (size_t)j * D + k);
+            small_update(S, MD + (size_t)j * D + k);
+        }
+    }
+}
+
 // Row passes of the x-row CTAs: one block of 128 rows per CTA until the x-row CTAs of all frames exceed ~8 resident CTAs
 // per SM, then proportionally more (at most 8).  DICP_SMALL_XPASS overrides (tuning sweeps only).
 inline int small_xpass(long long frames, long long maxNx, int sms) {
@@ -752,6 +948,18 @@ inline int small_xpass(long long frames, long long maxNx, int sms) {
     // a power of two: the kernels sweep 4 rows of a thread together (then 2, then 1), and a leftover single-row pass costs
     // about as much as a four-row one (latency-bound), so 5 passes were 4 + 1 = two sweeps where 4 passes are one
     return r >= 8 ? 8 : r >= 4 ? 4 : r >= 2 ? 2 : 1;
+}
+
+// BIG forward instantiation: 4 rows of a thread swept together whenever that still leaves ~2 CTAs per SM, else 2, else 1
+inline int small_xpass_big(long long frames, long long maxNx, int sms) {
+    static const int forced = [] {
+        const char* e = getenv("DICP_SMALL_XPASS");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 1 && v <= 64) ? v : 0;
+    }();
+    if (forced) return forced;
+    const long long ctas = frames * ((maxNx + kSmallThreads - 1) / kSmallThreads);
+    return ctas >= 8LL * sms ? 4 : ctas >= 4LL * sms ? 2 : 1;
 }
 
 // dynamic shared memory of the two kernels: the staged column records (pair-interleaved, so an even number of columns)
@@ -772,6 +980,8 @@ inline size_t small_workspace_bytes(long long M, long long Nx) {
     size_t adj = (size_t)small_adj_nsplit((int)Nx) * 16 * (size_t)M * 4;
     const size_t ringb = (size_t)((Nx + kSmallThreads * 4 - 1) / (kSmallThreads * 4)) * 8 * 64 * 4;      // ring form: x CTAs (xpass = 1) x 8 x 64
     if (ringb > adj) adj = ringb;
+    const size_t midb = (size_t)((Nx + kRingRows - 1) / kRingRows) * 8 * (size_t)((M + kSymGroup - 1) / kSymGroup * kSymGroup) * 4;   // mid form
+    if (M > kRingMaxQ && midb > adj) adj = midb;
     return kSmallCounters * 4 + (fwd > adj ? fwd : adj) + 256;
 }
 

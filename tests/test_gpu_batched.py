@@ -38,6 +38,13 @@ CASES = [
     (3, "classic", "Euler", 5, [12, 64, 33], [700, 3000, 16384]),
     (3, "hybrid", "Euler", 4, [64, 1, 2], [16384, 5, 2049]),
     (2, "hybrid", "Euler", 3, [40, 9], [32768, 12345]),
+    # mid-size supports x many data points: the one-evaluation-per-pair adjoint stage of small_step.cuh (small_adj_mid_kernel: the
+    # 512-row x CTAs of all frames fill the SMs) and the 128-register forward instantiation, up to 2048 support points
+    (3, "hybrid", "Ralston", 2, [1500, 700, 65], [30000, 26000, 29999]),
+    (3, "logdet", "Euler", 2, [300, 2048], [40000, 40001]),
+    (2, "classic", "Euler", 2, [129, 1210, 100, 777], [30000, 513, 28000, 30001]),
+    (2, "hybrid", "Ralston", 2, [1025, 200], [45000, 38000]),
+    (2, "logdet", "Ralston", 2, [500, 200], [45000, 38000]),
 ]
 
 
@@ -96,6 +103,8 @@ def test_batched_closure_equals_per_frame_closure(D, version, scheme, nt, Ms, Nx
                 if K > 8 and k % 9 != 0:             # many-frame cases: check every 9th frame
                     continue
                 tol = 1.0 if max(Ms) <= 512 else 100.0       # same kernels / different engines (summation orders differ)
+                if max(Ms) > 64 and max(Nxs) >= 26000:       # mid-size adjoint stage: one evaluation per (x,q) pair, other order
+                    tol = max(tol, 10.0)
                 if plan.one_launch:
                     tol = 10.0                               # other summation order (per-thread sums over all stages), fixed origin
                 assert abs(plan.losses[k] - L) <= tol * 2e-6 * abs(L), (k, plan.losses[k], L)
