@@ -591,7 +591,7 @@ def em_roofline(dev, timeit, peaks):
 # configs[3]-shaped strong-scaling entry: total frames (divisible by 8) and the free energy the 1-GPU run reaches after its
 # 2 iterations (deterministic kernels, seeded synthetic frames): every N must reproduce it to 1e-4
 C4_FRAMES = 64
-C4_FE_1GPU = -6932346.558105469         # measured: 1 x B200, profiles/r02_bench_1gpu.json
+C4_FE_1GPU = -6932241.603818208         # measured: 1 x B200, profiles/r02_bench_1gpu.json (lock-step registration of all frames)
 
 NCU_DRAM_BYTES = {"classic": None, "hybrid": None, "logdet": 1990144}
 

@@ -271,12 +271,27 @@ static bool small_mid_applicable(long long maxM, long long maxNx, long long fram
     if (sym_mode() == 0 || maxM <= kRingMaxQ || maxNx <= 0 || forced == 0) return false;
     return forced == 1 || frames * ((maxNx + kRingRows - 1) / kRingRows) >= device_info().sms;
 }
+// data points per lane of an x CTA: 4 (fewest shuffles per pair) when that gives at least kMidWaves4 waves of x CTAs, else 2 (a
+// short grid of long CTAs ends in a badly filled last wave)
+static constexpr int kMidWaves4 = 2;
+static int small_mid_rows_per_lane(long long maxNx, long long frames) {
+    static const int forced = [] {           // DICP_SMALL_MID_R = 2 / 4: tuning sweeps only
+        const char* e = getenv("DICP_SMALL_MID_R");
+        const int v = e ? atoi(e) : 0;
+        return (v == 2 || v == 4) ? v : 0;
+    }();
+    if (forced) return forced;
+    const long long ctas4 = frames * ((maxNx + kRingRows - 1) / kRingRows);
+    return ctas4 >= (long long)kMidWaves4 * kSmallMinbBig * device_info().sms ? 4 : 2;
+}
 template <int DD, bool W, bool E>
 static void launch_small_mid(const SmallStep& S, long long maxM, long long maxNx, unsigned frames, cudaStream_t st) {
-    const dim3 grid((unsigned)((maxNx + kRingRows - 1) / kRingRows + (maxM + kSmallThreads - 1) / kSmallThreads), frames);
-    small_adj_mid_kernel<DD, W, E><<<grid, kSmallThreads, 0, st>>>(S);
+    const int R = small_mid_rows_per_lane(maxNx, frames), rows = kSmallThreads * R;
+    const dim3 grid((unsigned)((maxNx + rows - 1) / rows + (maxM + kSmallThreads - 1) / kSmallThreads), frames);
+    if (R == 4) small_adj_mid_kernel<DD, W, E, 4><<<grid, kSmallThreads, 0, st>>>(S);
+    else small_adj_mid_kernel<DD, W, E, 2><<<grid, kSmallThreads, 0, st>>>(S);
     const dim3 gfin((unsigned)((maxM + 31) / 32), frames);
-    small_mid_finish_kernel<DD, W, E><<<gfin, kSmallThreads, 0, st>>>(S);
+    small_mid_finish_kernel<DD, W, E><<<gfin, kSmallThreads, 0, st>>>(S, rows);
 }
 static void dispatch_small_mid(int D, int withlogdet, float eta, const SmallStep& S, long long maxM, long long maxNx,
                                unsigned frames, cudaStream_t st) {

@@ -744,7 +744,8 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep
 }
 
 // ---- adjoint stage, mid-size supports (kRingMaxQ < M <= kSmallMaxQ, data points present) ---------------------------------
-// The ring form above generalised to any number of column groups: an x CTA owns kRingRows = 512 data points (4 per lane) and
+// The ring form above generalised to any number of column groups: an x CTA owns 128 R data points (R = 4 per lane, or 2
+// when the 512-row CTAs of all frames would be too few waves: launch_small_mid in capi.cu) and
 // meets ALL support points, 64 at a time (one ring round of sym_ring_round per group of 32 column pairs: every (x_k, q_j) pair
 // is evaluated once, Op AdjXQ / AdjXQE, row AND column side).  The group's records are packed straight from the state vector
 // into a double-buffered shared-memory tile (the loads of group g + 1 are in flight during the ring round of group g; no pack
@@ -756,17 +757,17 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep
 // (small_adj_step_kernel) or ~15 launches per stage (tiled engine).  Deterministic, no atomics.
 static constexpr int kMidQChunk = 256;                             // support columns per staged chunk of a (q,q) CTA
 
-template <int D, bool WLD, bool ETA>
+template <int D, bool WLD, bool ETA, int R>
 __global__ void __launch_bounds__(kSmallThreads, kSmallMinbBig) small_adj_mid_kernel(SmallStep S) {
     using OpX = typename std::conditional<ETA, AdjXQE<D>, AdjXQ<D, WLD>>::type;
     using OpQQ = typename std::conditional<ETA, AdjQQEta<D, 1>, AdjQQ<D, false, 1>>::type;      // x present: see the ring form
     constexpr int NF = OpX::NF, REC = 2 * NF, STRIDE = SymStride<REC>::value, NC = OpX::NACC_COL, NAQ = OpQQ::NACC;
-    constexpr int R = kRingR, NW = kSmallThreads / 32, TILE = 32 * STRIDE;
+    constexpr int NW = kSmallThreads / 32, TILE = 32 * STRIDE, ROWS = kSmallThreads * R;      // ROWS data points per x CTA
     constexpr int SM_X = 2 * TILE + NW * NC * kSymGroup, SM_Q = kMidQChunk * OpQQ::NF;
     __shared__ __align__(16) float sm[SM_X > SM_Q ? SM_X : SM_Q];
     if (!small_select_frame(S)) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, M = S.M, Nx = S.Nx;
-    const int nXB = (Nx + kRingRows - 1) / kRingRows;
+    const int nXB = (Nx + ROWS - 1) / ROWS;
     if ((int)blockIdx.x >= nXB + (M + kSmallThreads - 1) / kSmallThreads) return;
     const size_t MD = (size_t)M * D, Ssz = 2 * MD + (size_t)Nx * D + 1;
     RhsParams P = small_params<D>(S);
@@ -783,7 +784,7 @@ __global__ void __launch_bounds__(kSmallThreads, kSmallMinbBig) small_adj_mid_ke
         int ri[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            ri[r] = (int)blockIdx.x * kRingRows + warp * (32 * R) + r * 32 + lane;
+            ri[r] = (int)blockIdx.x * ROWS + warp * (32 * R) + r * 32 + lane;
             rmask[r] = ri[r] < Nx ? 1.f : 0.f;
             OpX::load_row(P, ri[r] < Nx ? ri[r] : Nx - 1, row[r]);
         }
@@ -792,7 +793,7 @@ __global__ void __launch_bounds__(kSmallThreads, kSmallMinbBig) small_adj_mid_ke
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int k = 0; k < OpX::NACC; ++k) acc[r][k] = f2(0.f, 0.f);
-        const bool rows_ragged = ((int)blockIdx.x + 1) * kRingRows > Nx;
+        const bool rows_ragged = ((int)blockIdx.x + 1) * ROWS > Nx;
         // threads 0..63 pack one column each (zero record beyond M)
         float creg[OpX::COLF4 * 4];
         if (tid < kSymGroup) {
@@ -878,7 +879,7 @@ __global__ void __launch_bounds__(kSmallThreads, kSmallMinbBig) small_adj_mid_ke
 // grid (ceil(maxM / 32), frames): 32 support points x 4 thread groups per CTA; group g adds the x CTAs g, g + 4, ... in that
 // order, the groups are added in group order
 template <int D, bool WLD, bool ETA>
-__global__ void __launch_bounds__(kSmallThreads) small_mid_finish_kernel(SmallStep S) {
+__global__ void __launch_bounds__(kSmallThreads) small_mid_finish_kernel(SmallStep S, int rows_per_cta) {
     using OpX = typename std::conditional<ETA, AdjXQE<D>, AdjXQ<D, WLD>>::type;
     constexpr int NC = OpX::NACC_COL, FR = 32, G = kSmallThreads / FR;
     __shared__ float xch[G * NC * FR];
@@ -886,7 +887,7 @@ __global__ void __launch_bounds__(kSmallThreads) small_mid_finish_kernel(SmallSt
     const int tid = threadIdx.x, r = tid & (FR - 1), g = tid / FR, M = S.M, Nx = S.Nx;
     if ((int)blockIdx.x * FR >= M) return;
     const int j = (int)blockIdx.x * FR + r;
-    const int nXB = (Nx + kRingRows - 1) / kRingRows;
+    const int nXB = (Nx + rows_per_cta - 1) / rows_per_cta;
     const int mpad = (M + kSymGroup - 1) / kSymGroup * kSymGroup;
     const bool valid = j < M;
     float cs[NC];
@@ -980,7 +981,7 @@ inline size_t small_workspace_bytes(long long M, long long Nx) {
     size_t adj = (size_t)small_adj_nsplit((int)Nx) * 16 * (size_t)M * 4;
     const size_t ringb = (size_t)((Nx + kSmallThreads * 4 - 1) / (kSmallThreads * 4)) * 8 * 64 * 4;      // ring form: x CTAs (xpass = 1) x 8 x 64
     if (ringb > adj) adj = ringb;
-    const size_t midb = (size_t)((Nx + kRingRows - 1) / kRingRows) * 8 * (size_t)((M + kSymGroup - 1) / kSymGroup * kSymGroup) * 4;   // mid form
+    const size_t midb = (size_t)((Nx + kSmallThreads * 2 - 1) / (kSmallThreads * 2)) * 8 * (size_t)((M + kSymGroup - 1) / kSymGroup * kSymGroup) * 4;   // mid form
     if (M > kRingMaxQ && midb > adj) adj = midb;
     return kSmallCounters * 4 + (fwd > adj ? fwd : adj) + 256;
 }
