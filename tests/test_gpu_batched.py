@@ -334,3 +334,38 @@ def test_device_lbfgs_fixed_step_mode_and_masks():
     bh, bd = host.get_all(best=True), devo.get_all(best=True)
     for k in range(K):
         assert np.abs(bh[k, :sizes[k]] - bd[k, :sizes[k]]).max() <= 1e-2 * max(np.abs(bh[k, :sizes[k]]).max(), 1e-6)
+
+
+@pytest.mark.parametrize("version,scheme,D", [("hybrid", "Ralston", 3), ("logdet", "Euler", 3), ("classic", "Ralston", 2)])
+def test_midsize_support_stage_kernels_vs_oracle(version, scheme, D):
+    """Mid-size supports (150 / 333 points) x tens of thousands of data points per frame, evaluated by the lock-step stage kernels
+    (small_rhs_step_kernel in its 128-register form, small_adj_mid_kernel + small_mid_finish_kernel): loss and gradient of every
+    frame against the fp64 oracle (core/LDDMM.py:363-371 + core/PSR.py:498-516 restated in oracle/lddmm.py)."""
+    from diff_icp_b200 import shooting
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from oracle.lddmm import LDDMMOracle
+    sig, lam, nt = 0.2, 30.0, 2
+    Ms, Nxs = [150, 333, 97], [30000, 27001, 29500]
+    LM = LDDMMModel(sigma=sig, D=D, lambd=lam, version=version, scheme=scheme, nt=nt, spec=spec())
+    g = torch.Generator().manual_seed(11)
+    q0 = [torch.rand(m, D, generator=g) for m in Ms]
+    x0 = [torch.rand(n, D, generator=g) for n in Nxs]
+    y = [x + 0.03 * torch.randn(x.shape, generator=g) for x in x0]
+    inv = [0.5 + torch.rand(n, generator=g) for n in Nxs]
+    p = [0.01 * torch.randn(m, D, generator=g) for m in Ms]
+    plan = shooting.BatchedClosurePlan(D, nt, scheme, LM.withlogdet, sig, LM.eta, lam, dev(), Ms, Nxs, use_graph=False)
+    plan.set_geometry([q.to(dev()) for q in q0], [x.to(dev()) for x in x0])
+    plan.set_targets(torch.cat(y).to(dev()), torch.cat(inv).to(dev()))
+    plan.active[:] = 1
+    for k in range(len(Ms)):
+        plan.X[k, :Ms[k] * D] = p[k].reshape(-1).numpy()
+    plan.evaluate()
+    OR = LDDMMOracle(sigma=sig, D=D, lambd=lam, version=version, scheme=scheme, nt=nt, chunk=4096)
+    for k in range(len(Ms)):
+        po = p[k].double().requires_grad_(True)
+        Lo, _ = OR.loss(q0[k].double(), po, x0[k].double(), y[k].double(), inv[k].double())
+        (go,) = torch.autograd.grad(Lo, [po])
+        go = go.reshape(-1).numpy()
+        gk = plan.grads[k * plan.ostride:k * plan.ostride + Ms[k] * D]
+        assert abs(plan.losses[k] - float(Lo)) < 2e-5 * abs(float(Lo)), (k, plan.losses[k], float(Lo))
+        assert np.abs(gk - go).max() < 2e-4 * np.abs(go).max(), (k, np.abs(gk - go).max(), np.abs(go).max())
