@@ -271,22 +271,19 @@ static bool small_mid_applicable(long long maxM, long long maxNx, long long fram
     if (sym_mode() == 0 || maxM <= kRingMaxQ || maxNx <= 0 || forced == 0) return false;
     return forced == 1 || frames * ((maxNx + kRingRows - 1) / kRingRows) >= device_info().sms;
 }
-// data points per lane of an x CTA: 4 (fewest shuffles per pair) when that gives at least kMidWaves4 waves of x CTAs, else 2 (a
-// short grid of long CTAs ends in a badly filled last wave)
-static constexpr int kMidWaves4 = 2;
-static int small_mid_rows_per_lane(long long maxNx, long long frames) {
+// data points per lane of an x CTA: 4 (fewest shuffles per pair) or 2, by the fill of the grid's last wave (small_rows_by_waves)
+static int small_mid_rows_per_lane(long long maxM, long long maxNx, long long frames) {
     static const int forced = [] {           // DICP_SMALL_MID_R = 2 / 4: tuning sweeps only
         const char* e = getenv("DICP_SMALL_MID_R");
         const int v = e ? atoi(e) : 0;
         return (v == 2 || v == 4) ? v : 0;
     }();
     if (forced) return forced;
-    const long long ctas4 = frames * ((maxNx + kRingRows - 1) / kRingRows);
-    return ctas4 >= (long long)kMidWaves4 * kSmallMinbBig * device_info().sms ? 4 : 2;
+    return small_rows_by_waves(frames, maxNx, frames * ((maxM + kSmallThreads - 1) / kSmallThreads), device_info().sms, 2);
 }
 template <int DD, bool W, bool E>
 static void launch_small_mid(const SmallStep& S, long long maxM, long long maxNx, unsigned frames, cudaStream_t st) {
-    const int R = small_mid_rows_per_lane(maxNx, frames), rows = kSmallThreads * R;
+    const int R = small_mid_rows_per_lane(maxM, maxNx, frames), rows = kSmallThreads * R;
     const dim3 grid((unsigned)((maxNx + rows - 1) / rows + (maxM + kSmallThreads - 1) / kSmallThreads), frames);
     if (R == 4) small_adj_mid_kernel<DD, W, E, 4><<<grid, kSmallThreads, 0, st>>>(S);
     else small_adj_mid_kernel<DD, W, E, 2><<<grid, kSmallThreads, 0, st>>>(S);
@@ -658,7 +655,7 @@ int dicp_small_rhs_step(int D, int withlogdet, float sigma, float eta, int64_t M
     if (rc != DICP_OK) return rc;
     if (!s_eval || !F || (out && !base) || (eta != 0.f && !withlogdet)) return DICP_EBADARG;
     S.s_eval = s_eval; S.base = base; S.other = other; S.out = out; S.This = F; S.c_this = c_this; S.c_other = c_other;
-    const int xpass = small_big(M) ? small_xpass_big(1, Nx, device_info().sms) : small_xpass(1, Nx, device_info().sms);
+    const int xpass = small_big(M) ? small_xpass_big(1, Nx, M, device_info().sms) : small_xpass(1, Nx, device_info().sms);
     const unsigned grid = (unsigned)((Nx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass) + (M + kSmallThreads - 1) / kSmallThreads);
     cudaStream_t st = (cudaStream_t)stream;
     dispatch_small_rhs(D, withlogdet, eta, S, xpass, dim3(grid), M, st);
@@ -711,7 +708,7 @@ int dicp_batch_rhs_step(int D, int withlogdet, float sigma, float eta, int K, co
     if (rc != DICP_OK) return rc;
     if (!s_eval || !F || (out && !base) || (eta != 0.f && !withlogdet)) return DICP_EBADARG;
     S.s_eval = s_eval; S.base = base; S.other = other; S.out = out; S.This = F; S.c_this = c_this; S.c_other = c_other;
-    const int xpass = small_big(maxM) ? small_xpass_big(K, maxNx, device_info().sms) : small_xpass(K, maxNx, device_info().sms);
+    const int xpass = small_big(maxM) ? small_xpass_big(K, maxNx, maxM, device_info().sms) : small_xpass(K, maxNx, device_info().sms);
     const dim3 grid((unsigned)((maxNx + kSmallThreads * xpass - 1) / (kSmallThreads * xpass) +
                                (maxM + kSmallThreads - 1) / kSmallThreads), (unsigned)K);
     cudaStream_t st = (cudaStream_t)stream;

@@ -951,16 +951,31 @@ inline int small_xpass(long long frames, long long maxNx, int sms) {
     return r >= 8 ? 8 : r >= 4 ? 4 : r >= 2 ? 2 : 1;
 }
 
-// BIG forward instantiation: 4 rows of a thread swept together whenever that still leaves ~2 CTAs per SM, else 2, else 1
-inline int small_xpass_big(long long frames, long long maxNx, int sms) {
+// Mid-size supports: CTAs of 128 threads x `rows` data points per thread (rows = 4, 2 or 1; more rows per thread = fewer
+// shared-memory loads / shuffles per pair), 4 resident per SM.  A short grid of long CTAs ends in a badly filled last wave (8 frames
+// x 50k points at 4 rows: 1.46 waves, i.e. the time of 2), so the largest `rows` whose grid fills its last wave to >= 85 % is
+// taken, else the best-filled one.  `extra`: the other CTAs of the launch (support-point rows).
+inline int small_rows_by_waves(long long frames, long long maxNx, long long extra, int sms, int min_rows) {
+    int best = min_rows;
+    double best_eff = -1.0;
+    for (int rows = 4; rows >= min_rows; rows >>= 1) {
+        const long long n = frames * ((maxNx + (long long)kSmallThreads * rows - 1) / ((long long)kSmallThreads * rows)) + extra;
+        const double w = (double)n / ((double)kSmallMinbBig * sms);
+        const double eff = w / (double)(long long)(w + 0.999999);
+        if (eff >= 0.85) return rows;
+        if (eff > best_eff) { best_eff = eff; best = rows; }
+    }
+    return best;
+}
+// BIG forward instantiation: rows of a thread swept together = row passes of an x CTA
+inline int small_xpass_big(long long frames, long long maxNx, long long maxM, int sms) {
     static const int forced = [] {
         const char* e = getenv("DICP_SMALL_XPASS");
         const int v = e ? atoi(e) : 0;
         return (v >= 1 && v <= 64) ? v : 0;
     }();
     if (forced) return forced;
-    const long long ctas = frames * ((maxNx + kSmallThreads - 1) / kSmallThreads);
-    return ctas >= 8LL * sms ? 4 : ctas >= 4LL * sms ? 2 : 1;
+    return small_rows_by_waves(frames, maxNx, frames * ((maxM + kSmallThreads - 1) / kSmallThreads), sms, 1);
 }
 
 // dynamic shared memory of the two kernels: the staged column records (pair-interleaved, so an even number of columns)
