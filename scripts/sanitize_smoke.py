@@ -7,6 +7,8 @@ import sys
 import numpy as np
 import torch
 
+os.environ.setdefault("DICP_SMALL_MID", "1")       # read once by the library
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from diff_icp_b200 import em_ops, ops, shooting          # noqa: E402
 from diff_icp_b200.tools.point_sets import decimate, min2_sqdist      # noqa: E402
@@ -48,6 +50,15 @@ for D, scheme, eta in ((2, "Euler", 0.0), (3, "Ralston", 0.02)):
     plan.active[:] = 1
     plan.evaluate()
     plan.finalize([np.zeros((m, D), np.float32) for m in Ms], coverage_radius=0.5)
+# mid-size supports: 128-register forward stage, one-evaluation-per-pair adjoint stage (2 and 4 data points per lane), ragged frames
+# (DICP_SMALL_MID=1 above forces the mid form at these small sizes; run once more with DICP_SMALL_MID_R=4 for the 4-point form)
+for D, scheme, eta in ((3, "Ralston", 0.0), (2, "Euler", 0.02)):
+    Ms, Nxs = [130, 65, 257], [1500, 513, 2050]
+    plan = shooting.BatchedClosurePlan(D, 2, scheme, True, 0.3, eta, 10.0, dev, Ms, Nxs, use_graph=False)
+    plan.set_geometry([uni(m, D) for m in Ms], [uni(n, D) for n in Nxs])
+    plan.set_targets(uni(sum(Nxs), D), torch.full((sum(Nxs),), 5.0, device=dev))
+    plan.active[:] = 1
+    plan.evaluate()
 # EM: packed row passes, few-component column kernel, M step
 N, C, D = 5001, 13, 3
 X, mu, w = uni(N, D), uni(C, D), torch.zeros(C, device=dev)
