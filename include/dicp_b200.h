@@ -196,6 +196,12 @@ int dicp_log_resp(int D, float sigma, const float* X, int64_t N, const float* mu
  * workspace: dicp_small_workspace_bytes(M, Nx) bytes, ZERO-initialised before its first use (it holds ticket counters
  * that the kernels reset themselves), private to one launch sequence.
  *
+ * Kernel forms behind the two entry points (chosen by the library from M, Nx and the frame count; same arguments, results
+ * equal to fp32 rounding): up to 64 support points one launch per stage (adjoint: ring form, every (x,q) pair once); above, a
+ * forward stage compiled for 128 registers and an adjoint stage of two launches (ring rounds over 64-column groups packed from
+ * the state vector + a finish launch that merges the column sums); without data points or with too few CTAs to fill the SMs,
+ * the one-launch form that splits the data columns over CTAs.
+ *
  * forward stage:  F = rhs(s_eval);  out = base + c_this*F + c_other*other   (other, out nullable)
  *   Euler step            s_eval = base = s_t, c_this = h
  *   Ralston stage 1 / 2   (tools/integrators.py:42-48)  c_this = 2h/3  /  base = s_t, other = F1, c_this = 3h/4, c_other = h/4 */
