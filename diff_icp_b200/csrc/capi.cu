@@ -264,10 +264,9 @@ static void dispatch_small_ring(int D, int withlogdet, float eta, const SmallSte
 // mid form of the adjoint stage (small_adj_mid_kernel + small_mid_finish_kernel): more than kRingMaxQ support points and
 // enough data points that the 512-row x CTAs of all frames fill the SMs at least once
 static bool small_mid_applicable(long long maxM, long long maxNx, long long frames) {
-    static const int forced = [] {           // DICP_SMALL_MID = 0 / 1: never / whenever it can run (tests, tuning sweeps)
-        const char* e = getenv("DICP_SMALL_MID");
-        return e ? atoi(e) : -1;
-    }();
+    // DICP_SMALL_MID = 0 / 1: never / whenever it can run (tests, tuning sweeps; read at every call so that a test can switch it)
+    const char* e = getenv("DICP_SMALL_MID");
+    const int forced = e ? atoi(e) : -1;
     if (sym_mode() == 0 || maxM <= kRingMaxQ || maxNx <= 0 || forced == 0) return false;
     return forced == 1 || frames * ((maxNx + kRingRows - 1) / kRingRows) >= device_info().sms;
 }

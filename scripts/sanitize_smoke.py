@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import torch
 
-os.environ.setdefault("DICP_SMALL_MID", "1")       # read once by the library
+os.environ.setdefault("DICP_SMALL_MID", "1")       # forces the mid-size stage kernels wherever they can run
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from diff_icp_b200 import em_ops, ops, shooting          # noqa: E402

@@ -58,9 +58,10 @@ def run_two_set(golden, to_dev, monkeypatch, case, ordering):
     is selected through the reference's own 'xB = GMM' hack (:131-136).  ordering="keops": the product's default path."""
     from diff_icp_b200.api.ICP_two_set import ICP_two_set
     from diff_icp_b200.core.GMM import GaussianMixtureUnif
-    g = golden("two_set")
+    g = golden("two_set_fine" if case == "decimfine" else "two_set")
     xA, xB = to_dev(g["in_xA"]), to_dev(g["in_xB"])
-    support = {"dense": {"scheme": "dense"}, "decim": {"scheme": "decim", "rho": 1.0}}[case]
+    support = {"dense": {"scheme": "dense"}, "decim": {"scheme": "decim", "rho": 1.0},
+               "decimfine": {"scheme": "decim", "rho": 0.7}}[case]
     tr = FETrace(monkeypatch)
     if ordering == "torch":
         G = GaussianMixtureUnif(xB, sigma=0.1, computversion="torch")          # default spec, like the API itself

@@ -352,7 +352,7 @@ def _patch_coverage():
     GaussKernel.check_coverage = lambda self, X, Y, R: ((X[:, None, :] - Y[None, :, :]) ** 2).sum(-1).min(dim=1).values > (R * self.sigma) ** 2
 
 
-def gen_two_set():
+def gen_two_set(cases=None, fname="two_set.npz"):
     """api.ICP_two_set of the unmodified reference (api/ICP_two_set.py:73-288): 3-D clouds, dense support, API-default
     full logdet model, sigma optimised; 3 outer iterations.  Two cases: no outliers / optimised
     outlier weight is NOT run (device-less zeros in log_ratio_to_proba make it CPU-only in the reference anyway, fine here)."""
@@ -369,7 +369,7 @@ def gen_two_set():
     warp = torch.exp(-((xall[:, None, :] - cen[None]) ** 2).sum(-1) / (2 * 0.3 ** 2)) @ amp
     xB = (xall + warp)[torch.randperm(NA + NB, generator=g)[:NB]] + 0.01 * torch.randn(NB, 3, generator=g)
     out["in_xA"], out["in_xB"] = xA.numpy(), xB.contiguous().numpy()
-    for case, gmm_par, num_opt in (
+    for case, gmm_par, num_opt in cases or (
             ("dense", {"sigma": 0.1, "optimize_sigma": True, "outlier_weight": None}, {"support_LDDMM": {"scheme": "dense"}}),
             ("decim", {"sigma": 0.1, "optimize_sigma": True, "outlier_weight": None}, {"support_LDDMM": {"scheme": "decim", "rho": 1.0}}),
     ):
@@ -396,8 +396,15 @@ def gen_two_set():
             out[f"{case}_{prec}_FE_trace"] = np.array(FE_TRACE)           # after every GMM_opt / Reg_opt (and set-up) update
             for it in range(len(evol["a0"])):
                 out[f"{case}_{prec}_a0_it{it}"] = evol["a0"][it][0].numpy()
-    np.savez_compressed(os.path.join(OUT, "two_set.npz"), **out)
-    print("two_set.npz", len(out))
+    np.savez_compressed(os.path.join(OUT, fname), **out)
+    print(fname, len(out), {k: out[k].shape for k in out if k.endswith("gold_q0")})
+
+
+def gen_two_set_fine():
+    """The same two clouds with a finer decimated support (spacing 0.7 sigma_LDDMM: between 64 and 512 support points, the
+    mid-size regime of the stage kernels; written to its own file so that two_set.npz stays byte-identical)."""
+    gen_two_set(cases=(("decimfine", {"sigma": 0.1, "optimize_sigma": True, "outlier_weight": None},
+                        {"support_LDDMM": {"scheme": "decim", "rho": 0.7}}),), fname="two_set_fine.npz")
 
 
 def structure_sets(K, Ns, seed):
@@ -666,7 +673,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:          # regenerate selected fixtures only
         for what in sys.argv[1:]:
             {"pointsets": lambda: gen_pointsets(rk), "v2p": lambda: gen_v2p(rl), "two_set": gen_two_set,
-             "atlas_s3": gen_atlas_s3, "kernels": lambda: gen_kernels(rk), "lddmm": lambda: gen_lddmm(rl),
+             "two_set_fine": gen_two_set_fine, "atlas_s3": gen_atlas_s3, "kernels": lambda: gen_kernels(rk), "lddmm": lambda: gen_lddmm(rl),
              "gmm": lambda: gen_gmm(rg), "psr": gen_psr, "keops_order": gen_keops_ordering, "keops_order_spread": gen_keops_ordering_spread}[what]()
         sys.exit(0)
     gen_kernels(rk)
@@ -676,6 +683,7 @@ if __name__ == "__main__":
     gen_pointsets(rk)
     gen_v2p(rl)
     gen_two_set()
+    gen_two_set_fine()
     gen_atlas_s3()
     gen_keops_ordering()
     gen_keops_ordering_spread()

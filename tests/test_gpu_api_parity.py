@@ -36,6 +36,16 @@ def test_two_set_api_matches_reference(golden, monkeypatch, default_spec_on_gpu,
     run_two_set(golden, cu, monkeypatch, case, ordering)
 
 
+@pytest.mark.parametrize("mid", ["0", "1"])
+def test_two_set_api_midsize_support_matches_reference(golden, monkeypatch, default_spec_on_gpu, mid):
+    """113 support points (decimation at 0.7 sigma_LDDMM) for 400 data points: the stage kernels in their one-launch form (mid = 0)
+    and in the mid-size form (mid = 1: 128-register forward stage, ring adjoint over 64-column groups + finish launch), which the
+    library only picks by itself when the data points fill the SMs; both against the run of the unmodified reference."""
+    monkeypatch.setenv("DICP_SMALL_MID", mid)
+    PSR = run_two_set(golden, cu, monkeypatch, "decimfine", "torch")
+    assert PSR.q0[0].shape[0] == 113
+
+
 @pytest.mark.parametrize("lockstep", [True, False])
 @pytest.mark.parametrize("ordering", ["torch", "keops"])
 def test_atlas_three_structures_matches_reference(golden, monkeypatch, ordering, lockstep):
