@@ -16,7 +16,9 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        subprocess.check_call(["sh", os.path.join(ROOT, "tests", "hostemu", "build.sh")])
+        if os.environ.get("DICP_HOSTEMU_BUILT") != "1":          # once per test session: spawned ranks inherit the flag
+            subprocess.check_call(["sh", os.path.join(ROOT, "tests", "hostemu", "build.sh")])
+            os.environ["DICP_HOSTEMU_BUILT"] = "1"
         _lib = ctypes.CDLL(os.path.join(ROOT, "tests", "hostemu", "_build", "libdicp_hostemu.so"))
     return _lib
 

@@ -3,5 +3,8 @@
 set -e
 here="$(cd "$(dirname "$0")" && pwd)"
 mkdir -p "$here/_build"
-g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -I/usr/local/cuda/include \
-    -o "$here/_build/libdicp_hostemu.so" "$here/hostemu.cpp"
+# compiled next to the target and renamed: processes that build at the same time (the two ranks of the gloo tests) never load a
+# half-written library
+tmp="$here/_build/libdicp_hostemu.so.$$"
+g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -I/usr/local/cuda/include -o "$tmp" "$here/hostemu.cpp"
+mv -f "$tmp" "$here/_build/libdicp_hostemu.so"
