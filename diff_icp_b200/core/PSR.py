@@ -345,14 +345,25 @@ class DiffPSR(MultiPSR):
     # (64 frames x 10k points, 25 support points, Reg_opt of one iteration): with the L-BFGS state machines on the HOST and the
     # one-launch closure, a second group hides the host work of a round behind the other group's kernel (16.2 / 14.7 / 14.9 /
     # 16.2 ms with 1 / 2 / 3 / 4 groups); with the state machines on the DEVICE (the default where the one-launch closure
-    # applies) there is no host work per round left to hide: 12.8 / 12.7 / 16.0 ms with 1 / 2 / 4 groups.  Default 1.
-    lockstep_groups = 1
-    lockstep_group_min_frames = 8          # below 2 x this many frames a second group is never formed
+    # applies) there is no host work per round left to hide: 12.8 / 12.7 / 16.0 ms with 1 / 2 / 4 groups.
+    # With MID-SIZE supports (more than 64 points: stage kernels of 0.2-1.3 ms) groups pay for another reason: every
+    # stage launch of a group ends in a partly filled wave of long CTAs, and the last lock-step rounds have few active frames;
+    # the other groups' launches fill those holes.  Reg_opt of the configs[3]-shaped atlas (1210 support points, 50k data points
+    # per frame), 1 / 2 / 4 / 8 groups: 64 frames 3490 / 3230 / 3123 / 3349 ms, 16 frames 923 / 871 / 799 / 857 ms, 8 frames
+    # 406 / 368 / 354 ms, 4 frames 205 / 184 ms.
+    # Default None = 1 group for small supports, min(4, K // 2) groups for mid-size supports; an integer forces the count
+    # (subject to lockstep_group_min_frames).
+    lockstep_groups = None
+    lockstep_group_min_frames = 8          # forced counts: below 2 x this many frames a second group is never formed
 
     def _frame_groups(self):
-        G = max(1, int(self.lockstep_groups))
-        while G > 1 and self.K < G * self.lockstep_group_min_frames:
-            G -= 1
+        if self.lockstep_groups is None:
+            mid = max(int(q.shape[0]) for q in self.q0) > 64
+            G = max(1, min(4, self.K // 2)) if mid else 1
+        else:
+            G = max(1, int(self.lockstep_groups))
+            while G > 1 and self.K < G * self.lockstep_group_min_frames:
+                G -= 1
         bounds = [round(g * self.K / G) for g in range(G + 1)]
         return [list(range(bounds[g], bounds[g + 1])) for g in range(G)]
 

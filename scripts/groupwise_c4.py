@@ -46,7 +46,7 @@ def full_frames_3d(frames, n_points, seed=1234):
 
 
 def run_c4(rank, world, dev, comm, n_frames=256, n_points=50000, C=20, iters=3, graph=True, lockstep=True, scheme="Ralston",
-           workers=None, rho=None):
+           workers=None, rho=None, groups=None, group_min=None):
     from diff_icp_b200.core.GMM import GaussianMixtureUnif
     from diff_icp_b200.core.LDDMM import LDDMMModel
     from diff_icp_b200.core.PSR import DiffPSR
@@ -64,6 +64,10 @@ def run_c4(rank, world, dev, comm, n_frames=256, n_points=50000, C=20, iters=3, 
     P.batched_lbfgs = bool(lockstep)
     if workers is not None:
         P.frame_workers = int(workers)
+    if groups is not None:
+        P.lockstep_groups = int(groups)
+    if group_min is not None:
+        P.lockstep_group_min_frames = int(group_min)
     P.set_support_scheme("grid", rho=math.sqrt(2) if rho is None else float(rho))
     P.reinitialize_GMM()
     times = []
@@ -92,7 +96,7 @@ def run_c4(rank, world, dev, comm, n_frames=256, n_points=50000, C=20, iters=3, 
             "support_points": int(P.q0[0].shape[0]),
             "model": f"hybrid, {scheme} nt=10, sigma=0.2, lambda=500, 3-D grid support rho=sqrt(2)",
             "scaling": "strong (frames sharded k mod G over ranks)", "cuda_graph": bool(graph),
-            "lockstep_lbfgs": bool(lockstep) and plan is not None,
+            "lockstep_lbfgs": bool(lockstep) and plan is not None, "lockstep_groups": len(plans or []),
             "closure_rounds_total": None if plan is None else plan.evaluations,
             "FE": P.FE, "sigma": [g.sigma for g in P.GMMi],
             "gmm_opt_ms": [1e3 * a for a, _ in times], "reg_opt_ms": [1e3 * b for _, b in times],
@@ -109,6 +113,8 @@ def main():
     ap.add_argument("--rho", type=float, default=None, help="grid spacing in units of sigma (default sqrt(2))")
     ap.add_argument("--workers", type=int, default=None, help="frames registered concurrently on the per-frame path (threads + streams)")
     ap.add_argument("--scheme", default="Ralston")
+    ap.add_argument("--groups", type=int, default=None, help="lock-step frame groups (DiffPSR.lockstep_groups)")
+    ap.add_argument("--group-min", type=int, default=None, help="DiffPSR.lockstep_group_min_frames")
     args = ap.parse_args()
     rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     dev = torch.device("cuda", lr)
@@ -120,7 +126,7 @@ def main():
         from diff_icp_b200.dist import StatsComm
         comm = StatsComm()
     res = run_c4(rank, world, dev, comm, args.frames, args.points, 20, args.iters, args.graph, args.lockstep, args.scheme,
-                 args.workers, args.rho)
+                 args.workers, args.rho, args.groups, args.group_min)
     if rank == 0:
         print(json.dumps(res))
     if comm is not None:
