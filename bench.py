@@ -419,6 +419,9 @@ def run_b200(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+REF_REDUCTIONS = {"classic": 2, "hybrid": 3, "logdet": 7}
+
+
 def kernel_roofline(args, LM, q, p, dev, ops):
     """Time dicp_rhs_adjoint and dicp_rhs_forward alone (CUDA events, median of 20), measure the FP32 / SFU pipe peaks
     live with the probe kernels, and report the binding-pipe fraction."""
@@ -511,7 +514,11 @@ def kernel_roofline(args, LM, q, p, dev, ops):
                     "frac_lanes_clock": fp_rate_adj / lanes_clock,
                     "physical_pair_evaluations_per_s": (0.5 if symmetric else 1.0) * pairs / t_adj},
         "forward": {"s_per_launch_eager": t_fwd_eager, "s_per_launch": t_fwd, "pairs_per_s": pairs / t_fwd, "fp32_per_pair": alg["fwd_fp32"], "frac": frac_fwd,
-                    "frac_lanes_clock": fp_rate_fwd / lanes_clock},
+                    "frac_lanes_clock": fp_rate_fwd / lanes_clock,
+                    # SURVEY.md 8(d), metric 1: physical pairs/s x the reference reductions ONE fused visit of a pair replaces
+                    # (x = None: classic KRed + GenDKRed = 2, hybrid + GradKRed = 3, logdet 7; core/LDDMM.py:176-227)
+                    "reference_reductions_replaced": REF_REDUCTIONS[args.variant],
+                    "reference_equivalent_pairs_per_s": REF_REDUCTIONS[args.variant] * pairs / t_fwd},
         "measured_peaks": {"ffma_per_s": peaks["ffma"], "mufu_ex2_per_s": peaks["mufu_ex2"], "sms": sms},
         "em_step": em,
     }
