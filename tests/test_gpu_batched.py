@@ -44,6 +44,7 @@ CASES = [
     (3, "logdet", "Euler", 2, [300, 2048], [40000, 40001]),
     (2, "classic", "Euler", 2, [129, 1210, 100, 777], [30000, 513, 28000, 30001]),
     (2, "hybrid", "Ralston", 2, [1025, 200], [45000, 38000]),
+    (3, "hybrid", "Euler", 2, [300, 7, 64, 1], [30000, 26000, 512, 40000]),      # tiny supports in a mid-size batch
     (2, "logdet", "Ralston", 2, [500, 200], [45000, 38000]),
 ]
 
@@ -369,3 +370,30 @@ def test_midsize_support_stage_kernels_vs_oracle(version, scheme, D):
         gk = plan.grads[k * plan.ostride:k * plan.ostride + Ms[k] * D]
         assert abs(plan.losses[k] - float(Lo)) < 2e-5 * abs(float(Lo)), (k, plan.losses[k], float(Lo))
         assert np.abs(gk - go).max() < 2e-4 * np.abs(go).max(), (k, np.abs(gk - go).max(), np.abs(go).max())
+
+
+def test_single_frame_midsize_stage_kernels_vs_oracle():
+    """ONE frame with enough data points to fill the SMs with 512-row CTAs (80 000 points, 150 support points): the per-frame
+    closure (shooting.ClosurePlan -> dicp_small_rhs_step / dicp_small_adj_step) takes the mid-size stage kernels by itself;
+    loss and gradient against the fp64 oracle."""
+    from diff_icp_b200 import shooting
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    from oracle.lddmm import LDDMMOracle
+    D, M, Nx, sig, lam, nt = 3, 150, 80000, 0.2, 30.0, 2
+    LM = LDDMMModel(sigma=sig, D=D, lambd=lam, version="hybrid", scheme="Ralston", nt=nt, spec=spec())
+    g = torch.Generator().manual_seed(17)
+    q0, x0 = torch.rand(M, D, generator=g), torch.rand(Nx, D, generator=g)
+    y = x0 + 0.03 * torch.randn(Nx, D, generator=g)
+    inv = 0.5 + torch.rand(Nx, generator=g)
+    p = 0.01 * torch.randn(M, D, generator=g)
+    sp = LM._spec_for(M, Nx, dev())
+    cp = shooting.ClosurePlan(sp, False, lam)
+    assert cp.plan.small
+    cp.set_problem(q0.to(dev()), x0.to(dev()), y.to(dev()), inv.to(dev()))
+    L, gr = cp.evaluate(p.to(dev()))
+    OR = LDDMMOracle(sigma=sig, D=D, lambd=lam, version="hybrid", scheme="Ralston", nt=nt, chunk=4096)
+    po = p.double().requires_grad_(True)
+    Lo, _ = OR.loss(q0.double(), po, x0.double(), y.double(), inv.double())
+    (go,) = torch.autograd.grad(Lo, [po])
+    assert abs(float(L) - float(Lo)) < 2e-5 * abs(float(Lo))
+    assert np.abs(gr.cpu().numpy() - go.numpy()).max() < 2e-4 * np.abs(go.numpy()).max()
