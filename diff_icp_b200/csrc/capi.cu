@@ -272,12 +272,9 @@ static bool small_mid_applicable(long long maxM, long long maxNx, long long fram
 }
 // data points per lane of an x CTA: 4 (fewest shuffles per pair) or 2, by the fill of the grid's last wave (small_rows_by_waves)
 static int small_mid_rows_per_lane(long long maxM, long long maxNx, long long frames) {
-    static const int forced = [] {           // DICP_SMALL_MID_R = 2 / 4: tuning sweeps only
-        const char* e = getenv("DICP_SMALL_MID_R");
-        const int v = e ? atoi(e) : 0;
-        return (v == 2 || v == 4) ? v : 0;
-    }();
-    if (forced) return forced;
+    const char* e = getenv("DICP_SMALL_MID_R");      // 2 / 4: tests and tuning sweeps (read at every call)
+    const int forced = e ? atoi(e) : 0;
+    if (forced == 2 || forced == 4) return forced;
     return small_rows_by_waves(frames, maxNx, frames * ((maxM + kSmallThreads - 1) / kSmallThreads), device_info().sms, 2);
 }
 template <int DD, bool W, bool E>

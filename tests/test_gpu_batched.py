@@ -397,3 +397,57 @@ def test_single_frame_midsize_stage_kernels_vs_oracle():
     (go,) = torch.autograd.grad(Lo, [po])
     assert abs(float(L) - float(Lo)) < 2e-5 * abs(float(Lo))
     assert np.abs(gr.cpu().numpy() - go.numpy()).max() < 2e-4 * np.abs(go.numpy()).max()
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_midsize_form_equals_one_launch_form_on_random_shapes(seed, monkeypatch):
+    """The two forms of the stage kernels for supports above 64 points (DICP_SMALL_MID = 0: x-row CTAs + column-split q-row CTAs in
+    one launch, every (x,q) pair twice; = 1: ring rounds over 64-column groups + finish launch, every pair once, 2 or 4 data points
+    per lane) on random ragged batches: support sizes 1..2048 incl. the 64 / 65 and 2048 edges, data sizes around the 256 / 512-row
+    CTA edges, all three models, both schemes, D = 2 and 3, random active masks.  Same formulas, other summation orders."""
+    from diff_icp_b200 import shooting
+    from diff_icp_b200.core.LDDMM import LDDMMModel
+    rng = np.random.default_rng(100 + seed)
+    D = int(rng.choice([2, 3]))
+    version = ["classic", "hybrid", "logdet"][seed % 3]
+    scheme = ["Euler", "Ralston"][(seed // 3) % 2]
+    K = int(rng.integers(1, 5))
+    edgesM = [65, 64, 2048, 1, 129, 1210, 2047, 66]
+    edgesN = [1, 255, 256, 257, 511, 512, 513, 1025, 3000]
+    Ms = [int(rng.choice(edgesM)) if rng.random() < 0.5 else int(rng.integers(1, 700)) for _ in range(K)]
+    Ms[0] = max(Ms[0], 65 + seed)                       # at least one support above the ring form's 64 points
+    Nxs = [int(rng.choice(edgesN)) if rng.random() < 0.6 else int(rng.integers(1, 5000)) for _ in range(K)]
+    sig, lam, nt = 0.25, 40.0, 2
+    LM = LDDMMModel(sigma=sig, D=D, lambd=lam, version=version, scheme=scheme, nt=nt, spec=spec())
+    g = torch.Generator().manual_seed(1000 + seed)
+    q0 = [torch.rand(m, D, generator=g).to(dev()) for m in Ms]
+    x0 = [torch.rand(n, D, generator=g).to(dev()) for n in Nxs]
+    y = [torch.rand(n, D, generator=g).to(dev()) for n in Nxs]
+    inv = [(0.5 + torch.rand(n, generator=g)).to(dev()) for n in Nxs]
+    p = [0.01 * torch.randn(m, D, generator=g) for m in Ms]
+    act = [1] + [int(rng.random() < 0.7) for _ in range(K - 1)]
+    res = {}
+    for mid, rows in (("0", None), ("1", "2"), ("1", "4")):
+        monkeypatch.setenv("DICP_SMALL_MID", mid)
+        if rows is None:
+            monkeypatch.delenv("DICP_SMALL_MID_R", raising=False)
+        else:
+            monkeypatch.setenv("DICP_SMALL_MID_R", rows)
+        plan = shooting.BatchedClosurePlan(D, nt, scheme, LM.withlogdet, sig, LM.eta, lam, dev(), Ms, Nxs, use_graph=False)
+        plan.one_launch = False
+        plan.set_geometry(q0, x0)
+        plan.set_targets(torch.cat(y), torch.cat(inv))
+        plan.active[:] = act
+        for k in range(K):
+            plan.X[k, :Ms[k] * D] = p[k].reshape(-1).numpy()
+        plan.evaluate()
+        res[(mid, rows)] = (plan.losses.copy(), plan.grads.copy(), plan.ostride)
+    L0, g0, os_ = res[("0", None)]
+    for key in (("1", "2"), ("1", "4")):
+        L1, g1, _ = res[key]
+        for k in range(K):
+            if not act[k]:
+                continue
+            a, b = g0[k * os_:k * os_ + Ms[k] * D], g1[k * os_:k * os_ + Ms[k] * D]
+            assert abs(L0[k] - L1[k]) <= 1e-5 * abs(L0[k]), (key, k, Ms, Nxs, L0[k], L1[k])
+            assert np.abs(a - b).max() <= 2e-5 * np.abs(a).max(), (key, k, Ms, Nxs, np.abs(a - b).max(), np.abs(a).max())
