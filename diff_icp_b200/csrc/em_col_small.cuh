@@ -25,6 +25,15 @@ static constexpr int kEmColGroup = 16;     // CTAs per level-1 merge group
 static constexpr int kEmColCtasPerSm = DICP_EM_CTAS_PER_SM;   // CTAs per SM of the column-statistics kernels (latency-bound: more resident warps)
 static constexpr int kEmRowR = 4;          // points per thread in the row passes
 static constexpr int kEmRowRows = 128 * kEmRowR;
+#ifndef DICP_EM_ROW_RFULL
+#define DICP_EM_ROW_RFULL 2                // points per thread swept together in the FULL row pass (9-11 packed accumulators per point)
+#endif
+#ifndef DICP_EM_ROW_MINB
+#define DICP_EM_ROW_MINB 5                 // resident CTAs asked of the compiler for the row-pass kernel (register cap)
+// measured on B200 (full pass, 640k x 50 2-D / 1.07M x 20 3-D / 4M x 8 3-D): 4 points, no cap (148 registers) 48.9 / 50.9 / 77.6 us;
+// 2 points 44.5 / 51.2 / 89.7; 4 points, 4 CTAs 47.0 / 46.4 / 76.8; 2 points, 5 CTAs (94 registers) 43.2 / 46.7 / 75.3; 1 point,
+// 6 CTAs 46.5 / 46.8 / 83.8 -- the pass is bound by its instruction count (~50 per point and component pair), not by occupancy
+#endif
 
 // acc <- merge (in a fixed order) of the partials s in [s0, s1) of component c: thread group g takes s0+g, s0+g+G, ...
 // (loads of a batch of 8 issued before they are combined), then the groups are merged in group order through `xch`.
@@ -318,7 +327,7 @@ inline void em_lse_col_small_grid(long long N, int sms, int* blocks, int* passes
 // partials added in block order by scalar_reduce_kernel.  HBM-bound for C <~ 9 (12D + 8 bytes per point and EM step).
 
 template <int D, bool LITE>
-__global__ void __launch_bounds__(128) em_row_small_kernel(EmParams P, int N, int C, int passes,
+__global__ void __launch_bounds__(128, DICP_EM_ROW_MINB) em_row_small_kernel(EmParams P, int N, int C, int passes,
                                                            float* __restrict__ blockscal) {
     using Op = EmRow<D, LITE>;
     constexpr int NF = Op::NF, NACC = Op::NACC, NSCAL = Op::NSCAL, PF4 = NF / 2, REC = 2 * NF;
@@ -341,14 +350,17 @@ __global__ void __launch_bounds__(128) em_row_small_kernel(EmParams P, int N, in
     float scal[NSCAL > 0 ? NSCAL : 1];
 #pragma unroll
     for (int k = 0; k < NSCAL; ++k) scal[k] = 0.f;
-    // `passes` groups of kEmRowRows rows per CTA: the staging of the components is paid once per CTA
-    for (int ps = 0; ps < passes; ++ps) {
-        typename Op::Row row[kEmRowR];
-        F2 acc[kEmRowR][NACC];
-        const int base = (blockIdx.x * passes + ps) * kEmRowRows + tid;
+    // `passes` groups of kEmRowRows rows per CTA: the staging of the components is paid once per CTA; a group is swept RS rows of
+    // a thread at a time
+    constexpr int RS = LITE ? kEmRowR : DICP_EM_ROW_RFULL;
+    static_assert(kEmRowR % RS == 0, "row sweep");
+    for (int ps = 0; ps < passes * (kEmRowR / RS); ++ps) {
+        typename Op::Row row[RS];
+        F2 acc[RS][NACC];
+        const int base = blockIdx.x * passes * kEmRowRows + ps * (128 * RS) + tid;
         if (base - tid >= N) break;
 #pragma unroll
-        for (int r = 0; r < kEmRowR; ++r) {
+        for (int r = 0; r < RS; ++r) {
             const int i = base + r * 128;
             Op::load_row(P, i < N ? i : N - 1, row[r]);
             Op::init_packed(acc[r]);
@@ -361,10 +373,10 @@ __global__ void __launch_bounds__(128) em_row_small_kernel(EmParams P, int N, in
                 c[2 * k] = f2(v.x, v.y);
                 c[2 * k + 1] = f2(v.z, v.w);
             }
-            Op::template pair_rows<F2, kEmRowR>(P, row, c, acc);
+            Op::template pair_rows<F2, RS>(P, row, c, acc);
         }
 #pragma unroll
-        for (int r = 0; r < kEmRowR; ++r) {
+        for (int r = 0; r < RS; ++r) {
             const int i = base + r * 128;
             if (i < N) {
                 float a[NACC], rs[NSCAL > 0 ? NSCAL : 1];
