@@ -35,7 +35,7 @@ def spiral_frames(K, N, seed=1234):
 
 
 def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, iters=3, graph=True, workers=1,
-                  lockstep=True, weak=False, groups=None):
+                  lockstep=True, weak=False, groups=None, scheme="Euler"):
     """Returns the dict reported as `groupwise_psr_iteration` (rank 0) -- times are the max over ranks.
     weak=True: `n_frames` frames PER RANK (atlas of n_frames * world frames) instead of n_frames in total."""
     if weak:
@@ -49,7 +49,7 @@ def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, ite
     mine = shard_frames(n_frames, rank, world)
     torch.manual_seed(1234)
     G = GaussianMixtureUnif(torch.zeros(C, 2), spec=spec)
-    LM = LDDMMModel(sigma=0.2, D=2, lambd=500.0, version="hybrid", scheme="Euler", nt=10, spec=spec)
+    LM = LDDMMModel(sigma=0.2, D=2, lambd=500.0, version="hybrid", scheme=scheme, nt=10, spec=spec)
     LM.use_cuda_graph = bool(graph)
     P = DiffPSR([frames[k].to(dev) for k in mine], G, LM, dataspec=spec, compspec=spec, comm=comm)
     P.printstuff = False
@@ -79,7 +79,7 @@ def run_groupwise(rank, world, dev, comm, n_frames=64, n_points=10000, C=50, ite
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         times = tt.tolist()
     return {"metric": "groupwise_psr_iteration_ms", "n_gpus": world, "frames": n_frames, "points_per_frame": n_points,
-            "C": C, "support_points": int(P.q0[0].shape[0]), "model": "hybrid, Euler nt=10, grid support rho=sqrt(2), 2-D",
+            "C": C, "support_points": int(P.q0[0].shape[0]), "model": f"hybrid, {scheme} nt=10, grid support rho=sqrt(2), 2-D",
             "scaling": "weak (frames per rank fixed)" if weak else "strong (frames sharded over ranks)", "cuda_graph": bool(graph), "frame_workers": workers, "lockstep_lbfgs": bool(lockstep), "lockstep_groups": len(getattr(P, "_bplan", None) or []),
             "FE": P.FE, "sigma": P.GMMi[0].sigma,
             "gmm_opt_ms": [1e3 * a for a, _ in times], "reg_opt_ms": [1e3 * b for _, b in times],
@@ -96,6 +96,7 @@ def main():
     ap.add_argument("--workers", type=int, default=1)
     ap.add_argument("--lockstep", type=int, default=1)
     ap.add_argument("--weak", type=int, default=0, help="1: --frames is the number of frames per rank")
+    ap.add_argument("--scheme", default="Euler", help="Euler (examples/diffICP_multi.py) or Ralston (the model's default)")
     ap.add_argument("--groups", type=int, default=None, help="frame groups of the lock-step registration (default: DiffPSR's)")
     args = ap.parse_args()
     rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -107,7 +108,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
         from diff_icp_b200.dist import StatsComm
         comm = StatsComm()
-    res = run_groupwise(rank, world, dev, comm, args.frames, args.points, args.C, args.iters, args.graph, args.workers, args.lockstep, bool(args.weak), args.groups)
+    res = run_groupwise(rank, world, dev, comm, args.frames, args.points, args.C, args.iters, args.graph, args.workers, args.lockstep, bool(args.weak), args.groups, args.scheme)
     if rank == 0:
         print(json.dumps(res))
     if comm is not None:
