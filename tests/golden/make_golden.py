@@ -431,14 +431,14 @@ def structure_sets(K, Ns, seed):
     return frames, mus, sigs
 
 
-def gen_atlas_s3():
+def gen_atlas_s3(K=3, Ns=90, seed=712, rho=1.0, fname="atlas_s3.npz"):
     """api.ICP_atlas with S = 3 structures (core/PSR.py:242-271 per-structure GMM loop, :498-516 per-structure sigma in
     the data loss), 3 frames, 3-D, decimated support (the reference's grid is 2-D only), hybrid model, Euler."""
     import diffICP.core.GMM as rg
     import diffICP.api.ICP_atlas as ra
     _patch_coverage()
     out = {}
-    frames, mus, sigs = structure_sets(3, 90, 712)
+    frames, mus, sigs = structure_sets(K, Ns, seed)
     g = torch.Generator().manual_seed(9)
     Cs = (6, 5, 4)
     mu_init = []
@@ -447,7 +447,7 @@ def gen_atlas_s3():
         mu_init.append(alls[torch.randperm(len(alls), generator=g)[:Cs[s]]].clone())
         out[f"in_mu{s}"] = mu_init[s].numpy()
         out[f"in_sigma{s}"] = np.array(2.0 * sigs[s] + 0.05)
-        for k in range(3):
+        for k in range(K):
             out[f"in_x{k}_{s}"] = frames[k][s].numpy()
     for prec, dt in [("ref32", torch.float32), ("gold", torch.float64)]:
         sp = spec_of(dt)
@@ -457,14 +457,14 @@ def gen_atlas_s3():
                                  GMM_parameters={"init_components": GM, "optimize_weights": True},
                                  registration_parameters={"type": "diffeomorphic", "lambda_LDDMM": 100.0, "sigma_LDDMM": 0.3},
                                  numerical_options={"computversion": "torch", "compspec": sp, "dataspec": sp,
-                                                    "support_LDDMM": {"scheme": "decim", "rho": 1.0}},
+                                                    "support_LDDMM": {"scheme": "decim", "rho": rho}},
                                  optim_options={"max_iterations": 3, "max_repeat_GMM": 10, "convergence_tolerance": 1e-3},
                                  printstuff=False)
         out[f"{prec}_FE"] = np.array(float(PSR.FE))
         out[f"{prec}_Cfe"] = np.array([float(c) for c in PSR.Cfe])
         out[f"{prec}_FE_trace"] = np.array(FE_TRACE)
         for it in range(len(evol["a0"])):
-            for k in range(3):
+            for k in range(K):
                 out[f"{prec}_a0_it{it}_{k}"] = evol["a0"][it][k].numpy()
         out[f"{prec}_quadloss"] = np.asarray(PSR.quadloss, dtype=np.float64)
         out[f"{prec}_regloss"] = np.array([float(r) for r in PSR.regloss])
@@ -472,12 +472,18 @@ def gen_atlas_s3():
             out[f"{prec}_sigma{s}"] = np.array(float(PSR.GMMi[s].sigma))
             out[f"{prec}_mu{s}"] = PSR.GMMi[s].mu.numpy()
             out[f"{prec}_w{s}"] = PSR.GMMi[s].w.numpy()
-            for k in range(3):
+            for k in range(K):
                 out[f"{prec}_x1_{k}_{s}"] = PSR.x1[k, s].numpy()
-        for k in range(3):
+        for k in range(K):
             out[f"{prec}_q0_{k}"] = PSR.q0[k].numpy()
-    np.savez_compressed(os.path.join(OUT, "atlas_s3.npz"), **out)
-    print("atlas_s3.npz", len(out))
+    np.savez_compressed(os.path.join(OUT, fname), **out)
+    print(fname, len(out), [out[f"gold_q0_{k}"].shape[0] for k in range(K)])
+
+
+def gen_atlas_mid():
+    """The same three-structure atlas with 4 larger frames and a finer decimated support (spacing 0.5 sigma_LDDMM): more than 64
+    support points per frame, i.e. the mid-size stage kernels and the frame groups of the lock-step registration end to end."""
+    gen_atlas_s3(K=4, Ns=150, seed=713, rho=0.5, fname="atlas_mid.npz")
 
 
 class _keops_ordering:
@@ -673,7 +679,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:          # regenerate selected fixtures only
         for what in sys.argv[1:]:
             {"pointsets": lambda: gen_pointsets(rk), "v2p": lambda: gen_v2p(rl), "two_set": gen_two_set,
-             "two_set_fine": gen_two_set_fine, "atlas_s3": gen_atlas_s3, "kernels": lambda: gen_kernels(rk), "lddmm": lambda: gen_lddmm(rl),
+             "two_set_fine": gen_two_set_fine, "atlas_s3": gen_atlas_s3, "atlas_mid": gen_atlas_mid, "kernels": lambda: gen_kernels(rk), "lddmm": lambda: gen_lddmm(rl),
              "gmm": lambda: gen_gmm(rg), "psr": gen_psr, "keops_order": gen_keops_ordering, "keops_order_spread": gen_keops_ordering_spread}[what]()
         sys.exit(0)
     gen_kernels(rk)
@@ -685,5 +691,6 @@ if __name__ == "__main__":
     gen_two_set()
     gen_two_set_fine()
     gen_atlas_s3()
+    gen_atlas_mid()
     gen_keops_ordering()
     gen_keops_ordering_spread()

@@ -54,6 +54,22 @@ def test_atlas_three_structures_matches_reference(golden, monkeypatch, ordering,
     run_atlas_s3(golden, cu, monkeypatch, spec(), ordering)
 
 
+@pytest.mark.parametrize("mid", ["0", "1"])
+def test_atlas_midsize_supports_matches_reference(golden, monkeypatch, mid):
+    """4 frames x 3 structures with 78-94 support points per frame (decimation at 0.5 sigma_LDDMM), lock-step registration in two
+    frame groups (DiffPSR.lockstep_groups = None: automatic above 64 support points); stage kernels in the one-launch form
+    (mid = 0) and in the mid-size form (mid = 1), against the run of the unmodified reference.  Free-energy floor 1e-3 of the
+    trace's scale instead of 5e-4: after the first registration all runs agree to 2e-5 (-1966.52 / -1966.53 here, -1966.56 / -1966.58
+    reference fp32 / fp64); the second and third unconverged L-BFGS steps amplify the summation-order differences of the two
+    kernel forms to 1 and 2.6 units of 3700 (the reference's own fp32 / fp64 runs drift apart by 0.7), one form above and one
+    below the fp64 trace.  Momenta against the fp64 run: after the first registration 2e-4 / 7e-5 / 0 / 2.5e-4 per frame (reference
+    fp32: 1.7e-4 / 5e-5 / 0 / 3e-5); after the second the reference's own fp32 run is off by 1.2e-2 and 1.6e-2 on two frames and
+    the two kernel forms by 3e-2 on one resp. three frames -- hence the floor of 3 % of sigma_LDDMM on points and centroids."""
+    monkeypatch.setenv("DICP_SMALL_MID", mid)
+    PSR = run_atlas_s3(golden, cu, monkeypatch, spec(), "torch", name="atlas_mid", K=4, rho=0.5, fe_floor=1e-3, pt_floor=3e-2)
+    assert min(int(q.shape[0]) for q in PSR.q0) > 64 and len(PSR._bplan) == 2
+
+
 @pytest.mark.parametrize("lockstep", [True, False])
 def test_atlas_2d_keops_ordering_matches_reference_loop(golden, monkeypatch, lockstep):
     from diff_icp_b200.core.PSR import DiffPSR
