@@ -79,3 +79,34 @@ def test_api_option_handling(monkeypatch):
                           optim_options={"max_iterations": 2, "max_repeat_GMM": 3}, printstuff=False)
     assert PSR.LMi.withlogdet and not PSR.LMi.gradcomponent and PSR.LMi.scheme == "Euler" and PSR.LMi.nt == 10
     assert PSR.support_scheme == "grid" and len(evol["a0"]) == 2 and np.isfinite(PSR.FE)
+
+
+def test_lockstep_frame_groups_rule():
+    """DiffPSR._frame_groups: one group for small supports, min(4, K // 2) contiguous groups above 64 support points (the other
+    groups' launches fill the partly filled last waves and the late lock-step rounds of a group), a forced count subject to
+    lockstep_group_min_frames; every frame in exactly one group, in order."""
+    from diff_icp_b200.core.PSR import DiffPSR
+
+    class Stub:
+        lockstep_groups = None
+        lockstep_group_min_frames = 8
+        _frame_groups = DiffPSR._frame_groups
+
+    def groups(K, M, forced=None, gmin=8):
+        s = Stub()
+        s.K, s.q0 = K, [torch.zeros(M if k else max(M - 3, 1), 2) for k in range(K)]
+        s.lockstep_groups, s.lockstep_group_min_frames = forced, gmin
+        g = s._frame_groups()
+        assert [k for grp in g for k in grp] == list(range(K)) and all(len(grp) > 0 for grp in g)
+        return [len(grp) for grp in g]
+
+    assert groups(64, 25) == [64]                       # small supports: one group (device L-BFGS, one-launch closure)
+    assert groups(64, 64) == [64]
+    assert groups(64, 65) == [16, 16, 16, 16]
+    assert groups(8, 1210) == [2, 2, 2, 2]
+    assert groups(5, 300) == [2, 3] or groups(5, 300) == [3, 2]
+    assert groups(3, 300) == [3]
+    assert groups(1, 300) == [1]
+    assert groups(64, 25, forced=2) == [32, 32]
+    assert groups(10, 25, forced=2) == [10]             # forced counts need 2 x lockstep_group_min_frames frames
+    assert groups(10, 25, forced=2, gmin=4) == [5, 5]
