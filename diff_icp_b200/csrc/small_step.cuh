@@ -755,10 +755,14 @@ __global__ void __launch_bounds__(kSmallThreads) small_adj_ring_kernel(SmallStep
 // (small_mid_finish_kernel) adds the x CTAs' column sums in CTA order, finishes the support points' gradients and applies their
 // cotangent update.  Two launches per adjoint stage; before, mid-size supports paid every (x,q) pair twice
 // (small_adj_step_kernel) or ~15 launches per stage (tiled engine).  Deterministic, no atomics.
+#ifndef DICP_MID_MINB
+#define DICP_MID_MINB kSmallMinbBig         // resident CTAs asked for the mid-size adjoint stage; measured on B200: 3 (168 registers)
+                                            // instead of 4 (128) changes nothing (Reg_opt of 16 configs[3] frames 919 vs 914 ms)
+#endif
 static constexpr int kMidQChunk = 256;                             // support columns per staged chunk of a (q,q) CTA
 
 template <int D, bool WLD, bool ETA, int R>
-__global__ void __launch_bounds__(kSmallThreads, kSmallMinbBig) small_adj_mid_kernel(SmallStep S) {
+__global__ void __launch_bounds__(kSmallThreads, DICP_MID_MINB) small_adj_mid_kernel(SmallStep S) {
     using OpX = typename std::conditional<ETA, AdjXQE<D>, AdjXQ<D, WLD>>::type;
     using OpQQ = typename std::conditional<ETA, AdjQQEta<D, 1>, AdjQQ<D, false, 1>>::type;      // x present: see the ring form
     constexpr int NF = OpX::NF, REC = 2 * NF, STRIDE = SymStride<REC>::value, NC = OpX::NACC_COL, NAQ = OpQQ::NACC;
